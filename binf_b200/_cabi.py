@@ -1,0 +1,267 @@
+"""ctypes binding of libbinf_b200.so -- the only route from Python to the CUDA kernels.
+
+There is no CPU fallback: if the library is missing or cannot be loaded, importing a
+compute entry point raises.  Signatures mirror include/binf_b200.h one to one.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbinf_b200.so")
+
+OK, EINVAL, ECUDA, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4
+MODEL_POLYNOMIAL, MODEL_CHROMATIN = 1, 2
+FLAG_PRIOR_GRAD = 1
+GIBBS_NONE, GIBBS_TAU_FIRST, GIBBS_TAU_LAST = 0, 1, 2
+
+
+class BinfB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("binf_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+class HmcOpts(C.Structure):
+    _fields_ = [("n_steps", C.c_int32), ("n_traj", C.c_int32), ("n_adapt", C.c_int32),
+                ("gibbs_mode", C.c_int32), ("adapt_up", C.c_double), ("adapt_down", C.c_double),
+                ("seed", C.c_uint64), ("draw", C.c_uint64), ("chain_base", C.c_uint64)]
+
+
+_vp, _i, _d, _u64, _ll = C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_longlong
+_pi, _pd, _pll = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_longlong)
+
+# name -> (restype, argtypes); kept in the order of include/binf_b200.h
+SIGNATURES = {
+    "binfb_version": (_i, []),
+    "binfb_last_error": (C.c_char_p, []),
+    "binfb_device_count": (_i, [_pi]),
+    "binfb_device_props": (_i, [_i, _pi, _pi, _pi, _pi]),
+    "binfb_model_create_polynomial": (_i, [_vp, _vp, _i, _i, _vp, _vp, _d, _d, C.c_uint, _i,
+                                           C.POINTER(_vp)]),
+    "binfb_model_create_chromatin": (_i, [_i, _vp, _d, _d, _d, _d, _d, _d, _d, C.c_uint, _i,
+                                          C.POINTER(_vp)]),
+    "binfb_model_destroy": (_i, [_vp]),
+    "binfb_model_info": (_i, [_vp, _pi, _pi, _pll, _pi]),
+    "binfb_model_set_gamma_prior": (_i, [_vp, _d, _d]),
+    "binfb_model_set_option": (_i, [_vp, C.c_char_p, _d]),
+    "binfb_logprob_grad": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "binfb_logprob_grad_host": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "binfb_forward_host": (_i, [_vp, _vp, _i, _vp]),
+    "binfb_hmc_run": (_i, [_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(HmcOpts)] + [_vp] * 11),
+    "binfb_hmc_run_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(HmcOpts)] + [_vp] * 10),
+    "binfb_gibbs_precision": (_i, [_vp, _vp, _vp, _vp, _i, _u64, _u64, _u64, _vp, _vp, _vp]),
+    "binfb_gibbs_precision_host": (_i, [_vp, _vp, _vp, _vp, _i, _u64, _u64, _u64, _vp, _vp]),
+    "binfb_swap_decide": (_i, [_vp, _vp, _d, _d, _i, _u64, _u64, _u64, _u64, _vp, _vp]),
+    "binfb_swap_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "binfb_rng_fill_host": (_i, [_u64, _u64, _u64, _i, _i, _d, _vp, _vp, _vp, _i]),
+    "binfb_chromatin_stream_layout": (_i, [_i, _vp, _vp, _ll, _pll, _pi, _pi]),
+    "binfb_microbench": (_i, [_i, _i, _pd, _pd, _pd, _pd]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libbinf_b200.so not found at %s -- build it with `python -m binf_b200.build` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(code):
+    if code != OK:
+        raise BinfB200Error(code, lib().binfb_last_error().decode())
+
+
+def ptr(a):
+    """void* of a numpy array (None -> NULL), an int device pointer, or a torch tensor."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(a.data_ptr())  # torch tensor
+
+
+def f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def device_count():
+    n = C.c_int(0)
+    check(lib().binfb_device_count(C.byref(n)))
+    return n.value
+
+
+def device_props(device=0):
+    sm, smem, clk, cc = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    check(lib().binfb_device_props(device, C.byref(sm), C.byref(smem), C.byref(clk), C.byref(cc)))
+    return dict(sm_count=sm.value, smem_optin=smem.value, clock_khz=clk.value, cc=cc.value)
+
+
+def microbench(device=0, iters=2000):
+    a, b, c, d = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+    check(lib().binfb_microbench(device, iters, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+    return dict(ffma_tflops=a.value, ffma2_tflops=b.value, mufu_gops=c.value, sm_clock_mhz=d.value)
+
+
+def chromatin_stream_layout(n_beads, y_pairs):
+    """Host-only: the contact stream exactly as the pair kernel consumes it."""
+    y = f32(y_pairs)
+    n_floats, q, t = C.c_longlong(), C.c_int(), C.c_int()
+    check(lib().binfb_chromatin_stream_layout(n_beads, ptr(y), None, 0, C.byref(n_floats),
+                                              C.byref(q), C.byref(t)))
+    out = np.empty(n_floats.value, dtype=np.float32)
+    check(lib().binfb_chromatin_stream_layout(n_beads, ptr(y), ptr(out), out.size, None, None, None))
+    return out, q.value, t.value
+
+
+def rng_fill(seed, draw, chain_base, n_chains, dim, gamma_shape=1.0, device=0):
+    normals = np.empty((n_chains, dim), dtype=np.float32)
+    uniforms = np.empty(n_chains, dtype=np.float32)
+    gammas = np.empty(n_chains, dtype=np.float64)
+    check(lib().binfb_rng_fill_host(seed, draw, chain_base, n_chains, dim, gamma_shape,
+                                    ptr(normals), ptr(uniforms), ptr(gammas), device))
+    return normals, uniforms, gammas
+
+
+class Model(object):
+    """Owning wrapper of a `binfb_model*`."""
+
+    def __init__(self, handle):
+        self._h = handle
+        kind, dim, n_data, dev = C.c_int(), C.c_int(), C.c_longlong(), C.c_int()
+        check(lib().binfb_model_info(self._h, C.byref(kind), C.byref(dim), C.byref(n_data),
+                                     C.byref(dev)))
+        self.kind, self.dim, self.n_data, self.device = kind.value, dim.value, n_data.value, dev.value
+
+    @classmethod
+    def polynomial(cls, xs, ys, n_coeff, prior_mean=None, prior_var=None, gamma_shape=1.0,
+                   gamma_rate=1.0, flags=0, device=0):
+        xs, ys = f64(xs), f64(ys)
+        pm, pv = f64(prior_mean), f64(prior_var)
+        h = C.c_void_p()
+        check(lib().binfb_model_create_polynomial(ptr(xs), ptr(ys), len(xs), n_coeff, ptr(pm),
+                                                  ptr(pv), gamma_shape, gamma_rate, flags, device,
+                                                  C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def chromatin(cls, n_beads, y_pairs, alpha, d_c, k_bb, l0, conf_s=0.0, gamma_shape=1.0,
+                  gamma_rate=1.0, flags=0, device=0):
+        y = f32(y_pairs)
+        assert y.shape == (n_beads * (n_beads - 1) // 2,)
+        h = C.c_void_p()
+        check(lib().binfb_model_create_chromatin(n_beads, ptr(y), alpha, d_c, k_bb, l0, conf_s,
+                                                 gamma_shape, gamma_rate, flags, device,
+                                                 C.byref(h)))
+        return cls(h)
+
+    def close(self):
+        if self._h is not None:
+            lib().binfb_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_gamma_prior(self, shape, rate):
+        check(lib().binfb_model_set_gamma_prior(self._h, shape, rate))
+
+    def set_option(self, key, value):
+        check(lib().binfb_model_set_option(self._h, key.encode(), float(value)))
+
+    # ---- host-buffer entry points (numpy in, numpy out) ------------------------------------
+    def logprob_grad(self, q, tau, beta=None, want_grad=True):
+        q = f32(q).reshape(-1, self.dim)
+        n = q.shape[0]
+        tau = np.ascontiguousarray(np.broadcast_to(f32(tau), (n,)))
+        beta = None if beta is None else np.ascontiguousarray(np.broadcast_to(f32(beta), (n,)))
+        logp, chi2 = np.empty(n), np.empty(n)
+        grad = np.empty_like(q) if want_grad else None
+        check(lib().binfb_logprob_grad_host(self._h, ptr(q), ptr(tau), ptr(beta), n, ptr(logp),
+                                            ptr(grad), ptr(chi2)))
+        return logp, grad, chi2
+
+    def forward(self, q):
+        q = f32(q).reshape(-1, self.dim)
+        mock = np.empty((q.shape[0], self.n_data), dtype=np.float32)
+        check(lib().binfb_forward_host(self._h, ptr(q), q.shape[0], ptr(mock)))
+        return mock
+
+    def hmc_run(self, q, tau, eps, n_steps, n_traj=1, beta=None, p0=None, u=None,
+                gamma_draws=None, n_adapt=0, adapt_up=1.05, adapt_down=0.95,
+                gibbs_mode=GIBBS_NONE, seed=0, draw=0, chain_base=0, want_end=False):
+        """Returns a dict; q/tau/eps are NOT modified in place (copies are returned)."""
+        q = np.array(f32(q).reshape(-1, self.dim))
+        n = q.shape[0]
+        tau = np.array(np.broadcast_to(f32(tau), (n,)))
+        eps = np.array(np.broadcast_to(f32(eps), (n,)))
+        beta = None if beta is None else np.ascontiguousarray(np.broadcast_to(f32(beta), (n,)))
+        p0 = None if p0 is None else f32(p0).reshape(n, self.dim)
+        u = None if u is None else f32(u).reshape(n)
+        gamma_draws = None if gamma_draws is None else f64(gamma_draws).reshape(n)
+        opts = HmcOpts(n_steps, n_traj, n_adapt, gibbs_mode, adapt_up, adapt_down, seed, draw,
+                       chain_base)
+        accepted = np.empty(n, dtype=np.uint8)
+        e0, e1 = np.empty(n), np.empty(n)
+        q_end = np.empty_like(q) if want_end else None
+        p_end = np.empty_like(q) if want_end else None
+        nacc = np.empty(n, dtype=np.int32)
+        stats = np.zeros(4)
+        check(lib().binfb_hmc_run_host(self._h, ptr(q), ptr(tau), ptr(beta), ptr(eps), n,
+                                       C.byref(opts), ptr(p0), ptr(u), ptr(gamma_draws),
+                                       ptr(accepted), ptr(e0), ptr(e1), ptr(q_end), ptr(p_end),
+                                       ptr(nacc), ptr(stats)))
+        return dict(q=q, tau=tau, eps=eps, accepted=accepted.astype(bool), e_before=e0,
+                    e_after=e1, q_end=q_end, p_end=p_end, n_accepted=nacc, stats=stats)
+
+    def gibbs_precision(self, q, tau, beta=None, gamma_draws=None, seed=0, draw=0, chain_base=0):
+        q = f32(q).reshape(-1, self.dim)
+        n = q.shape[0]
+        tau = np.array(np.broadcast_to(f32(tau), (n,)))
+        beta = None if beta is None else np.ascontiguousarray(np.broadcast_to(f32(beta), (n,)))
+        gamma_draws = None if gamma_draws is None else f64(gamma_draws).reshape(n)
+        chi2 = np.empty(n)
+        check(lib().binfb_gibbs_precision_host(self._h, ptr(q), ptr(tau), ptr(beta), n, seed, draw,
+                                               chain_base, ptr(gamma_draws), ptr(chi2)))
+        return tau, chi2
+
+    # ---- device-pointer entry points (torch CUDA tensors; asynchronous on `stream`) ----------
+    def hmc_run_device(self, q, tau, eps, opts, beta=None, p0=None, u=None, gamma_draws=None,
+                       accepted=None, e_before=None, e_after=None, q_end=None, p_end=None,
+                       n_accepted=None, stats=None, stream=None):
+        check(lib().binfb_hmc_run(self._h, ptr(q), ptr(tau), ptr(beta), ptr(eps), q.shape[0],
+                                  C.byref(opts), ptr(p0), ptr(u), ptr(gamma_draws), ptr(accepted),
+                                  ptr(e_before), ptr(e_after), ptr(q_end), ptr(p_end),
+                                  ptr(n_accepted), ptr(stats), ptr(stream)))
+
+    def logprob_grad_device(self, q, tau, beta=None, logp=None, grad=None, chi2=None, stream=None):
+        check(lib().binfb_logprob_grad(self._h, ptr(q), ptr(tau), ptr(beta), q.shape[0], ptr(logp),
+                                       ptr(grad), ptr(chi2), ptr(stream)))
+
+    def gibbs_precision_device(self, q, tau, chi2, beta=None, gamma_draws=None, seed=0, draw=0,
+                               chain_base=0, stream=None):
+        check(lib().binfb_gibbs_precision(self._h, ptr(q), ptr(tau), ptr(beta), q.shape[0], seed,
+                                          draw, chain_base, ptr(gamma_draws), ptr(chi2),
+                                          ptr(stream)))

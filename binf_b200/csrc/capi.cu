@@ -1,0 +1,520 @@
+// C ABI of libbinf_b200.so (declared in include/binf_b200.h).
+#include <math.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace binfb {
+
+static thread_local std::string g_error;
+
+void set_error(const std::string &msg) { g_error = msg; }
+
+int cuda_fail(cudaError_t e, const char *what) {
+    g_error = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();  // clear the sticky-less error state
+    return BINFB_ECUDA;
+}
+
+static int check_model(const binfb_model *m) {
+    if (!m) {
+        set_error("null model handle");
+        return BINFB_EINVAL;
+    }
+    return BINFB_OK;
+}
+
+static HmcArgs make_hmc_args(const binfb_model *m, float *q, float *tau, const float *beta,
+                             float *eps, int C, const binfb_hmc_opts *o, const float *p0,
+                             const float *u, const double *gamma_draws, uint8_t *accepted,
+                             double *e_before, double *e_after, float *q_end, float *p_end,
+                             int32_t *n_accepted, double *stats) {
+    HmcArgs a;
+    a.q = q, a.tau = tau, a.beta = beta, a.eps = eps, a.C = C;
+    a.L = o->n_steps, a.n_traj = o->n_traj, a.n_adapt = o->n_adapt, a.gibbs_mode = o->gibbs_mode;
+    a.adapt_up = (float)o->adapt_up, a.adapt_down = (float)o->adapt_down;
+    a.seed = o->seed, a.draw = o->draw, a.chain_base = o->chain_base;
+    a.p0 = p0, a.u = u, a.gamma_draws = gamma_draws;
+    a.accepted = accepted, a.e_before = e_before, a.e_after = e_after;
+    a.q_end = q_end, a.p_end = p_end, a.n_accepted = n_accepted, a.stats = stats;
+    a.gamma_shape = m->gamma_shape, a.gamma_rate = m->gamma_rate;
+    return a;
+}
+
+static int check_hmc(const binfb_model *m, int C, const binfb_hmc_opts *o, const void *q,
+                     const void *tau, const void *eps, const void *p0, const void *u) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (!o || !q || !tau || !eps) {
+        set_error("hmc_run: q, tau, eps and opts are required");
+        return BINFB_EINVAL;
+    }
+    if (C < 1 || o->n_steps < 1 || o->n_traj < 1) {
+        set_error("hmc_run: n_chains, n_steps and n_traj must be >= 1");
+        return BINFB_EINVAL;
+    }
+    if ((p0 || u) && o->n_traj != 1) {
+        set_error("hmc_run: injected momenta / uniforms require n_traj == 1");
+        return BINFB_EINVAL;
+    }
+    if (o->gibbs_mode < 0 || o->gibbs_mode > 2) {
+        set_error("hmc_run: bad gibbs_mode");
+        return BINFB_EINVAL;
+    }
+    return BINFB_OK;
+}
+
+// scratch device memory for the *_host entry points: one growing arena per model
+struct Arena {
+    binfb_model *m;
+    size_t used = 0;
+    std::vector<size_t> sizes;
+    explicit Arena(binfb_model *mm) : m(mm) {}
+    size_t plan(size_t bytes) {
+        const size_t off = used;
+        used += (bytes + 255) / 256 * 256;
+        return off;
+    }
+    int commit() {
+        if (used > m->hb_bytes) {
+            if (m->hb) cudaFree(m->hb);
+            m->hb = nullptr, m->hb_bytes = 0;
+            BINFB_CUDA(cudaMalloc(&m->hb, used));
+            m->hb_bytes = used;
+        }
+        return BINFB_OK;
+    }
+    template <typename T>
+    T *at(size_t off) {
+        return reinterpret_cast<T *>(m->hb + off);
+    }
+};
+
+static int host_stream(binfb_model *m) {
+    if (!m->hstream) BINFB_CUDA(cudaStreamCreateWithFlags(&m->hstream, cudaStreamNonBlocking));
+    return BINFB_OK;
+}
+
+}  // namespace binfb
+
+using namespace binfb;
+
+extern "C" {
+
+int binfb_version(void) { return BINFB_VERSION; }
+
+const char *binfb_last_error(void) { return g_error.c_str(); }
+
+int binfb_device_count(int *count) {
+    if (!count) return BINFB_EINVAL;
+    *count = 0;
+    BINFB_CUDA(cudaGetDeviceCount(count));
+    return BINFB_OK;
+}
+
+int binfb_device_props(int device, int *sm_count, int *smem_optin, int *clock_khz, int *cc) {
+    cudaDeviceProp p;
+    BINFB_CUDA(cudaGetDeviceProperties(&p, device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (smem_optin) *smem_optin = (int)p.sharedMemPerBlockOptin;
+    if (clock_khz) cudaDeviceGetAttribute(clock_khz, cudaDevAttrClockRate, device);
+    if (cc) *cc = p.major * 10 + p.minor;
+    return BINFB_OK;
+}
+
+static int model_common_init(binfb_model *m, int device) {
+    m->device = device;
+    BINFB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    BINFB_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major < 10) {
+        set_error("binf_b200 kernels are built for sm_100a (Blackwell) only; device is sm_" +
+                  std::to_string(p.major * 10 + p.minor));
+        return BINFB_EUNSUPPORTED;
+    }
+    m->sm_count = p.multiProcessorCount;
+    m->smem_optin = (int)p.sharedMemPerBlockOptin;
+    return BINFB_OK;
+}
+
+int binfb_model_create_polynomial(const double *xs, const double *ys, int n_data, int n_coeff,
+                                  const double *prior_mean, const double *prior_var,
+                                  double gamma_shape, double gamma_rate, unsigned flags, int device,
+                                  binfb_model **out) {
+    if (!xs || !ys || !out || n_data < 1) {
+        set_error("model_create_polynomial: xs, ys, out required, n_data >= 1");
+        return BINFB_EINVAL;
+    }
+    if (n_coeff < 1 || n_coeff > 8) {
+        set_error("model_create_polynomial: n_coeff must be in 1..8");
+        return BINFB_EUNSUPPORTED;
+    }
+    binfb_model *m = new binfb_model();
+    int rc = model_common_init(m, device);
+    if (rc) {
+        delete m;
+        return rc;
+    }
+    m->kind = BINFB_MODEL_POLYNOMIAL, m->dim = n_coeff, m->n_data = n_data;
+    m->gamma_shape = gamma_shape, m->gamma_rate = gamma_rate;
+    PolyModel &pm = m->poly;
+    pm.N = n_data, pm.K = n_coeff, pm.stride = (n_coeff + 3) / 4 * 4, pm.flags = flags;
+    for (int k = 0; k < 8; ++k) {
+        pm.prior_mean[k] = (k < n_coeff && prior_mean) ? (float)prior_mean[k] : 0.f;
+        pm.prior_inv_var[k] = (k < n_coeff && prior_var) ? (float)(1.0 / prior_var[k]) : 0.f;
+    }
+    // rows [x, x^2, .., x^(K-1), y, pad]: powers formed in float64 like the reference's
+    // xs ** i (binf/example/likelihood.py:30), rounded once to float32
+    std::vector<float> rows((size_t)n_data * pm.stride, 0.f);
+    for (int n = 0; n < n_data; ++n) {
+        double pw = 1.0;
+        for (int k = 1; k < n_coeff; ++k) {
+            pw *= xs[n];
+            rows[(size_t)n * pm.stride + k - 1] = (float)pw;
+        }
+        rows[(size_t)n * pm.stride + n_coeff - 1] = (float)ys[n];
+    }
+    cudaError_t e = cudaMalloc(&pm.rows, rows.size() * sizeof(float));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(pm.rows, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        binfb_model_destroy(m);
+        return cuda_fail(e, "polynomial data upload");
+    }
+    *out = m;
+    return BINFB_OK;
+}
+
+int binfb_model_create_chromatin(int n_beads, const float *y_pairs, double alpha, double d_c,
+                                 double k_bb, double l0, double conf_s, double gamma_shape,
+                                 double gamma_rate, unsigned flags, int device, binfb_model **out) {
+    if (!y_pairs || !out || n_beads < 2) {
+        set_error("model_create_chromatin: y_pairs, out required, n_beads >= 2");
+        return BINFB_EINVAL;
+    }
+    binfb_model *m = new binfb_model();
+    int rc = model_common_init(m, device);
+    if (rc) {
+        delete m;
+        return rc;
+    }
+    m->kind = BINFB_MODEL_CHROMATIN, m->dim = 3 * n_beads;
+    m->n_data = (long long)n_beads * (n_beads - 1) / 2;
+    m->gamma_shape = gamma_shape, m->gamma_rate = gamma_rate;
+    ChromModel &cm = m->chrom;
+    cm.n = n_beads, cm.n_pad = (n_beads + 3) / 4 * 4, cm.Q = cm.n_pad / 4, cm.KS = cm.Q / 2;
+    cm.NRB = (cm.Q + 31) / 32;
+    cm.M = m->n_data;
+    cm.alpha = (float)alpha, cm.d_c = (float)d_c, cm.k_bb = (float)k_bb, cm.l0 = (float)l0;
+    cm.inv_s2 = conf_s > 0.0 ? (float)(1.0 / (conf_s * conf_s)) : 0.f;
+    cm.flags = flags;
+    long long n_floats = 0;
+    int Q = 0, T = 0;
+    rc = chrom_build_stream(n_beads, y_pairs, nullptr, 0, &n_floats, &Q, &T);
+    if (rc) {
+        delete m;
+        return rc;
+    }
+    cm.T = T, cm.T_pad = (T + CHROM_STAGE_STEPS - 1) / CHROM_STAGE_STEPS * CHROM_STAGE_STEPS;
+    std::vector<float> stream((size_t)n_floats);
+    rc = chrom_build_stream(n_beads, y_pairs, stream.data(), n_floats, nullptr, nullptr, nullptr);
+    cudaError_t e = cudaSuccess;
+    if (!rc) e = cudaMalloc(&cm.ystream, (size_t)n_floats * sizeof(float));
+    if (!rc && e == cudaSuccess)
+        e = cudaMemcpy(cm.ystream, stream.data(), (size_t)n_floats * sizeof(float), cudaMemcpyHostToDevice);
+    if (!rc && e == cudaSuccess) e = cudaMalloc(&cm.ypairs, (size_t)cm.M * sizeof(float));
+    if (!rc && e == cudaSuccess)
+        e = cudaMemcpy(cm.ypairs, y_pairs, (size_t)cm.M * sizeof(float), cudaMemcpyHostToDevice);
+    if (rc || e != cudaSuccess) {
+        binfb_model_destroy(m);
+        return rc ? rc : cuda_fail(e, "chromatin data upload");
+    }
+    *out = m;
+    return BINFB_OK;
+}
+
+int binfb_model_destroy(binfb_model *m) {
+    if (!m) return BINFB_OK;
+    cudaSetDevice(m->device);
+    cudaFree(m->poly.rows);
+    ChromModel &c = m->chrom;
+    cudaFree(c.ystream), cudaFree(c.ypairs), cudaFree(c.qw), cudaFree(c.pw), cudaFree(c.h0);
+    cudaFree(c.chi2_0), cudaFree(c.chi2_state), cudaFree(c.tau_w), cudaFree(c.sched);
+    if (m->hb) cudaFree(m->hb);
+    if (m->hstream) cudaStreamDestroy(m->hstream);
+    delete m;
+    return BINFB_OK;
+}
+
+int binfb_model_info(const binfb_model *m, int *kind, int *dim, long long *n_data, int *device) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (kind) *kind = m->kind;
+    if (dim) *dim = m->dim;
+    if (n_data) *n_data = m->n_data;
+    if (device) *device = m->device;
+    return BINFB_OK;
+}
+
+int binfb_model_set_gamma_prior(binfb_model *m, double shape, double rate) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    m->gamma_shape = shape, m->gamma_rate = rate;
+    return BINFB_OK;
+}
+
+int binfb_model_set_option(binfb_model *m, const char *key, double value) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (!key) return BINFB_EINVAL;
+    const int v = value < 0 ? -1 : (int)value;
+    if (!strcmp(key, "poly.group")) m->poly.opt_group = v;
+    else if (!strcmp(key, "poly.chains_per_thread")) m->poly.opt_jchains = v;
+    else if (!strcmp(key, "poly.block")) m->poly.opt_block = v;
+    else if (!strcmp(key, "chrom.warps")) m->chrom.opt_warps = v;
+    else {
+        set_error(std::string("unknown option: ") + key);
+        return BINFB_EINVAL;
+    }
+    return BINFB_OK;
+}
+
+int binfb_logprob_grad(binfb_model *m, const float *q, const float *tau, const float *beta, int C,
+                       double *logp, float *grad, double *chi2, void *stream) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (!q || !tau || C < 1) {
+        set_error("logprob_grad: q, tau required, n_chains >= 1");
+        return BINFB_EINVAL;
+    }
+    BINFB_CUDA(cudaSetDevice(m->device));
+    GradArgs a;
+    a.q = q, a.tau = tau, a.beta = beta, a.C = C, a.logp = logp, a.grad = grad, a.chi2 = chi2;
+    a.gamma_shape = m->gamma_shape, a.gamma_rate = m->gamma_rate;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (m->kind == BINFB_MODEL_POLYNOMIAL) return poly_grad_launch(m->poly, a, m->sm_count, m->smem_optin, s);
+    return chrom_grad_launch(m->chrom, a, m->sm_count, m->smem_optin, s);
+}
+
+int binfb_logprob_grad_host(binfb_model *m, const float *q, const float *tau, const float *beta,
+                            int C, double *logp, float *grad, double *chi2) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (!q || !tau || C < 1) {
+        set_error("logprob_grad_host: q, tau required, n_chains >= 1");
+        return BINFB_EINVAL;
+    }
+    BINFB_CUDA(cudaSetDevice(m->device));
+    if ((rc = host_stream(m))) return rc;
+    const size_t D = m->dim;
+    Arena ar(m);
+    const size_t oq = ar.plan(C * D * 4), ot = ar.plan(C * 4), ob = ar.plan(C * 4), ol = ar.plan(C * 8),
+                 og = ar.plan(C * D * 4), oc = ar.plan(C * 8);
+    if ((rc = ar.commit())) return rc;
+    cudaStream_t s = m->hstream;
+    BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(oq), q, C * D * 4, cudaMemcpyHostToDevice, s));
+    BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(ot), tau, C * 4, cudaMemcpyHostToDevice, s));
+    if (beta) BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(ob), beta, C * 4, cudaMemcpyHostToDevice, s));
+    rc = binfb_logprob_grad(m, ar.at<float>(oq), ar.at<float>(ot), beta ? ar.at<float>(ob) : nullptr, C,
+                            ar.at<double>(ol), grad ? ar.at<float>(og) : nullptr, ar.at<double>(oc), s);
+    if (rc) return rc;
+    if (logp) BINFB_CUDA(cudaMemcpyAsync(logp, ar.at<double>(ol), C * 8, cudaMemcpyDeviceToHost, s));
+    if (grad) BINFB_CUDA(cudaMemcpyAsync(grad, ar.at<float>(og), C * D * 4, cudaMemcpyDeviceToHost, s));
+    if (chi2) BINFB_CUDA(cudaMemcpyAsync(chi2, ar.at<double>(oc), C * 8, cudaMemcpyDeviceToHost, s));
+    BINFB_CUDA(cudaStreamSynchronize(s));
+    return BINFB_OK;
+}
+
+int binfb_forward_host(binfb_model *m, const float *q, int C, float *mock) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (!q || !mock || C < 1) {
+        set_error("forward_host: q, mock required, n_chains >= 1");
+        return BINFB_EINVAL;
+    }
+    BINFB_CUDA(cudaSetDevice(m->device));
+    if ((rc = host_stream(m))) return rc;
+    const size_t D = m->dim, N = (size_t)m->n_data;
+    Arena ar(m);
+    const size_t oq = ar.plan(C * D * 4), om = ar.plan(C * N * 4);
+    if ((rc = ar.commit())) return rc;
+    cudaStream_t s = m->hstream;
+    BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(oq), q, C * D * 4, cudaMemcpyHostToDevice, s));
+    if (m->kind == BINFB_MODEL_POLYNOMIAL) rc = poly_forward_launch(m->poly, ar.at<float>(oq), C, ar.at<float>(om), s);
+    else rc = chrom_forward_launch(m->chrom, ar.at<float>(oq), C, ar.at<float>(om), s);
+    if (rc) return rc;
+    BINFB_CUDA(cudaMemcpyAsync(mock, ar.at<float>(om), C * N * 4, cudaMemcpyDeviceToHost, s));
+    BINFB_CUDA(cudaStreamSynchronize(s));
+    return BINFB_OK;
+}
+
+int binfb_hmc_run(binfb_model *m, float *q, float *tau, const float *beta, float *eps, int C,
+                  const binfb_hmc_opts *opts, const float *p0, const float *u,
+                  const double *gamma_draws, uint8_t *accepted, double *e_before, double *e_after,
+                  float *q_end, float *p_end, int32_t *n_accepted, double *stats, void *stream) {
+    int rc = check_hmc(m, C, opts, q, tau, eps, p0, u);
+    if (rc) return rc;
+    BINFB_CUDA(cudaSetDevice(m->device));
+    const HmcArgs a = make_hmc_args(m, q, tau, beta, eps, C, opts, p0, u, gamma_draws, accepted,
+                                    e_before, e_after, q_end, p_end, n_accepted, stats);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (m->kind == BINFB_MODEL_POLYNOMIAL) return poly_hmc_launch(m->poly, a, m->sm_count, m->smem_optin, s);
+    return chrom_hmc_launch(m->chrom, a, m->sm_count, m->smem_optin, s);
+}
+
+int binfb_hmc_run_host(binfb_model *m, float *q, float *tau, const float *beta, float *eps, int C,
+                       const binfb_hmc_opts *opts, const float *p0, const float *u,
+                       const double *gamma_draws, uint8_t *accepted, double *e_before,
+                       double *e_after, float *q_end, float *p_end, int32_t *n_accepted,
+                       double *stats) {
+    int rc = check_hmc(m, C, opts, q, tau, eps, p0, u);
+    if (rc) return rc;
+    BINFB_CUDA(cudaSetDevice(m->device));
+    if ((rc = host_stream(m))) return rc;
+    const size_t D = m->dim;
+    Arena ar(m);
+    const size_t oq = ar.plan(C * D * 4), ot = ar.plan(C * 4), ob = ar.plan(C * 4), oe = ar.plan(C * 4),
+                 op = ar.plan(C * D * 4), ou = ar.plan(C * 4), og = ar.plan(C * 8), oa = ar.plan(C),
+                 o0 = ar.plan(C * 8), o1 = ar.plan(C * 8), oqe = ar.plan(C * D * 4),
+                 ope = ar.plan(C * D * 4), on = ar.plan(C * 4), os = ar.plan(32);
+    if ((rc = ar.commit())) return rc;
+    cudaStream_t s = m->hstream;
+    BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(oq), q, C * D * 4, cudaMemcpyHostToDevice, s));
+    BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(ot), tau, C * 4, cudaMemcpyHostToDevice, s));
+    BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(oe), eps, C * 4, cudaMemcpyHostToDevice, s));
+    if (beta) BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(ob), beta, C * 4, cudaMemcpyHostToDevice, s));
+    if (p0) BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(op), p0, C * D * 4, cudaMemcpyHostToDevice, s));
+    if (u) BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(ou), u, C * 4, cudaMemcpyHostToDevice, s));
+    if (gamma_draws)
+        BINFB_CUDA(cudaMemcpyAsync(ar.at<double>(og), gamma_draws, C * 8, cudaMemcpyHostToDevice, s));
+    if (stats) BINFB_CUDA(cudaMemsetAsync(ar.at<double>(os), 0, 32, s));
+    rc = binfb_hmc_run(m, ar.at<float>(oq), ar.at<float>(ot), beta ? ar.at<float>(ob) : nullptr,
+                       ar.at<float>(oe), C, opts, p0 ? ar.at<float>(op) : nullptr,
+                       u ? ar.at<float>(ou) : nullptr, gamma_draws ? ar.at<double>(og) : nullptr,
+                       accepted ? ar.at<uint8_t>(oa) : nullptr, e_before ? ar.at<double>(o0) : nullptr,
+                       e_after ? ar.at<double>(o1) : nullptr, q_end ? ar.at<float>(oqe) : nullptr,
+                       p_end ? ar.at<float>(ope) : nullptr, n_accepted ? ar.at<int32_t>(on) : nullptr,
+                       stats ? ar.at<double>(os) : nullptr, s);
+    if (rc) return rc;
+    BINFB_CUDA(cudaMemcpyAsync(q, ar.at<float>(oq), C * D * 4, cudaMemcpyDeviceToHost, s));
+    BINFB_CUDA(cudaMemcpyAsync(tau, ar.at<float>(ot), C * 4, cudaMemcpyDeviceToHost, s));
+    BINFB_CUDA(cudaMemcpyAsync(eps, ar.at<float>(oe), C * 4, cudaMemcpyDeviceToHost, s));
+    if (accepted) BINFB_CUDA(cudaMemcpyAsync(accepted, ar.at<uint8_t>(oa), C, cudaMemcpyDeviceToHost, s));
+    if (e_before) BINFB_CUDA(cudaMemcpyAsync(e_before, ar.at<double>(o0), C * 8, cudaMemcpyDeviceToHost, s));
+    if (e_after) BINFB_CUDA(cudaMemcpyAsync(e_after, ar.at<double>(o1), C * 8, cudaMemcpyDeviceToHost, s));
+    if (q_end) BINFB_CUDA(cudaMemcpyAsync(q_end, ar.at<float>(oqe), C * D * 4, cudaMemcpyDeviceToHost, s));
+    if (p_end) BINFB_CUDA(cudaMemcpyAsync(p_end, ar.at<float>(ope), C * D * 4, cudaMemcpyDeviceToHost, s));
+    if (n_accepted) BINFB_CUDA(cudaMemcpyAsync(n_accepted, ar.at<int32_t>(on), C * 4, cudaMemcpyDeviceToHost, s));
+    if (stats) BINFB_CUDA(cudaMemcpyAsync(stats, ar.at<double>(os), 32, cudaMemcpyDeviceToHost, s));
+    BINFB_CUDA(cudaStreamSynchronize(s));
+    return BINFB_OK;
+}
+
+int binfb_gibbs_precision(binfb_model *m, const float *q, float *tau, const float *beta, int C,
+                          uint64_t seed, uint64_t draw, uint64_t chain_base,
+                          const double *gamma_draws, double *chi2, void *stream) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (!q || !tau || !chi2 || C < 1) {
+        set_error("gibbs_precision: q, tau, chi2 (device scratch/output [C]) required");
+        return BINFB_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    // chi^2 at the current state: one fused forward pass (GammaSampler._calculate_rate calls
+    // Likelihood.log_prob(precision=1), binf/example/samplers.py:34-38)
+    rc = binfb_logprob_grad(m, q, tau, beta, C, nullptr, nullptr, chi2, stream);
+    if (rc) return rc;
+    return gibbs_tau_launch(chi2, tau, beta, C, (double)m->n_data, m->gamma_shape, m->gamma_rate, seed,
+                            draw, chain_base, gamma_draws, s);
+}
+
+int binfb_gibbs_precision_host(binfb_model *m, const float *q, float *tau, const float *beta, int C,
+                               uint64_t seed, uint64_t draw, uint64_t chain_base,
+                               const double *gamma_draws, double *chi2) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (!q || !tau || C < 1) {
+        set_error("gibbs_precision_host: q, tau required");
+        return BINFB_EINVAL;
+    }
+    BINFB_CUDA(cudaSetDevice(m->device));
+    if ((rc = host_stream(m))) return rc;
+    const size_t D = m->dim;
+    Arena ar(m);
+    const size_t oq = ar.plan(C * D * 4), ot = ar.plan(C * 4), ob = ar.plan(C * 4), og = ar.plan(C * 8),
+                 oc = ar.plan(C * 8);
+    if ((rc = ar.commit())) return rc;
+    cudaStream_t s = m->hstream;
+    BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(oq), q, C * D * 4, cudaMemcpyHostToDevice, s));
+    BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(ot), tau, C * 4, cudaMemcpyHostToDevice, s));
+    if (beta) BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(ob), beta, C * 4, cudaMemcpyHostToDevice, s));
+    if (gamma_draws)
+        BINFB_CUDA(cudaMemcpyAsync(ar.at<double>(og), gamma_draws, C * 8, cudaMemcpyHostToDevice, s));
+    rc = binfb_gibbs_precision(m, ar.at<float>(oq), ar.at<float>(ot), beta ? ar.at<float>(ob) : nullptr, C,
+                               seed, draw, chain_base, gamma_draws ? ar.at<double>(og) : nullptr,
+                               ar.at<double>(oc), s);
+    if (rc) return rc;
+    BINFB_CUDA(cudaMemcpyAsync(tau, ar.at<float>(ot), C * 4, cudaMemcpyDeviceToHost, s));
+    if (chi2) BINFB_CUDA(cudaMemcpyAsync(chi2, ar.at<double>(oc), C * 8, cudaMemcpyDeviceToHost, s));
+    BINFB_CUDA(cudaStreamSynchronize(s));
+    return BINFB_OK;
+}
+
+int binfb_swap_decide(const double *ll_a, const double *ll_b, double beta_a, double beta_b, int C,
+                      uint64_t seed, uint64_t attempt, uint64_t pair_id, uint64_t chain_base,
+                      uint8_t *accept, void *stream) {
+    if (!ll_a || !ll_b || !accept || C < 1) {
+        set_error("swap_decide: ll_a, ll_b, accept required");
+        return BINFB_EINVAL;
+    }
+    return swap_decide_launch(ll_a, ll_b, beta_a, beta_b, C, seed, attempt, pair_id, chain_base, accept,
+                              (cudaStream_t)stream);
+}
+
+int binfb_swap_apply(float *q_mine, const float *q_theirs, float *eps_mine, const float *eps_theirs,
+                     const uint8_t *accept, int C, int dim, void *stream) {
+    if (!q_mine || !q_theirs || !accept || C < 1 || dim < 1) {
+        set_error("swap_apply: q_mine, q_theirs, accept required");
+        return BINFB_EINVAL;
+    }
+    return swap_apply_launch(q_mine, q_theirs, eps_mine, eps_theirs, accept, C, dim, (cudaStream_t)stream);
+}
+
+int binfb_rng_fill_host(uint64_t seed, uint64_t draw, uint64_t chain_base, int C, int D,
+                        double gamma_shape, float *normals, float *uniforms, double *gammas,
+                        int device) {
+    if (C < 1 || D < 1) return BINFB_EINVAL;
+    BINFB_CUDA(cudaSetDevice(device));
+    float *dn = nullptr, *du = nullptr;
+    double *dg = nullptr;
+    if (normals) BINFB_CUDA(cudaMalloc(&dn, (size_t)C * D * 4));
+    if (uniforms) BINFB_CUDA(cudaMalloc(&du, (size_t)C * 4));
+    if (gammas) BINFB_CUDA(cudaMalloc(&dg, (size_t)C * 8));
+    int rc = rng_fill_launch(seed, draw, chain_base, C, D, gamma_shape, dn, du, dg, 0);
+    if (!rc) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess && normals) e = cudaMemcpy(normals, dn, (size_t)C * D * 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && uniforms) e = cudaMemcpy(uniforms, du, (size_t)C * 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && gammas) e = cudaMemcpy(gammas, dg, (size_t)C * 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "rng_fill");
+    }
+    cudaFree(dn), cudaFree(du), cudaFree(dg);
+    return rc;
+}
+
+int binfb_chromatin_stream_layout(int n_beads, const float *y_pairs, float *out, long long capacity,
+                                  long long *n_floats, int *n_quads, int *n_steps) {
+    return chrom_build_stream(n_beads, y_pairs, out, capacity, n_floats, n_quads, n_steps);
+}
+
+int binfb_microbench(int device, int iters, double *ffma_tflops, double *ffma2_tflops,
+                     double *mufu_gops, double *sm_clock_mhz) {
+    if (iters < 1) return BINFB_EINVAL;
+    return microbench_run(device, iters, ffma_tflops, ffma2_tflops, mufu_gops, sm_clock_mhz);
+}
+
+}  // extern "C"

@@ -1,0 +1,629 @@
+// Fused HMC / log-prob+gradient for the chromatin bead-chain posterior -- sm_100a.
+//
+// What it replaces: for the contact-frequency model of SURVEY.md A.2 expressed behind the
+// reference API, every pdf.gradient / pdf.log_prob call made by HMCSampler._leapfrog / .sample
+// (binf/samplers/hmc.py:92-125,136-164), i.e. Posterior._evaluate_gradient
+// (binf/pdf/posteriors.py:173-187) -> Likelihood._evaluate_gradient = J(theta).dot(dE/dmock)
+// (binf/pdf/likelihoods.py:148-155) with the GaussianErrorModel (binf/example/likelihood.py:54-61),
+// the structure prior, the Metropolis test and the step-size adaption (hmc.py:151-157), and the
+// conjugate precision update (binf/example/samplers.py:27-51).  The 3n x M Jacobian (12 GB at
+// n = 1000) is never formed: the pair loop applies it on the fly.
+//
+// Work decomposition
+//   * one WARP per chain; W (<= 8) chains per CTA share one stream of contact data y.
+//   * beads are grouped in quads (4 beads).  Quad a is paired with quads (a+k) mod Q,
+//     k = 1..Q/2 ("circulant half shell"): every unordered quad pair is visited exactly once and
+//     every quad has the same number of partners, so there is no triangular waste.  Lane l of the
+//     warp owns quad a = 32*rb + l of row block rb; its 4 bead positions and force accumulators
+//     stay in registers for the whole row block.  Each step is a 4x4 block of bead pairs: 12
+//     positions + 12 partner-force accumulators + 16 contacts in registers, 16 pair evaluations.
+//   * within a step the 32 lanes address 32 distinct partner quads, so the read-modify-write of the
+//     partner forces in shared memory is conflict- and race-free without atomics.
+//   * contacts are pre-laid-out on the host in exactly the order the lanes consume them
+//     ([row block][step][row r][lane] float4).  A producer warp streams that array through a
+//     4-stage shared-memory ring with 1-D bulk async copies (TMA engine, UBLKCP) completing on
+//     mbarriers; all W consumer warps read the same stage, so L2->SM traffic is 1/W of naive.
+//   * scheduling: a work item is (trajectory, leapfrog pass, group of W chains).  CTAs are
+//     persistent and claim items from an atomic counter; a per-group pass counter (release/acquire)
+//     orders the passes of one group.  Between passes q and p round-trip through L2 (24 KB per
+//     chain per pass, <0.1 % of the pass) -- this removes the 3.46-waves quantisation a
+//     "whole trajectory per CTA" launch has at C = 4096 on 148 SMs.
+#include <math.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace binfb {
+
+constexpr float CHROM_SOFT = 1e-12f;
+constexpr int SS = CHROM_STAGE_STEPS;
+constexpr int NS = CHROM_STAGES;
+constexpr int STEP_FLOAT4 = 4 * 32;                 // float4 per warp-step
+constexpr int STAGE_FLOAT4 = SS * STEP_FLOAT4;
+constexpr uint32_t STAGE_BYTES = STAGE_FLOAT4 * 16;
+
+struct ChromDev {
+    int n, n_pad, Q, KS, NRB, T, T_pad, q_even;
+    const float4 *ystream;
+    float A, B;  // exp(alpha (d - d_c)) = 2^(A d + B)
+    float alpha, k_bb, l0, inv_s2;
+    double M;
+    // workspace
+    float *qw, *pw;
+    double *h0, *chi2_0, *chi2_state;
+    float *tau_w;
+    int *counter, *pass_done;
+};
+
+enum { CHROM_MODE_GRAD = 0, CHROM_MODE_HMC = 1 };
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// one bead pair: 19 FP32-pipe instructions + 3 MUFU (31 flop by the SURVEY.md 8d count)
+template <bool ENERGY>
+__device__ __forceinline__ void chrom_pair(float xi, float yi, float zi, float xj, float yj,
+                                           float zj, float y, float A, float B, float &fix,
+                                           float &fiy, float &fiz, float &fjx, float &fjy,
+                                           float &fjz, float &chi) {
+    const float dx = xi - xj, dy = yi - yj, dz = zi - zj;
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, CHROM_SOFT)));
+    const float inv = mufu_rsqrt(r2);
+    const float d = r2 * inv;
+    const float e = mufu_ex2(fmaf(d, A, B));
+    const float m = mufu_rcp(1.0f + e);
+    const float res = m - y;
+    const float w = fmaf(-m, m, m);
+    const float coef = res * w * inv;
+    fix = fmaf(coef, dx, fix), fiy = fmaf(coef, dy, fiy), fiz = fmaf(coef, dz, fiz);
+    fjx = fmaf(-coef, dx, fjx), fjy = fmaf(-coef, dy, fjy), fjz = fmaf(-coef, dz, fjz);
+    if (ENERGY) chi = fmaf(res, res, chi);
+}
+
+__device__ __forceinline__ void unpack4(const float4 v, float (&a)[4]) {
+    a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w;
+}
+__device__ __forceinline__ float4 pack4(const float (&a)[4]) {
+    return make_float4(a[0], a[1], a[2], a[3]);
+}
+
+struct WarpSmem {
+    float *xs, *ys, *zs, *fx, *fy, *fz;
+};
+
+// The pair sweep of one chain: fills fx/fy/fz with sum_j coef_ij (x_i - x_j) (the likelihood
+// force up to the factor -alpha*beta*tau) and returns this lane's share of chi^2.
+template <bool ENERGY>
+__device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const WarpSmem &sm,
+                                              const float4 *ystage, uint64_t *full, uint64_t *empty,
+                                              uint32_t &stage_idx, bool chain_valid, int lane) {
+    float4 *xs4 = reinterpret_cast<float4 *>(sm.xs), *ys4 = reinterpret_cast<float4 *>(sm.ys),
+           *zs4 = reinterpret_cast<float4 *>(sm.zs);
+    float4 *fx4 = reinterpret_cast<float4 *>(sm.fx), *fy4 = reinterpret_cast<float4 *>(sm.fy),
+           *fz4 = reinterpret_cast<float4 *>(sm.fz);
+    const float A = cd.A, B = cd.B;
+    double chi2 = 0.0;
+    float xi[4], yi[4], zi[4], fi[4][3];
+    int rb = 0, k = 0, a = lane;
+    bool active = false;
+    uint32_t slot = 0;
+    for (int t = 0; t < cd.T_pad; ++t) {
+        const int ts = t % SS;
+        if (ts == 0) {
+            slot = stage_idx % NS;
+            mbar_wait(&full[slot], (stage_idx / NS) & 1u);
+        }
+        if (t < cd.T && chain_valid) {
+            if (k == 0) {
+                a = rb * 32 + lane;
+                active = a < cd.Q;
+                const int aa = active ? a : 0;
+                unpack4(xs4[aa], xi), unpack4(ys4[aa], yi), unpack4(zs4[aa], zi);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) fi[r][0] = fi[r][1] = fi[r][2] = 0.f;
+            }
+            const float4 *yb = ystage + (size_t)slot * STAGE_FLOAT4 + ts * STEP_FLOAT4 + lane;
+            if (active) {
+                float chi = 0.f;
+                if (k == 0) {
+                    // the 6 pairs inside the lane's own quad
+                    float yv[4][4];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) unpack4(yb[r * 32], yv[r]);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = r + 1; c < 4; ++c)
+                            chrom_pair<ENERGY>(xi[r], yi[r], zi[r], xi[c], yi[c], zi[c], yv[r][c], A, B,
+                                               fi[r][0], fi[r][1], fi[r][2], fi[c][0], fi[c][1],
+                                               fi[c][2], chi);
+                } else {
+                    int b = a + k;
+                    if (b >= cd.Q) b -= cd.Q;
+                    const bool half_dup = (k == cd.KS) && cd.q_even && (a >= (cd.Q >> 1));
+                    if (!half_dup) {
+                        float xj[4], yj[4], zj[4], fjx[4], fjy[4], fjz[4], yv[4][4];
+                        unpack4(xs4[b], xj), unpack4(ys4[b], yj), unpack4(zs4[b], zj);
+                        unpack4(fx4[b], fjx), unpack4(fy4[b], fjy), unpack4(fz4[b], fjz);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) unpack4(yb[r * 32], yv[r]);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                chrom_pair<ENERGY>(xi[r], yi[r], zi[r], xj[c], yj[c], zj[c], yv[r][c],
+                                                   A, B, fi[r][0], fi[r][1], fi[r][2], fjx[c],
+                                                   fjy[c], fjz[c], chi);
+                        fx4[b] = pack4(fjx), fy4[b] = pack4(fjy), fz4[b] = pack4(fjz);
+                    }
+                }
+                if (ENERGY) chi2 += (double)chi;
+            }
+            __syncwarp();
+            if (k == cd.KS) {
+                if (active) {
+                    float4 v = fx4[a];
+                    v.x += fi[0][0], v.y += fi[1][0], v.z += fi[2][0], v.w += fi[3][0];
+                    fx4[a] = v;
+                    v = fy4[a];
+                    v.x += fi[0][1], v.y += fi[1][1], v.z += fi[2][1], v.w += fi[3][1];
+                    fy4[a] = v;
+                    v = fz4[a];
+                    v.x += fi[0][2], v.y += fi[1][2], v.z += fi[2][2], v.w += fi[3][2];
+                    fz4[a] = v;
+                }
+                __syncwarp();
+            }
+        }
+        if (++k > cd.KS) k = 0, ++rb;
+        if (ts == SS - 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+            ++stage_idx;
+        }
+    }
+    return chi2;
+}
+
+__device__ __forceinline__ double warp_sum(double v) { return group_allreduce_sum<32>(v); }
+
+struct ChromCall {
+    int mode;
+    HmcArgs h;   // HMC mode
+    GradArgs g;  // GRAD mode
+    int W;       // chains (consumer warps) per CTA
+    int n_groups, total_items;
+};
+
+__global__ void __launch_bounds__(288, 1) chrom_kernel(ChromDev cd, ChromCall call) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int W = call.W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool is_producer = warp == W;
+    // ---- shared memory carve-up: [stages][barriers][item][W x 6 x n_pad floats]
+    float4 *ystage = reinterpret_cast<float4 *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NS * STAGE_BYTES);
+    uint64_t *empty = full + NS;
+    int *s_item = reinterpret_cast<int *>(empty + NS);
+    float *chain_base_smem = reinterpret_cast<float *>(smem_raw + (size_t)NS * STAGE_BYTES + 128);
+    WarpSmem sm;
+    {
+        float *b = chain_base_smem + (size_t)(is_producer ? 0 : warp) * 6 * cd.n_pad;
+        sm.xs = b, sm.ys = b + cd.n_pad, sm.zs = b + 2 * cd.n_pad;
+        sm.fx = b + 3 * cd.n_pad, sm.fy = b + 4 * cd.n_pad, sm.fz = b + 5 * cd.n_pad;
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], W);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int D = 3 * cd.n;
+    const int n_stage_pass = cd.T_pad / SS;
+    const int passes = call.mode == CHROM_MODE_HMC ? call.h.L + 1 : 1;
+    uint32_t stage_idx = 0;  // running stage counter, identical in every warp
+
+    for (;;) {
+        // ---- claim a work item and wait for the previous pass of its chain group ----------
+        if (threadIdx.x == 0) {
+            const int it = atomicAdd(cd.counter, 1);
+            if (it < call.total_items) {
+                const int o = it % call.n_groups;
+                const int need = it / call.n_groups;  // passes of this group that must be done
+                if (need > 0)
+                    while (ld_acquire(cd.pass_done + o) < need) __nanosleep(64);
+            }
+            *s_item = it;
+        }
+        __syncthreads();
+        const int item = *s_item;
+        if (item >= call.total_items) break;
+        const int o = item % call.n_groups;
+        const int seq = item / call.n_groups;  // = tr * passes + k
+        const int tr = seq / passes, k = seq % passes;
+
+        if (is_producer) {
+            if (lane == 0) {
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(cd.ystream);
+                for (int s = 0; s < n_stage_pass; ++s) {
+                    const uint32_t slot = stage_idx % NS;
+                    mbar_wait(&empty[slot], ((stage_idx / NS) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&full[slot], STAGE_BYTES);
+                    bulk_copy_g2s(ystage + (size_t)slot * STAGE_FLOAT4, src + (size_t)s * STAGE_BYTES,
+                                  STAGE_BYTES, &full[slot]);
+                    ++stage_idx;
+                }
+            }
+        } else {
+            const int c = o * W + warp;
+            const int C = call.mode == CHROM_MODE_HMC ? call.h.C : call.g.C;
+            const bool valid = c < C;
+            const bool hmc = call.mode == CHROM_MODE_HMC;
+            const HmcArgs &h = call.h;
+            const bool energy = !hmc || k == 0 || k == h.L;
+            float eps_c = 0.f, beta_c = 1.f;
+            double kin0 = 0.0;
+            if (valid) {
+                // ---- phase A: positions (+ drift) into shared memory ---------------------
+                const size_t off = (size_t)c * D;
+                const float *src = hmc ? (k == 0 ? h.q : cd.qw) : call.g.q;
+                if (hmc) {
+                    eps_c = __ldcg(h.eps + c);
+                    beta_c = h.beta ? h.beta[c] : 1.f;
+                } else {
+                    beta_c = call.g.beta ? call.g.beta[c] : 1.f;
+                }
+                float kin = 0.f;
+                for (int e = lane; e < D; e += 32) {
+                    float v = __ldcg(src + off + e);
+                    if (hmc) {
+                        if (k == 0) {
+                            const float pv = h.p0 ? h.p0[off + e]
+                                                  : rng_normal(h.seed, h.chain_base + c,
+                                                               h.draw + (uint64_t)tr, (uint32_t)e);
+                            __stcg(cd.pw + off + e, pv);
+                            kin = fmaf(pv, pv, kin);
+                        } else {
+                            v = fmaf(eps_c, __ldcg(cd.pw + off + e), v);  // q += eps p (hmc.py:119,122)
+                        }
+                    }
+                    const int bead = e / 3, comp = e - 3 * bead;
+                    sm.xs[comp * cd.n_pad + bead] = v;
+                }
+                kin0 = warp_sum((double)kin);
+                for (int i = cd.n + lane; i < cd.n_pad; i += 32) {
+                    // padding beads: far away from everything => contact 0, force 0
+                    sm.xs[i] = 1.0e4f * (float)(1 + i - cd.n), sm.ys[i] = 3.0e4f, sm.zs[i] = -2.0e4f;
+                }
+                for (int i = lane; i < 3 * cd.n_pad; i += 32) sm.fx[i] = 0.f;
+            }
+            __syncwarp();
+            // ---- phase B: pair sweep -----------------------------------------------------
+            double chi2 = energy ? chrom_sweep<true>(cd, sm, ystage, full, empty, stage_idx, valid, lane)
+                                 : chrom_sweep<false>(cd, sm, ystage, full, empty, stage_idx, valid, lane);
+            __syncwarp();
+            if (valid) {
+                // ---- phase C: forces, kick, energies ----------------------------------------
+                if (energy) chi2 = warp_sum(chi2);
+                const size_t off = (size_t)c * D;
+                float tau_c;
+                if (hmc) {
+                    if (k == 0) {
+                        tau_c = __ldcg(h.tau + c);
+                        if (h.gibbs_mode == BINFB_GIBBS_TAU_FIRST) {
+                            const double shape = 0.5 * (double)beta_c * cd.M + h.gamma_shape - 1.0;
+                            const double rate = 0.5 * (double)beta_c * chi2 + h.gamma_rate;
+                            const double gd = h.gamma_draws
+                                                  ? h.gamma_draws[c]
+                                                  : rng_gamma(h.seed, h.chain_base + c,
+                                                              h.draw + (uint64_t)tr, shape);
+                            tau_c = (float)(gd / rate);
+                            if (lane == 0) __stcg(h.tau + c, tau_c);
+                        }
+                        if (lane == 0) __stcg(cd.tau_w + c, tau_c);
+                    } else {
+                        tau_c = __ldcg(cd.tau_w + c);
+                    }
+                } else {
+                    tau_c = call.g.tau[c];
+                }
+                const float scale = -cd.alpha * beta_c * tau_c;
+                const float kick = hmc ? ((k == 0 || k == h.L) ? 0.5f * eps_c : eps_c) : 0.f;
+                float e_prior = 0.f, kin = 0.f;
+                for (int i = lane; i < cd.n; i += 32) {
+                    const float x = sm.xs[i], y = sm.ys[i], z = sm.zs[i];
+                    float gx = scale * sm.fx[i], gy = scale * sm.fy[i], gz = scale * sm.fz[i];
+                    if (i > 0) {
+                        const float bx = x - sm.xs[i - 1], by = y - sm.ys[i - 1], bz = z - sm.zs[i - 1];
+                        const float r2 = fmaf(bz, bz, fmaf(by, by, fmaf(bx, bx, CHROM_SOFT)));
+                        const float inv = rsqrtf(r2), d = r2 * inv;
+                        const float cc = cd.k_bb * (d - cd.l0) * inv;
+                        gx = fmaf(cc, bx, gx), gy = fmaf(cc, by, gy), gz = fmaf(cc, bz, gz);
+                    }
+                    if (i < cd.n - 1) {
+                        const float bx = sm.xs[i + 1] - x, by = sm.ys[i + 1] - y, bz = sm.zs[i + 1] - z;
+                        const float r2 = fmaf(bz, bz, fmaf(by, by, fmaf(bx, bx, CHROM_SOFT)));
+                        const float inv = rsqrtf(r2), d = r2 * inv;
+                        const float dl = d - cd.l0;
+                        const float cc = cd.k_bb * dl * inv;
+                        gx = fmaf(-cc, bx, gx), gy = fmaf(-cc, by, gy), gz = fmaf(-cc, bz, gz);
+                        e_prior = fmaf(0.5f * cd.k_bb * dl, dl, e_prior);
+                    }
+                    if (cd.inv_s2 > 0.f) {
+                        gx = fmaf(cd.inv_s2, x, gx), gy = fmaf(cd.inv_s2, y, gy), gz = fmaf(cd.inv_s2, z, gz);
+                        e_prior = fmaf(0.5f * cd.inv_s2, fmaf(x, x, fmaf(y, y, z * z)), e_prior);
+                    }
+                    if (hmc) {
+                        float *pp = cd.pw + off + 3 * i;
+                        const float px = fmaf(-kick, gx, __ldcg(pp)), py = fmaf(-kick, gy, __ldcg(pp + 1)),
+                                    pz = fmaf(-kick, gz, __ldcg(pp + 2));
+                        __stcg(pp, px), __stcg(pp + 1, py), __stcg(pp + 2, pz);
+                        kin = fmaf(px, px, fmaf(py, py, fmaf(pz, pz, kin)));
+                        float *qq = cd.qw + off + 3 * i;
+                        __stcg(qq, x), __stcg(qq + 1, y), __stcg(qq + 2, z);
+                    } else if (call.g.grad) {
+                        float *gg = call.g.grad + off + 3 * i;
+                        gg[0] = gx, gg[1] = gy, gg[2] = gz;
+                    }
+                }
+                if (energy) {
+                    const double ep = warp_sum((double)e_prior);
+                    const double t = (double)tau_c, lt = log(t);
+                    const double ga = hmc ? h.gamma_shape : call.g.gamma_shape;
+                    const double gb = hmc ? h.gamma_rate : call.g.gamma_rate;
+                    const double U = (double)beta_c * (0.5 * t * chi2 - 0.5 * cd.M * lt) + ep -
+                                     ((ga - 1.0) * lt - gb * t);
+                    if (!hmc) {
+                        if (lane == 0) {
+                            if (call.g.logp) call.g.logp[c] = -U;
+                            if (call.g.chi2) call.g.chi2[c] = chi2;
+                        }
+                    } else if (k == 0) {
+                        if (lane == 0) {
+                            __stcg(cd.h0 + c, U + 0.5 * kin0);
+                            __stcg(cd.chi2_0 + c, chi2);
+                        }
+                    }
+                    if (hmc && k == h.L) {
+                        const double h1 = U + 0.5 * warp_sum((double)kin);
+                        const double h0 = __ldcg(cd.h0 + c);
+                        const double dh = h1 - h0;
+                        const uint64_t draw = h.draw + (uint64_t)tr;
+                        float uu;
+                        if (h.u) uu = h.u[c];
+                        else {
+                            const u32x4 r = philox4x32_10(h.seed ^ (draw >> 32) * 0x9E3779B97F4A7C15ull,
+                                                          h.chain_base + c, (uint32_t)draw,
+                                                          (uint32_t)RNG_ACCEPT << 24);
+                            uu = u32_to_unit_open0(r.x);
+                        }
+                        // Metropolis (hmc.py:151); NaN energies reject
+                        const bool acc = (dh == dh) && ((double)uu < exp(fmin(709.0, fmax(-308.0, -dh))));
+                        const bool last = tr == h.n_traj - 1;
+                        if (last) {
+                            for (int e = lane; e < D; e += 32) {
+                                const int bead = e / 3, comp = e - 3 * bead;
+                                if (h.q_end) h.q_end[off + e] = sm.xs[comp * cd.n_pad + bead];
+                                if (h.p_end) h.p_end[off + e] = __ldcg(cd.pw + off + e);
+                            }
+                        }
+                        if (acc) {
+                            for (int e = lane; e < D; e += 32) {
+                                const int bead = e / 3, comp = e - 3 * bead;
+                                __stcg(h.q + off + e, sm.xs[comp * cd.n_pad + bead]);
+                            }
+                        }
+                        const double chi2_cur = acc ? chi2 : __ldcg(cd.chi2_0 + c);
+                        if (lane == 0) {
+                            __stcg(cd.chi2_state + c, chi2_cur);
+                            if (tr < h.n_adapt)  // hmc.py:188-191
+                                __stcg(h.eps + c, eps_c * (acc ? h.adapt_up : h.adapt_down));
+                            if (h.accepted) h.accepted[c] = acc ? 1 : 0;
+                            if (h.e_before) h.e_before[c] = h0;
+                            if (h.e_after) h.e_after[c] = h1;
+                            if (h.n_accepted) h.n_accepted[c] += acc ? 1 : 0;
+                            if (h.stats) {
+                                atomicAdd(h.stats + 0, acc ? 1.0 : 0.0);
+                                atomicAdd(h.stats + 1, 1.0);
+                                atomicAdd(h.stats + 2, (double)eps_c);
+                                atomicAdd(h.stats + 3, (dh == dh) ? exp(fmin(0.0, -dh)) : 0.0);
+                            }
+                        }
+                        if (h.gibbs_mode == BINFB_GIBBS_TAU_LAST) {
+                            const double shape = 0.5 * (double)beta_c * cd.M + h.gamma_shape - 1.0;
+                            const double rate = 0.5 * (double)beta_c * chi2_cur + h.gamma_rate;
+                            const double gd = h.gamma_draws
+                                                  ? h.gamma_draws[c]
+                                                  : rng_gamma(h.seed, h.chain_base + c, draw, shape);
+                            if (lane == 0) __stcg(h.tau + c, (float)(gd / rate));
+                        }
+                    }
+                }
+            }
+        }
+        // ---- publish the pass ---------------------------------------------------------------
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release(cd.pass_done + o, seq + 1);
+    }
+}
+
+// mock contacts for all pairs (AbstractForwardModel.__call__ of the contact model)
+__global__ void chrom_forward_kernel(int n, long long M, float A, float B, const float *q,
+                                     float *mock) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M) return;
+    const int c = blockIdx.y;
+    // invert numpy.triu_indices(n, 1) ordering
+    const double nn = (double)n;
+    long long i = (long long)(nn - 2.0 - floor(sqrt(-8.0 * (double)idx + 4.0 * nn * (nn - 1.0) - 7.0) / 2.0 - 0.5));
+    long long row_start = i * n - i * (i + 1) / 2;
+    while (i > 0 && idx < row_start) --i, row_start = i * n - i * (i + 1) / 2;
+    while (idx >= row_start + (n - 1 - i)) ++i, row_start = i * n - i * (i + 1) / 2;
+    const long long j = idx - row_start + i + 1;
+    const float *x = q + (size_t)c * 3 * n;
+    const float dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, CHROM_SOFT)));
+    const float d = r2 * rsqrtf(r2);
+    mock[(size_t)c * M + idx] = 1.0f / (1.0f + exp2f(fmaf(d, A, B)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static inline long long tri_index(long long n, long long i, long long j) {  // i < j
+    return i * n - i * (i + 1) / 2 + (j - i - 1);
+}
+
+int chrom_build_stream(int n, const float *y_pairs, float *out, long long capacity,
+                       long long *n_floats, int *Q_out, int *T_out) {
+    if (n < 2) {
+        set_error("chromatin model needs at least 2 beads");
+        return BINFB_EINVAL;
+    }
+    const int n_pad = (n + 3) / 4 * 4, Q = n_pad / 4, KS = Q / 2, NRB = (Q + 31) / 32;
+    const int T = NRB * (KS + 1), T_pad = (T + SS - 1) / SS * SS;
+    const long long total = (long long)T_pad * STEP_FLOAT4 * 4;
+    if (n_floats) *n_floats = total;
+    if (Q_out) *Q_out = Q;
+    if (T_out) *T_out = T;
+    if (!out) return BINFB_OK;
+    if (capacity < total) {
+        set_error("chromatin stream buffer too small");
+        return BINFB_EINVAL;
+    }
+    const bool q_even = (Q % 2) == 0;
+    for (long long i = 0; i < total; ++i) out[i] = 0.f;
+    for (int rb = 0; rb < NRB; ++rb)
+        for (int k = 0; k <= KS; ++k) {
+            const long long t = (long long)rb * (KS + 1) + k;
+            for (int lane = 0; lane < 32; ++lane) {
+                const int a = rb * 32 + lane;
+                if (a >= Q) continue;
+                int b = a + k;
+                if (b >= Q) b -= Q;
+                if (k > 0 && k == KS && q_even && a >= Q / 2) continue;
+                for (int r = 0; r < 4; ++r)
+                    for (int c = 0; c < 4; ++c) {
+                        const int i = 4 * a + r, j = 4 * b + c;
+                        if (i >= n || j >= n) continue;
+                        if (k == 0 && r >= c) continue;
+                        const long long idx = i < j ? tri_index(n, i, j) : tri_index(n, j, i);
+                        out[((t * 4 + r) * 32 + lane) * 4 + c] = y_pairs[idx];
+                    }
+            }
+        }
+    return BINFB_OK;
+}
+
+int chrom_reserve(ChromModel &m, int C) {
+    const int D = 3 * m.n;
+    if (C > m.ws_chains) {
+        cudaFree(m.qw), cudaFree(m.pw), cudaFree(m.h0), cudaFree(m.chi2_0), cudaFree(m.chi2_state),
+            cudaFree(m.tau_w);
+        m.qw = m.pw = m.tau_w = nullptr;
+        m.h0 = m.chi2_0 = m.chi2_state = nullptr;
+        m.ws_chains = 0;
+        BINFB_CUDA(cudaMalloc(&m.qw, (size_t)C * D * sizeof(float)));
+        BINFB_CUDA(cudaMalloc(&m.pw, (size_t)C * D * sizeof(float)));
+        BINFB_CUDA(cudaMalloc(&m.h0, (size_t)C * sizeof(double)));
+        BINFB_CUDA(cudaMalloc(&m.chi2_0, (size_t)C * sizeof(double)));
+        BINFB_CUDA(cudaMalloc(&m.chi2_state, (size_t)C * sizeof(double)));
+        BINFB_CUDA(cudaMalloc(&m.tau_w, (size_t)C * sizeof(float)));
+        m.ws_chains = C;
+    }
+    const int need = 1 + C;  // item counter + one pass counter per chain group (W >= 1)
+    if (need > m.sched_len) {
+        cudaFree(m.sched);
+        m.sched = nullptr;
+        m.sched_len = 0;
+        BINFB_CUDA(cudaMalloc(&m.sched, (size_t)need * sizeof(int)));
+        m.sched_len = need;
+    }
+    return BINFB_OK;
+}
+
+static ChromDev chrom_dev(const ChromModel &m) {
+    ChromDev d;
+    d.n = m.n, d.n_pad = m.n_pad, d.Q = m.Q, d.KS = m.KS, d.NRB = m.NRB, d.T = m.T, d.T_pad = m.T_pad;
+    d.q_even = (m.Q % 2) == 0;
+    d.ystream = reinterpret_cast<const float4 *>(m.ystream);
+    const double log2e = 1.4426950408889634;
+    d.A = (float)((double)m.alpha * log2e);
+    d.B = (float)(-(double)m.alpha * (double)m.d_c * log2e);
+    d.alpha = m.alpha, d.k_bb = m.k_bb, d.l0 = m.l0, d.inv_s2 = m.inv_s2;
+    d.M = (double)m.M;
+    d.qw = m.qw, d.pw = m.pw, d.h0 = m.h0, d.chi2_0 = m.chi2_0, d.chi2_state = m.chi2_state;
+    d.tau_w = m.tau_w;
+    d.counter = m.sched, d.pass_done = m.sched + 1;
+    return d;
+}
+
+static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int smem_optin,
+                        cudaStream_t s) {
+    int rc = chrom_reserve(m, C);
+    if (rc) return rc;
+    const size_t fixed = (size_t)NS * STAGE_BYTES + 128;
+    const size_t per_warp = (size_t)6 * m.n_pad * sizeof(float);
+    int W = (int)(((size_t)smem_optin - fixed) / per_warp);
+    if (W > 8) W = 8;
+    if (m.opt_warps > 0 && m.opt_warps < W) W = m.opt_warps;
+    if (W > C) W = C;
+    if (W < 1) {
+        set_error("chromatin model: one chain does not fit in shared memory (n_beads too large for "
+                  "the warp-per-chain kernel)");
+        return BINFB_EUNSUPPORTED;
+    }
+    call.W = W;
+    call.n_groups = (C + W - 1) / W;
+    const int passes = call.mode == CHROM_MODE_HMC ? call.h.L + 1 : 1;
+    const int n_traj = call.mode == CHROM_MODE_HMC ? call.h.n_traj : 1;
+    const long long total = (long long)call.n_groups * passes * n_traj;
+    if (total > 2000000000LL) {
+        set_error("chromatin model: too many work items in one launch");
+        return BINFB_EUNSUPPORTED;
+    }
+    call.total_items = (int)total;
+    const size_t smem = fixed + per_warp * W;
+    BINFB_CUDA(cudaMemsetAsync(m.sched, 0, (size_t)(1 + call.n_groups) * sizeof(int), s));
+    BINFB_CUDA(cudaFuncSetAttribute(chrom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = call.n_groups < sm_count ? call.n_groups : sm_count;
+    chrom_kernel<<<grid, (W + 1) * 32, smem, s>>>(chrom_dev(m), call);
+    BINFB_CUDA(cudaGetLastError());
+    return BINFB_OK;
+}
+
+int chrom_hmc_launch(ChromModel &m, const HmcArgs &a, int sm_count, int smem_optin, cudaStream_t s) {
+    ChromCall call;
+    call.mode = CHROM_MODE_HMC;
+    call.h = a;
+    call.g = GradArgs();
+    if (a.n_accepted) BINFB_CUDA(cudaMemsetAsync(a.n_accepted, 0, (size_t)a.C * sizeof(int32_t), s));
+    return chrom_launch(m, call, a.C, sm_count, smem_optin, s);
+}
+
+int chrom_grad_launch(ChromModel &m, const GradArgs &a, int sm_count, int smem_optin, cudaStream_t s) {
+    ChromCall call;
+    call.mode = CHROM_MODE_GRAD;
+    call.h = HmcArgs();
+    call.g = a;
+    return chrom_launch(m, call, a.C, sm_count, smem_optin, s);
+}
+
+int chrom_forward_launch(const ChromModel &m, const float *q, int C, float *mock, cudaStream_t s) {
+    const double log2e = 1.4426950408889634;
+    const float A = (float)((double)m.alpha * log2e);
+    const float B = (float)(-(double)m.alpha * (double)m.d_c * log2e);
+    dim3 grid((unsigned)((m.M + 255) / 256), (unsigned)C);
+    chrom_forward_kernel<<<grid, 256, 0, s>>>(m.n, m.M, A, B, q, mock);
+    BINFB_CUDA(cudaGetLastError());
+    return BINFB_OK;
+}
+
+}  // namespace binfb

@@ -1,0 +1,127 @@
+// Host-side model descriptor and launcher declarations shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/binf_b200.h"
+
+namespace binfb {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define BINFB_CUDA(call)                                              \
+    do {                                                              \
+        cudaError_t e__ = (call);                                     \
+        if (e__ != cudaSuccess) return ::binfb::cuda_fail(e__, #call); \
+    } while (0)
+
+// arguments common to every HMC launch (device pointers)
+struct HmcArgs {
+    float *q;            // [C, D] state, in/out
+    float *tau;          // [C] in/out
+    const float *beta;   // [C] or null
+    float *eps;          // [C] in/out
+    int C;
+    int L, n_traj, n_adapt, gibbs_mode;
+    float adapt_up, adapt_down;
+    uint64_t seed, draw, chain_base;
+    const float *p0;     // [C, D] or null
+    const float *u;      // [C] or null
+    const double *gamma_draws;  // [C] or null
+    uint8_t *accepted;   // [C] or null
+    double *e_before, *e_after;  // [C] or null
+    float *q_end, *p_end;        // [C, D] or null
+    int32_t *n_accepted; // [C] or null
+    double *stats;       // [4] or null
+    double gamma_shape, gamma_rate;  // Gamma prior on tau
+};
+
+struct GradArgs {
+    const float *q;
+    const float *tau;
+    const float *beta;
+    int C;
+    double *logp;
+    float *grad;
+    double *chi2;
+    double gamma_shape, gamma_rate;
+};
+
+// ---- polynomial --------------------------------------------------------------------------
+struct PolyModel {
+    int N = 0, K = 0, stride = 0;  // data points, coefficients, floats per smem row
+    float *rows = nullptr;         // device [N, stride]: x, x^2, .., x^(K-1), y, pad
+    float prior_mean[8], prior_inv_var[8];
+    unsigned flags = 0;
+    int opt_group = -1, opt_jchains = -1, opt_block = -1;
+};
+int poly_hmc_launch(const PolyModel &m, const HmcArgs &a, int sm_count, int smem_optin,
+                    cudaStream_t s);
+int poly_grad_launch(const PolyModel &m, const GradArgs &a, int sm_count, int smem_optin,
+                     cudaStream_t s);
+int poly_forward_launch(const PolyModel &m, const float *q, int C, float *mock, cudaStream_t s);
+
+// ---- chromatin -----------------------------------------------------------------------------
+struct ChromModel {
+    int n = 0, n_pad = 0, Q = 0, KS = 0, NRB = 0;
+    int T = 0, T_pad = 0;          // warp-steps per force evaluation (padded to the stage size)
+    long long M = 0;
+    float *ystream = nullptr;      // device [T_pad][4][32] float4
+    float *ypairs = nullptr;       // device [M] (triu order; forward/mock kernel only)
+    float alpha = 0, d_c = 0, k_bb = 0, l0 = 0, inv_s2 = 0;
+    unsigned flags = 0;
+    int opt_warps = -1;
+    // per-launch workspace (grown on demand)
+    int ws_chains = 0;
+    float *qw = nullptr, *pw = nullptr;   // [C, D] working position / momentum
+    double *h0 = nullptr, *chi2_0 = nullptr, *chi2_state = nullptr;  // [C]
+    float *tau_w = nullptr;               // [C] precision used by the running trajectory
+    int *sched = nullptr;                 // [1 + n_octets]: item counter, per-octet pass counters
+    int sched_len = 0;
+};
+constexpr int CHROM_STAGE_STEPS = 4;  // warp-steps per bulk-copy stage (4 * 2 KiB)
+constexpr int CHROM_STAGES = 4;
+int chrom_build_stream(int n, const float *y_pairs, float *out, long long capacity,
+                       long long *n_floats, int *Q, int *T);
+int chrom_reserve(ChromModel &m, int C);
+int chrom_hmc_launch(ChromModel &m, const HmcArgs &a, int sm_count, int smem_optin,
+                     cudaStream_t s);
+int chrom_grad_launch(ChromModel &m, const GradArgs &a, int sm_count, int smem_optin,
+                      cudaStream_t s);
+int chrom_forward_launch(const ChromModel &m, const float *q, int C, float *mock, cudaStream_t s);
+
+// ---- misc ----------------------------------------------------------------------------------
+int gibbs_tau_launch(const double *chi2, float *tau, const float *beta, int C, double n_data,
+                     double shape, double rate, uint64_t seed, uint64_t draw, uint64_t chain_base,
+                     const double *gamma_draws, cudaStream_t s);
+int rng_fill_launch(uint64_t seed, uint64_t draw, uint64_t chain_base, int C, int D,
+                    double gamma_shape, float *normals, float *uniforms, double *gammas,
+                    cudaStream_t s);
+int swap_decide_launch(const double *ll_a, const double *ll_b, double beta_a, double beta_b, int C,
+                       uint64_t seed, uint64_t attempt, uint64_t pair_id, uint64_t chain_base,
+                       uint8_t *accept, cudaStream_t s);
+int swap_apply_launch(float *q_mine, const float *q_theirs, float *eps_mine,
+                      const float *eps_theirs, const uint8_t *accept, int C, int D,
+                      cudaStream_t s);
+int microbench_run(int device, int iters, double *ffma, double *ffma2, double *mufu,
+                   double *clock_mhz);
+
+}  // namespace binfb
+
+struct binfb_model {
+    int kind = 0;
+    int device = 0;
+    int dim = 0;
+    long long n_data = 0;
+    int sm_count = 0, smem_optin = 0;
+    double gamma_shape = 1.0, gamma_rate = 1.0;
+    binfb::PolyModel poly;
+    binfb::ChromModel chrom;
+    // cached device buffers for the *_host entry points
+    size_t hb_bytes = 0;
+    char *hb = nullptr;
+    cudaStream_t hstream = nullptr;
+};

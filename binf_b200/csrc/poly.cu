@@ -1,0 +1,530 @@
+// Fused HMC for the polynomial (Vandermonde) posterior -- sm_100a.
+//
+// Replaces, per chain and per trajectory, the reference's HMCSampler.sample / _leapfrog
+// (binf/samplers/hmc.py:92-125,136-164) together with every pdf.gradient / pdf.log_prob call
+// they make: Posterior (binf/pdf/posteriors.py:125-187) -> Likelihood
+// (binf/pdf/likelihoods.py:141-155) -> polynomial ForwardModel + GaussianErrorModel
+// (binf/example/likelihood.py:24-30,54-61) and the priors (binf/example/priors.py:23-25,49-54).
+//
+// Mapping: a chain is owned by a group of G lanes (G = 1..32, power of two); each lane
+// walks every G-th data row and the group butterfly-reduces the K gradient sums, so all G
+// lanes hold bitwise-identical q, p for the whole trajectory (registers; nothing but the final
+// state goes back to HBM).  A thread carries J independent chains to reuse each shared-memory
+// data row (one LDS.128 feeds 8*J FP32 instructions).  The data rows
+// [x, x^2, .., x^(K-1), y] live in shared memory for the whole launch.
+#include <math.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace binfb {
+
+struct PolyDev {
+    const float *rows;
+    int N;
+    unsigned flags;
+    float prior_mean[8], prior_inv_var[8];
+};
+
+template <int K>
+struct PolyRow {
+    static constexpr int STRIDE = ((K + 3) / 4) * 4;
+};
+
+// One data row for J chains: residual via Horner (K-1 FMA + 1 ADD), gradient sums (1 ADD +
+// K-1 FMA), optional chi^2 (1 FMA)  ->  14 flop per chain-datum at K = 4.
+template <int K, int J, bool ENERGY>
+__device__ __forceinline__ void poly_row(const float *__restrict__ rowp, const float (&c)[J][K],
+                                         float (&acc)[J][K], float (&part)[J]) {
+    constexpr int S = PolyRow<K>::STRIDE;
+    float row[S];
+#pragma unroll
+    for (int v = 0; v < S / 4; ++v) {
+        const float4 t = reinterpret_cast<const float4 *>(rowp)[v];
+        row[4 * v + 0] = t.x, row[4 * v + 1] = t.y, row[4 * v + 2] = t.z, row[4 * v + 3] = t.w;
+    }
+    const float y = row[K - 1];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        float t = c[j][K - 1];
+#pragma unroll
+        for (int k = K - 2; k >= 0; --k) t = fmaf(t, row[0], c[j][k]);
+        const float res = t - y;
+        acc[j][0] += res;
+#pragma unroll
+        for (int k = 1; k < K; ++k) acc[j][k] = fmaf(res, row[k - 1], acc[j][k]);
+        if (ENERGY) part[j] = fmaf(res, res, part[j]);
+    }
+}
+
+// all rows r = g, g+G, ... of a shared-memory chunk
+template <int K, int G, int J, bool ENERGY>
+__device__ __forceinline__ void poly_chunk(const float *__restrict__ srows, int n_rows, int g,
+                                           const float (&c)[J][K], float (&acc)[J][K],
+                                           double (&chi2)[J]) {
+    constexpr int S = PolyRow<K>::STRIDE;
+    constexpr int U = 8;
+    const int cnt = (n_rows - g + G - 1) / G;  // rows of this lane
+    const float *p = srows + (size_t)g * S;
+    int i = 0;
+    for (; i + U <= cnt; i += U) {
+        float part[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) part[j] = 0.f;
+#pragma unroll
+        for (int uu = 0; uu < U; ++uu) poly_row<K, J, ENERGY>(p + (size_t)uu * G * S, c, acc, part);
+        p += (size_t)U * G * S;
+        if (ENERGY) {
+#pragma unroll
+            for (int j = 0; j < J; ++j) chi2[j] += (double)part[j];
+        }
+    }
+    if (i < cnt) {
+        float part[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) part[j] = 0.f;
+        for (; i < cnt; ++i) {
+            poly_row<K, J, ENERGY>(p, c, acc, part);
+            p += (size_t)G * S;
+        }
+        if (ENERGY) {
+#pragma unroll
+            for (int j = 0; j < J; ++j) chi2[j] += (double)part[j];
+        }
+    }
+}
+
+__device__ __forceinline__ void poly_load_rows(float *srows, const float *__restrict__ grows,
+                                               int n_floats) {
+    const float4 *src = reinterpret_cast<const float4 *>(grows);
+    float4 *dst = reinterpret_cast<float4 *>(srows);
+    for (int i = threadIdx.x; i < n_floats / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// raw gradient sums  graw_k = sum_n (mock_n - y_n) x_n^k  and chi^2 = sum_n (mock_n - y_n)^2,
+// identical on all G lanes of the group
+template <int K, int G, int J, bool ENERGY>
+__device__ __forceinline__ void poly_grad_pass(const PolyDev &pm, float *srows, int rows_per_chunk,
+                                               int n_chunks, int g, const float (&c)[J][K],
+                                               float (&graw)[J][K], double (&chi2)[J]) {
+    constexpr int S = PolyRow<K>::STRIDE;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        chi2[j] = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) graw[j][k] = 0.f;
+    }
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int r0 = ch * rows_per_chunk;
+        const int n_rows = min(rows_per_chunk, pm.N - r0);
+        if (n_chunks > 1) {
+            __syncthreads();
+            poly_load_rows(srows, pm.rows + (size_t)r0 * S, n_rows * S);
+            __syncthreads();
+        }
+        poly_chunk<K, G, J, ENERGY>(srows, n_rows, g, c, graw, chi2);
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) graw[j][k] = group_allreduce_sum<G>(graw[j][k]);
+        if (ENERGY) chi2[j] = group_allreduce_sum<G>(chi2[j]);
+    }
+}
+
+// U(q) = -log p(q | tau) in float64 (binf/pdf/posteriors.py:141-151 summed components)
+template <int K>
+__device__ __forceinline__ double poly_potential(const PolyDev &pm, const float (&q)[K], double chi2,
+                                                 float tau, float beta, double ga, double gb) {
+    const double t = (double)tau;
+    double prior = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double d = (double)q[k] - (double)pm.prior_mean[k];
+        prior += d * d * (double)pm.prior_inv_var[k];
+    }
+    const double lt = log(t);
+    return (double)beta * (0.5 * t * chi2 - 0.5 * (double)pm.N * lt) + 0.5 * prior -
+           ((ga - 1.0) * lt - gb * t);
+}
+
+template <int K>
+__device__ __forceinline__ void poly_force(const PolyDev &pm, const float (&q)[K],
+                                           const float (&graw)[K], float bt, float (&f)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        f[k] = bt * graw[k];
+        if (pm.flags & BINFB_FLAG_PRIOR_GRAD)
+            f[k] = fmaf(q[k] - pm.prior_mean[k], pm.prior_inv_var[k], f[k]);
+    }
+}
+
+__device__ __forceinline__ float draw_tau(const HmcArgs &a, double n_data, double chi2, float beta,
+                                          uint64_t chain, int cid, uint64_t draw) {
+    const double shape = 0.5 * (double)beta * n_data + a.gamma_shape - 1.0;
+    const double rate = 0.5 * (double)beta * chi2 + a.gamma_rate;
+    const double gdraw =
+        a.gamma_draws ? a.gamma_draws[cid] : rng_gamma(a.seed, chain, draw, shape);
+    return (float)(gdraw / rate);
+}
+
+template <int K, int G, int J>
+__global__ void __launch_bounds__(J == 1 ? 1024 : 896, 1)
+    poly_hmc_kernel(PolyDev pm, HmcArgs a, int iters, int rows_per_chunk, int n_chunks) {
+    extern __shared__ __align__(16) float srows[];
+    constexpr int S = PolyRow<K>::STRIDE;
+    if (n_chunks == 1) {
+        poly_load_rows(srows, pm.rows, pm.N * S);
+        __syncthreads();
+    }
+    const int g = threadIdx.x % G;
+    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long n_groups = ((long long)gridDim.x * blockDim.x) / G;
+    double st_acc = 0.0, st_prop = 0.0, st_eps = 0.0, st_pacc = 0.0;
+
+    for (int it = 0; it < iters; ++it) {
+        const long long tuple = (long long)it * n_groups + group;
+        int cid[J];
+        bool valid[J];
+        float q[J][K], p[J][K], graw[J][K], f[K];
+        float tau[J], beta[J], eps[J];
+        int nacc[J];
+        double chi2[J], chi2_cur[J], h0[J], h1[J];
+        bool acc[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const long long c = tuple * J + j;
+            valid[j] = c < a.C;
+            cid[j] = valid[j] ? (int)c : a.C - 1;
+#pragma unroll
+            for (int k = 0; k < K; ++k) q[j][k] = a.q[(size_t)cid[j] * K + k];
+            tau[j] = a.tau[cid[j]];
+            beta[j] = a.beta ? a.beta[cid[j]] : 1.0f;
+            eps[j] = a.eps[cid[j]];
+            nacc[j] = 0;
+            acc[j] = false;
+            h0[j] = h1[j] = 0.0;
+        }
+        for (int tr = 0; tr < a.n_traj; ++tr) {
+            const uint64_t draw = a.draw + (uint64_t)tr;
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    p[j][k] = a.p0 ? a.p0[(size_t)cid[j] * K + k]
+                                   : rng_normal(a.seed, a.chain_base + cid[j], draw, k);
+            // ---- force evaluation 0 (+ energy at q0) -----------------------------------
+            poly_grad_pass<K, G, J, true>(pm, srows, rows_per_chunk, n_chunks, g, q, graw, chi2);
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                if (a.gibbs_mode == BINFB_GIBBS_TAU_FIRST)
+                    tau[j] = draw_tau(a, (double)pm.N, chi2[j], beta[j], a.chain_base + cid[j],
+                                      cid[j], draw);
+                chi2_cur[j] = chi2[j];
+                double kin = 0.0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) kin += (double)p[j][k] * (double)p[j][k];
+                h0[j] = poly_potential<K>(pm, q[j], chi2[j], tau[j], beta[j], a.gamma_shape,
+                                          a.gamma_rate) + 0.5 * kin;
+                poly_force<K>(pm, q[j], graw[j], beta[j] * tau[j], f);
+                const float he = 0.5f * eps[j];
+#pragma unroll
+                for (int k = 0; k < K; ++k) p[j][k] = fmaf(-he, f[k], p[j][k]);  // hmc.py:116
+            }
+            // ---- L-1 full steps (hmc.py:118-120) -----------------------------------------
+            for (int s = 1; s < a.L; ++s) {
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+#pragma unroll
+                    for (int k = 0; k < K; ++k) q[j][k] = fmaf(eps[j], p[j][k], q[j][k]);
+                poly_grad_pass<K, G, J, false>(pm, srows, rows_per_chunk, n_chunks, g, q, graw, chi2);
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    poly_force<K>(pm, q[j], graw[j], beta[j] * tau[j], f);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) p[j][k] = fmaf(-eps[j], f[k], p[j][k]);
+                }
+            }
+            // ---- last drift + half kick (hmc.py:122-123) + energy at q_L -------------------
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+#pragma unroll
+                for (int k = 0; k < K; ++k) q[j][k] = fmaf(eps[j], p[j][k], q[j][k]);
+            poly_grad_pass<K, G, J, true>(pm, srows, rows_per_chunk, n_chunks, g, q, graw, chi2);
+            const bool last = tr == a.n_traj - 1;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                poly_force<K>(pm, q[j], graw[j], beta[j] * tau[j], f);
+                const float he = 0.5f * eps[j];
+                double kin = 0.0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    p[j][k] = fmaf(-he, f[k], p[j][k]);
+                    kin += (double)p[j][k] * (double)p[j][k];
+                }
+                h1[j] = poly_potential<K>(pm, q[j], chi2[j], tau[j], beta[j], a.gamma_shape,
+                                          a.gamma_rate) + 0.5 * kin;
+                // Metropolis (hmc.py:151): NaN energies reject
+                const float uu = a.u ? a.u[cid[j]]
+                                     : rng_uniform(a.seed, a.chain_base + cid[j], draw, RNG_ACCEPT);
+                const double dh = h1[j] - h0[j];
+                const double pacc = exp(fmin(0.0, -dh));
+                acc[j] = (double)uu < exp(fmin(709.0, fmax(-308.0, -dh)));
+                if (last && valid[j] && g == 0) {
+                    if (a.q_end)
+                        for (int k = 0; k < K; ++k) a.q_end[(size_t)cid[j] * K + k] = q[j][k];
+                    if (a.p_end)
+                        for (int k = 0; k < K; ++k) a.p_end[(size_t)cid[j] * K + k] = p[j][k];
+                }
+                if (acc[j]) {
+                    chi2_cur[j] = chi2[j];
+                    nacc[j]++;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) q[j][k] = a.q[(size_t)cid[j] * K + k];
+                }
+                if (valid[j] && g == 0) {
+                    st_acc += acc[j] ? 1.0 : 0.0;
+                    st_prop += 1.0;
+                    st_eps += (double)eps[j];
+                    st_pacc += (dh == dh) ? pacc : 0.0;
+                }
+                if (tr < a.n_adapt) eps[j] *= acc[j] ? a.adapt_up : a.adapt_down;  // hmc.py:188-191
+                if (a.gibbs_mode == BINFB_GIBBS_TAU_LAST)
+                    tau[j] = draw_tau(a, (double)pm.N, chi2_cur[j], beta[j], a.chain_base + cid[j],
+                                      cid[j], draw);
+            }
+            // the state array is the rejection fallback: commit accepted moves before the
+            // next trajectory re-reads it
+            if (a.n_traj > 1) {
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                    if (valid[j] && g == 0 && acc[j])
+                        for (int k = 0; k < K; ++k) a.q[(size_t)cid[j] * K + k] = q[j][k];
+                __syncwarp();
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            if (valid[j] && g == 0) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) a.q[(size_t)cid[j] * K + k] = q[j][k];
+                a.tau[cid[j]] = tau[j];
+                a.eps[cid[j]] = eps[j];
+                if (a.accepted) a.accepted[cid[j]] = acc[j] ? 1 : 0;
+                if (a.e_before) a.e_before[cid[j]] = h0[j];
+                if (a.e_after) a.e_after[cid[j]] = h1[j];
+                if (a.n_accepted) a.n_accepted[cid[j]] = nacc[j];
+            }
+        }
+    }
+    if (a.stats) {
+        st_acc = group_allreduce_sum<32>(st_acc);
+        st_prop = group_allreduce_sum<32>(st_prop);
+        st_eps = group_allreduce_sum<32>(st_eps);
+        st_pacc = group_allreduce_sum<32>(st_pacc);
+        if ((threadIdx.x & 31) == 0 && st_prop > 0.0) {
+            atomicAdd(a.stats + 0, st_acc);
+            atomicAdd(a.stats + 1, st_prop);
+            atomicAdd(a.stats + 2, st_eps);
+            atomicAdd(a.stats + 3, st_pacc);
+        }
+    }
+}
+
+template <int K, int G, int J>
+__global__ void __launch_bounds__(J == 1 ? 1024 : 896, 1)
+    poly_grad_kernel(PolyDev pm, GradArgs a, int iters, int rows_per_chunk, int n_chunks) {
+    extern __shared__ __align__(16) float srows[];
+    constexpr int S = PolyRow<K>::STRIDE;
+    if (n_chunks == 1) {
+        poly_load_rows(srows, pm.rows, pm.N * S);
+        __syncthreads();
+    }
+    const int g = threadIdx.x % G;
+    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long n_groups = ((long long)gridDim.x * blockDim.x) / G;
+    for (int it = 0; it < iters; ++it) {
+        const long long tuple = (long long)it * n_groups + group;
+        int cid[J];
+        bool valid[J];
+        float q[J][K], graw[J][K], f[K];
+        double chi2[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const long long c = tuple * J + j;
+            valid[j] = c < a.C;
+            cid[j] = valid[j] ? (int)c : a.C - 1;
+#pragma unroll
+            for (int k = 0; k < K; ++k) q[j][k] = a.q[(size_t)cid[j] * K + k];
+        }
+        poly_grad_pass<K, G, J, true>(pm, srows, rows_per_chunk, n_chunks, g, q, graw, chi2);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            if (!valid[j] || g != 0) continue;
+            const float tau = a.tau[cid[j]];
+            const float beta = a.beta ? a.beta[cid[j]] : 1.0f;
+            if (a.logp)
+                a.logp[cid[j]] =
+                    -poly_potential<K>(pm, q[j], chi2[j], tau, beta, a.gamma_shape, a.gamma_rate);
+            if (a.chi2) a.chi2[cid[j]] = chi2[j];
+            if (a.grad) {
+                poly_force<K>(pm, q[j], graw[j], beta * tau, f);
+#pragma unroll
+                for (int k = 0; k < K; ++k) a.grad[(size_t)cid[j] * K + k] = f[k];
+            }
+        }
+    }
+}
+
+template <int K>
+__global__ void poly_forward_kernel(const float *__restrict__ rows, int N, const float *q, int C,
+                                    float *mock) {
+    constexpr int S = PolyRow<K>::STRIDE;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)C * N) return;
+    const int c = (int)(i / N), n = (int)(i % N);
+    const float x = K > 1 ? rows[(size_t)n * S] : 0.f;
+    float t = q[(size_t)c * K + K - 1];
+#pragma unroll
+    for (int k = K - 2; k >= 0; --k) t = fmaf(t, x, q[(size_t)c * K + k]);
+    mock[i] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: launch-shape heuristics and template dispatch
+// ---------------------------------------------------------------------------------------------
+struct PolyPlan {
+    int G, J, grid, block, iters, rows_per_chunk, n_chunks;
+    size_t smem;
+};
+
+static bool g_allowed(int K, int G) {
+    if (K == 4) return true;
+    return G == 1 || G == 4 || G == 32;
+}
+
+static PolyPlan poly_plan(const PolyModel &m, int C, int sm_count, int smem_optin) {
+    PolyPlan pl;
+    pl.J = (m.K == 4 && (long long)C >= 64LL * sm_count) ? 2 : 1;
+    if (m.opt_jchains == 1 || m.opt_jchains == 2) pl.J = (m.K == 4) ? m.opt_jchains : 1;
+    const int max_block = pl.J == 1 ? 1024 : 896;
+    const long long tuples = ((long long)C + pl.J - 1) / pl.J;
+    // lanes per chain: fill ~max_block threads per SM, the largest power of two that fits
+    int G = 1;
+    while (G < 32 && tuples * (G * 2) <= (long long)sm_count * max_block) G *= 2;
+    if (m.opt_group > 0) G = m.opt_group;
+    while (!g_allowed(m.K, G) && G > 1) G /= 2;
+    pl.G = G;
+    const long long threads = tuples * G;
+    long long grid = threads >= 32LL * sm_count ? sm_count : (threads + 31) / 32;
+    long long block = (threads + grid - 1) / grid;
+    block = ((block + 31) / 32) * 32;
+    if (m.opt_block > 0) block = m.opt_block;
+    if (block > max_block) block = max_block;
+    pl.grid = (int)grid;
+    pl.block = (int)block;
+    const long long n_groups = grid * block / G;
+    pl.iters = (int)((tuples + n_groups - 1) / n_groups);
+    const size_t row_bytes = (size_t)m.stride * sizeof(float);
+    const size_t cap = (size_t)smem_optin - 1024;
+    if ((size_t)m.N * row_bytes <= cap) {
+        pl.rows_per_chunk = m.N;
+        pl.n_chunks = 1;
+    } else {
+        pl.rows_per_chunk = (int)(cap / row_bytes) / 256 * 256;
+        pl.n_chunks = (m.N + pl.rows_per_chunk - 1) / pl.rows_per_chunk;
+    }
+    pl.smem = (size_t)pl.rows_per_chunk * row_bytes;
+    return pl;
+}
+
+static PolyDev poly_dev(const PolyModel &m) {
+    PolyDev d;
+    d.rows = m.rows;
+    d.N = m.N;
+    d.flags = m.flags;
+    for (int k = 0; k < 8; ++k) d.prior_mean[k] = m.prior_mean[k], d.prior_inv_var[k] = m.prior_inv_var[k];
+    return d;
+}
+
+template <typename Kern, typename Args>
+static int poly_launch_one(Kern kern, const PolyModel &m, const Args &a, const PolyPlan &pl,
+                           cudaStream_t s) {
+    BINFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    kern<<<pl.grid, pl.block, pl.smem, s>>>(poly_dev(m), a, pl.iters, pl.rows_per_chunk, pl.n_chunks);
+    BINFB_CUDA(cudaGetLastError());
+    return BINFB_OK;
+}
+
+#define POLY_DISPATCH_G(KERNEL, K_, J_)                                                     \
+    switch (pl.G) {                                                                         \
+        case 1: return poly_launch_one(KERNEL<K_, 1, J_>, m, a, pl, s);                      \
+        case 4: return poly_launch_one(KERNEL<K_, 4, J_>, m, a, pl, s);                      \
+        case 32: return poly_launch_one(KERNEL<K_, 32, J_>, m, a, pl, s);                    \
+        default: break;                                                                     \
+    }
+
+#define POLY_DISPATCH_G_FULL(KERNEL, K_, J_)                                                \
+    switch (pl.G) {                                                                         \
+        case 1: return poly_launch_one(KERNEL<K_, 1, J_>, m, a, pl, s);                      \
+        case 2: return poly_launch_one(KERNEL<K_, 2, J_>, m, a, pl, s);                      \
+        case 4: return poly_launch_one(KERNEL<K_, 4, J_>, m, a, pl, s);                      \
+        case 8: return poly_launch_one(KERNEL<K_, 8, J_>, m, a, pl, s);                      \
+        case 16: return poly_launch_one(KERNEL<K_, 16, J_>, m, a, pl, s);                    \
+        case 32: return poly_launch_one(KERNEL<K_, 32, J_>, m, a, pl, s);                    \
+        default: break;                                                                     \
+    }
+
+#define POLY_DISPATCH(KERNEL)                                                               \
+    switch (m.K) {                                                                          \
+        case 1: POLY_DISPATCH_G(KERNEL, 1, 1) break;                                         \
+        case 2: POLY_DISPATCH_G(KERNEL, 2, 1) break;                                         \
+        case 3: POLY_DISPATCH_G(KERNEL, 3, 1) break;                                         \
+        case 4:                                                                             \
+            if (pl.J == 2) {                                                                \
+                POLY_DISPATCH_G_FULL(KERNEL, 4, 2)                                           \
+            } else {                                                                        \
+                POLY_DISPATCH_G_FULL(KERNEL, 4, 1)                                           \
+            }                                                                               \
+            break;                                                                          \
+        case 5: POLY_DISPATCH_G(KERNEL, 5, 1) break;                                         \
+        case 6: POLY_DISPATCH_G(KERNEL, 6, 1) break;                                         \
+        case 7: POLY_DISPATCH_G(KERNEL, 7, 1) break;                                         \
+        case 8: POLY_DISPATCH_G(KERNEL, 8, 1) break;                                         \
+        default: break;                                                                     \
+    }
+
+int poly_hmc_launch(const PolyModel &m, const HmcArgs &a, int sm_count, int smem_optin,
+                    cudaStream_t s) {
+    const PolyPlan pl = poly_plan(m, a.C, sm_count, smem_optin);
+    POLY_DISPATCH(poly_hmc_kernel)
+    set_error("polynomial model: unsupported (n_coeff, group) combination");
+    return BINFB_EUNSUPPORTED;
+}
+
+int poly_grad_launch(const PolyModel &m, const GradArgs &a, int sm_count, int smem_optin,
+                     cudaStream_t s) {
+    const PolyPlan pl = poly_plan(m, a.C, sm_count, smem_optin);
+    POLY_DISPATCH(poly_grad_kernel)
+    set_error("polynomial model: unsupported (n_coeff, group) combination");
+    return BINFB_EUNSUPPORTED;
+}
+
+int poly_forward_launch(const PolyModel &m, const float *q, int C, float *mock, cudaStream_t s) {
+    const long long total = (long long)C * m.N;
+    const int block = 256;
+    const int grid = (int)((total + block - 1) / block);
+    switch (m.K) {
+#define FW(K_) case K_: poly_forward_kernel<K_><<<grid, block, 0, s>>>(m.rows, m.N, q, C, mock); break;
+        FW(1) FW(2) FW(3) FW(4) FW(5) FW(6) FW(7) FW(8)
+#undef FW
+        default:
+            set_error("polynomial model: n_coeff must be 1..8");
+            return BINFB_EUNSUPPORTED;
+    }
+    BINFB_CUDA(cudaGetLastError());
+    return BINFB_OK;
+}
+
+}  // namespace binfb

@@ -1,0 +1,180 @@
+/*
+ * binf_b200 -- C ABI of the B200-native HMC hot path of simeoncarstens/binf.
+ *
+ * The reference is pure Python and has NO FFI boundary; its seams are two
+ * duck-types: the pdf seam (`pdf.log_prob(**{name: x})`, `pdf.gradient(**{name: x})`,
+ * binf/samplers/hmc.py:114,143) and the sampler seam (`.pdf`, `.state`, `.sample()`,
+ * binf/samplers/gibbs.py:52,121-125,148).  Each entry point below names the reference
+ * code whose arithmetic it replaces.  Reference paths are relative to the reference root.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 (BINFB_OK) or a negative error code and
+ *     leaves a message retrievable with binfb_last_error() (thread-local).
+ *   - a model handle is bound to one CUDA device; calls on distinct handles are thread-safe.
+ *   - "dev" pointers are CUDA device pointers on the model's device; work is enqueued on
+ *     `stream` (a cudaStream_t passed as void*, NULL = default stream) and is asynchronous.
+ *     "_host" variants take ordinary host pointers, copy in, run, copy out and synchronise.
+ *   - positions q are row-major float32 [n_chains, dim], chain c at q + c*dim; energies and
+ *     log-probabilities are float64.
+ *   - chains are addressed by a global id (chain_base + local index) in the Philox counter,
+ *     so results do not depend on how chains are sharded over GPUs.
+ */
+#ifndef BINF_B200_H
+#define BINF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BINFB_VERSION 100 /* 0.1.0 */
+
+#define BINFB_OK 0
+#define BINFB_EINVAL (-1)       /* bad argument */
+#define BINFB_ECUDA (-2)        /* CUDA runtime error (message has the CUDA string) */
+#define BINFB_EUNSUPPORTED (-3) /* shape outside what the kernels implement */
+#define BINFB_ENOMEM (-4)
+
+/* model kinds */
+#define BINFB_MODEL_POLYNOMIAL 1
+#define BINFB_MODEL_CHROMATIN 2
+
+/* model flags */
+#define BINFB_FLAG_PRIOR_GRAD 1u /* polynomial: add the Gaussian-prior force (c-mu)/v that the
+                                    reference's Posterior.gradient silently drops (quirk Q1,
+                                    binf/pdf/posteriors.py:182-185, binf/example/priors.py:45) */
+
+/* Gibbs coupling of the precision update with a trajectory (binf/samplers/gibbs.py:146-149
+ * sweeps variables in sorted-name order: 'precision' < 'structure', 'coefficients' < 'precision') */
+#define BINFB_GIBBS_NONE 0
+#define BINFB_GIBBS_TAU_FIRST 1 /* draw tau | q, then run the trajectory with the new tau */
+#define BINFB_GIBBS_TAU_LAST 2  /* run the trajectory, then draw tau | q_new */
+
+typedef struct binfb_model binfb_model;
+
+typedef struct binfb_hmc_opts {
+    int32_t n_steps;    /* L, leapfrog steps per trajectory      (HMCSampler.nsteps, hmc.py:54)      */
+    int32_t n_traj;     /* trajectories (HMCSampler.sample calls) fused into this launch             */
+    int32_t n_adapt;    /* the first n_adapt trajectories adapt the step size (hmc.py:153-157)       */
+    int32_t gibbs_mode; /* BINFB_GIBBS_*                                                             */
+    double adapt_up;    /* eps *= adapt_up   after an accepted move (hmc.py:188-189)                 */
+    double adapt_down;  /* eps *= adapt_down after a rejected move  (hmc.py:190-191)                 */
+    uint64_t seed;      /* Philox key                                                                */
+    uint64_t draw;      /* index of the first trajectory of this call in the sampler's history       */
+    uint64_t chain_base;/* global id of local chain 0                                                */
+} binfb_hmc_opts;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int binfb_version(void);
+const char *binfb_last_error(void);
+/* number of visible CUDA devices; SM count, opt-in shared memory per block (bytes), SM clock
+ * (kHz) and compute capability (major*10+minor) of one of them */
+int binfb_device_count(int *count);
+int binfb_device_props(int device, int *sm_count, int *smem_optin, int *clock_khz, int *cc);
+
+/* ---- models -------------------------------------------------------------------------------- */
+/* Polynomial forward model + Gaussian error model + Gaussian/Gamma priors:
+ * binf/example/likelihood.py:11-68, binf/example/priors.py:10-64.  xs, ys: host float64
+ * [n_data]; prior_mean/prior_var: host float64 [n_coeff]. */
+int binfb_model_create_polynomial(const double *xs, const double *ys, int n_data, int n_coeff,
+                                  const double *prior_mean, const double *prior_var,
+                                  double gamma_shape, double gamma_rate, unsigned flags,
+                                  int device, binfb_model **out);
+
+/* Chromatin bead chain with a logistic contact forward model behind the reference's
+ * AbstractForwardModel / GaussianErrorModel / AbstractPrior API (build-defined, SURVEY.md A.2;
+ * the reference's Likelihood._evaluate_gradient, binf/pdf/likelihoods.py:148-155, is what the
+ * pair kernel fuses).  y_pairs: host float32 [n(n-1)/2] in numpy.triu_indices(n, 1) order. */
+int binfb_model_create_chromatin(int n_beads, const float *y_pairs, double alpha, double d_c,
+                                 double k_bb, double l0, double conf_s, double gamma_shape,
+                                 double gamma_rate, unsigned flags, int device,
+                                 binfb_model **out);
+int binfb_model_destroy(binfb_model *m);
+int binfb_model_info(const binfb_model *m, int *kind, int *dim, long long *n_data, int *device);
+/* update the Gamma prior on the precision (it enters log_prob and the Gibbs update only) */
+int binfb_model_set_gamma_prior(binfb_model *m, double shape, double rate);
+/* tuning knobs ("poly.group", "poly.chains_per_thread", "poly.block", "chrom.warps", ...);
+ * value < 0 restores the heuristic */
+int binfb_model_set_option(binfb_model *m, const char *key, double value);
+
+/* ---- pdf seam: AbstractBinfPDF.log_prob / gradient ------------------------------------------ */
+/* log_prob of the conditional posterior over the sampled variable at per-chain precision tau
+ * (binf/pdf/posteriors.py:125-151) and the gradient of the ENERGY -log p
+ * (binf/pdf/posteriors.py:173-187 -> binf/pdf/likelihoods.py:148-155).  beta (NULL = 1) tempers
+ * the likelihood term.  Outputs may be NULL: logp [C] f64, grad [C, dim] f32, chi2 [C] f64
+ * (sum of squared residuals, what GammaSampler needs: binf/example/samplers.py:34-41). */
+int binfb_logprob_grad(binfb_model *m, const float *q_dev, const float *tau_dev,
+                       const float *beta_dev, int n_chains, double *logp_dev, float *grad_dev,
+                       double *chi2_dev, void *stream);
+int binfb_logprob_grad_host(binfb_model *m, const float *q, const float *tau, const float *beta,
+                            int n_chains, double *logp, float *grad, double *chi2);
+/* forward model mock data (AbstractForwardModel.__call__, binf/__init__.py:105-120 ->
+ * binf/example/likelihood.py:24-26): mock [C, n_data] f32 */
+int binfb_forward_host(binfb_model *m, const float *q, int n_chains, float *mock);
+
+/* ---- sampler seam: HMCSampler.sample / _leapfrog -------------------------------------------- */
+/* n_traj fused HMC transitions per chain: momentum draw, L-step leapfrog with L+1 force
+ * evaluations, Metropolis accept, per-chain step-size adaption, optional conjugate precision
+ * update (binf/samplers/hmc.py:92-125,136-164,183-191; binf/example/samplers.py:27-51).
+ *   q [C, dim] in/out; tau [C] in/out; beta [C] or NULL; eps [C] in/out.
+ *   p0 [C, dim] / u [C]: injected momenta / uniforms (parity tests; require n_traj == 1) or NULL
+ *   for Philox draws.  gamma_draws [C]: injected standard-Gamma variates or NULL.
+ *   accepted [C] u8, e_before/e_after [C] f64, q_end/p_end [C, dim]: last trajectory's accept
+ *   flag, Hamiltonians and leapfrog end point (any may be NULL); n_accepted [C] i32 counts over
+ *   the call; stats_dev [4] f64 is atomically incremented by {accepted, proposed, sum eps,
+ *   sum exp(min(0,-dH))} for the diagnostics all-reduce (NULL to skip). */
+int binfb_hmc_run(binfb_model *m, float *q_dev, float *tau_dev, const float *beta_dev,
+                  float *eps_dev, int n_chains, const binfb_hmc_opts *opts, const float *p0_dev,
+                  const float *u_dev, const double *gamma_draws_dev, uint8_t *accepted_dev,
+                  double *e_before_dev, double *e_after_dev, float *q_end_dev, float *p_end_dev,
+                  int32_t *n_accepted_dev, double *stats_dev, void *stream);
+int binfb_hmc_run_host(binfb_model *m, float *q, float *tau, const float *beta, float *eps,
+                       int n_chains, const binfb_hmc_opts *opts, const float *p0, const float *u,
+                       const double *gamma_draws, uint8_t *accepted, double *e_before,
+                       double *e_after, float *q_end, float *p_end, int32_t *n_accepted,
+                       double *stats);
+
+/* ---- GammaSampler.sample (binf/example/samplers.py:27-51) ----------------------------------- */
+/* tau[c] = Gamma(beta*n_data/2 + a - 1, 1) / (beta*chi2(q[c])/2 + b)   (shape quirk Q3 kept) */
+int binfb_gibbs_precision(binfb_model *m, const float *q_dev, float *tau_dev,
+                          const float *beta_dev, int n_chains, uint64_t seed, uint64_t draw,
+                          uint64_t chain_base, const double *gamma_draws_dev, double *chi2_dev,
+                          void *stream);
+int binfb_gibbs_precision_host(binfb_model *m, const float *q, float *tau, const float *beta,
+                               int n_chains, uint64_t seed, uint64_t draw, uint64_t chain_base,
+                               const double *gamma_draws, double *chi2);
+
+/* ---- replica exchange (build-defined; the reference only alludes to it at
+ *      binf/samplers/hmc.py:171-177) --------------------------------------------------------- */
+/* accept[c] = u < exp(-(beta_a - beta_b)(ll_a[c] - ll_b[c])), u from Philox(seed; attempt,
+ * pair_id, chain_base + c) so that both partners reach the same decision without talking. */
+int binfb_swap_decide(const double *ll_a_dev, const double *ll_b_dev, double beta_a,
+                      double beta_b, int n_chains, uint64_t seed, uint64_t attempt,
+                      uint64_t pair_id, uint64_t chain_base, uint8_t *accept_dev, void *stream);
+/* q_mine[c] <- q_theirs[c] (and eps likewise if non-NULL) where accept[c] */
+int binfb_swap_apply(float *q_mine_dev, const float *q_theirs_dev, float *eps_mine_dev,
+                     const float *eps_theirs_dev, const uint8_t *accept_dev, int n_chains,
+                     int dim, void *stream);
+
+/* ---- test / measurement helpers ------------------------------------------------------------- */
+/* the device RNG streams, for statistical tests: normals [C, dim] f32 exactly as the momentum
+ * draw of trajectory `draw`; uniforms [C]; standard gammas of the given shape [C] f64 */
+int binfb_rng_fill_host(uint64_t seed, uint64_t draw, uint64_t chain_base, int n_chains, int dim,
+                        double gamma_shape, float *normals, float *uniforms, double *gammas,
+                        int device);
+/* host-side layout pass of the chromatin contact stream (no GPU needed): writes the number of
+ * float32 the kernel streams per force evaluation; if out != NULL (capacity floats) fills it */
+int binfb_chromatin_stream_layout(int n_beads, const float *y_pairs, float *out,
+                                  long long capacity, long long *n_floats, int *n_quads,
+                                  int *n_steps);
+/* FP32 pipe microbenchmarks used as roofline denominators: dependent-chain-free FFMA, packed
+ * FFMA2 and MUFU (rsqrt/ex2/rcp mix) issue loops over the whole device.  Results in
+ * TFLOP/s (2 flop per FMA lane-op) and Gop/s. */
+int binfb_microbench(int device, int iters, double *ffma_tflops, double *ffma2_tflops,
+                     double *mufu_gops, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BINF_B200_H */

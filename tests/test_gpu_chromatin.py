@@ -1,0 +1,153 @@
+"""GPU parity: chromatin pair kernel vs the reference-generated golden vectors (small n, the
+reference's dense J.dot(g) path) and vs the matrix-free oracle at n = 1000, plus
+size-independent properties (Newton's third law, translation invariance, reversibility)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+import binf_port as port
+import chromatin_port as chrom
+
+pytestmark = pytest.mark.gpu
+CASES = ["chromatin_n24", "chromatin_n37_L20", "chromatin_n30_big_step"]
+
+
+def make_model(g):
+    from binf_b200 import _cabi
+    return _cabi.Model.chromatin(int(g["n_beads"]), g["y"], float(g["alpha"]), float(g["d_c"]),
+                                 float(g["k_bb"]), float(g["l0"]), 0.0, float(g["gamma_shape"]),
+                                 float(g["gamma_rate"]))
+
+
+def inf_norm(a):
+    return np.max(np.abs(a), axis=-1, keepdims=True)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_logprob_and_gradient_vs_reference(gpu, name):
+    g = load_golden(name)
+    m = make_model(g)
+    logp, grad, chi2 = m.logprob_grad(g["q0"], float(g["tau"]))
+    np.testing.assert_allclose(logp, g["log_prob"], rtol=1e-5)
+    assert np.all(np.abs(grad - g["gradient"]) <= 1e-4 * inf_norm(g["gradient"]))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_trajectory_vs_reference(gpu, name):
+    g = load_golden(name)
+    m = make_model(g)
+    L = int(g["nsteps"])
+    r = m.hmc_run(g["q0"], float(g["tau"]), float(g["timestep"]), L, p0=g["p0"], u=g["u"], want_end=True)
+    tol = 1e-4 if L <= 5 else 1e-3
+    assert np.all(np.abs(r["q_end"] - g["q_end"]) <= tol * inf_norm(g["q_end"]))
+    assert np.all(np.abs(r["p_end"] - g["p_end"]) <= tol * np.maximum(inf_norm(g["p_end"]), 1.0))
+    np.testing.assert_allclose(r["e_before"], g["e_before"], rtol=1e-5)
+    dh_ref = g["e_after"] - g["e_before"]
+    assert np.all(np.abs((r["e_after"] - r["e_before"]) - dh_ref) <= 5e-3 + 1e-3 * np.abs(dh_ref))
+    decided = np.abs(np.log(g["u"]) + dh_ref) > 0.02
+    assert np.array_equal(r["accepted"][decided], g["accepted"][decided])
+
+
+@pytest.mark.parametrize("n", [2, 5, 8, 64, 130, 257])
+def test_ragged_sizes_vs_oracle(gpu, n):
+    """quad padding, odd/even quad counts, partial row blocks"""
+    from binf_b200 import _cabi
+    X, y = chrom.synthetic_chromatin(n, seed=n)
+    o = chrom.ChromatinModel(n, y, 2.0, 2.5, 3.0, 1.0, conf_s=20.0, gamma_shape=2.0, gamma_rate=0.5)
+    m = _cabi.Model.chromatin(n, y, 2.0, 2.5, 3.0, 1.0, conf_s=20.0, gamma_shape=2.0, gamma_rate=0.5)
+    rng = np.random.RandomState(n)
+    C = 11
+    q = X.reshape(-1)[None] + 0.2 * rng.normal(size=(C, 3 * n))
+    tau = rng.uniform(20, 80, size=C)
+    beta = rng.uniform(0.2, 1.0, size=C)
+    logp, grad, chi2 = m.logprob_grad(q, tau, beta)
+    for c in range(C):
+        assert logp[c] == pytest.approx(o.log_prob(q[c], tau[c], beta[c]), rel=1e-5)
+        ref = o.gradient(q[c], tau[c], beta[c])
+        assert np.all(np.abs(grad[c] - ref) <= 1e-4 * np.max(np.abs(ref)))
+        assert chi2[c] == pytest.approx(o.chi2(q[c]), rel=1e-5)
+
+
+def test_n1000_vs_matrix_free_oracle(gpu):
+    """Config-3 size: 1000 beads, 499,500 pairs per force evaluation."""
+    from binf_b200 import _cabi
+    n = 1000
+    X, y = chrom.synthetic_chromatin(n, seed=0)
+    o = chrom.ChromatinModel(n, y, 2.0, 2.5, 4.0, 1.0)
+    m = _cabi.Model.chromatin(n, y, 2.0, 2.5, 4.0, 1.0)
+    rng = np.random.RandomState(1)
+    C = 20  # not a multiple of the chains-per-CTA
+    q = X.reshape(-1)[None] + 0.1 * rng.normal(size=(C, 3 * n))
+    tau = np.full(C, 400.0)
+    logp, grad, chi2 = m.logprob_grad(q, tau)
+    for c in (0, 7, 19):
+        assert logp[c] == pytest.approx(o.log_prob(q[c], 400.0), rel=1e-5)
+        ref = o.gradient(q[c], 400.0)
+        assert np.all(np.abs(grad[c] - ref) <= 1e-4 * np.max(np.abs(ref)))
+    # Newton's third law: likelihood + backbone forces are pairwise => they sum to zero
+    f = grad.reshape(C, n, 3).sum(axis=1)
+    assert np.all(np.abs(f) <= 1e-3 * np.max(np.abs(grad)))
+    # translation invariance of log_prob
+    logp2, _, _ = m.logprob_grad(q + np.tile([3.0, -2.0, 1.0], n)[None], tau, want_grad=False)
+    np.testing.assert_allclose(logp2, logp, rtol=2e-6)
+    # short trajectory against the oracle integrator
+    p0, u = rng.normal(size=(2, 3 * n)), np.array([0.5, 0.5])
+    r = m.hmc_run(q[:2], 400.0, 0.002, 3, p0=p0, u=u, want_end=True)
+    for c in range(2):
+        ref = port.hmc_sample(lambda x: o.log_prob(x, 400.0), lambda x: o.gradient(x, 400.0), q[c],
+                              0.002, 3, p0[c], u[c])
+        assert np.max(np.abs(r["q_end"][c] - ref["q_end"])) <= 1e-4 * np.max(np.abs(ref["q_end"]))
+        assert np.max(np.abs(r["p_end"][c] - ref["p_end"])) <= 1e-4 * np.max(np.abs(ref["p_end"]))
+        assert r["e_before"][c] == pytest.approx(ref["e_before"], rel=1e-6)
+        assert (r["e_after"][c] - r["e_before"][c]) == pytest.approx(ref["e_after"] - ref["e_before"], abs=2e-2)
+
+
+def test_reversibility_and_energy_conservation(gpu):
+    from binf_b200 import _cabi
+    n = 257
+    X, y = chrom.synthetic_chromatin(n, seed=3)
+    m = _cabi.Model.chromatin(n, y, 2.0, 2.5, 4.0, 1.0)
+    rng = np.random.RandomState(4)
+    C = 37
+    q0 = X.reshape(-1)[None] + 0.05 * rng.normal(size=(C, 3 * n))
+    p0 = rng.normal(size=q0.shape)
+    u = np.full(C, 1e-30)
+    fwd = m.hmc_run(q0, 100.0, 0.003, 12, p0=p0, u=u, want_end=True)
+    assert fwd["accepted"].all()
+    assert np.max(np.abs(fwd["e_after"] - fwd["e_before"])) < 0.5
+    back = m.hmc_run(fwd["q_end"], 100.0, 0.003, 12, p0=-fwd["p_end"], u=u, want_end=True)
+    assert np.max(np.abs(back["q_end"] - q0)) < 2e-4 * np.max(np.abs(q0))
+    assert np.max(np.abs(back["p_end"] + p0)) < 5e-3
+
+
+def test_fused_gibbs_sweeps_and_multi_trajectory(gpu):
+    """tau-first Gibbs coupling ('precision' < 'structure' in the reference's sorted sweep) with an
+    injected Gamma variate, then statistical sanity of many fused sweeps with Philox draws."""
+    from binf_b200 import _cabi
+    n = 64
+    X, y = chrom.synthetic_chromatin(n, seed=9)
+    o = chrom.ChromatinModel(n, y, 2.0, 2.5, 4.0, 1.0, gamma_shape=1.0, gamma_rate=1.0)
+    m = _cabi.Model.chromatin(n, y, 2.0, 2.5, 4.0, 1.0, gamma_shape=1.0, gamma_rate=1.0)
+    rng = np.random.RandomState(2)
+    C = 24
+    q0 = X.reshape(-1)[None] + 0.05 * rng.normal(size=(C, 3 * n))
+    gd = rng.gamma(0.5 * o.n_pairs, size=C)
+    p0, u = rng.normal(size=q0.shape), rng.uniform(size=C)
+    r = m.hmc_run(q0, 1.0, 0.004, 4, p0=p0, u=u, gamma_draws=gd, gibbs_mode=_cabi.GIBBS_TAU_FIRST, want_end=True)
+    for c in range(C):
+        shape, rate = port.gamma_precision_params(o.chi2(q0[c]), o.n_pairs, 1.0, 1.0)
+        tau_c = gd[c] / rate
+        assert r["tau"][c] == pytest.approx(tau_c, rel=2e-5)
+        ref = port.hmc_sample(lambda x: o.log_prob(x, tau_c), lambda x: o.gradient(x, tau_c), q0[c],
+                              0.004, 4, p0[c], u[c])
+        assert np.max(np.abs(r["q_end"][c] - ref["q_end"])) <= 1e-4 * np.max(np.abs(ref["q_end"]))
+        assert r["e_before"][c] == pytest.approx(ref["e_before"], rel=1e-5)
+    # 40 fused sweeps: precision concentrates near 1/noise^2 = 400, acceptance is healthy
+    r = m.hmc_run(q0, 100.0, 0.002, 10, n_traj=40, gibbs_mode=_cabi.GIBBS_TAU_FIRST, seed=5)
+    assert 150 < np.median(r["tau"]) < 600
+    assert r["n_accepted"].mean() / 40 > 0.5
+    assert r["stats"][1] == C * 40 and r["stats"][0] == r["n_accepted"].sum()
+    # step-size adaption: accepted => x1.05, rejected => x0.95 (hmc.py:188-191)
+    r = m.hmc_run(q0, 100.0, 0.002, 5, n_traj=3, n_adapt=3, seed=6)
+    expect = 0.002 * 1.05 ** r["n_accepted"] * 0.95 ** (3 - r["n_accepted"])
+    np.testing.assert_allclose(r["eps"], expect, rtol=1e-5)
