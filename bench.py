@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native HMC hot path (metric of BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload chromatin|poly]
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port)
+
+A "step" is one Gibbs sweep over every chain of the batch: the conjugate precision update
+followed by one HMC trajectory of L leapfrog steps (L+1 fused force evaluations) and the
+Metropolis test -- one launch of the fused kernel.  metric = leapfrog steps/s =
+chains x L x sweeps / device time.  Default workload = BASELINE.json configs[2], the
+1000-bead chromatin posterior the north star's target is quoted on (4,096 chains per GPU,
+weak scaling: every rank owns its own 4,096 chains, no data-path collective; the only
+collective is the 4-double diagnostics all-reduce at the end of the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR = 31.0          # per unordered bead pair and force evaluation
+FLOP_PER_DATUM = 14.0         # per chain, datum and force evaluation (K = 4)
+
+WORKLOADS = {
+    "chromatin": dict(name="chromatin_n1000_c4096_L20_gibbs", n_beads=1000, chains=4096, L=20,
+                      eps=1.5e-3, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, noise=0.05),
+    "poly": dict(name="poly_K4_N1000_c65536_L20", n_data=1000, chains=65536, L=20, eps=0.009,
+                 tau=2.5),
+}
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic inputs; generated without touching oracle/ so the product arm
+# never imports the checker
+# --------------------------------------------------------------------------------------------
+def chromatin_inputs(w, chains, seed):
+    n = w["n_beads"]
+    rng = np.random.RandomState(0)
+    X = np.cumsum(rng.normal(size=(n, 3)) * w["l0"], axis=0)
+    X -= X.mean(axis=0)
+    i, j = np.triu_indices(n, 1)
+    d = np.sqrt(np.sum((X[i] - X[j]) ** 2, axis=-1) + 1e-12)
+    with np.errstate(over="ignore"):
+        y = 1.0 / (1.0 + np.exp(w["alpha"] * (d - w["d_c"]))) + rng.normal(size=d.shape) * w["noise"]
+    rng = np.random.RandomState(1 + seed)
+    q = (X.reshape(-1)[None, :] + 0.1 * rng.normal(size=(chains, 3 * n))).astype(np.float32)
+    return y.astype(np.float32), q
+
+
+def poly_inputs(w, chains, seed):
+    rng = np.random.RandomState(0)
+    xs = np.linspace(-2, 2, w["n_data"])
+    ys = rng.normal(np.polynomial.polynomial.polyval(xs, [2.0, -4.0, 1.0, 1.5]), 1 / np.sqrt(2.5))
+    rng = np.random.RandomState(1 + seed)
+    q = (np.ones((chains, 4)) + 0.1 * rng.normal(size=(chains, 4))).astype(np.float32)
+    return xs, ys, q
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4)
+                          if r[3 + k].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------
+# the reference arm / CPU baseline: the oracle port timed on the host cores
+# --------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    workload, seed, budget_s = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import binf_port as port
+    import chromatin_port as chrom
+    rng = np.random.RandomState(100 + seed)
+    if workload == "chromatin":
+        w = WORKLOADS["chromatin"]
+        X, y = chrom.synthetic_chromatin(w["n_beads"], w["alpha"], w["d_c"], w["l0"], w["noise"], 0)
+        model = chrom.ChromatinModel(w["n_beads"], y, w["alpha"], w["d_c"], w["k_bb"], w["l0"])
+        q = X.reshape(-1) + 0.1 * rng.normal(size=3 * w["n_beads"])
+        tau, n_pairs = 100.0, model.n_pairs
+        steps, t0 = 0, time.perf_counter()
+        while True:
+            # one Gibbs sweep of the reference: precision update, then one HMC transition
+            tau = float(port.gamma_precision_sample(model.chi2(q), n_pairs, 1.0, 1.0, rng))
+            r = port.hmc_sample(lambda x: model.log_prob(x, tau), lambda x: model.gradient(x, tau), q,
+                                w["eps"], w["L"], rng.normal(size=q.shape), rng.uniform())
+            q = r["q"]
+            steps += w["L"]
+            if time.perf_counter() - t0 > budget_s:
+                break
+        return steps, time.perf_counter() - t0
+    w = WORKLOADS["poly"]
+    xs = np.linspace(-2, 2, w["n_data"])
+    ys = rng.normal(np.polynomial.polynomial.polyval(xs, [2.0, -4.0, 1.0, 1.5]), 1 / np.sqrt(2.5))
+    pp = port.PolynomialPosterior(xs, ys, np.zeros(4), 5 * np.ones(4), 1.0, 1.0)
+    q, tau = np.ones(4), w["tau"]
+    steps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        r = port.hmc_sample(lambda c: pp.log_prob(c, tau), lambda c: pp.gradient(c, tau), q, w["eps"],
+                            w["L"], rng.normal(size=4), rng.uniform())
+        q = r["q"]
+        steps += w["L"]
+    return steps, time.perf_counter() - t0
+
+
+def cpu_baseline(workload, budget_s, cores=None):
+    """P independent single-chain processes of the oracle port (float64 numpy, the reference's
+    arithmetic), aggregate leapfrog steps/s."""
+    import multiprocessing as mp
+    cores = cores or len(os.sched_getaffinity(0))
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(workload, s, budget_s) for s in range(cores)])
+    value = sum(st / el for st, el in res)
+    sample = "%d single-chain processes x %.0f s of Gibbs sweeps (%d trajectories total)" % (
+        cores, budget_s, sum(st for st, _ in res) // WORKLOADS[workload]["L"])
+    return dict(value=value, unit="leapfrog steps/s", cores=cores, kind="port", sample=sample)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    t0 = time.perf_counter()
+    per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    cpu_baseline(args.workload, 1.0)  # warm-up (imports, page-in)
+    vals = [cpu_baseline(args.workload, per_step) for _ in range(max(1, min(args.steps, 3)))]
+    best = max(vals, key=lambda v: v["value"])
+    line = dict(impl="reference", metric="HMC leapfrog steps/s (chains x steps)", value=best["value"],
+                unit="leapfrog steps/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic",
+                config=dict(workload=w["name"], note="oracle port of the reference's numpy path; "
+                            "the reference itself is Python 2 + CSB and cannot travel to the box"),
+                cpu_baseline=best,
+                e2e=dict(value=best["value"], unit="leapfrog steps/s", h2d_bytes_per_step=0,
+                         d2h_bytes_per_step=0),
+                wall_s=time.perf_counter() - t0)
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# the product arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from binf_b200 import _cabi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOADS[args.workload]
+    C = args.chains or w["chains"]
+    L = w["L"]
+    eps0 = args.eps or w["eps"]
+    chain_base = rank * C
+
+    if args.workload == "chromatin":
+        y, q_host = chromatin_inputs(w, C, rank)
+        model = _cabi.Model.chromatin(w["n_beads"], y, w["alpha"], w["d_c"], w["k_bb"], w["l0"], 0.0,
+                                      1.0, 1.0, device=local)
+        tau0, gibbs = 100.0, _cabi.GIBBS_TAU_FIRST
+        units = float(model.n_data)            # pairs per force evaluation
+        flop_per_launch = FLOP_PER_PAIR * units * (L + 1) * C
+        bytes_per_launch = 2.0 * 4 * q_host.shape[1] * C + 4.0 * units
+    else:
+        xs, ys, q_host = poly_inputs(w, C, rank)
+        model = _cabi.Model.polynomial(xs, ys, 4, np.zeros(4), 5 * np.ones(4), 1.0, 1.0, device=local)
+        tau0, gibbs = w["tau"], _cabi.GIBBS_NONE
+        units = float(w["n_data"])
+        flop_per_launch = (FLOP_PER_DATUM * (L + 1) + 4) * units * C
+        bytes_per_launch = 2.0 * 4 * 4 * C
+    D = q_host.shape[1]
+
+    q = torch.from_numpy(q_host).to(dev)
+    tau = torch.full((C,), tau0, device=dev, dtype=torch.float32)
+    eps = torch.full((C,), eps0, device=dev, dtype=torch.float32)
+    accepted = torch.zeros(C, device=dev, dtype=torch.uint8)
+    nacc = torch.zeros(C, device=dev, dtype=torch.int32)
+    stats = torch.zeros(4, device=dev, dtype=torch.float64)
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8) if args.workload == "poly" else None
+    stream = torch.cuda.current_stream().cuda_stream
+    draw = [0]
+
+    def step():
+        opts = _cabi.HmcOpts(L, 1, 0, gibbs, 1.05, 0.95, args.seed, draw[0], chain_base)
+        model.hmc_run_device(q, tau, eps, opts, accepted=accepted, n_accepted=nacc, stats=stats,
+                             stream=stream)
+        draw[0] += 1
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    stats.zero_()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    sync_all()
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        if flush is not None:
+            flush.fill_(k)                      # L2 flush between timed iterations (not timed)
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    if flush is None:
+        total_ms = ev[0][0].elapsed_time(ev[-1][1])   # one bracket over all K steps
+    else:
+        total_ms = float(sum(kernel_ms))
+    if world > 1:
+        dist.all_reduce(stats)                  # the diagnostics reduction (4 doubles, NCCL)
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    sync_all()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    clocks = sampler.summary() if sampler else None
+    st = stats.cpu().numpy()
+    value = world * C * L * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: the same sweep through the host-buffer C-ABI call (pinned host memory) --------
+    e2e = None
+    if not args.no_e2e:
+        qh = torch.from_numpy(q_host.copy()).pin_memory().numpy()
+        th = torch.full((C,), tau0, dtype=torch.float32).pin_memory().numpy()
+        eh = torch.full((C,), eps0, dtype=torch.float32).pin_memory().numpy()
+        ah = np.empty(C, dtype=np.uint8)
+        n_e2e = max(2, min(args.steps, 5))
+        from ctypes import byref
+
+        def host_step(k):
+            opts = _cabi.HmcOpts(L, 1, 0, gibbs, 1.05, 0.95, args.seed, 1000 + k, chain_base)
+            _cabi.check(_cabi.lib().binfb_hmc_run_host(
+                model._h, _cabi.ptr(qh), _cabi.ptr(th), None, _cabi.ptr(eh), C, byref(opts), None, None,
+                None, _cabi.ptr(ah), None, None, None, None, None, None))
+        host_step(0)
+        sync_all()
+        t0 = time.perf_counter()
+        for k in range(n_e2e):
+            host_step(1 + k)
+        el = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([el], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        e2e = dict(value=world * C * L * n_e2e / el, unit="leapfrog steps/s",
+                   h2d_bytes_per_step=int(4 * C * D + 8 * C), d2h_bytes_per_step=int(4 * C * D + 9 * C),
+                   steps=n_e2e, api="binfb_hmc_run_host (pinned host buffers in, synchronous)")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel ------------------------------------------------
+    ms_kernel = float(np.mean(kernel_ms))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    mb = _cabi.microbench(local, 3000)
+    achieved = flop_per_launch / (ms_kernel * 1e-3) / 1e12
+    roofline = dict(
+        bound="fp32_fma", achieved=achieved, peak=mb["ffma_tflops"], unit="TFLOP/s",
+        frac=achieved / mb["ffma_tflops"], traffic=None,
+        peak_source="live FFMA issue microbenchmark in this run (binfb_microbench); "
+                    "MEASURED_PEAKS.json has no non-tensor FP32 figure",
+        peak_formula_tflops=148 * 128 * 2 * 1.965e9 / 1e12,
+        ffma2_tflops=mb["ffma2_tflops"], mufu_gops=mb["mufu_gops"],
+        flop_per_launch=flop_per_launch, kernel_ms=ms_kernel,
+        hbm_sanity=dict(algorithmic_gb_per_launch=bytes_per_launch / 1e9,
+                        achieved_gbs=bytes_per_launch / (ms_kernel * 1e-3) / 1e9,
+                        peak_gbs=peaks.get("hbm_gbs"),
+                        note="compulsory HBM bytes are O(chains x dim) per trajectory: not the bound"))
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args.workload, args.cpu_seconds)
+    line = dict(metric="HMC leapfrog steps/s (chains x steps)", value=value, unit="leapfrog steps/s",
+                n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=total_ms / args.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic",
+                config=dict(workload=w["name"], chains_per_gpu=C, leapfrog_steps=L, timestep=eps0,
+                            parallelism="chain-sharded x%d (no data-path collective)" % world,
+                            l2="working set %.0f MB per step > 126 MB L2" % (3 * 4 * C * D / 1e6)
+                            if flush is None else "L2 flushed (256 MiB fill) between timed steps",
+                            gibbs="precision update fused in front of each trajectory"
+                            if gibbs else "none"),
+                acceptance_rate=float(st[0] / st[1]) if st[1] else None,
+                e2e=e2e, gpu_launches=args.steps, wall_ms=wall_ms, clocks=clocks, roofline=roofline,
+                cpu_baseline=cpu)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="chromatin", choices=sorted(WORKLOADS))
+    ap.add_argument("--chains", type=int, default=0)
+    ap.add_argument("--eps", type=float, default=0.0)
+    ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
