@@ -56,7 +56,7 @@ SIGNATURES = {
     "binfb_swap_decide": (_i, [_vp, _vp, _d, _d, _i, _u64, _u64, _u64, _u64, _vp, _vp]),
     "binfb_swap_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "binfb_rng_fill_host": (_i, [_u64, _u64, _u64, _i, _i, _d, _vp, _vp, _vp, _i]),
-    "binfb_chromatin_stream_layout": (_i, [_i, _vp, _vp, _ll, _pll, _pi, _pi]),
+    "binfb_chromatin_stream_layout": (_i, [_i, _vp, _i, _i, _vp, _ll, _pll, _pi]),
     "binfb_microbench": (_i, [_i, _i, _pd, _pd, _pd, _pd]),
 }
 
@@ -122,15 +122,18 @@ def microbench(device=0, iters=2000):
     return dict(ffma_tflops=a.value, ffma2_tflops=b.value, mufu_gops=c.value, sm_clock_mhz=d.value)
 
 
-def chromatin_stream_layout(n_beads, y_pairs):
-    """Host-only: the contact stream exactly as the pair kernel consumes it."""
+def chromatin_stream_layout(n_beads, y_pairs, roles=0, smem_bytes=0):
+    """Host-only: the contact stream exactly as the pair kernel consumes it, and the plan."""
     y = f32(y_pairs)
-    n_floats, q, t = C.c_longlong(), C.c_int(), C.c_int()
-    check(lib().binfb_chromatin_stream_layout(n_beads, ptr(y), None, 0, C.byref(n_floats),
-                                              C.byref(q), C.byref(t)))
+    n_floats = C.c_longlong()
+    plan = (C.c_int * 6)()
+    check(lib().binfb_chromatin_stream_layout(n_beads, ptr(y), roles, smem_bytes, None, 0,
+                                              C.byref(n_floats), plan))
     out = np.empty(n_floats.value, dtype=np.float32)
-    check(lib().binfb_chromatin_stream_layout(n_beads, ptr(y), ptr(out), out.size, None, None, None))
-    return out, q.value, t.value
+    check(lib().binfb_chromatin_stream_layout(n_beads, ptr(y), roles, smem_bytes, ptr(out), out.size,
+                                              None, None))
+    keys = ("quads", "partner_steps", "row_blocks", "roles", "slots_per_row_block", "chains_per_cta")
+    return out, dict(zip(keys, list(plan)))
 
 
 def rng_fill(seed, draw, chain_base, n_chains, dim, gamma_shape=1.0, device=0):
@@ -165,7 +168,9 @@ class Model(object):
 
     @classmethod
     def chromatin(cls, n_beads, y_pairs, alpha, d_c, k_bb, l0, conf_s=0.0, gamma_shape=1.0,
-                  gamma_rate=1.0, flags=0, device=0):
+                  gamma_rate=1.0, flags=0, device=0, roles=0):
+        """roles: warps per chain (0 = heuristic; forcing it is a test hook, flags bits 8..11)."""
+        flags |= (roles & 0xf) << 8
         y = f32(y_pairs)
         assert y.shape == (n_beads * (n_beads - 1) // 2,)
         h = C.c_void_p()

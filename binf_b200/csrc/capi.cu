@@ -206,22 +206,21 @@ int binfb_model_create_chromatin(int n_beads, const float *y_pairs, double alpha
     m->n_data = (long long)n_beads * (n_beads - 1) / 2;
     m->gamma_shape = gamma_shape, m->gamma_rate = gamma_rate;
     ChromModel &cm = m->chrom;
-    cm.n = n_beads, cm.n_pad = (n_beads + 3) / 4 * 4, cm.Q = cm.n_pad / 4, cm.KS = cm.Q / 2;
-    cm.NRB = (cm.Q + 31) / 32;
+    cm.n = n_beads;
     cm.M = m->n_data;
     cm.alpha = (float)alpha, cm.d_c = (float)d_c, cm.k_bb = (float)k_bb, cm.l0 = (float)l0;
     cm.inv_s2 = conf_s > 0.0 ? (float)(1.0 / (conf_s * conf_s)) : 0.f;
     cm.flags = flags;
-    long long n_floats = 0;
-    int Q = 0, T = 0;
-    rc = chrom_build_stream(n_beads, y_pairs, nullptr, 0, &n_floats, &Q, &T);
-    if (rc) {
+    const int force_roles = (int)((flags >> 8) & 0xf);  // test hook: bits 8..11 force R
+    cm.plan = chrom_plan(n_beads, m->smem_optin, force_roles);
+    if (cm.plan.W < 1) {
         delete m;
-        return rc;
+        set_error("model_create_chromatin: n_beads too large for the shared-memory resident kernel");
+        return BINFB_EUNSUPPORTED;
     }
-    cm.T = T, cm.T_pad = (T + CHROM_STAGE_STEPS - 1) / CHROM_STAGE_STEPS * CHROM_STAGE_STEPS;
-    std::vector<float> stream((size_t)n_floats);
-    rc = chrom_build_stream(n_beads, y_pairs, stream.data(), n_floats, nullptr, nullptr, nullptr);
+    std::vector<float> stream((size_t)cm.plan.stream_floats);
+    rc = chrom_build_stream(n_beads, y_pairs, cm.plan, stream.data());
+    const long long n_floats = cm.plan.stream_floats;
     cudaError_t e = cudaSuccess;
     if (!rc) e = cudaMalloc(&cm.ystream, (size_t)n_floats * sizeof(float));
     if (!rc && e == cudaSuccess)
@@ -506,9 +505,24 @@ int binfb_rng_fill_host(uint64_t seed, uint64_t draw, uint64_t chain_base, int C
     return rc;
 }
 
-int binfb_chromatin_stream_layout(int n_beads, const float *y_pairs, float *out, long long capacity,
-                                  long long *n_floats, int *n_quads, int *n_steps) {
-    return chrom_build_stream(n_beads, y_pairs, out, capacity, n_floats, n_quads, n_steps);
+int binfb_chromatin_stream_layout(int n_beads, const float *y_pairs, int roles, int smem_bytes,
+                                  float *out, long long capacity, long long *n_floats, int *plan6) {
+    if (n_beads < 2 || roles < 0 || roles > 8 || (roles & (roles - 1))) {
+        set_error("chromatin_stream_layout: n_beads >= 2, roles in {0 (auto),1,2,4,8}");
+        return BINFB_EINVAL;
+    }
+    const ChromPlan pl = chrom_plan(n_beads, smem_bytes > 0 ? smem_bytes : 232448, roles);
+    if (n_floats) *n_floats = pl.stream_floats;
+    if (plan6) {
+        plan6[0] = pl.Q, plan6[1] = pl.KS, plan6[2] = pl.NRB, plan6[3] = pl.R, plan6[4] = pl.Lr,
+        plan6[5] = pl.W;
+    }
+    if (!out) return BINFB_OK;
+    if (!y_pairs || capacity < pl.stream_floats) {
+        set_error("chromatin_stream_layout: buffer too small");
+        return BINFB_EINVAL;
+    }
+    return chrom_build_stream(n_beads, y_pairs, pl, out);
 }
 
 int binfb_microbench(int device, int iters, double *ffma_tflops, double *ffma2_tflops,

@@ -10,19 +10,22 @@
 // n = 1000) is never formed: the pair loop applies it on the fly.
 //
 // Work decomposition
-//   * one WARP per chain; W (<= 8) chains per CTA share one stream of contact data y.
+//   * R warps ("roles") per chain, W chains per CTA (W*R <= 16 consumer warps) sharing one stream
+//     of contact data y; R = 1 for small n (16 chains fit in shared memory), R = 2 at n = 1000.
 //   * beads are grouped in quads (4 beads).  Quad a is paired with quads (a+k) mod Q,
 //     k = 1..Q/2 ("circulant half shell"): every unordered quad pair is visited exactly once and
 //     every quad has the same number of partners, so there is no triangular waste.  Lane l of the
 //     warp owns quad a = 32*rb + l of row block rb; its 4 bead positions and force accumulators
-//     stay in registers for the whole row block.  Each step is a 4x4 block of bead pairs: 12
+//     stay in registers for the whole row block.  The R roles of a chain split the partner
+//     offsets k of a row block into R contiguous ranges.  Each step is a 4x4 block of bead pairs: 12
 //     positions + 12 partner-force accumulators + 16 contacts in registers, 16 pair evaluations.
 //   * within a step the 32 lanes address 32 distinct partner quads, so the read-modify-write of the
 //     partner forces in shared memory is conflict- and race-free without atomics.
 //   * contacts are pre-laid-out on the host in exactly the order the lanes consume them
-//     ([row block][step][row r][lane] float4).  A producer warp streams that array through a
-//     4-stage shared-memory ring with 1-D bulk async copies (TMA engine, UBLKCP) completing on
-//     mbarriers; all W consumer warps read the same stage, so L2->SM traffic is 1/W of naive.
+//     ([row block][slot][role][row r][lane] float4).  Lane 0 of warp 0 streams that array through
+//     a 4-stage shared-memory ring with 1-D bulk async copies (TMA engine, UBLKCP) completing on
+//     mbarriers, two stages ahead of the consumers; all warps read the same stage, so L2->SM
+//     traffic is 1/W of naive.
 //   * scheduling: a work item is (trajectory, leapfrog pass, group of W chains).  CTAs are
 //     persistent and claim items from an atomic counter; a per-group pass counter (release/acquire)
 //     orders the passes of one group.  Between passes q and p round-trip through L2 (24 KB per
@@ -36,14 +39,13 @@
 namespace binfb {
 
 constexpr float CHROM_SOFT = 1e-12f;
-constexpr int SS = CHROM_STAGE_STEPS;
 constexpr int NS = CHROM_STAGES;
-constexpr int STEP_FLOAT4 = 4 * 32;                 // float4 per warp-step
-constexpr int STAGE_FLOAT4 = SS * STEP_FLOAT4;
-constexpr uint32_t STAGE_BYTES = STAGE_FLOAT4 * 16;
+constexpr int STEP_FLOAT4 = 4 * 32;  // float4 per warp-step (16 contacts per lane)
+constexpr int STEP_BYTES = STEP_FLOAT4 * 16;
 
 struct ChromDev {
-    int n, n_pad, Q, KS, NRB, T, T_pad, q_even;
+    int n, n_pad, Q, KS, NRB, q_even;
+    int R, Lr, SS, S_pad;  // roles per chain, slots per row block, steps per stage, padded slots
     const float4 *ystream;
     float A, B;  // exp(alpha (d - d_c)) = 2^(A d + B)
     float alpha, k_bb, l0, inv_s2;
@@ -64,6 +66,10 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
 }
 __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// barrier over the warps of one chain (ids 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void chain_bar(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 // one bead pair: 19 FP32-pipe instructions + 3 MUFU (31 flop by the SURVEY.md 8d count)
@@ -93,43 +99,81 @@ __device__ __forceinline__ float4 pack4(const float (&a)[4]) {
     return make_float4(a[0], a[1], a[2], a[3]);
 }
 
-struct WarpSmem {
+struct ChainSmem {
     float *xs, *ys, *zs, *fx, *fy, *fz;
+    double *red;  // [8] cross-role reduction scratch
 };
 
-// The pair sweep of one chain: fills fx/fy/fz with sum_j coef_ij (x_i - x_j) (the likelihood
-// force up to the factor -alpha*beta*tau) and returns this lane's share of chi^2.
+struct Ring {
+    const float4 *ystage;
+    uint64_t *full, *empty;
+    // loader duty (warp 0, lane 0): global source of the pass and stage geometry
+    const unsigned char *src;
+    uint32_t stage_bytes;
+    int n_stage_pass;
+    bool loader;
+};
+
+constexpr int PREFETCH = 2;  // stages of lookahead; the slot refilled was released 2 stages ago
+
+// issue the bulk copy of local stage s_local of this pass (global stage index base + s_local)
+__device__ __forceinline__ void ring_issue(const Ring &ring, uint32_t base, int s_local) {
+    const uint32_t gi = base + (uint32_t)s_local;
+    const uint32_t sl = gi % NS;
+    mbar_wait(&ring.empty[sl], ((gi / NS) & 1u) ^ 1u);
+    mbar_arrive_expect_tx(&ring.full[sl], ring.stage_bytes);
+    bulk_copy_g2s(const_cast<unsigned char *>(reinterpret_cast<const unsigned char *>(ring.ystage)) +
+                      (size_t)sl * ring.stage_bytes,
+                  ring.src + (size_t)s_local * ring.stage_bytes, ring.stage_bytes, &ring.full[sl]);
+}
+
+// The pair sweep of one chain, shared by the R warps ("roles") of that chain.  Role r owns the
+// partner steps k in [r*Lr, (r+1)*Lr) of every row block.  Fills fx/fy/fz with
+// sum_j coef_ij (x_i - x_j) (the likelihood force up to the factor -alpha*beta*tau) and returns
+// this lane's share of chi^2.
+//
+// Race freedom of the partner-force read-modify-write in shared memory: within one warp-step the
+// 32 lanes address 32 distinct quads ((a+k) mod Q is a bijection of a).  Two roles r < r' of
+// one chain work on partner offsets k and k' >= k + Lr - drift, where drift <= NS*SS/R slots is
+// enforced by the shared stage ring; they can only meet on a quad if k' - k <= 31, which the
+// host-side plan excludes (Lr - NS*SS/R > 31 whenever R > 1).
 template <bool ENERGY>
-__device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const WarpSmem &sm,
-                                              const float4 *ystage, uint64_t *full, uint64_t *empty,
-                                              uint32_t &stage_idx, bool chain_valid, int lane) {
+__device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSmem &sm,
+                                              const Ring &ring, uint32_t &stage_idx,
+                                              bool chain_valid, int lane, int role, int bar_id) {
     float4 *xs4 = reinterpret_cast<float4 *>(sm.xs), *ys4 = reinterpret_cast<float4 *>(sm.ys),
            *zs4 = reinterpret_cast<float4 *>(sm.zs);
     float4 *fx4 = reinterpret_cast<float4 *>(sm.fx), *fy4 = reinterpret_cast<float4 *>(sm.fy),
            *fz4 = reinterpret_cast<float4 *>(sm.fz);
     const float A = cd.A, B = cd.B;
+    const int Q = cd.Q, KS = cd.KS, R = cd.R, Lr = cd.Lr, SS = cd.SS, halfQ = cd.Q >> 1;
+    const bool q_even = cd.q_even != 0;
+    const int stage_float4 = SS * STEP_FLOAT4;
     double chi2 = 0.0;
     float xi[4], yi[4], zi[4], fi[4][3];
-    int rb = 0, k = 0, a = lane;
+    int s = 0, a = lane, pos = role;  // slot in the row block, own quad, step position in the stage
     bool active = false;
-    uint32_t slot = 0;
-    for (int t = 0; t < cd.T_pad; ++t) {
-        const int ts = t % SS;
-        if (ts == 0) {
-            slot = stage_idx % NS;
-            mbar_wait(&full[slot], (stage_idx / NS) & 1u);
-        }
-        if (t < cd.T && chain_valid) {
-            if (k == 0) {
+    const uint32_t stage_base = stage_idx;
+    int s_local = 0;
+    if (ring.loader && lane == 0)
+        for (int i = 0; i <= PREFETCH && i < ring.n_stage_pass; ++i) ring_issue(ring, stage_base, i);
+    uint32_t slot = stage_idx % NS;
+    mbar_wait(&ring.full[slot], (stage_idx / NS) & 1u);
+    const float4 *ybase = ring.ystage + (size_t)slot * stage_float4;
+    int rb = 0;
+    for (int sidx = 0; sidx < cd.S_pad; ++sidx) {
+        if (rb < cd.NRB && chain_valid) {
+            if (s == 0) {
                 a = rb * 32 + lane;
-                active = a < cd.Q;
+                active = a < Q;
                 const int aa = active ? a : 0;
                 unpack4(xs4[aa], xi), unpack4(ys4[aa], yi), unpack4(zs4[aa], zi);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) fi[r][0] = fi[r][1] = fi[r][2] = 0.f;
             }
-            const float4 *yb = ystage + (size_t)slot * STAGE_FLOAT4 + ts * STEP_FLOAT4 + lane;
-            if (active) {
+            const int k = role * Lr + s;
+            const float4 *yb = ybase + pos * STEP_FLOAT4 + lane;
+            if (active && k <= KS) {
                 float chi = 0.f;
                 if (k == 0) {
                     // the 6 pairs inside the lane's own quad
@@ -145,14 +189,14 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const WarpSmem
                                                fi[c][2], chi);
                 } else {
                     int b = a + k;
-                    if (b >= cd.Q) b -= cd.Q;
-                    const bool half_dup = (k == cd.KS) && cd.q_even && (a >= (cd.Q >> 1));
+                    if (b >= Q) b -= Q;
+                    const bool half_dup = (k == KS) && q_even && (a >= halfQ);
                     if (!half_dup) {
                         float xj[4], yj[4], zj[4], fjx[4], fjy[4], fjz[4], yv[4][4];
                         unpack4(xs4[b], xj), unpack4(ys4[b], yj), unpack4(zs4[b], zj);
-                        unpack4(fx4[b], fjx), unpack4(fy4[b], fjy), unpack4(fz4[b], fjz);
 #pragma unroll
                         for (int r = 0; r < 4; ++r) unpack4(yb[r * 32], yv[r]);
+                        unpack4(fx4[b], fjx), unpack4(fy4[b], fjy), unpack4(fz4[b], fjz);
 #pragma unroll
                         for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -166,26 +210,42 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const WarpSmem
                 if (ENERGY) chi2 += (double)chi;
             }
             __syncwarp();
-            if (k == cd.KS) {
-                if (active) {
-                    float4 v = fx4[a];
-                    v.x += fi[0][0], v.y += fi[1][0], v.z += fi[2][0], v.w += fi[3][0];
-                    fx4[a] = v;
-                    v = fy4[a];
-                    v.x += fi[0][1], v.y += fi[1][1], v.z += fi[2][1], v.w += fi[3][1];
-                    fy4[a] = v;
-                    v = fz4[a];
-                    v.x += fi[0][2], v.y += fi[1][2], v.z += fi[2][2], v.w += fi[3][2];
-                    fz4[a] = v;
+            if (s == Lr - 1) {
+                // end of the row block: fold the register-resident forces of the own quad into
+                // shared memory, one role at a time
+                for (int rr = 0; rr < R; ++rr) {
+                    if (R > 1) chain_bar(bar_id, R * 32);
+                    if (rr == role && active) {
+                        float4 v = fx4[a];
+                        v.x += fi[0][0], v.y += fi[1][0], v.z += fi[2][0], v.w += fi[3][0];
+                        fx4[a] = v;
+                        v = fy4[a];
+                        v.x += fi[0][1], v.y += fi[1][1], v.z += fi[2][1], v.w += fi[3][1];
+                        fy4[a] = v;
+                        v = fz4[a];
+                        v.x += fi[0][2], v.y += fi[1][2], v.z += fi[2][2], v.w += fi[3][2];
+                        fz4[a] = v;
+                    }
                 }
-                __syncwarp();
+                if (R > 1) chain_bar(bar_id, R * 32);
+                else __syncwarp();
             }
         }
-        if (++k > cd.KS) k = 0, ++rb;
-        if (ts == SS - 1) {
+        if (++s == Lr) s = 0, ++rb;
+        pos += R;
+        if (pos >= SS) {
+            pos -= SS;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[slot]);
+            if (lane == 0) mbar_arrive(&ring.empty[slot]);
             ++stage_idx;
+            ++s_local;
+            if (sidx + 1 < cd.S_pad) {
+                if (ring.loader && lane == 0 && s_local + PREFETCH < ring.n_stage_pass)
+                    ring_issue(ring, stage_base, s_local + PREFETCH);
+                slot = stage_idx % NS;
+                mbar_wait(&ring.full[slot], (stage_idx / NS) & 1u);
+                ybase = ring.ystage + (size_t)slot * stage_float4;
+            }
         }
     }
     return chi2;
@@ -193,40 +253,63 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const WarpSmem
 
 __device__ __forceinline__ double warp_sum(double v) { return group_allreduce_sum<32>(v); }
 
+// sum over all lanes of all R warps of a chain; every thread gets the same value
+__device__ __forceinline__ double chain_sum(double v, const ChainSmem &sm, int lane, int role, int R,
+                                            int bar_id) {
+    v = warp_sum(v);
+    if (R == 1) return v;
+    if (lane == 0) sm.red[role] = v;
+    chain_bar(bar_id, R * 32);
+    double t = 0.0;
+    for (int r = 0; r < R; ++r) t += sm.red[r];
+    chain_bar(bar_id, R * 32);
+    return t;
+}
+
 struct ChromCall {
     int mode;
     HmcArgs h;   // HMC mode
     GradArgs g;  // GRAD mode
-    int W;       // chains (consumer warps) per CTA
+    int W;       // chains per CTA (W * R warps)
     int n_groups, total_items;
 };
 
-__global__ void __launch_bounds__(288, 1) chrom_kernel(ChromDev cd, ChromCall call) {
+__global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall call) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int W = call.W;
+    const int W = call.W, R = cd.R;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool is_producer = warp == W;
-    // ---- shared memory carve-up: [stages][barriers][item][W x 6 x n_pad floats]
-    float4 *ystage = reinterpret_cast<float4 *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NS * STAGE_BYTES);
-    uint64_t *empty = full + NS;
-    int *s_item = reinterpret_cast<int *>(empty + NS);
-    float *chain_base_smem = reinterpret_cast<float *>(smem_raw + (size_t)NS * STAGE_BYTES + 128);
-    WarpSmem sm;
+    const int chain_local = warp / R, role = warp % R;
+    const int bar_id = 1 + chain_local;
+    const uint32_t stage_bytes = (uint32_t)cd.SS * STEP_BYTES;
+    // ---- shared memory carve-up: [stages][barriers, item][W x (6 n_pad floats + 8 doubles)]
+    Ring ring;
+    ring.ystage = reinterpret_cast<const float4 *>(smem_raw);
+    ring.full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NS * stage_bytes);
+    ring.empty = ring.full + NS;
+    ring.src = reinterpret_cast<const unsigned char *>(cd.ystream);
+    ring.stage_bytes = stage_bytes;
+    ring.n_stage_pass = cd.S_pad * R / cd.SS;
+    ring.loader = warp == 0;
+    int *s_item = reinterpret_cast<int *>(ring.empty + NS);
+    unsigned char *chains = smem_raw + (size_t)NS * stage_bytes + 128;
+    const size_t per_chain = (size_t)6 * cd.n_pad * sizeof(float) + 64;
+    ChainSmem sm;
     {
-        float *b = chain_base_smem + (size_t)(is_producer ? 0 : warp) * 6 * cd.n_pad;
+        unsigned char *b0 = chains + per_chain * chain_local;
+        sm.red = reinterpret_cast<double *>(b0);
+        float *b = reinterpret_cast<float *>(b0 + 64);
         sm.xs = b, sm.ys = b + cd.n_pad, sm.zs = b + 2 * cd.n_pad;
         sm.fx = b + 3 * cd.n_pad, sm.fy = b + 4 * cd.n_pad, sm.fz = b + 5 * cd.n_pad;
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NS; ++i) mbar_init(&full[i], 1), mbar_init(&empty[i], W);
+        for (int i = 0; i < NS; ++i) mbar_init(&ring.full[i], 1), mbar_init(&ring.empty[i], W * R);
         mbar_fence_init();
     }
     __syncthreads();
 
     const int D = 3 * cd.n;
-    const int n_stage_pass = cd.T_pad / SS;
     const int passes = call.mode == CHROM_MODE_HMC ? call.h.L + 1 : 1;
+    const int cthreads = R * 32, ctid = role * 32 + lane;  // threads of this chain
     uint32_t stage_idx = 0;  // running stage counter, identical in every warp
 
     for (;;) {
@@ -237,7 +320,7 @@ __global__ void __launch_bounds__(288, 1) chrom_kernel(ChromDev cd, ChromCall ca
                 const int o = it % call.n_groups;
                 const int need = it / call.n_groups;  // passes of this group that must be done
                 if (need > 0)
-                    while (ld_acquire(cd.pass_done + o) < need) __nanosleep(64);
+                    while (ld_acquire(cd.pass_done + o) < need) __nanosleep(100);
             }
             *s_item = it;
         }
@@ -248,20 +331,8 @@ __global__ void __launch_bounds__(288, 1) chrom_kernel(ChromDev cd, ChromCall ca
         const int seq = item / call.n_groups;  // = tr * passes + k
         const int tr = seq / passes, k = seq % passes;
 
-        if (is_producer) {
-            if (lane == 0) {
-                const unsigned char *src = reinterpret_cast<const unsigned char *>(cd.ystream);
-                for (int s = 0; s < n_stage_pass; ++s) {
-                    const uint32_t slot = stage_idx % NS;
-                    mbar_wait(&empty[slot], ((stage_idx / NS) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&full[slot], STAGE_BYTES);
-                    bulk_copy_g2s(ystage + (size_t)slot * STAGE_FLOAT4, src + (size_t)s * STAGE_BYTES,
-                                  STAGE_BYTES, &full[slot]);
-                    ++stage_idx;
-                }
-            }
-        } else {
-            const int c = o * W + warp;
+        {
+            const int c = o * W + chain_local;
             const int C = call.mode == CHROM_MODE_HMC ? call.h.C : call.g.C;
             const bool valid = c < C;
             const bool hmc = call.mode == CHROM_MODE_HMC;
@@ -269,9 +340,9 @@ __global__ void __launch_bounds__(288, 1) chrom_kernel(ChromDev cd, ChromCall ca
             const bool energy = !hmc || k == 0 || k == h.L;
             float eps_c = 0.f, beta_c = 1.f;
             double kin0 = 0.0;
+            const size_t off = (size_t)(valid ? c : 0) * D;
             if (valid) {
                 // ---- phase A: positions (+ drift) into shared memory ---------------------
-                const size_t off = (size_t)c * D;
                 const float *src = hmc ? (k == 0 ? h.q : cd.qw) : call.g.q;
                 if (hmc) {
                     eps_c = __ldcg(h.eps + c);
@@ -280,38 +351,55 @@ __global__ void __launch_bounds__(288, 1) chrom_kernel(ChromDev cd, ChromCall ca
                     beta_c = call.g.beta ? call.g.beta[c] : 1.f;
                 }
                 float kin = 0.f;
-                for (int e = lane; e < D; e += 32) {
-                    float v = __ldcg(src + off + e);
-                    if (hmc) {
-                        if (k == 0) {
-                            const float pv = h.p0 ? h.p0[off + e]
-                                                  : rng_normal(h.seed, h.chain_base + c,
-                                                               h.draw + (uint64_t)tr, (uint32_t)e);
-                            __stcg(cd.pw + off + e, pv);
-                            kin = fmaf(pv, pv, kin);
-                        } else {
-                            v = fmaf(eps_c, __ldcg(cd.pw + off + e), v);  // q += eps p (hmc.py:119,122)
+                if (hmc && k == 0) {
+                    for (int e = ctid; e < D; e += cthreads) {
+                        const float v = __ldcg(src + off + e);
+                        const float pv = h.p0 ? h.p0[off + e]
+                                              : rng_normal(h.seed, h.chain_base + c,
+                                                           h.draw + (uint64_t)tr, (uint32_t)e);
+                        __stcg(cd.pw + off + e, pv);
+                        kin = fmaf(pv, pv, kin);
+                        const int bead = e / 3, comp = e - 3 * bead;
+                        sm.xs[comp * cd.n_pad + bead] = v;
+                    }
+                } else {
+                    constexpr int U = 8;
+                    for (int e0 = ctid; e0 < D; e0 += cthreads * U) {
+                        float v[U], pv[U];
+#pragma unroll
+                        for (int uu = 0; uu < U; ++uu) {
+                            const int e = e0 + uu * cthreads;
+                            v[uu] = e < D ? __ldcg(src + off + e) : 0.f;
+                            pv[uu] = (hmc && e < D) ? __ldcg(cd.pw + off + e) : 0.f;
+                        }
+#pragma unroll
+                        for (int uu = 0; uu < U; ++uu) {
+                            const int e = e0 + uu * cthreads;
+                            if (e < D) {
+                                const int bead = e / 3, comp = e - 3 * bead;
+                                // q += eps p (hmc.py:119,122)
+                                sm.xs[comp * cd.n_pad + bead] = fmaf(eps_c, pv[uu], v[uu]);
+                            }
                         }
                     }
-                    const int bead = e / 3, comp = e - 3 * bead;
-                    sm.xs[comp * cd.n_pad + bead] = v;
                 }
-                kin0 = warp_sum((double)kin);
-                for (int i = cd.n + lane; i < cd.n_pad; i += 32) {
+                for (int i = cd.n + ctid; i < cd.n_pad; i += cthreads) {
                     // padding beads: far away from everything => contact 0, force 0
                     sm.xs[i] = 1.0e4f * (float)(1 + i - cd.n), sm.ys[i] = 3.0e4f, sm.zs[i] = -2.0e4f;
                 }
-                for (int i = lane; i < 3 * cd.n_pad; i += 32) sm.fx[i] = 0.f;
+                for (int i = ctid; i < 3 * cd.n_pad; i += cthreads) sm.fx[i] = 0.f;
+                if (hmc && k == 0) kin0 = chain_sum((double)kin, sm, lane, role, R, bar_id);
             }
-            __syncwarp();
+            if (R > 1) chain_bar(bar_id, cthreads);
+            else __syncwarp();
             // ---- phase B: pair sweep -----------------------------------------------------
-            double chi2 = energy ? chrom_sweep<true>(cd, sm, ystage, full, empty, stage_idx, valid, lane)
-                                 : chrom_sweep<false>(cd, sm, ystage, full, empty, stage_idx, valid, lane);
-            __syncwarp();
+            double chi2 = energy ? chrom_sweep<true>(cd, sm, ring, stage_idx, valid, lane, role, bar_id)
+                                 : chrom_sweep<false>(cd, sm, ring, stage_idx, valid, lane, role, bar_id);
+            if (R > 1) chain_bar(bar_id, cthreads);
+            else __syncwarp();
             if (valid) {
                 // ---- phase C: forces, kick, energies ----------------------------------------
-                if (energy) chi2 = warp_sum(chi2);
-                const size_t off = (size_t)c * D;
+                if (energy) chi2 = chain_sum(chi2, sm, lane, role, R, bar_id);
                 float tau_c;
                 if (hmc) {
                     if (k == 0) {
@@ -324,9 +412,9 @@ __global__ void __launch_bounds__(288, 1) chrom_kernel(ChromDev cd, ChromCall ca
                                                   : rng_gamma(h.seed, h.chain_base + c,
                                                               h.draw + (uint64_t)tr, shape);
                             tau_c = (float)(gd / rate);
-                            if (lane == 0) __stcg(h.tau + c, tau_c);
+                            if (ctid == 0) __stcg(h.tau + c, tau_c);
                         }
-                        if (lane == 0) __stcg(cd.tau_w + c, tau_c);
+                        if (ctid == 0) __stcg(cd.tau_w + c, tau_c);
                     } else {
                         tau_c = __ldcg(cd.tau_w + c);
                     }
@@ -336,62 +424,79 @@ __global__ void __launch_bounds__(288, 1) chrom_kernel(ChromDev cd, ChromCall ca
                 const float scale = -cd.alpha * beta_c * tau_c;
                 const float kick = hmc ? ((k == 0 || k == h.L) ? 0.5f * eps_c : eps_c) : 0.f;
                 float e_prior = 0.f, kin = 0.f;
-                for (int i = lane; i < cd.n; i += 32) {
-                    const float x = sm.xs[i], y = sm.ys[i], z = sm.zs[i];
-                    float gx = scale * sm.fx[i], gy = scale * sm.fy[i], gz = scale * sm.fz[i];
-                    if (i > 0) {
-                        const float bx = x - sm.xs[i - 1], by = y - sm.ys[i - 1], bz = z - sm.zs[i - 1];
-                        const float r2 = fmaf(bz, bz, fmaf(by, by, fmaf(bx, bx, CHROM_SOFT)));
-                        const float inv = rsqrtf(r2), d = r2 * inv;
-                        const float cc = cd.k_bb * (d - cd.l0) * inv;
-                        gx = fmaf(cc, bx, gx), gy = fmaf(cc, by, gy), gz = fmaf(cc, bz, gz);
-                    }
-                    if (i < cd.n - 1) {
-                        const float bx = sm.xs[i + 1] - x, by = sm.ys[i + 1] - y, bz = sm.zs[i + 1] - z;
-                        const float r2 = fmaf(bz, bz, fmaf(by, by, fmaf(bx, bx, CHROM_SOFT)));
-                        const float inv = rsqrtf(r2), d = r2 * inv;
-                        const float dl = d - cd.l0;
-                        const float cc = cd.k_bb * dl * inv;
-                        gx = fmaf(-cc, bx, gx), gy = fmaf(-cc, by, gy), gz = fmaf(-cc, bz, gz);
-                        e_prior = fmaf(0.5f * cd.k_bb * dl, dl, e_prior);
-                    }
-                    if (cd.inv_s2 > 0.f) {
-                        gx = fmaf(cd.inv_s2, x, gx), gy = fmaf(cd.inv_s2, y, gy), gz = fmaf(cd.inv_s2, z, gz);
-                        e_prior = fmaf(0.5f * cd.inv_s2, fmaf(x, x, fmaf(y, y, z * z)), e_prior);
-                    }
+                constexpr int UC = 4;
+                for (int i0 = ctid; i0 < cd.n; i0 += cthreads * UC) {
+                    float pold[UC][3];
                     if (hmc) {
-                        float *pp = cd.pw + off + 3 * i;
-                        const float px = fmaf(-kick, gx, __ldcg(pp)), py = fmaf(-kick, gy, __ldcg(pp + 1)),
-                                    pz = fmaf(-kick, gz, __ldcg(pp + 2));
-                        __stcg(pp, px), __stcg(pp + 1, py), __stcg(pp + 2, pz);
-                        kin = fmaf(px, px, fmaf(py, py, fmaf(pz, pz, kin)));
-                        float *qq = cd.qw + off + 3 * i;
-                        __stcg(qq, x), __stcg(qq + 1, y), __stcg(qq + 2, z);
-                    } else if (call.g.grad) {
-                        float *gg = call.g.grad + off + 3 * i;
-                        gg[0] = gx, gg[1] = gy, gg[2] = gz;
+#pragma unroll
+                        for (int uu = 0; uu < UC; ++uu) {
+                            const int i = i0 + uu * cthreads;
+                            const float *pp = cd.pw + off + 3 * (i < cd.n ? i : 0);
+                            pold[uu][0] = __ldcg(pp), pold[uu][1] = __ldcg(pp + 1), pold[uu][2] = __ldcg(pp + 2);
+                        }
+                    }
+#pragma unroll
+                    for (int uu = 0; uu < UC; ++uu) {
+                        const int i = i0 + uu * cthreads;
+                        if (i >= cd.n) continue;
+                        const float x = sm.xs[i], y = sm.ys[i], z = sm.zs[i];
+                        float gx = scale * sm.fx[i], gy = scale * sm.fy[i], gz = scale * sm.fz[i];
+                        if (i > 0) {
+                            const float bx = x - sm.xs[i - 1], by = y - sm.ys[i - 1], bz = z - sm.zs[i - 1];
+                            const float r2 = fmaf(bz, bz, fmaf(by, by, fmaf(bx, bx, CHROM_SOFT)));
+                            const float inv = rsqrtf(r2), d = r2 * inv;
+                            const float cc = cd.k_bb * (d - cd.l0) * inv;
+                            gx = fmaf(cc, bx, gx), gy = fmaf(cc, by, gy), gz = fmaf(cc, bz, gz);
+                        }
+                        if (i < cd.n - 1) {
+                            const float bx = sm.xs[i + 1] - x, by = sm.ys[i + 1] - y, bz = sm.zs[i + 1] - z;
+                            const float r2 = fmaf(bz, bz, fmaf(by, by, fmaf(bx, bx, CHROM_SOFT)));
+                            const float inv = rsqrtf(r2), d = r2 * inv;
+                            const float dl = d - cd.l0;
+                            const float cc = cd.k_bb * dl * inv;
+                            gx = fmaf(-cc, bx, gx), gy = fmaf(-cc, by, gy), gz = fmaf(-cc, bz, gz);
+                            e_prior = fmaf(0.5f * cd.k_bb * dl, dl, e_prior);
+                        }
+                        if (cd.inv_s2 > 0.f) {
+                            gx = fmaf(cd.inv_s2, x, gx), gy = fmaf(cd.inv_s2, y, gy), gz = fmaf(cd.inv_s2, z, gz);
+                            e_prior = fmaf(0.5f * cd.inv_s2, fmaf(x, x, fmaf(y, y, z * z)), e_prior);
+                        }
+                        if (hmc) {
+                            float *pp = cd.pw + off + 3 * i;
+                            const float px = fmaf(-kick, gx, pold[uu][0]), py = fmaf(-kick, gy, pold[uu][1]),
+                                        pz = fmaf(-kick, gz, pold[uu][2]);
+                            __stcg(pp, px), __stcg(pp + 1, py), __stcg(pp + 2, pz);
+                            kin = fmaf(px, px, fmaf(py, py, fmaf(pz, pz, kin)));
+                            if (k < h.L) {
+                                float *qq = cd.qw + off + 3 * i;
+                                __stcg(qq, x), __stcg(qq + 1, y), __stcg(qq + 2, z);
+                            }
+                        } else if (call.g.grad) {
+                            float *gg = call.g.grad + off + 3 * i;
+                            gg[0] = gx, gg[1] = gy, gg[2] = gz;
+                        }
                     }
                 }
                 if (energy) {
-                    const double ep = warp_sum((double)e_prior);
+                    const double ep = chain_sum((double)e_prior, sm, lane, role, R, bar_id);
                     const double t = (double)tau_c, lt = log(t);
                     const double ga = hmc ? h.gamma_shape : call.g.gamma_shape;
                     const double gb = hmc ? h.gamma_rate : call.g.gamma_rate;
                     const double U = (double)beta_c * (0.5 * t * chi2 - 0.5 * cd.M * lt) + ep -
                                      ((ga - 1.0) * lt - gb * t);
                     if (!hmc) {
-                        if (lane == 0) {
+                        if (ctid == 0) {
                             if (call.g.logp) call.g.logp[c] = -U;
                             if (call.g.chi2) call.g.chi2[c] = chi2;
                         }
                     } else if (k == 0) {
-                        if (lane == 0) {
+                        if (ctid == 0) {
                             __stcg(cd.h0 + c, U + 0.5 * kin0);
                             __stcg(cd.chi2_0 + c, chi2);
                         }
                     }
                     if (hmc && k == h.L) {
-                        const double h1 = U + 0.5 * warp_sum((double)kin);
+                        const double h1 = U + 0.5 * chain_sum((double)kin, sm, lane, role, R, bar_id);
                         const double h0 = __ldcg(cd.h0 + c);
                         const double dh = h1 - h0;
                         const uint64_t draw = h.draw + (uint64_t)tr;
@@ -406,28 +511,28 @@ __global__ void __launch_bounds__(288, 1) chrom_kernel(ChromDev cd, ChromCall ca
                         // Metropolis (hmc.py:151); NaN energies reject
                         const bool acc = (dh == dh) && ((double)uu < exp(fmin(709.0, fmax(-308.0, -dh))));
                         const bool last = tr == h.n_traj - 1;
-                        if (last) {
-                            for (int e = lane; e < D; e += 32) {
+                        if (last && (h.q_end || h.p_end)) {
+                            for (int e = ctid; e < D; e += cthreads) {
                                 const int bead = e / 3, comp = e - 3 * bead;
                                 if (h.q_end) h.q_end[off + e] = sm.xs[comp * cd.n_pad + bead];
                                 if (h.p_end) h.p_end[off + e] = __ldcg(cd.pw + off + e);
                             }
                         }
                         if (acc) {
-                            for (int e = lane; e < D; e += 32) {
+                            for (int e = ctid; e < D; e += cthreads) {
                                 const int bead = e / 3, comp = e - 3 * bead;
                                 __stcg(h.q + off + e, sm.xs[comp * cd.n_pad + bead]);
                             }
                         }
                         const double chi2_cur = acc ? chi2 : __ldcg(cd.chi2_0 + c);
-                        if (lane == 0) {
+                        if (ctid == 0) {
                             __stcg(cd.chi2_state + c, chi2_cur);
                             if (tr < h.n_adapt)  // hmc.py:188-191
                                 __stcg(h.eps + c, eps_c * (acc ? h.adapt_up : h.adapt_down));
                             if (h.accepted) h.accepted[c] = acc ? 1 : 0;
                             if (h.e_before) h.e_before[c] = h0;
                             if (h.e_after) h.e_after[c] = h1;
-                            if (h.n_accepted) h.n_accepted[c] += acc ? 1 : 0;
+                            if (h.n_accepted) __stcg(h.n_accepted + c, __ldcg(h.n_accepted + c) + (acc ? 1 : 0));
                             if (h.stats) {
                                 atomicAdd(h.stats + 0, acc ? 1.0 : 0.0);
                                 atomicAdd(h.stats + 1, 1.0);
@@ -441,7 +546,7 @@ __global__ void __launch_bounds__(288, 1) chrom_kernel(ChromDev cd, ChromCall ca
                             const double gd = h.gamma_draws
                                                   ? h.gamma_draws[c]
                                                   : rng_gamma(h.seed, h.chain_base + c, draw, shape);
-                            if (lane == 0) __stcg(h.tau + c, (float)(gd / rate));
+                            if (ctid == 0) __stcg(h.tau + c, (float)(gd / rate));
                         }
                     }
                 }
@@ -481,44 +586,67 @@ static inline long long tri_index(long long n, long long i, long long j) {  // i
     return i * n - i * (i + 1) / 2 + (j - i - 1);
 }
 
-int chrom_build_stream(int n, const float *y_pairs, float *out, long long capacity,
-                       long long *n_floats, int *Q_out, int *T_out) {
-    if (n < 2) {
-        set_error("chromatin model needs at least 2 beads");
-        return BINFB_EINVAL;
+// Launch geometry: W chains per CTA, R warps ("roles") per chain, W*R <= 16 consumer warps.
+// R > 1 only when the partner-step ranges of two roles can never overlap within the drift the
+// stage ring allows (see chrom_sweep): Lr - NS*SS/R >= 40.
+ChromPlan chrom_plan(int n, int smem_optin, int force_roles) {
+    ChromPlan pl;
+    pl.n_pad = (n + 3) / 4 * 4, pl.Q = pl.n_pad / 4, pl.KS = pl.Q / 2, pl.NRB = (pl.Q + 31) / 32;
+    const size_t per_chain = (size_t)6 * pl.n_pad * sizeof(float) + 64;
+    int best_R = 1;
+    for (int R = 2; R <= 8; R *= 2) {
+        const int SS = R > 4 ? R : 4;
+        const size_t fixed = (size_t)NS * SS * STEP_BYTES + 128;
+        if ((size_t)smem_optin < fixed + per_chain) break;
+        const int wmax = (int)(((size_t)smem_optin - fixed) / per_chain);
+        const int Lr = (pl.KS + 1 + R - 1) / R;
+        const bool safe = Lr - NS * SS / R >= 40;
+        // more roles only pay off while the chains alone cannot fill 16 warps
+        if (safe && wmax * (R / 2) < 16) best_R = R;
     }
-    const int n_pad = (n + 3) / 4 * 4, Q = n_pad / 4, KS = Q / 2, NRB = (Q + 31) / 32;
-    const int T = NRB * (KS + 1), T_pad = (T + SS - 1) / SS * SS;
-    const long long total = (long long)T_pad * STEP_FLOAT4 * 4;
-    if (n_floats) *n_floats = total;
-    if (Q_out) *Q_out = Q;
-    if (T_out) *T_out = T;
-    if (!out) return BINFB_OK;
-    if (capacity < total) {
-        set_error("chromatin stream buffer too small");
-        return BINFB_EINVAL;
-    }
+    if (force_roles > 0) best_R = force_roles;
+    pl.R = best_R;
+    pl.SS = pl.R > 4 ? pl.R : 4;
+    pl.Lr = (pl.KS + 1 + pl.R - 1) / pl.R;
+    const int spr = pl.SS / pl.R;  // slots per stage
+    pl.S_pad = (pl.NRB * pl.Lr + spr - 1) / spr * spr;
+    pl.fixed_smem = (size_t)NS * pl.SS * STEP_BYTES + 128;
+    pl.per_chain_smem = per_chain;
+    int W = (size_t)smem_optin > pl.fixed_smem ? (int)(((size_t)smem_optin - pl.fixed_smem) / per_chain) : 0;
+    if (W > 16 / pl.R) W = 16 / pl.R;
+    pl.W = W;
+    pl.stream_floats = (long long)pl.S_pad * pl.R * STEP_FLOAT4 * 4;
+    return pl;
+}
+
+// Contact stream in consumption order: step t' = (rb*Lr + s)*R + role holds, for lane l and row r,
+// the float4 y[4a+r][4b..4b+3] with a = 32 rb + l, b = (a + k) mod Q, k = role*Lr + s.
+int chrom_build_stream(int n, const float *y_pairs, const ChromPlan &pl, float *out) {
+    const int Q = pl.Q, KS = pl.KS;
     const bool q_even = (Q % 2) == 0;
-    for (long long i = 0; i < total; ++i) out[i] = 0.f;
-    for (int rb = 0; rb < NRB; ++rb)
-        for (int k = 0; k <= KS; ++k) {
-            const long long t = (long long)rb * (KS + 1) + k;
-            for (int lane = 0; lane < 32; ++lane) {
-                const int a = rb * 32 + lane;
-                if (a >= Q) continue;
-                int b = a + k;
-                if (b >= Q) b -= Q;
-                if (k > 0 && k == KS && q_even && a >= Q / 2) continue;
-                for (int r = 0; r < 4; ++r)
-                    for (int c = 0; c < 4; ++c) {
-                        const int i = 4 * a + r, j = 4 * b + c;
-                        if (i >= n || j >= n) continue;
-                        if (k == 0 && r >= c) continue;
-                        const long long idx = i < j ? tri_index(n, i, j) : tri_index(n, j, i);
-                        out[((t * 4 + r) * 32 + lane) * 4 + c] = y_pairs[idx];
-                    }
+    for (long long i = 0; i < pl.stream_floats; ++i) out[i] = 0.f;
+    for (int rb = 0; rb < pl.NRB; ++rb)
+        for (int s = 0; s < pl.Lr; ++s)
+            for (int role = 0; role < pl.R; ++role) {
+                const int k = role * pl.Lr + s;
+                if (k > KS) continue;
+                const long long t = ((long long)rb * pl.Lr + s) * pl.R + role;
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int a = rb * 32 + lane;
+                    if (a >= Q) continue;
+                    int b = a + k;
+                    if (b >= Q) b -= Q;
+                    if (k > 0 && k == KS && q_even && a >= Q / 2) continue;
+                    for (int r = 0; r < 4; ++r)
+                        for (int c = 0; c < 4; ++c) {
+                            const int i = 4 * a + r, j = 4 * b + c;
+                            if (i >= n || j >= n) continue;
+                            if (k == 0 && r >= c) continue;
+                            const long long idx = i < j ? tri_index(n, i, j) : tri_index(n, j, i);
+                            out[((t * 4 + r) * 32 + lane) * 4 + c] = y_pairs[idx];
+                        }
+                }
             }
-        }
     return BINFB_OK;
 }
 
@@ -551,8 +679,10 @@ int chrom_reserve(ChromModel &m, int C) {
 
 static ChromDev chrom_dev(const ChromModel &m) {
     ChromDev d;
-    d.n = m.n, d.n_pad = m.n_pad, d.Q = m.Q, d.KS = m.KS, d.NRB = m.NRB, d.T = m.T, d.T_pad = m.T_pad;
-    d.q_even = (m.Q % 2) == 0;
+    const ChromPlan &pl = m.plan;
+    d.n = m.n, d.n_pad = pl.n_pad, d.Q = pl.Q, d.KS = pl.KS, d.NRB = pl.NRB;
+    d.q_even = (pl.Q % 2) == 0;
+    d.R = pl.R, d.Lr = pl.Lr, d.SS = pl.SS, d.S_pad = pl.S_pad;
     d.ystream = reinterpret_cast<const float4 *>(m.ystream);
     const double log2e = 1.4426950408889634;
     d.A = (float)((double)m.alpha * log2e);
@@ -569,15 +699,13 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
                         cudaStream_t s) {
     int rc = chrom_reserve(m, C);
     if (rc) return rc;
-    const size_t fixed = (size_t)NS * STAGE_BYTES + 128;
-    const size_t per_warp = (size_t)6 * m.n_pad * sizeof(float);
-    int W = (int)(((size_t)smem_optin - fixed) / per_warp);
-    if (W > 8) W = 8;
+    const ChromPlan &pl = m.plan;
+    int W = pl.W;
     if (m.opt_warps > 0 && m.opt_warps < W) W = m.opt_warps;
     if (W > C) W = C;
     if (W < 1) {
         set_error("chromatin model: one chain does not fit in shared memory (n_beads too large for "
-                  "the warp-per-chain kernel)");
+                  "this kernel)");
         return BINFB_EUNSUPPORTED;
     }
     call.W = W;
@@ -590,11 +718,11 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
         return BINFB_EUNSUPPORTED;
     }
     call.total_items = (int)total;
-    const size_t smem = fixed + per_warp * W;
+    const size_t smem = pl.fixed_smem + pl.per_chain_smem * W;
     BINFB_CUDA(cudaMemsetAsync(m.sched, 0, (size_t)(1 + call.n_groups) * sizeof(int), s));
     BINFB_CUDA(cudaFuncSetAttribute(chrom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = call.n_groups < sm_count ? call.n_groups : sm_count;
-    chrom_kernel<<<grid, (W + 1) * 32, smem, s>>>(chrom_dev(m), call);
+    chrom_kernel<<<grid, W * pl.R * 32, smem, s>>>(chrom_dev(m), call);
     BINFB_CUDA(cudaGetLastError());
     return BINFB_OK;
 }

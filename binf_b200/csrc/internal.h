@@ -65,11 +65,18 @@ int poly_grad_launch(const PolyModel &m, const GradArgs &a, int sm_count, int sm
 int poly_forward_launch(const PolyModel &m, const float *q, int C, float *mock, cudaStream_t s);
 
 // ---- chromatin -----------------------------------------------------------------------------
+struct ChromPlan {
+    int n_pad = 0, Q = 0, KS = 0, NRB = 0;  // padded beads, quads, partner steps, row blocks
+    int R = 1, W = 1;                       // warps per chain, chains per CTA
+    int Lr = 0, SS = 4, S_pad = 0;          // slots per row block, steps per stage, padded slots
+    size_t fixed_smem = 0, per_chain_smem = 0;
+    long long stream_floats = 0;
+};
 struct ChromModel {
-    int n = 0, n_pad = 0, Q = 0, KS = 0, NRB = 0;
-    int T = 0, T_pad = 0;          // warp-steps per force evaluation (padded to the stage size)
+    int n = 0;
+    ChromPlan plan;
     long long M = 0;
-    float *ystream = nullptr;      // device [T_pad][4][32] float4
+    float *ystream = nullptr;      // device [S_pad * R][4][32] float4
     float *ypairs = nullptr;       // device [M] (triu order; forward/mock kernel only)
     float alpha = 0, d_c = 0, k_bb = 0, l0 = 0, inv_s2 = 0;
     unsigned flags = 0;
@@ -82,10 +89,9 @@ struct ChromModel {
     int *sched = nullptr;                 // [1 + n_octets]: item counter, per-octet pass counters
     int sched_len = 0;
 };
-constexpr int CHROM_STAGE_STEPS = 4;  // warp-steps per bulk-copy stage (4 * 2 KiB)
-constexpr int CHROM_STAGES = 4;
-int chrom_build_stream(int n, const float *y_pairs, float *out, long long capacity,
-                       long long *n_floats, int *Q, int *T);
+constexpr int CHROM_STAGES = 4;  // depth of the bulk-copy ring (stages of max(4, R) warp-steps)
+ChromPlan chrom_plan(int n, int smem_optin, int force_roles);
+int chrom_build_stream(int n, const float *y_pairs, const ChromPlan &pl, float *out);
 int chrom_reserve(ChromModel &m, int C);
 int chrom_hmc_launch(ChromModel &m, const HmcArgs &a, int sm_count, int smem_optin,
                      cudaStream_t s);

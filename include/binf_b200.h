@@ -163,11 +163,12 @@ int binfb_swap_apply(float *q_mine_dev, const float *q_theirs_dev, float *eps_mi
 int binfb_rng_fill_host(uint64_t seed, uint64_t draw, uint64_t chain_base, int n_chains, int dim,
                         double gamma_shape, float *normals, float *uniforms, double *gammas,
                         int device);
-/* host-side layout pass of the chromatin contact stream (no GPU needed): writes the number of
- * float32 the kernel streams per force evaluation; if out != NULL (capacity floats) fills it */
-int binfb_chromatin_stream_layout(int n_beads, const float *y_pairs, float *out,
-                                  long long capacity, long long *n_floats, int *n_quads,
-                                  int *n_steps);
+/* host-side layout pass of the chromatin contact stream (no GPU needed).  roles = warps per
+ * chain (0 = the heuristic for smem_bytes of opt-in shared memory, 0 = 227 KiB).  Writes the number
+ * of float32 the kernel streams per force evaluation and plan6 = {quads, partner steps, row blocks,
+ * roles, slots per row block, chains per CTA}; if out != NULL (capacity floats) fills it. */
+int binfb_chromatin_stream_layout(int n_beads, const float *y_pairs, int roles, int smem_bytes,
+                                  float *out, long long capacity, long long *n_floats, int *plan6);
 /* FP32 pipe microbenchmarks used as roofline denominators: dependent-chain-free FFMA, packed
  * FFMA2 and MUFU (rsqrt/ex2/rcp mix) issue loops over the whole device.  Results in
  * TFLOP/s (2 flop per FMA lane-op) and Gop/s. */

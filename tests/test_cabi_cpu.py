@@ -33,40 +33,64 @@ def test_error_reporting_without_gpu():
     assert rc == _cabi.EINVAL and b"null model" in handle.binfb_last_error()
 
 
-@pytest.mark.parametrize("n", [2, 3, 4, 5, 8, 9, 24, 37, 130, 257, 1000])
-def test_contact_stream_covers_every_pair_once(n):
+def test_launch_plan_heuristic():
+    y = np.zeros(1, dtype=np.float32)
+    for n, roles, chains in [(64, 1, 16), (500, 1, 16), (1000, 2, 8), (2000, 4, 4), (5000, 8, 1)]:
+        h = _cabi.lib()
+        import ctypes as C
+        plan = (C.c_int * 6)()
+        nf = C.c_longlong()
+        _cabi.check(h.binfb_chromatin_stream_layout(n, None, 0, 0, None, 0, C.byref(nf), plan))
+        assert (plan[3], plan[5]) == (roles, chains), (n, list(plan))
+        # roles never overlap on a partner quad: Lr - ring drift > 31
+        if plan[3] > 1:
+            assert plan[4] - 4 * max(4, plan[3]) // plan[3] > 31
+
+
+@pytest.mark.parametrize("n,roles", [(2, 1), (3, 1), (4, 1), (5, 1), (8, 1), (9, 1), (24, 1),
+                                     (37, 1), (130, 1), (257, 1), (1000, 1), (1000, 2), (700, 2),
+                                     (1001, 0), (1400, 4)])
+def test_contact_stream_covers_every_pair_once(n, roles):
     m = n * (n - 1) // 2
-    y = (np.arange(m, dtype=np.float64) + 1.0).astype(np.float32)  # unique non-zero tags
-    stream, q, t = _cabi.chromatin_stream_layout(n, y)
-    n_pad = (n + 3) // 4 * 4
-    assert q == n_pad // 4
-    ks, nrb = q // 2, (q + 31) // 32
-    assert t == nrb * (ks + 1)
-    s = stream.reshape(-1, 4, 32, 4)[:t]            # [step][row r][lane][col c]
-    assert stream.size % (4 * 128 * 4) == 0          # padded to whole bulk-copy stages
-    assert not stream.reshape(-1, 4, 32, 4)[t:].any()
+    y = (np.arange(m, dtype=np.float64) % 16777213 + 1.0).astype(np.float32)  # non-zero tags
+    stream, plan = _cabi.chromatin_stream_layout(n, y, roles)
+    q, ks, nrb = plan["quads"], plan["partner_steps"], plan["row_blocks"]
+    R, lr = plan["roles"], plan["slots_per_row_block"]
+    assert q == (n + 3) // 4 and ks == q // 2 and nrb == (q + 31) // 32
+    assert lr == -(-(ks + 1) // R) and (roles == 0 or R == roles)
+    ss = max(4, R)
+    assert stream.size % (ss * 128 * 4) == 0          # whole bulk-copy stages
+    s = stream.reshape(-1, 4, 32, 4)                   # [step][row r][lane][col c]
     iu = np.triu_indices(n, 1)
     tag = np.zeros((n, n), dtype=np.float32)
     tag[iu] = y
     seen = np.zeros((n, n), dtype=np.int64)
-    # replay the kernel's schedule: lane l of row block rb owns quad a, partner quad (a+k)%q
+    used = np.zeros(s.shape[0], dtype=bool)
+    # replay the kernel's schedule: role r of row block rb, slot sl works on partner offset
+    # k = r*Lr + sl; lane l owns quad a = 32 rb + l, partner quad (a + k) % q
     for rb in range(nrb):
-        for k in range(ks + 1):
-            step = s[rb * (ks + 1) + k]
-            for lane in range(32):
-                a = rb * 32 + lane
-                if a >= q:
-                    assert not step[:, lane, :].any()
+        for sl in range(lr):
+            for role in range(R):
+                k = role * lr + sl
+                t = (rb * lr + sl) * R + role
+                used[t] = True
+                step = s[t]
+                if k > ks:
+                    assert not step.any()
                     continue
+                lanes = np.arange(32)
+                a = rb * 32 + lanes
+                ok = a < q
+                assert not step[:, ~ok, :].any()
                 b = (a + k) % q
                 for r in range(4):
                     for c in range(4):
-                        v = step[r, lane, c]
-                        if v == 0:
-                            continue
-                        i, j = 4 * a + r, 4 * b + c
-                        assert i < n and j < n and i != j
-                        lo, hi = min(i, j), max(i, j)
-                        assert tag[lo, hi] == v
-                        seen[lo, hi] += 1
+                        v = step[r, :, c]
+                        nz = (v != 0) & ok
+                        i, j = 4 * a[nz] + r, 4 * b[nz] + c
+                        assert (i < n).all() and (j < n).all() and (i != j).all()
+                        lo, hi = np.minimum(i, j), np.maximum(i, j)
+                        assert (tag[lo, hi] == v[nz]).all()
+                        np.add.at(seen, (lo, hi), 1)
+    assert not s[~used].any()
     assert (seen[iu] == 1).all() and seen.sum() == m

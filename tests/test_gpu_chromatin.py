@@ -68,13 +68,39 @@ def test_ragged_sizes_vs_oracle(gpu, n):
         assert chi2[c] == pytest.approx(o.chi2(q[c]), rel=1e-5)
 
 
-def test_n1000_vs_matrix_free_oracle(gpu):
+@pytest.mark.parametrize("n,roles", [(2000, 0), (2000, 2), (700, 2)])
+def test_multi_warp_chains_vs_oracle(gpu, n, roles):
+    """2 and 4 warps per chain (partner-step ranges split between the warps of a chain)"""
+    from binf_b200 import _cabi
+    X, y = chrom.synthetic_chromatin(n, seed=n)
+    o = chrom.ChromatinModel(n, y, 2.0, 2.5, 4.0, 1.0)
+    m = _cabi.Model.chromatin(n, y, 2.0, 2.5, 4.0, 1.0, roles=roles)
+    rng = np.random.RandomState(n)
+    C = 9
+    q = X.reshape(-1)[None] + 0.1 * rng.normal(size=(C, 3 * n))
+    logp, grad, chi2 = m.logprob_grad(q, 150.0)
+    for c in (0, 8):
+        assert logp[c] == pytest.approx(o.log_prob(q[c], 150.0), rel=1e-5)
+        ref = o.gradient(q[c], 150.0)
+        assert np.all(np.abs(grad[c] - ref) <= 1e-4 * np.max(np.abs(ref)))
+    f = grad.reshape(C, n, 3).sum(axis=1)
+    assert np.all(np.abs(f) <= 1e-3 * np.max(np.abs(grad)))
+    p0, u = rng.normal(size=(C, 3 * n)), np.full(C, 0.5)
+    r = m.hmc_run(q, 150.0, 0.002, 2, p0=p0, u=u, want_end=True)
+    ref = port.hmc_sample(lambda x: o.log_prob(x, 150.0), lambda x: o.gradient(x, 150.0), q[3], 0.002,
+                          2, p0[3], 0.5)
+    assert np.max(np.abs(r["q_end"][3] - ref["q_end"])) <= 1e-4 * np.max(np.abs(ref["q_end"]))
+    assert (r["e_after"][3] - r["e_before"][3]) == pytest.approx(ref["e_after"] - ref["e_before"], abs=3e-2)
+
+
+@pytest.mark.parametrize("roles", [0, 1])
+def test_n1000_vs_matrix_free_oracle(gpu, roles):
     """Config-3 size: 1000 beads, 499,500 pairs per force evaluation."""
     from binf_b200 import _cabi
     n = 1000
     X, y = chrom.synthetic_chromatin(n, seed=0)
     o = chrom.ChromatinModel(n, y, 2.0, 2.5, 4.0, 1.0)
-    m = _cabi.Model.chromatin(n, y, 2.0, 2.5, 4.0, 1.0)
+    m = _cabi.Model.chromatin(n, y, 2.0, 2.5, 4.0, 1.0, roles=roles)
     rng = np.random.RandomState(1)
     C = 20  # not a multiple of the chains-per-CTA
     q = X.reshape(-1)[None] + 0.1 * rng.normal(size=(C, 3 * n))
