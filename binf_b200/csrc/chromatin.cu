@@ -35,10 +35,11 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "pair_block.cuh"
 
 namespace binfb {
 
-constexpr float CHROM_SOFT = 1e-12f;
+constexpr float CHROM_SOFT = PAIR_SOFT;
 constexpr int NS = CHROM_STAGES;
 constexpr int STEP_FLOAT4 = 4 * 32;  // float4 per warp-step (16 contacts per lane)
 constexpr int STEP_BYTES = STEP_FLOAT4 * 16;
@@ -72,31 +73,8 @@ __device__ __forceinline__ void chain_bar(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-// one bead pair: 19 FP32-pipe instructions + 3 MUFU (31 flop by the SURVEY.md 8d count)
-template <bool ENERGY>
-__device__ __forceinline__ void chrom_pair(float xi, float yi, float zi, float xj, float yj,
-                                           float zj, float y, float A, float B, float &fix,
-                                           float &fiy, float &fiz, float &fjx, float &fjy,
-                                           float &fjz, float &chi) {
-    const float dx = xi - xj, dy = yi - yj, dz = zi - zj;
-    const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, CHROM_SOFT)));
-    const float inv = mufu_rsqrt(r2);
-    const float d = r2 * inv;
-    const float e = mufu_ex2(fmaf(d, A, B));
-    const float m = mufu_rcp(1.0f + e);
-    const float res = m - y;
-    const float w = fmaf(-m, m, m);
-    const float coef = res * w * inv;
-    fix = fmaf(coef, dx, fix), fiy = fmaf(coef, dy, fiy), fiz = fmaf(coef, dz, fiz);
-    fjx = fmaf(-coef, dx, fjx), fjy = fmaf(-coef, dy, fjy), fjz = fmaf(-coef, dz, fjz);
-    if (ENERGY) chi = fmaf(res, res, chi);
-}
-
 __device__ __forceinline__ void unpack4(const float4 v, float (&a)[4]) {
     a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w;
-}
-__device__ __forceinline__ float4 pack4(const float (&a)[4]) {
-    return make_float4(a[0], a[1], a[2], a[3]);
 }
 
 struct ChainSmem {
@@ -128,16 +106,22 @@ __device__ __forceinline__ void ring_issue(const Ring &ring, uint32_t base, int 
 }
 
 // The pair sweep of one chain, shared by the R warps ("roles") of that chain.  Role r owns the
-// partner steps k in [r*Lr, (r+1)*Lr) of every row block.  Fills fx/fy/fz with
+// partner steps k in [r*Lr, (r+1)*Lr) of every row block; SPR = SS/R of them per ring stage, and
+// Lr is a multiple of SPR so that a stage never straddles two row blocks.  Fills fx/fy/fz with
 // sum_j coef_ij (x_i - x_j) (the likelihood force up to the factor -alpha*beta*tau) and returns
 // this lane's share of chi^2.
+//
+// The 4x4 block is evaluated with packed FP32 (FFMA2/FADD2/FMUL2: two partner columns per
+// instruction, see pair_block.cuh): 9.5 FMA-pipe issue slots + 3 MUFU per pair.  The special
+// function unit (16 lanes/clk/SM) is the bounding pipe: 3 MUFU per pair = 24 SMSP-cycles per
+// warp-pair, the FMA pipe needs 19.
 //
 // Race freedom of the partner-force read-modify-write in shared memory: within one warp-step the
 // 32 lanes address 32 distinct quads ((a+k) mod Q is a bijection of a).  Two roles r < r' of
 // one chain work on partner offsets k and k' >= k + Lr - drift, where drift <= NS*SS/R slots is
 // enforced by the shared stage ring; they can only meet on a quad if k' - k <= 31, which the
-// host-side plan excludes (Lr - NS*SS/R > 31 whenever R > 1).
-template <bool ENERGY>
+// host-side plan excludes (Lr - NS*SS/R >= 40 whenever R > 1).
+template <bool ENERGY, int SPR>
 __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSmem &sm,
                                               const Ring &ring, uint32_t &stage_idx,
                                               bool chain_valid, int lane, int role, int bar_id) {
@@ -146,107 +130,150 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
     float4 *fx4 = reinterpret_cast<float4 *>(sm.fx), *fy4 = reinterpret_cast<float4 *>(sm.fy),
            *fz4 = reinterpret_cast<float4 *>(sm.fz);
     const float A = cd.A, B = cd.B;
-    const int Q = cd.Q, KS = cd.KS, R = cd.R, Lr = cd.Lr, SS = cd.SS, halfQ = cd.Q >> 1;
+    const float2 A2 = mk2(A, A), B2 = mk2(B, B);
+    const int Q = cd.Q, KS = cd.KS, R = cd.R, Lr = cd.Lr, halfQ = cd.Q >> 1;
     const bool q_even = cd.q_even != 0;
-    const int stage_float4 = SS * STEP_FLOAT4;
+    const int k_fast = q_even ? KS - 1 : KS;  // offsets 1..k_fast need no special handling
+    const int stage_float4 = cd.SS * STEP_FLOAT4;
+    const int n_sg = Lr / SPR;                 // stages per row block
     double chi2 = 0.0;
-    float xi[4], yi[4], zi[4], fi[4][3];
-    int s = 0, a = lane, pos = role;  // slot in the row block, own quad, step position in the stage
-    bool active = false;
     const uint32_t stage_base = stage_idx;
     int s_local = 0;
     if (ring.loader && lane == 0)
         for (int i = 0; i <= PREFETCH && i < ring.n_stage_pass; ++i) ring_issue(ring, stage_base, i);
-    uint32_t slot = stage_idx % NS;
-    mbar_wait(&ring.full[slot], (stage_idx / NS) & 1u);
-    const float4 *ybase = ring.ystage + (size_t)slot * stage_float4;
-    int rb = 0;
-    for (int sidx = 0; sidx < cd.S_pad; ++sidx) {
-        if (rb < cd.NRB && chain_valid) {
-            if (s == 0) {
-                a = rb * 32 + lane;
-                active = a < Q;
-                const int aa = active ? a : 0;
-                unpack4(xs4[aa], xi), unpack4(ys4[aa], yi), unpack4(zs4[aa], zi);
+
+    for (int rb = 0; rb < cd.NRB; ++rb) {
+        const int a = rb * 32 + lane;
+        const bool active = chain_valid && a < Q;
+        const int aa = active ? a : 0;
+        // own quad: negated positions as broadcast pairs, accumulators G = -(force sum)
+        float2 nx2[4], ny2[4], nz2[4], g[4][3];
+        {
+            float xi[4], yi[4], zi[4];
+            unpack4(xs4[aa], xi), unpack4(ys4[aa], yi), unpack4(zs4[aa], zi);
 #pragma unroll
-                for (int r = 0; r < 4; ++r) fi[r][0] = fi[r][1] = fi[r][2] = 0.f;
+            for (int r = 0; r < 4; ++r) {
+                nx2[r] = mk2(-xi[r], -xi[r]), ny2[r] = mk2(-yi[r], -yi[r]), nz2[r] = mk2(-zi[r], -zi[r]);
+                g[r][0] = g[r][1] = g[r][2] = mk2(0.f, 0.f);
             }
-            const int k = role * Lr + s;
-            const float4 *yb = ybase + pos * STEP_FLOAT4 + lane;
-            if (active && k <= KS) {
-                float chi = 0.f;
-                if (k == 0) {
-                    // the 6 pairs inside the lane's own quad
-                    float yv[4][4];
+        }
+        int k = role * Lr;  // partner offset of slot 0
+        int b = aa + k;
+        if (b >= Q) b -= Q;
+        for (int sg = 0; sg < n_sg; ++sg) {
+            const uint32_t slot = stage_idx % NS;
+            mbar_wait(&ring.full[slot], (stage_idx / NS) & 1u);
+            const float4 *ybase = ring.ystage + (size_t)slot * stage_float4 + role * STEP_FLOAT4 + lane;
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) unpack4(yb[r * 32], yv[r]);
+            for (int u = 0; u < SPR; ++u) {
+                const float4 *yb = ybase + u * R * STEP_FLOAT4;
+                if ((unsigned)(k - 1) < (unsigned)k_fast) {
+                    // ---- regular step: 16 pairs, every lane (inactive lanes compute on quad 0
+                    //      and never store) ------------------------------------------------------
+                    const float4 xj = xs4[b], yj = ys4[b], zj = zs4[b];
+                    const float4 fx = fx4[b], fy = fy4[b], fz = fz4[b];
+                    const float2 xj2[2] = {mk2(xj.x, xj.y), mk2(xj.z, xj.w)},
+                                 yj2[2] = {mk2(yj.x, yj.y), mk2(yj.z, yj.w)},
+                                 zj2[2] = {mk2(zj.x, zj.y), mk2(zj.z, zj.w)};
+                    float2 fx2[2] = {mk2(fx.x, fx.y), mk2(fx.z, fx.w)}, fy2[2] = {mk2(fy.x, fy.y), mk2(fy.z, fy.w)},
+                           fz2[2] = {mk2(fz.x, fz.y), mk2(fz.z, fz.w)};
+                    float2 c2 = mk2(0.f, 0.f);
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
+                    for (int r = 0; r < 4; ++r) {
+                        const float4 yv = yb[r * 32];
+                        pair_packed<ENERGY, false>(nx2[r], ny2[r], nz2[r], xj2[0], yj2[0], zj2[0],
+                                                   mk2(yv.x, yv.y), A2, B2, g[r][0], g[r][1], g[r][2],
+                                                   fx2[0], fy2[0], fz2[0], c2);
+                        pair_packed<ENERGY, false>(nx2[r], ny2[r], nz2[r], xj2[1], yj2[1], zj2[1],
+                                                   mk2(yv.z, yv.w), A2, B2, g[r][0], g[r][1], g[r][2],
+                                                   fx2[1], fy2[1], fz2[1], c2);
+                    }
+                    if (active) {
+                        fx4[b] = make_float4(fx2[0].x, fx2[0].y, fx2[1].x, fx2[1].y);
+                        fy4[b] = make_float4(fy2[0].x, fy2[0].y, fy2[1].x, fy2[1].y);
+                        fz4[b] = make_float4(fz2[0].x, fz2[0].y, fz2[1].x, fz2[1].y);
+                        if (ENERGY) chi2 += (double)(c2.x + c2.y);
+                    }
+                } else if (active && k <= KS) {
+                    float chi = 0.f;
+                    if (k == 0) {
+                        // ---- the 6 pairs inside the lane's own quad --------------------------------
+                        float yv[4][4];
 #pragma unroll
-                        for (int c = r + 1; c < 4; ++c)
-                            chrom_pair<ENERGY>(xi[r], yi[r], zi[r], xi[c], yi[c], zi[c], yv[r][c], A, B,
-                                               fi[r][0], fi[r][1], fi[r][2], fi[c][0], fi[c][1],
-                                               fi[c][2], chi);
-                } else {
-                    int b = a + k;
-                    if (b >= Q) b -= Q;
-                    const bool half_dup = (k == KS) && q_even && (a >= halfQ);
-                    if (!half_dup) {
+                        for (int r = 0; r < 3; ++r) unpack4(yb[r * 32], yv[r]);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+#pragma unroll
+                            for (int c = r + 1; c < 4; ++c) {
+                                float tx = 0.f, ty = 0.f, tz = 0.f;
+                                pair_scalar<ENERGY>(nx2[r].x, ny2[r].x, nz2[r].x, -nx2[c].x, -ny2[c].x,
+                                                    -nz2[c].x, yv[r][c], A, B, g[r][0].x, g[r][1].x,
+                                                    g[r][2].x, tx, ty, tz, chi);
+                                g[c][0].y -= tx, g[c][1].y -= ty, g[c][2].y -= tz;
+                            }
+                    } else if (!(q_even && a >= halfQ)) {
+                        // ---- k == KS with an even quad count: only the lower half of the quads owns
+                        //      the (q, q + Q/2) block ------------------------------------------------
                         float xj[4], yj[4], zj[4], fjx[4], fjy[4], fjz[4], yv[4][4];
                         unpack4(xs4[b], xj), unpack4(ys4[b], yj), unpack4(zs4[b], zj);
+                        unpack4(fx4[b], fjx), unpack4(fy4[b], fjy), unpack4(fz4[b], fjz);
 #pragma unroll
                         for (int r = 0; r < 4; ++r) unpack4(yb[r * 32], yv[r]);
-                        unpack4(fx4[b], fjx), unpack4(fy4[b], fjy), unpack4(fz4[b], fjz);
 #pragma unroll
                         for (int r = 0; r < 4; ++r)
 #pragma unroll
                             for (int c = 0; c < 4; ++c)
-                                chrom_pair<ENERGY>(xi[r], yi[r], zi[r], xj[c], yj[c], zj[c], yv[r][c],
-                                                   A, B, fi[r][0], fi[r][1], fi[r][2], fjx[c],
-                                                   fjy[c], fjz[c], chi);
-                        fx4[b] = pack4(fjx), fy4[b] = pack4(fjy), fz4[b] = pack4(fjz);
+                                pair_scalar<ENERGY>(nx2[r].x, ny2[r].x, nz2[r].x, xj[c], yj[c], zj[c],
+                                                    yv[r][c], A, B, g[r][0].x, g[r][1].x, g[r][2].x,
+                                                    fjx[c], fjy[c], fjz[c], chi);
+                        fx4[b] = make_float4(fjx[0], fjx[1], fjx[2], fjx[3]);
+                        fy4[b] = make_float4(fjy[0], fjy[1], fjy[2], fjy[3]);
+                        fz4[b] = make_float4(fjz[0], fjz[1], fjz[2], fjz[3]);
                     }
+                    if (ENERGY) chi2 += (double)chi;
                 }
-                if (ENERGY) chi2 += (double)chi;
+                ++k;
+                if (++b == Q) b = 0;
+                __syncwarp();
             }
-            __syncwarp();
-            if (s == Lr - 1) {
-                // end of the row block: fold the register-resident forces of the own quad into
-                // shared memory, one role at a time
-                for (int rr = 0; rr < R; ++rr) {
-                    if (R > 1) chain_bar(bar_id, R * 32);
-                    if (rr == role && active) {
-                        float4 v = fx4[a];
-                        v.x += fi[0][0], v.y += fi[1][0], v.z += fi[2][0], v.w += fi[3][0];
-                        fx4[a] = v;
-                        v = fy4[a];
-                        v.x += fi[0][1], v.y += fi[1][1], v.z += fi[2][1], v.w += fi[3][1];
-                        fy4[a] = v;
-                        v = fz4[a];
-                        v.x += fi[0][2], v.y += fi[1][2], v.z += fi[2][2], v.w += fi[3][2];
-                        fz4[a] = v;
-                    }
-                }
-                if (R > 1) chain_bar(bar_id, R * 32);
-                else __syncwarp();
-            }
-        }
-        if (++s == Lr) s = 0, ++rb;
-        pos += R;
-        if (pos >= SS) {
-            pos -= SS;
-            __syncwarp();
             if (lane == 0) mbar_arrive(&ring.empty[slot]);
             ++stage_idx;
             ++s_local;
-            if (sidx + 1 < cd.S_pad) {
-                if (ring.loader && lane == 0 && s_local + PREFETCH < ring.n_stage_pass)
-                    ring_issue(ring, stage_base, s_local + PREFETCH);
-                slot = stage_idx % NS;
-                mbar_wait(&ring.full[slot], (stage_idx / NS) & 1u);
-                ybase = ring.ystage + (size_t)slot * stage_float4;
+            if (ring.loader && lane == 0 && s_local + PREFETCH < ring.n_stage_pass)
+                ring_issue(ring, stage_base, s_local + PREFETCH);
+        }
+        // ---- end of the row block: fold the register-resident accumulators of the own quad into
+        //      shared memory (f -= G), one role at a time --------------------------------------------
+        for (int rr = 0; rr < R; ++rr) {
+            if (R > 1) chain_bar(bar_id, R * 32);
+            if (rr == role && active) {
+                float4 v = fx4[a];
+                v.x -= g[0][0].x + g[0][0].y, v.y -= g[1][0].x + g[1][0].y;
+                v.z -= g[2][0].x + g[2][0].y, v.w -= g[3][0].x + g[3][0].y;
+                fx4[a] = v;
+                v = fy4[a];
+                v.x -= g[0][1].x + g[0][1].y, v.y -= g[1][1].x + g[1][1].y;
+                v.z -= g[2][1].x + g[2][1].y, v.w -= g[3][1].x + g[3][1].y;
+                fy4[a] = v;
+                v = fz4[a];
+                v.x -= g[0][2].x + g[0][2].y, v.y -= g[1][2].x + g[1][2].y;
+                v.z -= g[2][2].x + g[2][2].y, v.w -= g[3][2].x + g[3][2].y;
+                fz4[a] = v;
             }
         }
+        if (R > 1) chain_bar(bar_id, R * 32);
+        else __syncwarp();
+    }
+    // stages that only pad the stream to a whole number of ring stages
+    while (s_local < ring.n_stage_pass) {
+        const uint32_t slot = stage_idx % NS;
+        mbar_wait(&ring.full[slot], (stage_idx / NS) & 1u);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ring.empty[slot]);
+        ++stage_idx;
+        ++s_local;
+        if (ring.loader && lane == 0 && s_local + PREFETCH < ring.n_stage_pass)
+            ring_issue(ring, stage_base, s_local + PREFETCH);
     }
     return chi2;
 }
@@ -393,8 +420,16 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
             if (R > 1) chain_bar(bar_id, cthreads);
             else __syncwarp();
             // ---- phase B: pair sweep -----------------------------------------------------
-            double chi2 = energy ? chrom_sweep<true>(cd, sm, ring, stage_idx, valid, lane, role, bar_id)
-                                 : chrom_sweep<false>(cd, sm, ring, stage_idx, valid, lane, role, bar_id);
+            double chi2;
+            if (cd.SS / R == 2)
+                chi2 = energy ? chrom_sweep<true, 2>(cd, sm, ring, stage_idx, valid, lane, role, bar_id)
+                              : chrom_sweep<false, 2>(cd, sm, ring, stage_idx, valid, lane, role, bar_id);
+            else if (cd.SS / R == 4)
+                chi2 = energy ? chrom_sweep<true, 4>(cd, sm, ring, stage_idx, valid, lane, role, bar_id)
+                              : chrom_sweep<false, 4>(cd, sm, ring, stage_idx, valid, lane, role, bar_id);
+            else
+                chi2 = energy ? chrom_sweep<true, 1>(cd, sm, ring, stage_idx, valid, lane, role, bar_id)
+                              : chrom_sweep<false, 1>(cd, sm, ring, stage_idx, valid, lane, role, bar_id);
             if (R > 1) chain_bar(bar_id, cthreads);
             else __syncwarp();
             if (valid) {
@@ -599,7 +634,7 @@ ChromPlan chrom_plan(int n, int smem_optin, int force_roles) {
         const size_t fixed = (size_t)NS * SS * STEP_BYTES + 128;
         if ((size_t)smem_optin < fixed + per_chain) break;
         const int wmax = (int)(((size_t)smem_optin - fixed) / per_chain);
-        const int Lr = (pl.KS + 1 + R - 1) / R;
+        const int Lr = ((pl.KS + 1 + R - 1) / R + SS / R - 1) / (SS / R) * (SS / R);
         const bool safe = Lr - NS * SS / R >= 40;
         // more roles only pay off while the chains alone cannot fill 16 warps
         if (safe && wmax * (R / 2) < 16) best_R = R;
@@ -607,9 +642,9 @@ ChromPlan chrom_plan(int n, int smem_optin, int force_roles) {
     if (force_roles > 0) best_R = force_roles;
     pl.R = best_R;
     pl.SS = pl.R > 4 ? pl.R : 4;
-    pl.Lr = (pl.KS + 1 + pl.R - 1) / pl.R;
-    const int spr = pl.SS / pl.R;  // slots per stage
-    pl.S_pad = (pl.NRB * pl.Lr + spr - 1) / spr * spr;
+    const int spr = pl.SS / pl.R;  // slots per stage and role
+    pl.Lr = ((pl.KS + 1 + pl.R - 1) / pl.R + spr - 1) / spr * spr;  // stages never straddle row blocks
+    pl.S_pad = pl.NRB * pl.Lr;
     pl.fixed_smem = (size_t)NS * pl.SS * STEP_BYTES + 128;
     pl.per_chain_smem = per_chain;
     int W = (size_t)smem_optin > pl.fixed_smem ? (int)(((size_t)smem_optin - pl.fixed_smem) / per_chain) : 0;

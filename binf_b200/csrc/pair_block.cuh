@@ -1,0 +1,113 @@
+// The 4x4 bead-pair block of the chromatin kernel, in several code shapes.
+//
+// All variants compute, for rows r (beads of the lane's own quad) and columns c (beads of the
+// partner quad):
+//     d = sqrt(|x_r - x_c|^2 + soft), e = 2^(A d + B), m = 1/(1+e), res = m - y_rc,
+//     coef = res * m(1-m) / d
+//     G_r += coef (x_c - x_r)      (= minus the force sum on the row bead; folded at flush time)
+//     F_c += coef (x_c - x_r)      (force sum on the column bead)
+//     chi += res^2                  (ENERGY only)
+// Sign convention: rows are kept negated (nx = -x_r) so that the pair difference is one packed
+// add; the row accumulator G therefore has the same sign as the column accumulator F and the
+// caller subtracts it when flushing.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace binfb {
+
+constexpr float PAIR_SOFT = 1e-12f;
+
+struct f2 {
+    float2 v;
+};
+__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+// 2^t for t in [-126, 126] on the FMA pipe: Cody-Waite split t = n + f, f in [-1/2, 1/2],
+// degree-5 near-minimax polynomial for 2^f (max rel. error 2.4e-7 incl. fp32 rounding), exponent patched in with one integer op.
+__device__ __forceinline__ float poly_ex2(float t) {
+    t = fminf(fmaxf(t, -126.0f), 126.0f);
+    const float magic = 12582912.0f;  // 1.5 * 2^23
+    const float tm = t + magic;
+    const float f = t - (tm - magic);
+    float p = 1.3390863366e-3f;  // Chebyshev-node interpolant of 2^f on [-1/2, 1/2]
+    p = fmaf(p, f, 9.6760319183e-3f);
+    p = fmaf(p, f, 5.5503571142e-2f);
+    p = fmaf(p, f, 2.4022107485e-1f);
+    p = fmaf(p, f, 6.9314718803e-1f);
+    p = fmaf(p, f, 1.0000000755f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(tm) << 23));
+}
+
+// packed version of poly_ex2 for t <= 126 (callers guarantee t > -126): 3 + 5 packed FMA-pipe
+// ops and 4 scalar ALU-pipe ops for two values
+__device__ __forceinline__ float2 poly_ex2_2(float2 t) {
+    t = mk2(fminf(t.x, 126.0f), fminf(t.y, 126.0f));
+    const float2 magic = mk2(12582912.0f, 12582912.0f);
+    const float2 tm = add2(t, magic);
+    const float2 nn = fma2(tm, mk2(-1.f, -1.f), magic);  // -(round(t))
+    const float2 f = add2(t, nn);
+    float2 p = fma2(mk2(1.3390863366e-3f, 1.3390863366e-3f), f, mk2(9.6760319183e-3f, 9.6760319183e-3f));
+    p = fma2(p, f, mk2(5.5503571142e-2f, 5.5503571142e-2f));
+    p = fma2(p, f, mk2(2.4022107485e-1f, 2.4022107485e-1f));
+    p = fma2(p, f, mk2(6.9314718803e-1f, 6.9314718803e-1f));
+    p = fma2(p, f, mk2(1.0000000755f, 1.0000000755f));
+    return mk2(__int_as_float(__float_as_int(p.x) + (__float_as_int(tm.x) << 23)),
+               __int_as_float(__float_as_int(p.y) + (__float_as_int(tm.y) << 23)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalar reference shape (one pair at a time; the compiler interleaves)
+// ---------------------------------------------------------------------------------------------
+template <bool ENERGY>
+__device__ __forceinline__ void pair_scalar(float nxi, float nyi, float nzi, float xj, float yj,
+                                            float zj, float y, float A, float B, float &gx,
+                                            float &gy, float &gz, float &fx, float &fy, float &fz,
+                                            float &chi) {
+    const float dx = xj + nxi, dy = yj + nyi, dz = zj + nzi;
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, PAIR_SOFT)));
+    const float inv = mufu_rsqrt(r2);
+    const float d = r2 * inv;
+    const float e = mufu_ex2(fmaf(d, A, B));
+    const float mn = mufu_rcp(fmaf(e, -1.0f, -1.0f));  // -m
+    const float rs = mn + y;                            // -(m - y)
+    const float wn = fmaf(mn, mn, mn);                  // -(m - m^2)
+    const float coef = rs * wn * inv;
+    gx = fmaf(coef, dx, gx), gy = fmaf(coef, dy, gy), gz = fmaf(coef, dz, gz);
+    fx = fmaf(coef, dx, fx), fy = fmaf(coef, dy, fy), fz = fmaf(coef, dz, fz);
+    if (ENERGY) chi = fmaf(rs, rs, chi);
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed shape: two columns (c, c+1) of one row per instruction (FFMA2 / FADD2 / FMUL2).
+// nx2 = (-x_r, -x_r) etc. are broadcast pairs; xj2, F2 are natural register pairs.
+// POLY: evaluate 2^t on the FMA pipe instead of MUFU.EX2 for this pack.
+// ---------------------------------------------------------------------------------------------
+template <bool ENERGY, bool POLY>
+__device__ __forceinline__ void pair_packed(float2 nx2, float2 ny2, float2 nz2, float2 xj2, float2 yj2,
+                                            float2 zj2, float2 y2, float2 A2, float2 B2, float2 &gx2,
+                                            float2 &gy2, float2 &gz2, float2 &fx2, float2 &fy2,
+                                            float2 &fz2, float2 &chi2) {
+    const float2 dx = add2(xj2, nx2), dy = add2(yj2, ny2), dz = add2(zj2, nz2);
+    const float2 r2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, mk2(PAIR_SOFT, PAIR_SOFT))));
+    const float2 inv = mk2(mufu_rsqrt(r2.x), mufu_rsqrt(r2.y));
+    const float2 d = mul2(r2, inv);
+    const float2 t = fma2(d, A2, B2);
+    float2 e;
+    if (POLY) e = poly_ex2_2(t);
+    else e = mk2(mufu_ex2(t.x), mufu_ex2(t.y));
+    const float2 sn = fma2(e, mk2(-1.f, -1.f), mk2(-1.f, -1.f));
+    const float2 mn = mk2(mufu_rcp(sn.x), mufu_rcp(sn.y));
+    const float2 rs = add2(mn, y2);
+    const float2 wn = fma2(mn, mn, mn);
+    const float2 coef = mul2(mul2(rs, wn), inv);
+    gx2 = fma2(coef, dx, gx2), gy2 = fma2(coef, dy, gy2), gz2 = fma2(coef, dz, gz2);
+    fx2 = fma2(coef, dx, fx2), fy2 = fma2(coef, dy, fy2), fz2 = fma2(coef, dz, fz2);
+    if (ENERGY) chi2 = fma2(rs, rs, chi2);
+}
+
+}  // namespace binfb

@@ -1,0 +1,243 @@
+// Stand-alone harness for the 4x4 bead-pair block of the chromatin kernel: same shared-memory
+// traffic (3 LDS.128 positions + 3 LDS.128/3 STS.128 partner forces + 4 LDS.128 contacts per
+// 16 pairs) and the same launch shape (16 warps, 1 CTA per SM), without the scheduler/ring.
+// Reports SMSP cycles per warp-pair (MUFU floor: 24) for several code shapes.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -I../../binf_b200/csrc -o pairbench.bin pairbench.cu
+#include <cstdio>
+#include <vector>
+#include <cuda_runtime.h>
+#include "pair_block.cuh"
+
+using namespace binfb;
+
+__device__ __forceinline__ void unpack4(const float4 v, float (&a)[4]) { a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w; }
+
+// VAR 0: scalar; 1: packed; 2: packed, NPOLY of the 8 packs per block use the FMA-pipe exp2;
+// VAR 3: like 2 with the next step's positions/contacts prefetched into registers
+template <int VAR, int NPOLY, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float *out, int steps, int Q, float A, float B) {
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chain = warp >> 1;
+    const int n_pad = 4 * Q;
+    float *ybuf = smem;                                  // 4 steps x 2 KiB of contacts
+    float *base = smem + 2048 + (size_t)chain * 6 * n_pad;
+    float4 *xs4 = (float4 *)base, *ys4 = (float4 *)(base + n_pad), *zs4 = (float4 *)(base + 2 * n_pad);
+    float4 *fx4 = (float4 *)(base + 3 * n_pad), *fy4 = (float4 *)(base + 4 * n_pad), *fz4 = (float4 *)(base + 5 * n_pad);
+    for (int i = threadIdx.x; i < 2048; i += THREADS) ybuf[i] = 0.3f + 1e-4f * i;
+    for (int i = (warp & 1) * 32 + lane; i < 3 * n_pad; i += 64) base[i] = init[i % 4096] * 3.0f;
+    for (int i = (warp & 1) * 32 + lane; i < 3 * n_pad; i += 64) base[3 * n_pad + i] = 0.f;
+    __syncthreads();
+    const int a = (warp & 1) * 32 + lane;  // own quad (two roles: different rows here, just for load)
+    float xi[4], yi[4], zi[4];
+    unpack4(xs4[a % Q], xi), unpack4(ys4[a % Q], yi), unpack4(zs4[a % Q], zi);
+    float chi_tot = 0.f;
+    int b = (a + 1 + (warp & 1) * 60) % Q;
+    if (VAR == 0) {
+        float g[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { g[r][0] = g[r][1] = g[r][2] = 0.f; xi[r] = -xi[r]; yi[r] = -yi[r]; zi[r] = -zi[r]; }
+        for (int st = 0; st < steps; ++st) {
+            float xj[4], yj[4], zj[4], fx[4], fy[4], fz[4], yv[4][4];
+            unpack4(xs4[b], xj), unpack4(ys4[b], yj), unpack4(zs4[b], zj);
+            const float4 *yb = (const float4 *)ybuf + (st & 3) * 128 + lane;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) unpack4(yb[r * 32], yv[r]);
+            unpack4(fx4[b], fx), unpack4(fy4[b], fy), unpack4(fz4[b], fz);
+            float chi = 0.f;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    pair_scalar<false>(xi[r], yi[r], zi[r], xj[c], yj[c], zj[c], yv[r][c], A, B, g[r][0], g[r][1], g[r][2], fx[c], fy[c], fz[c], chi);
+            fx4[b] = make_float4(fx[0], fx[1], fx[2], fx[3]);
+            fy4[b] = make_float4(fy[0], fy[1], fy[2], fy[3]);
+            fz4[b] = make_float4(fz[0], fz[1], fz[2], fz[3]);
+            chi_tot += chi;
+            if (++b >= Q) b = 0;
+            __syncwarp();
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) chi_tot += g[r][0] + g[r][1] + g[r][2];
+    } else if (VAR == 4) {
+        // 8 own rows (an octet: quads a2, a2+1) x 4 partner columns per step, rows packed in pairs,
+        // one partner column at a time.  y is column-major in the stage: [c][half][lane] float4.
+        float2 nX[4][3], g[4][3];
+        {
+            const int a2 = (2 * a) % Q, a3 = (2 * a + 1) % Q;
+            const float4 x0 = xs4[a2], y0 = ys4[a2], z0 = zs4[a2], x1 = xs4[a3], y1 = ys4[a3], z1 = zs4[a3];
+            nX[0][0] = mk2(-x0.x, -x0.y), nX[1][0] = mk2(-x0.z, -x0.w), nX[2][0] = mk2(-x1.x, -x1.y), nX[3][0] = mk2(-x1.z, -x1.w);
+            nX[0][1] = mk2(-y0.x, -y0.y), nX[1][1] = mk2(-y0.z, -y0.w), nX[2][1] = mk2(-y1.x, -y1.y), nX[3][1] = mk2(-y1.z, -y1.w);
+            nX[0][2] = mk2(-z0.x, -z0.y), nX[1][2] = mk2(-z0.z, -z0.w), nX[2][2] = mk2(-z1.x, -z1.y), nX[3][2] = mk2(-z1.z, -z1.w);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) g[r][0] = g[r][1] = g[r][2] = mk2(0.f, 0.f);
+        const float2 A2 = mk2(A, A), B2 = mk2(B, B);
+        for (int st = 0; st < steps; ++st) {
+            float xj[4], yj[4], zj[4], fx[4], fy[4], fz[4];
+            unpack4(xs4[b], xj), unpack4(ys4[b], yj), unpack4(zs4[b], zj);
+            unpack4(fx4[b], fx), unpack4(fy4[b], fy), unpack4(fz4[b], fz);
+            const float4 *yb = (const float4 *)ybuf + (st & 1) * 256 + lane;
+            float2 chi2 = mk2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float2 xc = mk2(xj[c], xj[c]), yc = mk2(yj[c], yj[c]), zc = mk2(zj[c], zj[c]);
+                float2 Fx = mk2(fx[c], 0.f), Fy = mk2(fy[c], 0.f), Fz = mk2(fz[c], 0.f);
+                const float4 ya = yb[(c * 2) * 32], ybb = yb[(c * 2 + 1) * 32];
+#pragma unroll
+                for (int rp = 0; rp < 4; ++rp) {
+                    const float2 y2 = rp == 0 ? mk2(ya.x, ya.y) : rp == 1 ? mk2(ya.z, ya.w) : rp == 2 ? mk2(ybb.x, ybb.y) : mk2(ybb.z, ybb.w);
+                    if ((c * 4 + rp) < NPOLY)
+                        pair_packed<false, true>(nX[rp][0], nX[rp][1], nX[rp][2], xc, yc, zc, y2, A2, B2, g[rp][0], g[rp][1], g[rp][2], Fx, Fy, Fz, chi2);
+                    else
+                        pair_packed<false, false>(nX[rp][0], nX[rp][1], nX[rp][2], xc, yc, zc, y2, A2, B2, g[rp][0], g[rp][1], g[rp][2], Fx, Fy, Fz, chi2);
+                }
+                fx[c] = Fx.x + Fx.y, fy[c] = Fy.x + Fy.y, fz[c] = Fz.x + Fz.y;
+            }
+            fx4[b] = make_float4(fx[0], fx[1], fx[2], fx[3]);
+            fy4[b] = make_float4(fy[0], fy[1], fy[2], fy[3]);
+            fz4[b] = make_float4(fz[0], fz[1], fz[2], fz[3]);
+            chi_tot += chi2.x + chi2.y;
+            if (++b >= Q) b = 0;
+            __syncwarp();
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) chi_tot += g[r][0].x + g[r][0].y + g[r][1].x + g[r][1].y + g[r][2].x + g[r][2].y;
+    } else if (VAR == 3) {
+        float2 nx2[4], ny2[4], nz2[4], g[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            nx2[r] = mk2(-xi[r], -xi[r]), ny2[r] = mk2(-yi[r], -yi[r]), nz2[r] = mk2(-zi[r], -zi[r]);
+            g[r][0] = g[r][1] = g[r][2] = mk2(0.f, 0.f);
+        }
+        const float2 A2 = mk2(A, A), B2 = mk2(B, B);
+        float4 xj = xs4[b], yj = ys4[b], zj = zs4[b];
+        float4 yv[4];
+        {
+            const float4 *yb = (const float4 *)ybuf + lane;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) yv[r] = yb[r * 32];
+        }
+        for (int st = 0; st < steps; ++st) {
+            int bn = b + 1;
+            if (bn >= Q) bn = 0;
+            float4 fx = fx4[b], fy = fy4[b], fz = fz4[b];
+            const float4 xn = xs4[bn], yn = ys4[bn], zn = zs4[bn];
+            float4 yvn[4];
+            const float4 *ybn = (const float4 *)ybuf + ((st + 1) & 3) * 128 + lane;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) yvn[r] = ybn[r * 32];
+            float2 xj2[2] = {mk2(xj.x, xj.y), mk2(xj.z, xj.w)}, yj2[2] = {mk2(yj.x, yj.y), mk2(yj.z, yj.w)},
+                   zj2[2] = {mk2(zj.x, zj.y), mk2(zj.z, zj.w)};
+            float2 fx2[2] = {mk2(fx.x, fx.y), mk2(fx.z, fx.w)}, fy2[2] = {mk2(fy.x, fy.y), mk2(fy.z, fy.w)},
+                   fz2[2] = {mk2(fz.x, fz.y), mk2(fz.z, fz.w)};
+            float2 chi2 = mk2(0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float2 y2 = h ? mk2(yv[r].z, yv[r].w) : mk2(yv[r].x, yv[r].y);
+                    if ((r * 2 + h) < NPOLY)
+                        pair_packed<false, true>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2, g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
+                    else
+                        pair_packed<false, false>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2, g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
+                }
+            }
+            fx4[b] = make_float4(fx2[0].x, fx2[0].y, fx2[1].x, fx2[1].y);
+            fy4[b] = make_float4(fy2[0].x, fy2[0].y, fy2[1].x, fy2[1].y);
+            fz4[b] = make_float4(fz2[0].x, fz2[0].y, fz2[1].x, fz2[1].y);
+            chi_tot += chi2.x + chi2.y;
+            b = bn;
+            xj = xn, yj = yn, zj = zn;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) yv[r] = yvn[r];
+            __syncwarp();
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) chi_tot += g[r][0].x + g[r][0].y + g[r][1].x + g[r][1].y + g[r][2].x + g[r][2].y;
+    } else {
+        float2 nx2[4], ny2[4], nz2[4], g[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            nx2[r] = mk2(-xi[r], -xi[r]), ny2[r] = mk2(-yi[r], -yi[r]), nz2[r] = mk2(-zi[r], -zi[r]);
+            g[r][0] = g[r][1] = g[r][2] = mk2(0.f, 0.f);
+        }
+        const float2 A2 = mk2(A, A), B2 = mk2(B, B);
+        for (int st = 0; st < steps; ++st) {
+            const float4 xj = xs4[b], yj = ys4[b], zj = zs4[b];
+            float4 fx = fx4[b], fy = fy4[b], fz = fz4[b];
+            float2 xj2[2] = {mk2(xj.x, xj.y), mk2(xj.z, xj.w)}, yj2[2] = {mk2(yj.x, yj.y), mk2(yj.z, yj.w)},
+                   zj2[2] = {mk2(zj.x, zj.y), mk2(zj.z, zj.w)};
+            float2 fx2[2] = {mk2(fx.x, fx.y), mk2(fx.z, fx.w)}, fy2[2] = {mk2(fy.x, fy.y), mk2(fy.z, fy.w)},
+                   fz2[2] = {mk2(fz.x, fz.y), mk2(fz.z, fz.w)};
+            const float4 *yb = (const float4 *)ybuf + (st & 3) * 128 + lane;
+            float2 chi2 = mk2(0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float4 yv = yb[r * 32];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float2 y2 = h ? mk2(yv.z, yv.w) : mk2(yv.x, yv.y);
+                    if (VAR == 2 && (r * 2 + h) < NPOLY)
+                        pair_packed<false, true>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2, g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
+                    else
+                        pair_packed<false, false>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2, g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
+                }
+            }
+            fx4[b] = make_float4(fx2[0].x, fx2[0].y, fx2[1].x, fx2[1].y);
+            fy4[b] = make_float4(fy2[0].x, fy2[0].y, fy2[1].x, fy2[1].y);
+            fz4[b] = make_float4(fz2[0].x, fz2[0].y, fz2[1].x, fz2[1].y);
+            chi_tot += chi2.x + chi2.y;
+            if (++b >= Q) b = 0;
+            __syncwarp();
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) chi_tot += g[r][0].x + g[r][0].y + g[r][1].x + g[r][1].y + g[r][2].x + g[r][2].y;
+    }
+    if (chi_tot == 1.2345f) out[0] = chi_tot;
+    __syncthreads();
+    if (threadIdx.x < 64) out[1 + blockIdx.x * 64 + threadIdx.x] = base[3 * n_pad + threadIdx.x];
+}
+
+template <int VAR, int NPOLY, int THREADS, int PAIRS = 16>
+void run(const char *name, const float *init, float *out, int sms, double clk) {
+    const int Q = 250, steps = 4000;
+    const int chains = THREADS / 64;
+    const size_t smem = (2048 + (size_t)chains * 6 * 4 * Q) * sizeof(float);
+    cudaFuncSetAttribute(pairbench<VAR, NPOLY, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, pairbench<VAR, NPOLY, THREADS>);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    pairbench<VAR, NPOLY, THREADS><<<sms, THREADS, smem>>>(init, out, steps, Q, 2.885f, -7.21f);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int r = 0; r < 3; ++r) {
+        cudaEventRecord(e0);
+        pairbench<VAR, NPOLY, THREADS><<<sms, THREADS, smem>>>(init, out, steps, Q, 2.885f, -7.21f);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+    }
+    cudaError_t err = cudaGetLastError();
+    const double warp_pairs_per_smsp = (double)(THREADS / 32) / 4.0 * steps * (double)PAIRS;
+    const double cyc = best * 1e-3 * clk * 1e9 / warp_pairs_per_smsp;
+    printf("%-34s warps=%2d regs=%3d  %7.3f ms  %6.2f SMSP-cycles/warp-pair  (%4.1f%% of FP32 peak at 31 flop/pair) %s\n",
+           name, THREADS / 32, fa.numRegs, best, cyc, 100.0 * 31.0 / (2.0 * cyc), err == cudaSuccess ? "" : cudaGetErrorString(err));
+}
+
+int main() {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    std::vector<float> h(4096);
+    for (int i = 0; i < 4096; ++i) h[i] = (float)((i * 2654435761u) % 1000) / 1000.0f;
+    float *init, *out; cudaMalloc(&init, 4096 * 4); cudaMalloc(&out, (1 + 148 * 64) * 4);
+    cudaMemcpy(init, h.data(), 4096 * 4, cudaMemcpyHostToDevice);
+    const int sms = p.multiProcessorCount; const double g = clk / 1e6;
+    run<1, 0, 512>("packed 4x4", init, out, sms, g);
+    run<4, 0, 512, 32>("row-packed 8x4", init, out, sms, g);
+    run<4, 0, 384, 32>("row-packed 8x4", init, out, sms, g);
+    run<4, 0, 256, 32>("row-packed 8x4", init, out, sms, g);
+    run<4, 2, 512, 32>("row-packed 8x4, 2/16 poly", init, out, sms, g);
+    run<4, 4, 512, 32>("row-packed 8x4, 4/16 poly", init, out, sms, g);
+    run<4, 4, 384, 32>("row-packed 8x4, 4/16 poly", init, out, sms, g);
+    run<4, 6, 384, 32>("row-packed 8x4, 6/16 poly", init, out, sms, g);
+    return 0;
+}

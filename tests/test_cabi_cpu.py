@@ -57,8 +57,9 @@ def test_contact_stream_covers_every_pair_once(n, roles):
     q, ks, nrb = plan["quads"], plan["partner_steps"], plan["row_blocks"]
     R, lr = plan["roles"], plan["slots_per_row_block"]
     assert q == (n + 3) // 4 and ks == q // 2 and nrb == (q + 31) // 32
-    assert lr == -(-(ks + 1) // R) and (roles == 0 or R == roles)
     ss = max(4, R)
+    spr = ss // R
+    assert lr == -(-(-(-(ks + 1) // R)) // spr) * spr and (roles == 0 or R == roles)
     assert stream.size % (ss * 128 * 4) == 0          # whole bulk-copy stages
     s = stream.reshape(-1, 4, 32, 4)                   # [step][row r][lane][col c]
     iu = np.triu_indices(n, 1)
