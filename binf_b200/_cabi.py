@@ -126,13 +126,14 @@ def chromatin_stream_layout(n_beads, y_pairs, roles=0, smem_bytes=0):
     """Host-only: the contact stream exactly as the pair kernel consumes it, and the plan."""
     y = f32(y_pairs)
     n_floats = C.c_longlong()
-    plan = (C.c_int * 6)()
+    plan = (C.c_int * 8)()
     check(lib().binfb_chromatin_stream_layout(n_beads, ptr(y), roles, smem_bytes, None, 0,
                                               C.byref(n_floats), plan))
     out = np.empty(n_floats.value, dtype=np.float32)
     check(lib().binfb_chromatin_stream_layout(n_beads, ptr(y), roles, smem_bytes, ptr(out), out.size,
                                               None, None))
-    keys = ("quads", "partner_steps", "row_blocks", "roles", "slots_per_row_block", "chains_per_cta")
+    keys = ("quads", "partner_steps", "row_blocks", "roles", "slots_per_row_block", "chains_per_cta",
+            "stage_steps", "ring_depth")
     return out, dict(zip(keys, list(plan)))
 
 

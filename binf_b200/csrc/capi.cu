@@ -515,7 +515,7 @@ int binfb_chromatin_stream_layout(int n_beads, const float *y_pairs, int roles, 
     if (n_floats) *n_floats = pl.stream_floats;
     if (plan6) {
         plan6[0] = pl.Q, plan6[1] = pl.KS, plan6[2] = pl.NRB, plan6[3] = pl.R, plan6[4] = pl.Lr,
-        plan6[5] = pl.W;
+        plan6[5] = pl.W, plan6[6] = pl.SS, plan6[7] = pl.NS;
     }
     if (!out) return BINFB_OK;
     if (!y_pairs || capacity < pl.stream_floats) {

@@ -32,6 +32,7 @@
 //     chain per pass, <0.1 % of the pass) -- this removes the 3.46-waves quantisation a
 //     "whole trajectory per CTA" launch has at C = 4096 on 148 SMs.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -40,13 +41,13 @@
 namespace binfb {
 
 constexpr float CHROM_SOFT = PAIR_SOFT;
-constexpr int NS = CHROM_STAGES;
 constexpr int STEP_FLOAT4 = 4 * 32;  // float4 per warp-step (16 contacts per lane)
 constexpr int STEP_BYTES = STEP_FLOAT4 * 16;
 
 struct ChromDev {
     int n, n_pad, Q, KS, NRB, q_even;
     int R, Lr, SS, S_pad;  // roles per chain, slots per row block, steps per stage, padded slots
+    int NS;                // ring depth (power of two)
     const float4 *ystream;
     float A, B;  // exp(alpha (d - d_c)) = 2^(A d + B)
     float alpha, k_bb, l0, inv_s2;
@@ -89,16 +90,16 @@ struct Ring {
     const unsigned char *src;
     uint32_t stage_bytes;
     int n_stage_pass;
+    uint32_t ns_mask, ns_shift;  // ring depth NS = 1 << ns_shift
+    int prefetch;                // stages of lookahead = NS/2: the slot refilled was released NS/2 stages ago
     bool loader;
 };
-
-constexpr int PREFETCH = 2;  // stages of lookahead; the slot refilled was released 2 stages ago
 
 // issue the bulk copy of local stage s_local of this pass (global stage index base + s_local)
 __device__ __forceinline__ void ring_issue(const Ring &ring, uint32_t base, int s_local) {
     const uint32_t gi = base + (uint32_t)s_local;
-    const uint32_t sl = gi % NS;
-    mbar_wait(&ring.empty[sl], ((gi / NS) & 1u) ^ 1u);
+    const uint32_t sl = gi & ring.ns_mask;
+    mbar_wait(&ring.empty[sl], ((gi >> ring.ns_shift) & 1u) ^ 1u);
     mbar_arrive_expect_tx(&ring.full[sl], ring.stage_bytes);
     bulk_copy_g2s(const_cast<unsigned char *>(reinterpret_cast<const unsigned char *>(ring.ystage)) +
                       (size_t)sl * ring.stage_bytes,
@@ -140,7 +141,8 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
     const uint32_t stage_base = stage_idx;
     int s_local = 0;
     if (ring.loader && lane == 0)
-        for (int i = 0; i <= PREFETCH && i < ring.n_stage_pass; ++i) ring_issue(ring, stage_base, i);
+        for (int i = 0; i <= ring.prefetch && i < ring.n_stage_pass; ++i) ring_issue(ring, stage_base, i);
+    bool ready = false;  // the stage about to be consumed was already seen complete (early probe)
 
     for (int rb = 0; rb < cd.NRB; ++rb) {
         const int a = rb * 32 + lane;
@@ -161,12 +163,15 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
         int b = aa + k;
         if (b >= Q) b -= Q;
         for (int sg = 0; sg < n_sg; ++sg) {
-            const uint32_t slot = stage_idx % NS;
-            mbar_wait(&ring.full[slot], (stage_idx / NS) & 1u);
+            const uint32_t slot = stage_idx & ring.ns_mask;
+            if (!ready) mbar_wait(&ring.full[slot], (stage_idx >> ring.ns_shift) & 1u);
             const float4 *ybase = ring.ystage + (size_t)slot * stage_float4 + role * STEP_FLOAT4 + lane;
 #pragma unroll
             for (int u = 0; u < SPR; ++u) {
                 const float4 *yb = ybase + u * R * STEP_FLOAT4;
+                if (u == SPR - 1)  // probe the next stage now; the answer is back after this step
+                    ready = mbar_try_wait(&ring.full[(stage_idx + 1) & ring.ns_mask],
+                                          ((stage_idx + 1) >> ring.ns_shift) & 1u);
                 if ((unsigned)(k - 1) < (unsigned)k_fast) {
                     // ---- regular step: 16 pairs, every lane (inactive lanes compute on quad 0
                     //      and never store) ------------------------------------------------------
@@ -239,8 +244,8 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
             if (lane == 0) mbar_arrive(&ring.empty[slot]);
             ++stage_idx;
             ++s_local;
-            if (ring.loader && lane == 0 && s_local + PREFETCH < ring.n_stage_pass)
-                ring_issue(ring, stage_base, s_local + PREFETCH);
+            if (ring.loader && lane == 0 && s_local + ring.prefetch < ring.n_stage_pass)
+                ring_issue(ring, stage_base, s_local + ring.prefetch);
         }
         // ---- end of the row block: fold the register-resident accumulators of the own quad into
         //      shared memory (f -= G), one role at a time --------------------------------------------
@@ -266,14 +271,14 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
     }
     // stages that only pad the stream to a whole number of ring stages
     while (s_local < ring.n_stage_pass) {
-        const uint32_t slot = stage_idx % NS;
-        mbar_wait(&ring.full[slot], (stage_idx / NS) & 1u);
+        const uint32_t slot = stage_idx & ring.ns_mask;
+        mbar_wait(&ring.full[slot], (stage_idx >> ring.ns_shift) & 1u);
         __syncwarp();
         if (lane == 0) mbar_arrive(&ring.empty[slot]);
         ++stage_idx;
         ++s_local;
-        if (ring.loader && lane == 0 && s_local + PREFETCH < ring.n_stage_pass)
-            ring_issue(ring, stage_base, s_local + PREFETCH);
+        if (ring.loader && lane == 0 && s_local + ring.prefetch < ring.n_stage_pass)
+            ring_issue(ring, stage_base, s_local + ring.prefetch);
     }
     return chi2;
 }
@@ -311,8 +316,12 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
     // ---- shared memory carve-up: [stages][barriers, item][W x (6 n_pad floats + 8 doubles)]
     Ring ring;
     ring.ystage = reinterpret_cast<const float4 *>(smem_raw);
+    const int NS = cd.NS;
     ring.full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NS * stage_bytes);
     ring.empty = ring.full + NS;
+    ring.ns_mask = (uint32_t)NS - 1u;
+    ring.ns_shift = NS == 2 ? 1u : (NS == 4 ? 2u : 3u);
+    ring.prefetch = NS / 2;
     ring.src = reinterpret_cast<const unsigned char *>(cd.ystream);
     ring.stage_bytes = stage_bytes;
     ring.n_stage_pass = cd.S_pad * R / cd.SS;
@@ -624,13 +633,30 @@ static inline long long tri_index(long long n, long long i, long long j) {  // i
 // Launch geometry: W chains per CTA, R warps ("roles") per chain, W*R <= 16 consumer warps.
 // R > 1 only when the partner-step ranges of two roles can never overlap within the drift the
 // stage ring allows (see chrom_sweep): Lr - NS*SS/R >= 40.
+// stage size (warp-steps) and ring depth per role count
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+// BINFB_CHROM_SS / BINFB_CHROM_NS are tuning knobs for experiments (SS multiple of R, NS in {2,4,8})
+static int chrom_stage_steps(int R) {
+    const int ss = env_int("BINFB_CHROM_SS", 0);
+    if (ss >= R && ss % R == 0 && (ss / R == 1 || ss / R == 2 || ss / R == 4)) return ss;
+    return R <= 4 ? 4 : 8;  // measured on B200 at n = 1000: 4-step stages x 4 slots beat 8 x 2
+}
+static int chrom_ring_depth(int R) {
+    const int ns = env_int("BINFB_CHROM_NS", 0);
+    if (ns == 2 || ns == 4 || ns == 8) return ns;
+    return 4;
+}
+
 ChromPlan chrom_plan(int n, int smem_optin, int force_roles) {
     ChromPlan pl;
     pl.n_pad = (n + 3) / 4 * 4, pl.Q = pl.n_pad / 4, pl.KS = pl.Q / 2, pl.NRB = (pl.Q + 31) / 32;
     const size_t per_chain = (size_t)6 * pl.n_pad * sizeof(float) + 64;
     int best_R = 1;
     for (int R = 2; R <= 8; R *= 2) {
-        const int SS = R > 4 ? R : 4;
+        const int SS = chrom_stage_steps(R), NS = chrom_ring_depth(R);
         const size_t fixed = (size_t)NS * SS * STEP_BYTES + 128;
         if ((size_t)smem_optin < fixed + per_chain) break;
         const int wmax = (int)(((size_t)smem_optin - fixed) / per_chain);
@@ -641,7 +667,8 @@ ChromPlan chrom_plan(int n, int smem_optin, int force_roles) {
     }
     if (force_roles > 0) best_R = force_roles;
     pl.R = best_R;
-    pl.SS = pl.R > 4 ? pl.R : 4;
+    pl.SS = chrom_stage_steps(pl.R), pl.NS = chrom_ring_depth(pl.R);
+    const int NS = pl.NS;
     const int spr = pl.SS / pl.R;  // slots per stage and role
     pl.Lr = ((pl.KS + 1 + pl.R - 1) / pl.R + spr - 1) / spr * spr;  // stages never straddle row blocks
     pl.S_pad = pl.NRB * pl.Lr;
@@ -717,7 +744,7 @@ static ChromDev chrom_dev(const ChromModel &m) {
     const ChromPlan &pl = m.plan;
     d.n = m.n, d.n_pad = pl.n_pad, d.Q = pl.Q, d.KS = pl.KS, d.NRB = pl.NRB;
     d.q_even = (pl.Q % 2) == 0;
-    d.R = pl.R, d.Lr = pl.Lr, d.SS = pl.SS, d.S_pad = pl.S_pad;
+    d.R = pl.R, d.Lr = pl.Lr, d.SS = pl.SS, d.S_pad = pl.S_pad, d.NS = pl.NS;
     d.ystream = reinterpret_cast<const float4 *>(m.ystream);
     const double log2e = 1.4426950408889634;
     d.A = (float)((double)m.alpha * log2e);

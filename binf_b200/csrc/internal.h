@@ -69,6 +69,7 @@ struct ChromPlan {
     int n_pad = 0, Q = 0, KS = 0, NRB = 0;  // padded beads, quads, partner steps, row blocks
     int R = 1, W = 1;                       // warps per chain, chains per CTA
     int Lr = 0, SS = 4, S_pad = 0;          // slots per row block, steps per stage, padded slots
+    int NS = 4;                             // ring depth
     size_t fixed_smem = 0, per_chain_smem = 0;
     long long stream_floats = 0;
 };
@@ -89,7 +90,6 @@ struct ChromModel {
     int *sched = nullptr;                 // [1 + n_octets]: item counter, per-octet pass counters
     int sched_len = 0;
 };
-constexpr int CHROM_STAGES = 4;  // depth of the bulk-copy ring (stages of max(4, R) warp-steps)
 ChromPlan chrom_plan(int n, int smem_optin, int force_roles);
 int chrom_build_stream(int n, const float *y_pairs, const ChromPlan &pl, float *out);
 int chrom_reserve(ChromModel &m, int C);

@@ -165,8 +165,9 @@ int binfb_rng_fill_host(uint64_t seed, uint64_t draw, uint64_t chain_base, int n
                         int device);
 /* host-side layout pass of the chromatin contact stream (no GPU needed).  roles = warps per
  * chain (0 = the heuristic for smem_bytes of opt-in shared memory, 0 = 227 KiB).  Writes the number
- * of float32 the kernel streams per force evaluation and plan6 = {quads, partner steps, row blocks,
- * roles, slots per row block, chains per CTA}; if out != NULL (capacity floats) fills it. */
+ * of float32 the kernel streams per force evaluation and plan6[8] = {quads, partner steps, row
+ * blocks, roles, slots per row block, chains per CTA, warp-steps per ring stage, ring depth}; if
+ * out != NULL (capacity floats) fills it. */
 int binfb_chromatin_stream_layout(int n_beads, const float *y_pairs, int roles, int smem_bytes,
                                   float *out, long long capacity, long long *n_floats, int *plan6);
 /* FP32 pipe microbenchmarks used as roofline denominators: dependent-chain-free FFMA, packed

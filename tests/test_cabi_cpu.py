@@ -38,13 +38,13 @@ def test_launch_plan_heuristic():
     for n, roles, chains in [(64, 1, 16), (500, 1, 16), (1000, 2, 8), (2000, 4, 4), (5000, 8, 1)]:
         h = _cabi.lib()
         import ctypes as C
-        plan = (C.c_int * 6)()
+        plan = (C.c_int * 8)()
         nf = C.c_longlong()
         _cabi.check(h.binfb_chromatin_stream_layout(n, None, 0, 0, None, 0, C.byref(nf), plan))
         assert (plan[3], plan[5]) == (roles, chains), (n, list(plan))
         # roles never overlap on a partner quad: Lr - ring drift > 31
         if plan[3] > 1:
-            assert plan[4] - 4 * max(4, plan[3]) // plan[3] > 31
+            assert plan[4] - plan[7] * plan[6] // plan[3] > 31
 
 
 @pytest.mark.parametrize("n,roles", [(2, 1), (3, 1), (4, 1), (5, 1), (8, 1), (9, 1), (24, 1),
@@ -57,7 +57,7 @@ def test_contact_stream_covers_every_pair_once(n, roles):
     q, ks, nrb = plan["quads"], plan["partner_steps"], plan["row_blocks"]
     R, lr = plan["roles"], plan["slots_per_row_block"]
     assert q == (n + 3) // 4 and ks == q // 2 and nrb == (q + 31) // 32
-    ss = max(4, R)
+    ss = plan["stage_steps"]
     spr = ss // R
     assert lr == -(-(-(-(ks + 1) // R)) // spr) * spr and (roles == 0 or R == roles)
     assert stream.size % (ss * 128 * 4) == 0          # whole bulk-copy stages
