@@ -1,0 +1,106 @@
+"""Bindable parameter objects (what the reference takes from CSB's
+csb.statistics.pdf.parameterized: setup.py:25, binf/__init__.py:13, binf/example/likelihood.py:3).
+
+A parameter holds a value; it can be *bound* to a base parameter, after which it follows the base
+lazily (the base marks its dependants stale on `set`; they recompute on the next read).  This is
+how a value set on a Posterior reaches the error model inside a Likelihood
+(binf/pdf/posteriors.py:55, binf/pdf/likelihoods.py:87-88, binf/samplers/gibbs.py:54-62)."""
+import numpy as np
+
+
+class ParameterizationError(ValueError):
+    pass
+
+
+class ParameterValueError(ValueError):
+    def __init__(self, name, value):
+        super().__init__("%s = %r" % (name, value))
+        self.name, self.value = name, value
+
+
+class AbstractParameter(object):
+    def __init__(self, value=None, name=None, base=None):
+        self._name = str(name)
+        self._base = None
+        self._followers = []
+        self._stale = False
+        self._value = self._validate(value)
+        if base is not None:
+            self.bind_to(base)
+
+    # hooks -----------------------------------------------------------------------------
+    def _validate(self, value):
+        return value
+
+    def _compute(self, base_value):
+        return base_value
+
+    # API ---------------------------------------------------------------------------------
+    @property
+    def name(self):
+        return self._name
+
+    @property
+    def is_virtual(self):
+        return self._base is not None
+
+    @property
+    def value(self):
+        if self._stale:
+            self._value = self._validate(self._compute(self._base.value))
+            self._stale = False
+        return self._value
+
+    def set(self, value):
+        if self.is_virtual:
+            raise ParameterizationError("a bound parameter cannot be set directly: " + self._name)
+        self._value = self._validate(value)
+        self._stale = False
+        self._mark_followers()
+
+    def bind_to(self, base):
+        node = base
+        while node is not None:
+            if node is self:
+                raise ParameterizationError("circular parameter binding: " + self._name)
+            node = node._base
+        if self._base is not None and self in self._base._followers:
+            self._base._followers.remove(self)
+        self._base = base
+        base._followers.append(self)
+        self._stale = True
+        self._mark_followers()
+
+    def _mark_followers(self):
+        for f in self._followers:
+            f._stale = True
+            f._mark_followers()
+
+    def __repr__(self):
+        return "<%s %s=%r>" % (type(self).__name__, self._name, self.value)
+
+
+class Parameter(AbstractParameter):
+    """Scalar parameter (CSB's `Parameter`).  Batched chains may carry one value per chain: a
+    1-d array is kept as float64 array instead of being coerced with float()."""
+
+    def _validate(self, value):
+        if hasattr(value, "detach"):      # torch tensor: per-chain values living on the device
+            return value
+        try:
+            arr = np.asarray(value, dtype=np.float64)
+        except (TypeError, ValueError):
+            raise ParameterValueError(self._name, value)
+        return float(arr) if arr.ndim == 0 else arr
+
+
+class ArrayParameter(AbstractParameter):
+    """Array-valued parameter (reference: binf/__init__.py:238-244)."""
+
+    def _validate(self, value):
+        if hasattr(value, "detach"):
+            return value
+        try:
+            return np.array(value)
+        except (TypeError, ValueError):
+            raise ParameterValueError(self._name, value)
