@@ -92,6 +92,11 @@ def install():
     global _installed
     if not available():
         raise ImportError("reference tree not found at %s" % REFERENCE_ROOT)
+    # another package may have been registered under the name `binf` (binf_b200.install_as_binf)
+    stale = [k for k, m in sys.modules.items() if (k == "binf" or k.startswith("binf."))
+             and not str(getattr(m, "__file__", "")).startswith(REFERENCE_ROOT)]
+    for k in stale:
+        del sys.modules[k]
     if not _installed:
         if _STANDIN not in sys.path:
             sys.path.insert(0, _STANDIN)

@@ -256,6 +256,11 @@ def test_example_wiring_and_quirks():
     assert rate(post) == 0.2 and rate(cond) == 1.0          # quirk Q2 (example/priors.py:29)
     cond["precision"].set(4.0)                              # reaches the error model lazily
     assert cond.likelihoods["points"].error_model["precision"].value == 4.0
+    import sys
     binf = binf_b200.install_as_binf()
-    from binf.pdf.posteriors import Posterior as P2
-    assert P2 is type(post) and binf.ArrayParameter is ArrayParameter
+    try:
+        from binf.pdf.posteriors import Posterior as P2
+        assert P2 is type(post) and binf.ArrayParameter is ArrayParameter
+    finally:
+        for k in [k for k in sys.modules if k == "binf" or k.startswith("binf.")]:
+            del sys.modules[k]
