@@ -33,6 +33,10 @@ WORKLOADS = {
                       eps=1.5e-3, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, noise=0.05),
     "poly": dict(name="poly_K4_N1000_c65536_L20", n_data=1000, chains=65536, L=20, eps=0.009,
                  tau=2.5),
+    # BASELINE.json configs[4]: one inverse temperature per rank (geometric in [0.05, 1]), 512 chains
+    # per rank, a neighbour swap attempt (NCCL send/recv over NVLink) after every sweep
+    "rex": dict(name="chromatin_n1000_rex_512_per_rank_L20", n_beads=1000, chains=512, L=20,
+                eps=1.5e-3, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, noise=0.05),
 }
 
 
@@ -102,6 +106,7 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------
 def _cpu_worker(args):
     workload, seed, budget_s = args
+    workload = "chromatin" if workload == "rex" else workload
     os.environ["OMP_NUM_THREADS"] = "1"
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import binf_port as port
@@ -195,7 +200,8 @@ def run_ours(args):
     eps0 = args.eps or w["eps"]
     chain_base = rank * C
 
-    if args.workload == "chromatin":
+    rex = None
+    if args.workload in ("chromatin", "rex"):
         y, q_host = chromatin_inputs(w, C, rank)
         model = _cabi.Model.chromatin(w["n_beads"], y, w["alpha"], w["d_c"], w["k_bb"], w["l0"], 0.0,
                                       1.0, 1.0, device=local)
@@ -222,11 +228,28 @@ def run_ours(args):
     stream = torch.cuda.current_stream().cuda_stream
     draw = [0]
 
+    beta = None
+    if args.workload == "rex":
+        from binf_b200.distributed import ReplicaExchange
+        betas = [float(b) for b in np.geomspace(1.0, 0.05, world)] if world > 1 else [1.0]
+        beta = torch.full((C,), betas[rank], device=dev, dtype=torch.float32)
+        rex = ReplicaExchange(rank, world, betas[rank], seed=args.seed)
+        chi2 = torch.zeros(C, device=dev, dtype=torch.float64)
+        chain_base = rank * C
+
+    launches = [0]
+
     def step():
         opts = _cabi.HmcOpts(L, 1, 0, gibbs, 1.05, 0.95, args.seed, draw[0], chain_base)
-        model.hmc_run_device(q, tau, eps, opts, accepted=accepted, n_accepted=nacc, stats=stats,
-                             stream=stream)
+        model.hmc_run_device(q, tau, eps, opts, beta=beta, accepted=accepted, n_accepted=nacc,
+                             stats=stats, stream=stream)
         draw[0] += 1
+        launches[0] += 1
+        if rex is not None and world > 1:
+            model.logprob_grad_device(q, tau, chi2=chi2, stream=stream)
+            t = tau.double()
+            ll = -0.5 * t * chi2 + 0.5 * units * torch.log(t)
+            launches[0] += 1 + (2 if rex.swap(q, tau, ll, betas) is not None else 0)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -245,6 +268,7 @@ def run_ours(args):
           for _ in range(args.steps)]
     sync_all()
     t_wall = time.perf_counter()
+    launches[0] = 0
     for k in range(args.steps):
         if flush is not None:
             flush.fill_(k)                      # L2 flush between timed iterations (not timed)
@@ -270,7 +294,7 @@ def run_ours(args):
 
     # ---- e2e: the same sweep through the host-buffer C-ABI call (pinned host memory) --------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and rex is None:
         qh = torch.from_numpy(q_host.copy()).pin_memory().numpy()
         th = torch.full((C,), tau0, dtype=torch.float32).pin_memory().numpy()
         eh = torch.full((C,), eps0, dtype=torch.float32).pin_memory().numpy()
@@ -335,9 +359,11 @@ def run_ours(args):
                             l2="working set %.0f MB per step > 126 MB L2" % (3 * 4 * C * D / 1e6)
                             if flush is None else "L2 flushed (256 MiB fill) between timed steps",
                             gibbs="precision update fused in front of each trajectory"
-                            if gibbs else "none"),
+                            if gibbs else "none",
+                            replica_exchange=None if rex is None else dict(
+                                betas=betas, swap_rate_rank0=rex.n_swapped / max(1, rex.n_attempted))),
                 acceptance_rate=float(st[0] / st[1]) if st[1] else None,
-                e2e=e2e, gpu_launches=args.steps, wall_ms=wall_ms, clocks=clocks, roofline=roofline,
+                e2e=e2e, gpu_launches=launches[0], wall_ms=wall_ms, clocks=clocks, roofline=roofline,
                 cpu_baseline=cpu)
     print(json.dumps(line))
     if world > 1:
@@ -350,7 +376,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="chromatin", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="chromatin", choices=sorted(WORKLOADS))  # rex: N >= 2
     ap.add_argument("--chains", type=int, default=0)
     ap.add_argument("--eps", type=float, default=0.0)
     ap.add_argument("--seed", type=int, default=2026)
