@@ -763,6 +763,9 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
     if (rc) return rc;
     const ChromPlan &pl = m.plan;
     int W = pl.W;
+    // small batches: rather fewer chains per CTA than idle SMs
+    if ((C + W - 1) / W < sm_count) W = (C + sm_count - 1) / sm_count;
+    if (W > pl.W) W = pl.W;
     if (m.opt_warps > 0 && m.opt_warps < W) W = m.opt_warps;
     if (W > C) W = C;
     if (W < 1) {
