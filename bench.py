@@ -335,9 +335,25 @@ def run_ours(args):
         pass
     mb = _cabi.microbench(local, 3000)
     achieved = flop_per_launch / (ms_kernel * 1e-3) / 1e12
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if args.workload in tj and C == w["chains"]:
+            traffic = tj[args.workload]["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    sfu = None
+    if args.workload in ("chromatin", "rex"):
+        # the binding pipe of the pair kernel: 3 MUFU (rsqrt, ex2, rcp) per bead pair
+        sfu_gops = 3.0 * units * (L + 1) * C / (ms_kernel * 1e-3) / 1e9
+        sfu = dict(ops_per_pair=3, achieved_gops=sfu_gops, peak_gops=mb["mufu_gops"],
+                   frac=sfu_gops / mb["mufu_gops"],
+                   note="MUFU issues at 16 lanes/clk/SM: 24 SMSP-cycles per warp-pair vs 19 on the FMA "
+                        "pipe, so the special-function unit bounds this kernel at 31/(2*24) = 64.6 % of "
+                        "the FP32-FMA peak")
     roofline = dict(
         bound="fp32_fma", achieved=achieved, peak=mb["ffma_tflops"], unit="TFLOP/s",
-        frac=achieved / mb["ffma_tflops"], traffic=None,
+        frac=achieved / mb["ffma_tflops"], traffic=traffic, sfu=sfu,
         peak_source="live FFMA issue microbenchmark in this run (binfb_microbench); "
                     "MEASURED_PEAKS.json has no non-tensor FP32 figure",
         peak_formula_tflops=148 * 128 * 2 * 1.965e9 / 1e12,
