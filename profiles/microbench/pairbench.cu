@@ -103,6 +103,58 @@ __global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) chi_tot += g[r][0].x + g[r][0].y + g[r][1].x + g[r][1].y + g[r][2].x + g[r][2].y;
+    } else if (VAR == 6 || VAR == 7) {
+        // staged: VAR 6 = two half-blocks of 4 packs, VAR 7 = all 8 packs at once
+        constexpr int NP = VAR == 6 ? 4 : 8;
+        float2 nx2[4], ny2[4], nz2[4], g[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            nx2[r] = mk2(-xi[r], -xi[r]), ny2[r] = mk2(-yi[r], -yi[r]), nz2[r] = mk2(-zi[r], -zi[r]);
+            g[r][0] = g[r][1] = g[r][2] = mk2(0.f, 0.f);
+        }
+        const float2 A2 = mk2(A, A), B2 = mk2(B, B);
+        for (int st = 0; st < steps; ++st) {
+            const float4 xj = xs4[b], yj = ys4[b], zj = zs4[b];
+            float4 fx = fx4[b], fy = fy4[b], fz = fz4[b];
+            float2 xj2[2] = {mk2(xj.x, xj.y), mk2(xj.z, xj.w)}, yj2[2] = {mk2(yj.x, yj.y), mk2(yj.z, yj.w)},
+                   zj2[2] = {mk2(zj.x, zj.y), mk2(zj.z, zj.w)};
+            float2 fx2[2] = {mk2(fx.x, fx.y), mk2(fx.z, fx.w)}, fy2[2] = {mk2(fy.x, fy.y), mk2(fy.z, fy.w)},
+                   fz2[2] = {mk2(fz.x, fz.y), mk2(fz.z, fz.w)};
+            const float4 *yb = (const float4 *)ybuf + (st & 3) * 128 + lane;
+            float2 chi2 = mk2(0.f, 0.f);
+#pragma unroll
+            for (int blk = 0; blk < 8 / NP; ++blk) {
+                StagedPairs<false, NP> sp;
+                float2 yv[NP];
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const int r = (blk * NP + p) / 2, h = p & 1;
+                    sp.stage1(p, nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h]);
+                }
+#pragma unroll
+                for (int p = 0; p < NP; ++p) sp.stage2(p, A2, B2);
+#pragma unroll
+                for (int p = 0; p < NP; p += 2) {
+                    const float4 v = yb[((blk * NP + p) / 2) * 32];
+                    yv[p] = mk2(v.x, v.y), yv[p + 1] = mk2(v.z, v.w);
+                }
+#pragma unroll
+                for (int p = 0; p < NP; ++p) sp.stage3(p);
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const int r = (blk * NP + p) / 2, h = p & 1;
+                    sp.stage4(p, yv[p], g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
+                }
+            }
+            fx4[b] = make_float4(fx2[0].x, fx2[0].y, fx2[1].x, fx2[1].y);
+            fy4[b] = make_float4(fy2[0].x, fy2[0].y, fy2[1].x, fy2[1].y);
+            fz4[b] = make_float4(fz2[0].x, fz2[0].y, fz2[1].x, fz2[1].y);
+            chi_tot += chi2.x + chi2.y;
+            if (++b >= Q) b = 0;
+            __syncwarp();
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) chi_tot += g[r][0].x + g[r][0].y + g[r][1].x + g[r][1].y + g[r][2].x + g[r][2].y;
     } else if (VAR == 3) {
         float2 nx2[4], ny2[4], nz2[4], g[4][3];
 #pragma unroll
@@ -178,7 +230,9 @@ __global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const float2 y2 = h ? mk2(yv.z, yv.w) : mk2(yv.x, yv.y);
-                    if (VAR == 2 && (r * 2 + h) < NPOLY)
+                    if (VAR == 5)
+                        pair_packed_sr<false>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2, g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
+                    else if (VAR == 2 && (r * 2 + h) < NPOLY)
                         pair_packed<false, true>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2, g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
                     else
                         pair_packed<false, false>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2, g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
@@ -232,12 +286,10 @@ int main() {
     cudaMemcpy(init, h.data(), 4096 * 4, cudaMemcpyHostToDevice);
     const int sms = p.multiProcessorCount; const double g = clk / 1e6;
     run<1, 0, 512>("packed 4x4", init, out, sms, g);
-    run<4, 0, 512, 32>("row-packed 8x4", init, out, sms, g);
-    run<4, 0, 384, 32>("row-packed 8x4", init, out, sms, g);
-    run<4, 0, 256, 32>("row-packed 8x4", init, out, sms, g);
-    run<4, 2, 512, 32>("row-packed 8x4, 2/16 poly", init, out, sms, g);
-    run<4, 4, 512, 32>("row-packed 8x4, 4/16 poly", init, out, sms, g);
-    run<4, 4, 384, 32>("row-packed 8x4, 4/16 poly", init, out, sms, g);
-    run<4, 6, 384, 32>("row-packed 8x4, 6/16 poly", init, out, sms, g);
+    run<6, 0, 512>("staged 2 x 4 packs", init, out, sms, g);
+    run<7, 0, 512>("staged 8 packs", init, out, sms, g);
+    run<6, 0, 384>("staged 2 x 4 packs", init, out, sms, g);
+    run<7, 0, 384>("staged 8 packs", init, out, sms, g);
+    run<7, 0, 256>("staged 8 packs", init, out, sms, g);
     return 0;
 }
