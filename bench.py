@@ -33,6 +33,9 @@ WORKLOADS = {
                       eps=1.5e-3, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, noise=0.05),
     "poly": dict(name="poly_K4_N1000_c65536_L20", n_data=1000, chains=65536, L=20, eps=0.009,
                  tau=2.5),
+    # BASELINE.json configs[3]: 5000 beads, chains sharded across the GPUs (4 chains per SM and GPU)
+    "chromatin5k": dict(name="chromatin_n5000_c592_L20_gibbs", n_beads=5000, chains=592, L=20,
+                        eps=5e-4, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, noise=0.05),
     # BASELINE.json configs[4]: one inverse temperature per rank (geometric in [0.05, 1]), 512 chains
     # per rank, a neighbour swap attempt (NCCL send/recv over NVLink) after every sweep
     "rex": dict(name="chromatin_n1000_rex_512_per_rank_L20", n_beads=1000, chains=512, L=20,
@@ -106,7 +109,7 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------
 def _cpu_worker(args):
     workload, seed, budget_s = args
-    workload = "chromatin" if workload == "rex" else workload
+    workload = "chromatin" if workload in ("rex", "chromatin5k") else workload
     os.environ["OMP_NUM_THREADS"] = "1"
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import binf_port as port
@@ -201,7 +204,7 @@ def run_ours(args):
     chain_base = rank * C
 
     rex = None
-    if args.workload in ("chromatin", "rex"):
+    if args.workload in ("chromatin", "rex", "chromatin5k"):
         y, q_host = chromatin_inputs(w, C, rank)
         model = _cabi.Model.chromatin(w["n_beads"], y, w["alpha"], w["d_c"], w["k_bb"], w["l0"], 0.0,
                                       1.0, 1.0, device=local)
@@ -343,7 +346,7 @@ def run_ours(args):
     except Exception:
         pass
     sfu = None
-    if args.workload in ("chromatin", "rex"):
+    if args.workload in ("chromatin", "rex", "chromatin5k"):
         # the binding pipe of the pair kernel: 3 MUFU (rsqrt, ex2, rcp) per bead pair
         sfu_gops = 3.0 * units * (L + 1) * C / (ms_kernel * 1e-3) / 1e9
         sfu = dict(ops_per_pair=3, achieved_gops=sfu_gops, peak_gops=mb["mufu_gops"],

@@ -171,7 +171,7 @@ class Model(object):
     def chromatin(cls, n_beads, y_pairs, alpha, d_c, k_bb, l0, conf_s=0.0, gamma_shape=1.0,
                   gamma_rate=1.0, flags=0, device=0, roles=0):
         """roles: warps per chain (0 = heuristic; forcing it is a test hook, flags bits 8..11)."""
-        flags |= (roles & 0xf) << 8
+        flags |= (roles & 0x1f) << 8
         y = f32(y_pairs)
         assert y.shape == (n_beads * (n_beads - 1) // 2,)
         h = C.c_void_p()

@@ -211,7 +211,7 @@ int binfb_model_create_chromatin(int n_beads, const float *y_pairs, double alpha
     cm.alpha = (float)alpha, cm.d_c = (float)d_c, cm.k_bb = (float)k_bb, cm.l0 = (float)l0;
     cm.inv_s2 = conf_s > 0.0 ? (float)(1.0 / (conf_s * conf_s)) : 0.f;
     cm.flags = flags;
-    const int force_roles = (int)((flags >> 8) & 0xf);  // test hook: bits 8..11 force R
+    const int force_roles = (int)((flags >> 8) & 0x1f);  // test hook: bits 8..12 force R
     cm.plan = chrom_plan(n_beads, m->smem_optin, force_roles);
     if (cm.plan.W < 1) {
         delete m;

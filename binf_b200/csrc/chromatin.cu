@@ -642,7 +642,7 @@ static int env_int(const char *name, int dflt) {
 static int chrom_stage_steps(int R) {
     const int ss = env_int("BINFB_CHROM_SS", 0);
     if (ss >= R && ss % R == 0 && (ss / R == 1 || ss / R == 2 || ss / R == 4)) return ss;
-    return R <= 4 ? 4 : 8;  // measured on B200 at n = 1000: 4-step stages x 4 slots beat 8 x 2
+    return R <= 4 ? 4 : R;  // measured on B200 at n = 1000: 4-step stages x 4 slots beat 8 x 2
 }
 static int chrom_ring_depth(int R) {
     const int ns = env_int("BINFB_CHROM_NS", 0);
@@ -655,13 +655,16 @@ ChromPlan chrom_plan(int n, int smem_optin, int force_roles) {
     pl.n_pad = (n + 3) / 4 * 4, pl.Q = pl.n_pad / 4, pl.KS = pl.Q / 2, pl.NRB = (pl.Q + 31) / 32;
     const size_t per_chain = (size_t)6 * pl.n_pad * sizeof(float) + 64;
     int best_R = 1;
-    for (int R = 2; R <= 8; R *= 2) {
+    for (int R = 2; R <= 8; R *= 2) {  // 16 roles (32 KiB stages, 2 slots) measured slower at n = 5000
         const int SS = chrom_stage_steps(R), NS = chrom_ring_depth(R);
         const size_t fixed = (size_t)NS * SS * STEP_BYTES + 128;
         if ((size_t)smem_optin < fixed + per_chain) break;
         const int wmax = (int)(((size_t)smem_optin - fixed) / per_chain);
-        const int Lr = ((pl.KS + 1 + R - 1) / R + SS / R - 1) / (SS / R) * (SS / R);
-        const bool safe = Lr - NS * SS / R >= 40;
+        const int spr = SS / R;
+        const int Lr = ((pl.KS + 1 + R - 1) / R + spr - 1) / spr * spr;
+        // two roles of a chain are at most NS*spr - 1 slots apart (the ring holds NS stages of spr
+        // slots per role); they can only meet on a partner quad if their offsets differ by <= 31
+        const bool safe = Lr - (NS * spr - 1) >= 34;
         // more roles only pay off while the chains alone cannot fill 16 warps
         if (safe && wmax * (R / 2) < 16) best_R = R;
     }
@@ -676,6 +679,7 @@ ChromPlan chrom_plan(int n, int smem_optin, int force_roles) {
     pl.per_chain_smem = per_chain;
     int W = (size_t)smem_optin > pl.fixed_smem ? (int)(((size_t)smem_optin - pl.fixed_smem) / per_chain) : 0;
     if (W > 16 / pl.R) W = 16 / pl.R;
+    if (W < 1 && (size_t)smem_optin >= pl.fixed_smem + per_chain) W = 1;
     pl.W = W;
     pl.stream_floats = (long long)pl.S_pad * pl.R * STEP_FLOAT4 * 4;
     return pl;

@@ -44,7 +44,7 @@ def test_launch_plan_heuristic():
         assert (plan[3], plan[5]) == (roles, chains), (n, list(plan))
         # roles never overlap on a partner quad: Lr - ring drift > 31
         if plan[3] > 1:
-            assert plan[4] - plan[7] * plan[6] // plan[3] > 31
+            assert plan[4] - (plan[7] * plan[6] // plan[3] - 1) > 31
 
 
 @pytest.mark.parametrize("n,roles", [(2, 1), (3, 1), (4, 1), (5, 1), (8, 1), (9, 1), (24, 1),

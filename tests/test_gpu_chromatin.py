@@ -128,6 +128,63 @@ def test_n1000_vs_matrix_free_oracle(gpu, roles):
         assert (r["e_after"][c] - r["e_before"][c]) == pytest.approx(ref["e_after"] - ref["e_before"], abs=2e-2)
 
 
+def test_n5000_eight_warps_per_chain(gpu):
+    """Config-4 size: 5000 beads (12,497,500 pairs per force evaluation), one chain per CTA, 8 warps
+    per chain.  Oracle: float64 forces on a subset of beads (chunked), chi^2 over all pairs."""
+    from binf_b200 import _cabi
+    n, alpha, d_c, k_bb, l0, tau = 5000, 2.0, 2.5, 4.0, 1.0, 120.0
+    X, y = chrom.synthetic_chromatin(n, alpha, d_c, l0, 0.05, seed=7)
+    m = _cabi.Model.chromatin(n, y, alpha, d_c, k_bb, l0)
+    rng = np.random.RandomState(3)
+    C = 3
+    q = X.reshape(-1)[None] + 0.1 * rng.normal(size=(C, 3 * n))
+    logp, grad, chi2 = m.logprob_grad(q, tau)
+    # ---- float64 oracle, chunked over rows --------------------------------------------------
+    iu = np.triu_indices(n, 1)
+    Y = np.zeros((n, n), dtype=np.float32)
+    Y[iu] = y
+    Y = Y + Y.T
+    Xc = q[1].reshape(n, 3)
+    chi2_ref, rows = 0.0, np.r_[0:40, 2480:2520, 4960:5000]
+    f_ref = np.zeros((len(rows), 3))
+    for lo in range(0, n, 500):
+        blk = np.arange(lo, min(n, lo + 500))
+        diff = Xc[blk][:, None, :] - Xc[None, :, :]
+        d = np.sqrt(np.sum(diff * diff, axis=-1) + 1e-12)
+        with np.errstate(over="ignore"):
+            mm = 1.0 / (1.0 + np.exp(alpha * (d - d_c)))
+        res = mm - Y[blk]
+        res[np.arange(len(blk)), blk] = 0.0
+        chi2_ref += 0.5 * np.sum(res * res)
+        sel = np.isin(blk, rows)
+        if sel.any():
+            w = res[sel] * (-alpha) * mm[sel] * (1 - mm[sel]) / d[sel]
+            f_ref[np.isin(rows, blk)] = tau * np.einsum("ij,ija->ia", w, diff[sel])
+    assert chi2[1] == pytest.approx(chi2_ref, rel=1e-5)
+    b = Xc[1:] - Xc[:-1]
+    db = np.sqrt(np.sum(b * b, axis=-1) + 1e-12)
+    cb = (k_bb * (db - l0) / db)[:, None] * b
+    gp = np.zeros((n, 3))
+    gp[1:] += cb
+    gp[:-1] -= cb
+    g = grad[1].reshape(n, 3)
+    assert np.max(np.abs(g[rows] - (f_ref + gp[rows]))) <= 1e-4 * np.max(np.abs(g))
+    e_lik = -0.5 * tau * chi2_ref + 0.5 * len(y) * np.log(tau)
+    e_pri = -0.5 * k_bb * np.sum((db - l0) ** 2) + (1.0 - 1.0) * np.log(tau) - tau * 1.0
+    assert logp[1] == pytest.approx(e_lik + e_pri, rel=1e-5)
+    # pairwise forces sum to zero; log_prob is translation invariant
+    assert np.all(np.abs(grad.reshape(C, n, 3).sum(axis=1)) <= 1e-3 * np.max(np.abs(grad)))
+    logp2, _, _ = m.logprob_grad(q + np.tile([1.0, 2.0, -3.0], n)[None], tau, want_grad=False)
+    np.testing.assert_allclose(logp2, logp, rtol=2e-6)
+    # a short reversible trajectory
+    p0 = rng.normal(size=q.shape)
+    u = np.full(C, 1e-30)
+    fwd = m.hmc_run(q, tau, 0.001, 3, p0=p0, u=u, want_end=True)
+    back = m.hmc_run(fwd["q_end"], tau, 0.001, 3, p0=-fwd["p_end"], u=u, want_end=True)
+    assert np.max(np.abs(back["q_end"] - q)) < 2e-4 * np.max(np.abs(q))
+    assert np.max(np.abs(fwd["e_after"] - fwd["e_before"])) < 1.0
+
+
 def test_reversibility_and_energy_conservation(gpu):
     from binf_b200 import _cabi
     n = 257
