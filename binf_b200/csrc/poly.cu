@@ -57,6 +57,83 @@ __device__ __forceinline__ void poly_row(const float *__restrict__ rowp, const f
     }
 }
 
+// Packed variant for an even number of chains per thread: chains (2*jp, 2*jp+1) share one FFMA2 /
+// FADD2 (two FP32 lanes per instruction, the data row enters as a broadcast scalar operand).  Same
+// arithmetic per chain as poly_row; half the issue slots, so the FMA pipe -- not the issue port --
+// bounds the loop.
+template <int K, int JP, bool ENERGY>
+__device__ __forceinline__ void poly_row2(const float *__restrict__ rowp, const float2 (&c)[JP][K],
+                                          float2 (&acc)[JP][K], float2 (&part)[JP]) {
+    constexpr int S = PolyRow<K>::STRIDE;
+    float row[S];
+#pragma unroll
+    for (int v = 0; v < S / 4; ++v) {
+        const float4 t = reinterpret_cast<const float4 *>(rowp)[v];
+        row[4 * v + 0] = t.x, row[4 * v + 1] = t.y, row[4 * v + 2] = t.z, row[4 * v + 3] = t.w;
+    }
+    const float2 ny = make_float2(-row[K - 1], -row[K - 1]);
+    const float2 x = make_float2(row[0], row[0]);
+#pragma unroll
+    for (int j = 0; j < JP; ++j) {
+        float2 t = c[j][K - 1];
+#pragma unroll
+        for (int k = K - 2; k >= 0; --k) t = __ffma2_rn(t, x, c[j][k]);
+        const float2 res = __fadd2_rn(t, ny);
+        acc[j][0] = __fadd2_rn(acc[j][0], res);
+#pragma unroll
+        for (int k = 1; k < K; ++k) acc[j][k] = __ffma2_rn(res, make_float2(row[k - 1], row[k - 1]), acc[j][k]);
+        if (ENERGY) part[j] = __ffma2_rn(res, res, part[j]);
+    }
+}
+
+template <int K, int G, int J, bool ENERGY>
+__device__ __forceinline__ void poly_chunk2(const float *__restrict__ srows, int n_rows, int g,
+                                            const float (&cs)[J][K], float (&accs)[J][K],
+                                            double (&chi2)[J]) {
+    constexpr int S = PolyRow<K>::STRIDE;
+    constexpr int U = 8, JP = J / 2;
+    float2 c[JP][K], acc[JP][K];
+#pragma unroll
+    for (int j = 0; j < JP; ++j)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            c[j][k] = make_float2(cs[2 * j][k], cs[2 * j + 1][k]);
+            acc[j][k] = make_float2(accs[2 * j][k], accs[2 * j + 1][k]);
+        }
+    const int cnt = (n_rows - g + G - 1) / G;
+    const float *p = srows + (size_t)g * S;
+    int i = 0;
+    for (; i + U <= cnt; i += U) {
+        float2 part[JP];
+#pragma unroll
+        for (int j = 0; j < JP; ++j) part[j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int uu = 0; uu < U; ++uu) poly_row2<K, JP, ENERGY>(p + (size_t)uu * G * S, c, acc, part);
+        p += (size_t)U * G * S;
+        if (ENERGY) {
+#pragma unroll
+            for (int j = 0; j < JP; ++j) chi2[2 * j] += (double)part[j].x, chi2[2 * j + 1] += (double)part[j].y;
+        }
+    }
+    if (i < cnt) {
+        float2 part[JP];
+#pragma unroll
+        for (int j = 0; j < JP; ++j) part[j] = make_float2(0.f, 0.f);
+        for (; i < cnt; ++i) {
+            poly_row2<K, JP, ENERGY>(p, c, acc, part);
+            p += (size_t)G * S;
+        }
+        if (ENERGY) {
+#pragma unroll
+            for (int j = 0; j < JP; ++j) chi2[2 * j] += (double)part[j].x, chi2[2 * j + 1] += (double)part[j].y;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < JP; ++j)
+#pragma unroll
+        for (int k = 0; k < K; ++k) accs[2 * j][k] = acc[j][k].x, accs[2 * j + 1][k] = acc[j][k].y;
+}
+
 // all rows r = g, g+G, ... of a shared-memory chunk
 template <int K, int G, int J, bool ENERGY>
 __device__ __forceinline__ void poly_chunk(const float *__restrict__ srows, int n_rows, int g,
@@ -122,7 +199,8 @@ __device__ __forceinline__ void poly_grad_pass(const PolyDev &pm, float *srows, 
             poly_load_rows(srows, pm.rows + (size_t)r0 * S, n_rows * S);
             __syncthreads();
         }
-        poly_chunk<K, G, J, ENERGY>(srows, n_rows, g, c, graw, chi2);
+        if constexpr (J % 2 == 0) poly_chunk2<K, G, J, ENERGY>(srows, n_rows, g, c, graw, chi2);
+        else poly_chunk<K, G, J, ENERGY>(srows, n_rows, g, c, graw, chi2);
     }
 #pragma unroll
     for (int j = 0; j < J; ++j) {
@@ -168,8 +246,12 @@ __device__ __forceinline__ float draw_tau(const HmcArgs &a, double n_data, doubl
     return (float)(gdraw / rate);
 }
 
+// threads per CTA (one CTA per SM): 28 warps at <= 72 registers for 2 or 4 chains per thread
+// (4 chains with 4 lanes per chain: 16 warps, no register limit that matters)
+constexpr int poly_max_block(int G, int J) { return J == 1 ? 1024 : (J == 4 && G <= 4 ? 512 : 896); }
+
 template <int K, int G, int J>
-__global__ void __launch_bounds__(J == 1 ? 1024 : 896, 1)
+__global__ void __launch_bounds__(poly_max_block(G, J), 1)
     poly_hmc_kernel(PolyDev pm, HmcArgs a, int iters, int rows_per_chunk, int n_chunks) {
     extern __shared__ __align__(16) float srows[];
     constexpr int S = PolyRow<K>::STRIDE;
@@ -333,7 +415,7 @@ __global__ void __launch_bounds__(J == 1 ? 1024 : 896, 1)
 }
 
 template <int K, int G, int J>
-__global__ void __launch_bounds__(J == 1 ? 1024 : 896, 1)
+__global__ void __launch_bounds__(poly_max_block(G, J), 1)
     poly_grad_kernel(PolyDev pm, GradArgs a, int iters, int rows_per_chunk, int n_chunks) {
     extern __shared__ __align__(16) float srows[];
     constexpr int S = PolyRow<K>::STRIDE;
@@ -407,14 +489,20 @@ static bool g_allowed(int K, int G) {
 static PolyPlan poly_plan(const PolyModel &m, int C, int sm_count, int smem_optin) {
     PolyPlan pl;
     pl.J = (m.K == 4 && (long long)C >= 64LL * sm_count) ? 2 : 1;
-    if (m.opt_jchains == 1 || m.opt_jchains == 2) pl.J = (m.K == 4) ? m.opt_jchains : 1;
-    const int max_block = pl.J == 1 ? 1024 : 896;
+    // (4 chains per thread are instantiated for G = 4, 8 but measured slower than 2 x G=4 at C = 65,536:
+    //  3.46 warps per SMSP or register spills at 72 registers; opt in with poly.chains_per_thread = 4)
+    if (m.opt_jchains == 1 || m.opt_jchains == 2 || m.opt_jchains == 4) pl.J = (m.K == 4) ? m.opt_jchains : 1;
+    int max_block = pl.J == 1 ? 1024 : 896;
     const long long tuples = ((long long)C + pl.J - 1) / pl.J;
     // lanes per chain: fill ~max_block threads per SM, the largest power of two that fits
     int G = 1;
     while (G < 32 && tuples * (G * 2) <= (long long)sm_count * max_block) G *= 2;
     if (m.opt_group > 0) G = m.opt_group;
     while (!g_allowed(m.K, G) && G > 1) G /= 2;
+    if (pl.J == 4) {
+        G = G >= 8 ? 8 : 4;  // the only two shapes instantiated for 4 chains per thread
+        max_block = poly_max_block(G, 4);
+    }
     pl.G = G;
     const long long threads = tuples * G;
     long long grid = threads >= 32LL * sm_count ? sm_count : (threads + 31) / 32;
@@ -482,7 +570,10 @@ static int poly_launch_one(Kern kern, const PolyModel &m, const Args &a, const P
         case 2: POLY_DISPATCH_G(KERNEL, 2, 1) break;                                         \
         case 3: POLY_DISPATCH_G(KERNEL, 3, 1) break;                                         \
         case 4:                                                                             \
-            if (pl.J == 2) {                                                                \
+            if (pl.J == 4) {                                                                \
+                if (pl.G == 8) return poly_launch_one(KERNEL<4, 8, 4>, m, a, pl, s);         \
+                return poly_launch_one(KERNEL<4, 4, 4>, m, a, pl, s);                        \
+            } else if (pl.J == 2) {                                                         \
                 POLY_DISPATCH_G_FULL(KERNEL, 4, 2)                                           \
             } else {                                                                        \
                 POLY_DISPATCH_G_FULL(KERNEL, 4, 1)                                           \

@@ -63,7 +63,9 @@ def test_all_template_shapes_agree(gpu):
     g = load_golden("poly_n1000_mode")
     base = None
     for grp in (1, 2, 4, 8, 16, 32):
-        for j in (1, 2):
+        for j in (1, 2, 4):
+            if j == 4 and grp not in (4, 8):
+                continue
             m = make_model(g)
             m.set_option("poly.group", grp), m.set_option("poly.chains_per_thread", j)
             r = m.hmc_run(g["q0"], 2.5, float(g["timestep"]), 20, p0=g["p0"], u=g["u"], want_end=True)
