@@ -111,6 +111,37 @@ __device__ __forceinline__ void pair_packed(float2 nx2, float2 ny2, float2 nz2, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// hybrid shape.  Measured on B200 (profiles/microbench/ffma2_operands.cu): FFMA2 with three distinct
+// register operands occupies the FMA pipe 3.04 cycles (register-bank reads), two-operand packed ops
+// 2.04, a scalar FFMA with three distinct registers 1.15.  So two-operand work stays packed (half
+// the issue slots) and every three-operand FMA -- the six force accumulations and A*d+B -- is
+// scalar: 21.3 instead of 23.5 FMA-pipe cycles per pair.
+// ---------------------------------------------------------------------------------------------
+template <bool ENERGY>
+__device__ __forceinline__ void pair_hybrid(float2 nx2, float2 ny2, float2 nz2, float2 xj2, float2 yj2,
+                                            float2 zj2, float2 y2, float A, float B, float2 &gx2,
+                                            float2 &gy2, float2 &gz2, float2 &fx2, float2 &fy2,
+                                            float2 &fz2, float2 &chi2) {
+    const float2 dx = add2(xj2, nx2), dy = add2(yj2, ny2), dz = add2(zj2, nz2);
+    const float2 r2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, mk2(PAIR_SOFT, PAIR_SOFT))));
+    const float2 inv = mk2(mufu_rsqrt(r2.x), mufu_rsqrt(r2.y));
+    const float2 d = mul2(r2, inv);
+    const float2 e = mk2(mufu_ex2(fmaf(d.x, A, B)), mufu_ex2(fmaf(d.y, A, B)));
+    const float2 sn = fma2(e, mk2(-1.f, -1.f), mk2(-1.f, -1.f));
+    const float2 mn = mk2(mufu_rcp(sn.x), mufu_rcp(sn.y));
+    const float2 rs = add2(mn, y2);
+    const float2 wn = fma2(mn, mn, mn);
+    const float2 coef = mul2(mul2(rs, wn), inv);
+    gx2.x = fmaf(coef.x, dx.x, gx2.x), gx2.y = fmaf(coef.y, dx.y, gx2.y);
+    gy2.x = fmaf(coef.x, dy.x, gy2.x), gy2.y = fmaf(coef.y, dy.y, gy2.y);
+    gz2.x = fmaf(coef.x, dz.x, gz2.x), gz2.y = fmaf(coef.y, dz.y, gz2.y);
+    fx2.x = fmaf(coef.x, dx.x, fx2.x), fx2.y = fmaf(coef.y, dx.y, fx2.y);
+    fy2.x = fmaf(coef.x, dy.x, fy2.x), fy2.y = fmaf(coef.y, dy.y, fy2.y);
+    fz2.x = fmaf(coef.x, dz.x, fz2.x), fz2.y = fmaf(coef.y, dz.y, fz2.y);
+    if (ENERGY) chi2 = fma2(rs, rs, chi2);
+}
+
+// ---------------------------------------------------------------------------------------------
 // packed shape with a shared reciprocal: the two logistic denominators of a pack are inverted with
 // ONE MUFU.RCP of their product (1/a = b / (ab), 1/b = a / (ab)).  t is clamped to <= 30 so that
 // (1 + 2^t)^2 <= 2^61 cannot overflow; the clamp changes m by < 1e-9 (m < 2^-30 there).

@@ -15,9 +15,8 @@ class ForwardModel(AbstractForwardModel):
     """mock_n = sum_k c_k x_n^k  (likelihood.py:24-26)"""
 
     def __init__(self, xses, polynomial):
-        super(ForwardModel, self).__init__("polynomial")
-        self.xses = xses
-        self.polynomial = polynomial
+        AbstractForwardModel.__init__(self, "polynomial")
+        self.xses, self.polynomial = xses, polynomial
         self._register_variable("coefficients", differentiable=True)
         self.update_var_param_types(coefficients=ArrayParameter)
         self._set_original_variables()
@@ -42,9 +41,9 @@ class ForwardModel(AbstractForwardModel):
             "inside the fused kernel (reference: binf/pdf/likelihoods.py:148-155)")
 
     def clone(self):
-        copy = self.__class__(self.xses, self.polynomial)
-        self._set_parameters(copy)
-        return copy
+        twin = type(self)(self.xses, self.polynomial)
+        self._set_parameters(twin)
+        return twin
 
 
 class GaussianErrorModel(AbstractErrorModel):
@@ -52,11 +51,11 @@ class GaussianErrorModel(AbstractErrorModel):
     with the forward model on the device."""
 
     def __init__(self, ys):
-        super(GaussianErrorModel, self).__init__("error_model")
+        AbstractErrorModel.__init__(self, "error_model")
         self.ys = ys
-        self._register_variable("mock_data")
-        self._register_variable("precision")
-        self.update_var_param_types(mock_data=ArrayParameter, precision=ScalarParameter)
+        for variable, kind in (("mock_data", ArrayParameter), ("precision", ScalarParameter)):
+            self._register_variable(variable)
+            self.update_var_param_types(**{variable: kind})
         self._set_original_variables()
 
     def _evaluate_log_prob(self, mock_data, precision):
@@ -67,9 +66,9 @@ class GaussianErrorModel(AbstractErrorModel):
     _evaluate_gradient = _evaluate_log_prob
 
     def clone(self):
-        copy = self.__class__(self.ys)
-        copy.set_fixed_variables_from_pdf(self)
-        return copy
+        twin = type(self)(self.ys)
+        twin.set_fixed_variables_from_pdf(self)
+        return twin
 
 
 def make_likelihood(xses, ys, polynomial):

@@ -1,63 +1,70 @@
-"""Gamma prior on the precision, Gaussian prior on the coefficients
-(reference: binf/example/priors.py:10-73).  Scalar closed forms; they enter the device log_prob as
-model constants (binfb_model_create_polynomial / binfb_model_set_gamma_prior)."""
+"""Priors of the polynomial example: Gamma on the precision, Gaussian on the coefficients
+(binf/example/priors.py:10-73).  Closed forms of O(K) scalars; in a lowered Posterior they are model
+constants of the CUDA kernels (binfb_model_create_polynomial / binfb_model_set_gamma_prior)."""
 import numpy as np
 
 from binf_b200 import ArrayParameter
 from binf_b200.params import Parameter as ScalarParameter
 from binf_b200.pdf.priors import AbstractPrior
 
-# The reference's GammaPrior.clone passes `shape` twice (priors.py:29), so every conditional pdf
-# carries rate == shape (quirk Q2).  Reproduced by default; set to True for the intended behaviour.
+# Quirk Q2: the reference's GammaPrior.clone hands `shape` to both constructor arguments
+# (priors.py:29), so every conditional pdf -- they are all made through clone() -- has rate == shape.
+# Reproduced unless this switch is set.
 FIX_GAMMA_CLONE = False
 
 
+def _declare(prior, variable, param_type, differentiable=False):
+    prior._register_variable(variable, differentiable=differentiable)
+    prior.update_var_param_types(**{variable: param_type})
+    prior._set_original_variables()
+
+
 class GammaPrior(AbstractPrior):
+    """log p(tau) = (shape - 1) log tau - rate * tau   (priors.py:23-25)"""
+
     def __init__(self, shape, rate):
-        super(GammaPrior, self).__init__("precision_prior")
-        self.shape = shape
-        self.rate = rate
-        self._register_variable("precision")
-        self.update_var_param_types(precision=ScalarParameter)
-        self._set_original_variables()
+        AbstractPrior.__init__(self, "precision_prior")
+        self.shape, self.rate = shape, rate
+        _declare(self, "precision", ScalarParameter)
 
     def _evaluate_log_prob(self, precision):
-        return (self.shape - 1.0) * np.log(precision) - precision * self.rate
+        return (self.shape - 1.0) * np.log(precision) - self.rate * precision
 
     def clone(self):
-        copy = self.__class__(self.shape, self.rate if FIX_GAMMA_CLONE else self.shape)
-        copy.set_fixed_variables_from_pdf(self)
-        return copy
+        twin = type(self)(self.shape, self.rate if FIX_GAMMA_CLONE else self.shape)
+        twin.set_fixed_variables_from_pdf(self)
+        return twin
 
 
 class GaussianPrior(AbstractPrior):
-    """-1/2 sum (c - mu)^2 / v.  `differentiable=False` by default like the reference
-    (priors.py:45), which makes Posterior.gradient skip it (quirk Q1); pass differentiable=True
-    to include the force (c - mu)/v (device flag BINFB_FLAG_PRIOR_GRAD)."""
+    """log p(c) = -1/2 sum (c - means)^2 / variances   (priors.py:49-54).
+
+    Registered non-differentiable like the reference (priors.py:45), so Posterior.gradient leaves
+    its force out (quirk Q1); `differentiable=True` includes (c - means)/variances
+    (BINFB_FLAG_PRIOR_GRAD on the device)."""
 
     def __init__(self, means, variances, differentiable=False):
-        super(GaussianPrior, self).__init__("coefficients_prior")
-        self._register("means")
-        self._register("variances")
-        self["means"] = ArrayParameter(means, "means")
-        self["variances"] = ArrayParameter(variances, "variances")
-        self._differentiable = differentiable
-        self._register_variable("coefficients", differentiable=differentiable)
-        self.update_var_param_types(coefficients=ArrayParameter)
-        self._set_original_variables()
+        AbstractPrior.__init__(self, "coefficients_prior")
+        for key, value in (("means", means), ("variances", variances)):
+            self._register(key)
+            self[key] = ArrayParameter(value, key)
+        self._differentiable = bool(differentiable)
+        _declare(self, "coefficients", ArrayParameter, self._differentiable)
+
+    def _z(self, coefficients):
+        return np.asarray(coefficients, dtype=np.float64) - self["means"].value
 
     def _evaluate_log_prob(self, coefficients):
-        c = np.asarray(coefficients, dtype=np.float64)
-        return -0.5 * np.sum((c - self["means"].value) ** 2 / self["variances"].value, axis=-1)
+        return -0.5 * np.sum(self._z(coefficients) ** 2 / self["variances"].value, axis=-1)
 
     def _evaluate_gradient(self, coefficients):
-        return (np.asarray(coefficients, dtype=np.float64) - self["means"].value) / self["variances"].value
+        return self._z(coefficients) / self["variances"].value
 
     def clone(self):
-        return self.__class__(self["means"].value, self["variances"].value, self._differentiable)
+        return type(self)(self["means"].value, self["variances"].value, self._differentiable)
 
 
 def make_priors():
-    pp = GammaPrior(1.0, 0.2)
-    cp = GaussianPrior(means=np.zeros(4), variances=np.ones(4) * 5)
-    return {pp.name: pp, cp.name: cp}
+    """the priors example_script.py uses: Gamma(1, 0.2) and N(0, 5 I_4)  (priors.py:67-73)"""
+    priors = (GammaPrior(1.0, 0.2), GaussianPrior(means=np.zeros(4), variances=np.full(4, 5.0)))
+    return {p.name: p for p in priors}

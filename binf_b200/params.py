@@ -104,3 +104,46 @@ class ArrayParameter(AbstractParameter):
             return np.array(value)
         except (TypeError, ValueError):
             raise ParameterValueError(self._name, value)
+
+
+class ParameterNotFoundError(AttributeError):
+    """raised when a parameter name is not registered (binf/pdf/__init__.py:14)"""
+
+
+class ParameterRegistry(object):
+    """Ordered name -> parameter-object table shared by pdfs and models.  A name has to be
+    registered before an object can be stored under it; `_accepts` lets a subclass restrict what
+    may be stored."""
+
+    def _init_registry(self):
+        self._table = {}
+
+    def _register(self, name):
+        self._table.setdefault(name, None)
+
+    def _accepts(self, name, obj):
+        return True
+
+    def __getitem__(self, name):
+        try:
+            return self._table[name]
+        except KeyError:
+            raise ParameterNotFoundError(name)
+
+    def __setitem__(self, name, obj):
+        if name not in self._table:
+            raise ParameterNotFoundError(name)
+        if not self._accepts(name, obj):
+            raise TypeError(obj)
+        self._table[name] = obj
+
+    @property
+    def parameters(self):
+        return tuple(self._table)
+
+    def get_params(self):
+        return list(self._table.values())
+
+    def _fixed_values(self, original):
+        """values of the parameters that started life as variables"""
+        return {n: self._table[n].value for n in self._table if n in original}

@@ -1,54 +1,23 @@
-"""PDF base class (reference: binf/pdf/__init__.py:14-160)."""
-from collections import OrderedDict
-
+"""PDF base class: named variables + bindable parameters + log_prob / gradient / conditioning
+(the role of binf/pdf/__init__.py:14-160 in the reference)."""
 import numpy as np
 
 from binf_b200 import AbstractBinfNamedCallable
-from binf_b200.params import AbstractParameter
+from binf_b200.params import AbstractParameter, ParameterNotFoundError, ParameterRegistry  # noqa: F401
 
 
-class ParameterNotFoundError(AttributeError):
-    pass
-
-
-class AbstractBinfPDF(AbstractBinfNamedCallable):
-    """A density with named variables and a registry of bindable parameters
-    (CSB's ParameterizedDensity + AbstractBinfNamedCallable in the reference)."""
-
+class AbstractBinfPDF(ParameterRegistry, AbstractBinfNamedCallable):
     def __init__(self, name="", **args):
         AbstractBinfNamedCallable.__init__(self, name)
-        self._params = OrderedDict()
+        self._init_registry()
         self._var_param_types = {}
 
-    # -- parameter registry ------------------------------------------------------------------
-    def _register(self, name):
-        if name not in self._params:
-            self._params[name] = None
-
-    def __getitem__(self, param):
-        if param in self._params:
-            return self._params[param]
-        raise ParameterNotFoundError(param)
-
-    def __setitem__(self, param, value):
-        if param not in self._params:
-            raise ParameterNotFoundError(param)
-        if not isinstance(value, AbstractParameter):
-            raise TypeError(value)
-        self._params[param] = value
-
-    @property
-    def parameters(self):
-        return tuple(self._params)
-
-    def get_params(self):
-        return [self._params[n] for n in self.parameters]
+    def _accepts(self, name, obj):
+        return isinstance(obj, AbstractParameter)
 
     def set_params(self, *values, **named):
-        for p, v in zip(self.parameters, values):
-            self[p] = v
-        for p, v in named.items():
-            self[p] = v
+        for key, obj in list(zip(self.parameters, values)) + list(named.items()):
+            self[key] = obj
 
     @property
     def estimator(self):
@@ -57,35 +26,36 @@ class AbstractBinfPDF(AbstractBinfNamedCallable):
     def estimate(self, data):
         raise NotImplementedError
 
-    # -- evaluation ------------------------------------------------------------------------
+    # ---- evaluation: fixed parameters are merged into the keyword arguments first -------------
+    def _complete_variables(self, variables):
+        variables.update(self._fixed_values(self._original_variables))
+
     def _evaluate_log_prob(self, **variables):
         raise NotImplementedError
-
-    def _evaluate(self, **variables):
-        return np.exp(np.clip(self.log_prob(**variables), -308.0, 709.0))
 
     def log_prob(self, **variables):
         self._complete_variables(variables)
         return self._evaluate_log_prob(**variables)
 
     def gradient(self, **variables):
-        """Gradient of the ENERGY -log p (the sign HMCSampler._leapfrog expects, hmc.py:116)."""
+        """gradient of the ENERGY -log p, the sign HMCSampler._leapfrog subtracts (hmc.py:116)"""
         self._complete_variables(variables)
         return self._evaluate_gradient(**variables)
 
-    def _complete_variables(self, variables):
-        variables.update({p: self[p].value for p in self.parameters if p in self._original_variables})
+    def _evaluate(self, **variables):
+        return np.exp(np.clip(self.log_prob(**variables), -308.0, 709.0))
 
-    # -- conditioning -------------------------------------------------------------------------
+    # ---- conditioning ------------------------------------------------------------------------
     def clone(self):
         raise NotImplementedError
 
     def conditional_factory(self, **fixed_vars):
-        """A copy with some variables frozen to the given values (pdf/__init__.py:49-70)."""
-        result = self.clone()
-        result.fix_variables(**self._get_variables_intersection(fixed_vars))
-        return result
+        """copy of this pdf with the given variables frozen (pdf/__init__.py:49-70)"""
+        conditioned = self.clone()
+        conditioned.fix_variables(**self._get_variables_intersection(fixed_vars))
+        return conditioned
 
     def set_fixed_variables_from_pdf(self, pdf):
-        values = {p: pdf[p].value for p in pdf.parameters if p not in self.parameters}
-        self.fix_variables(**self._get_variables_intersection(values))
+        """freeze here whatever `pdf` has frozen and this object has not (pdf/__init__.py:142-151)"""
+        theirs = {n: pdf[n].value for n in pdf.parameters if n not in self.parameters}
+        self.fix_variables(**self._get_variables_intersection(theirs))

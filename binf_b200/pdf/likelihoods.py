@@ -65,42 +65,40 @@ class Likelihood(AbstractBinfPDF):
         return fwm, em
 
     # -- evaluation ------------------------------------------------------------------------------
-    def _lowered(self, variables):
+    def _device(self, variables):
+        """the fused device evaluation of this likelihood, or None for user-defined models"""
         from binf_b200.lowering import lower
-        try:
-            low = lower(self, n_coeff=self._n_free(variables))
-        except Exception:
-            raise
-        return low
+        coeffs = variables.get("coefficients")
+        return lower(self, n_coeff=None if coeffs is None else int(np.shape(coeffs)[-1]))
 
-    def _n_free(self, variables):
-        v = variables.get("coefficients")
-        return None if v is None else int(np.shape(v)[-1])
+    def _host_pieces(self, variables):
+        """generic plumbing for user-defined models: mock data and the error model's arguments"""
+        fwm_args, em_args = self._split_variables(variables)
+        return self.forward_model(**fwm_args), fwm_args, em_args
 
     def _evaluate_log_prob(self, **variables):
-        low = self._lowered(variables)
-        if low is not None:  # fused on the device: forward model + error model + reduction
-            return low.log_prob(variables[low.variable], variables)
-        fwm_variables, em_variables = self._split_variables(variables)
-        mock_data = self.forward_model(**fwm_variables)
-        return self.error_model.log_prob(mock_data=mock_data, **em_variables)
+        dev = self._device(variables)
+        if dev is not None:  # forward model + error model + reduction in one kernel
+            return dev.log_prob(variables[dev.variable], variables)
+        mock, _, em_args = self._host_pieces(variables)
+        return self.error_model.log_prob(mock_data=mock, **em_args)
 
     def _evaluate_gradient(self, **variables):
-        low = self._lowered(variables)
-        if low is not None:  # J(theta).dot(dE/dmock) without ever forming J
-            return low.gradient(variables[low.variable], variables)
-        fwm_variables, em_variables = self._split_variables(variables)
-        mock_data = self.forward_model(**fwm_variables)
-        jac = self.forward_model.jacobi_matrix(**fwm_variables)
-        em_grad = self.error_model.gradient(mock_data=mock_data, **em_variables)
-        return jac.dot(em_grad)
+        dev = self._device(variables)
+        if dev is not None:  # J(theta) . dE/dmock without ever forming J (likelihoods.py:148-155)
+            return dev.gradient(variables[dev.variable], variables)
+        mock, fwm_args, em_args = self._host_pieces(variables)
+        jacobian = self.forward_model.jacobi_matrix(**fwm_args)
+        return jacobian.dot(self.error_model.gradient(mock_data=mock, **em_args))
 
     def clone(self):
-        return self.__class__(self.name, self.forward_model.clone(), self.error_model.clone())
+        return type(self)(self.name, self.forward_model.clone(), self.error_model.clone())
 
     def conditional_factory(self, **fixed_vars):
-        fwm = self.forward_model.clone()
-        fwm.fix_variables(**fwm._get_variables_intersection(fixed_vars))
-        em = self.error_model.conditional_factory(
-            **self.error_model._get_variables_intersection(fixed_vars))
-        return self.__class__(self.name, fwm, em)
+        """freeze variables in copies of both components and wire a new likelihood around them
+        (likelihoods.py:165-174)"""
+        model = self.forward_model.clone()
+        model.fix_variables(**model._get_variables_intersection(fixed_vars))
+        errors = self.error_model
+        errors = errors.conditional_factory(**errors._get_variables_intersection(fixed_vars))
+        return type(self)(self.name, model, errors)

@@ -230,7 +230,9 @@ __global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const float2 y2 = h ? mk2(yv.z, yv.w) : mk2(yv.x, yv.y);
-                    if (VAR == 5)
+                    if (VAR == 8)
+                        pair_hybrid<false>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A, B, g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
+                    else if (VAR == 5)
                         pair_packed_sr<false>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2, g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
                     else if (VAR == 2 && (r * 2 + h) < NPOLY)
                         pair_packed<false, true>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2, g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
@@ -285,11 +287,9 @@ int main() {
     float *init, *out; cudaMalloc(&init, 4096 * 4); cudaMalloc(&out, (1 + 148 * 64) * 4);
     cudaMemcpy(init, h.data(), 4096 * 4, cudaMemcpyHostToDevice);
     const int sms = p.multiProcessorCount; const double g = clk / 1e6;
+    run<0, 0, 512>("scalar", init, out, sms, g);
     run<1, 0, 512>("packed 4x4", init, out, sms, g);
-    run<6, 0, 512>("staged 2 x 4 packs", init, out, sms, g);
-    run<7, 0, 512>("staged 8 packs", init, out, sms, g);
-    run<6, 0, 384>("staged 2 x 4 packs", init, out, sms, g);
-    run<7, 0, 384>("staged 8 packs", init, out, sms, g);
-    run<7, 0, 256>("staged 8 packs", init, out, sms, g);
+    run<8, 0, 512>("hybrid: packed 2-operand ops, scalar FMAs", init, out, sms, g);
+    run<8, 0, 384>("hybrid: packed 2-operand ops, scalar FMAs", init, out, sms, g);
     return 0;
 }
