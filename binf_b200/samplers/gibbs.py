@@ -118,14 +118,13 @@ class GibbsSampler(object):
         prior = gam._get_prior()
         low.model.set_gamma_prior(prior.shape, prior.rate)
         q = self._state.variables[other]
+        n_adapt = int(np.clip(hmc.timestep_adaption_limit - 1 - hmc.counter, 0, 1))
         if _is_tensor(q):
-            raise NotImplementedError("fused Gibbs sweeps on device-resident state: use "
-                                      "binf_b200.distributed.ChainShard")
+            return self._sample_fused_device(hmc, gam, other, mode, low, q, n_adapt)
         single = np.ndim(q) == 1
         q2 = np.asarray(q, dtype=np.float64).reshape(-1, low.dim)
         n = len(q2)
         tau = np.broadcast_to(np.asarray(self._state.variables["precision"], dtype=np.float64), (n,))
-        n_adapt = int(np.clip(hmc.timestep_adaption_limit - 1 - hmc.counter, 0, 1))
         r = low.model.hmc_run(q2, tau, hmc._eps, hmc.nsteps, beta=low.beta(n), n_adapt=n_adapt,
                               adapt_up=hmc.adaption_uprate, adapt_down=hmc.adaption_downrate,
                               gibbs_mode=mode, seed=hmc.seed, draw=hmc._draw, chain_base=hmc.chain_base)
@@ -139,6 +138,38 @@ class GibbsSampler(object):
         hmc._state = new_q[0] if single else new_q
         gam.state = float(new_tau[0]) if single else new_tau
         self._update_state(**{other: hmc._copy_state(hmc._state), "precision": gam.state})
+        low.refresh()
+        return self._state
+
+    def _sample_fused_device(self, hmc, gam, other, mode, low, q, n_adapt):
+        """chains resident in HBM: q [C, D] and precision [C] are CUDA tensors updated in place"""
+        import torch
+        from binf_b200 import _cabi
+        n, dev = q.shape[0], q.device
+        tau = self._state.variables["precision"]
+        if not hasattr(tau, "data_ptr"):
+            tau = torch.as_tensor(np.broadcast_to(np.asarray(tau, dtype=np.float32), (n,)).copy(), device=dev)
+        tau = tau.to(torch.float32).contiguous()
+        hmc.state = q
+        if hmc._eps_dev is None:
+            hmc._eps_dev = torch.as_tensor(hmc._eps, dtype=torch.float32, device=dev)
+            hmc._acc_dev = torch.zeros(n, dtype=torch.uint8, device=dev)
+            hmc._nacc_dev = torch.zeros(n, dtype=torch.int32, device=dev)
+            hmc._e0_dev = torch.zeros(n, dtype=torch.float64, device=dev)
+            hmc._e1_dev = torch.zeros(n, dtype=torch.float64, device=dev)
+        beta = low.beta(n)
+        beta_dev = None if beta is None else torch.as_tensor(beta, dtype=torch.float32, device=dev)
+        opts = _cabi.HmcOpts(hmc.nsteps, 1, n_adapt, mode, hmc.adaption_uprate, hmc.adaption_downrate,
+                             hmc.seed, hmc._draw, hmc.chain_base)
+        low.model.hmc_run_device(q, tau, hmc._eps_dev, opts, beta=beta_dev, accepted=hmc._acc_dev,
+                                 e_before=hmc._e0_dev, e_after=hmc._e1_dev, n_accepted=hmc._nacc_dev,
+                                 stream=torch.cuda.current_stream().cuda_stream)
+        hmc.counter += 1
+        hmc._draw += 1
+        hmc.n_accepted = hmc.n_accepted + hmc._nacc_dev.to(torch.int64)
+        hmc._last_move_accepted = hmc._acc_dev.bool()
+        gam.state = tau
+        self._update_state(**{other: q, "precision": tau})
         low.refresh()
         return self._state
 

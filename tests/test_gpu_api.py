@@ -169,3 +169,41 @@ def test_device_resident_state(gpu):
     for _ in range(5):
         s.sample()
     assert s.counter == 6 and 0.0 < s.acceptance_rate <= 1.0
+
+
+def test_fused_gibbs_on_device_resident_state_matches_host_path(gpu):
+    """the same fused sweeps with numpy state (host buffers) and with CUDA tensors (chains never
+    leave HBM): identical Philox streams => identical chains"""
+    import torch
+    import chromatin_port as chrom
+    from binf_b200.chromatin import make_chromatin_posterior
+    from binf_b200.example.samplers import GammaSampler
+    from binf_b200.samplers import BinfState
+    from binf_b200.samplers.gibbs import GibbsSampler
+    from binf_b200.samplers.hmc import HMCSampler
+    n, C = 64, 48
+    X, y = chrom.synthetic_chromatin(n, seed=11)
+    rng = np.random.RandomState(5)
+    q0 = (X.reshape(-1)[None] + 0.05 * rng.normal(size=(C, 3 * n))).astype(np.float32)
+
+    def build(structure, precision):
+        post = make_chromatin_posterior(n, y)
+        hmc = HMCSampler(post.conditional_factory(precision=precision), structure, 0.003, 8,
+                         timestep_adaption_limit=4, variable_name="structure", seed=21)
+        gam = GammaSampler(post.conditional_factory(structure=structure), precision, seed=22)
+        return GibbsSampler(post, BinfState(dict(structure=structure, precision=precision)),
+                            {"structure": hmc, "precision": gam})
+
+    host = build(q0.astype(np.float64), np.full(C, 100.0))
+    dev = build(torch.as_tensor(q0, device="cuda"), torch.full((C,), 100.0, device="cuda"))
+    assert host._fused_plan() is not None and dev._fused_plan() is not None
+    for _ in range(5):
+        sh, sd = host.sample(), dev.sample()
+    torch.cuda.synchronize()
+    qd = sd.variables["structure"].cpu().numpy()
+    np.testing.assert_allclose(qd, sh.variables["structure"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(sd.variables["precision"].cpu().numpy(), sh.variables["precision"], rtol=1e-6)
+    hh, hd = host.subsamplers["structure"], dev.subsamplers["structure"]
+    assert hh.acceptance_rate == pytest.approx(hd.acceptance_rate)
+    np.testing.assert_allclose(hd.timestep, hh.timestep, rtol=1e-6)
+    assert 100.0 < np.median(sh.variables["precision"]) < 1000.0     # noise sd 0.05 => tau ~ 400
