@@ -175,3 +175,55 @@ def test_rng_streams(gpu):
     assert abs(gm.mean() / 250.0 - 1) < 0.005 and abs(gm.var() / 250.0 - 1) < 0.1
     n2, _, _ = _cabi.rng_fill(seed=3, draw=7, chain_base=101, n_chains=4095, dim=64)
     assert np.array_equal(n[1:], n2)   # keyed by global chain id => sharding-invariant
+
+
+def test_harmonic_oscillator_closed_form(gpu):
+    """K = 1: E(c) = 1/2 tau sum (c - y_n)^2 is a 1-D harmonic oscillator with k = tau N around the
+    data mean, for which one leapfrog step is a known linear map."""
+    from binf_b200 import _cabi
+    rng = np.random.RandomState(3)
+    N, tau, eps, L = 64, 1.7, 0.013, 9
+    xs, ys = np.linspace(-1, 1, N), rng.normal(size=N)
+    m = _cabi.Model.polynomial(xs, ys, 1, np.zeros(1), np.full(1, 1e30), 1.0, 1.0)
+    C = 257
+    q0, p0 = rng.normal(size=(C, 1)), rng.normal(size=(C, 1))
+    r = m.hmc_run(q0, tau, eps, L, p0=p0, u=np.full(C, 1e-30), want_end=True)
+    k, x0 = tau * N, ys.mean()
+    # kick-drift-kick step as a matrix acting on (q - x0, p)
+    half = np.array([[1.0, 0.0], [-0.5 * eps * k, 1.0]])
+    drift = np.array([[1.0, eps], [0.0, 1.0]])
+    step = np.linalg.matrix_power(half.dot(drift).dot(half), L)
+    z = step.dot(np.vstack([q0[:, 0] - x0, p0[:, 0]]))
+    np.testing.assert_allclose(r["q_end"][:, 0], z[0] + x0, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(r["p_end"][:, 0], z[1], rtol=2e-5, atol=2e-4)
+    # energy error O((eps omega)^2) relative, and exact reversibility to fp32 round-off
+    assert np.max(np.abs(r["e_after"] - r["e_before"]) / np.abs(r["e_before"])) < (eps ** 2 * k)
+    back = m.hmc_run(r["q_end"], tau, eps, L, p0=-r["p_end"], u=np.full(C, 1e-30), want_end=True)
+    np.testing.assert_allclose(back["q_end"], q0, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(back["p_end"], -p0, rtol=1e-4, atol=1e-4)
+
+
+def test_acceptance_rate_parity_with_reference_sampler(gpu):
+    """L = 20, N = 1000: acceptance rate of 32,768 device chain-trajectories (Philox momenta) vs
+    12,288 chain-trajectories of the CPU port of the reference sampler, same equilibrium ensemble:
+    difference < 1 % absolute."""
+    g = load_golden("poly_n1000_mode")
+    xs, ys, tau = g["xs"], g["ys"], 2.5
+    V = np.vstack([xs ** i for i in range(4)])
+    A = tau * V.dot(V.T) + np.diag(1.0 / g["prior_variances"])
+    mean, cov = np.linalg.solve(A, tau * V.dot(ys)), np.linalg.inv(A)
+    rng = np.random.RandomState(9)
+    pp = port.PolynomialPosterior(xs, ys, g["prior_means"], g["prior_variances"], 1.0, 1.0)
+    eps, L = 0.0105, 20
+    m = make_model(g)
+    C = 32768
+    r = m.hmc_run(rng.multivariate_normal(mean, cov, size=C), tau, eps, L, seed=123)
+    acc_gpu = r["accepted"].mean()
+    qc = rng.multivariate_normal(mean, cov, size=12288)
+    rc = port.hmc_sample(lambda q: pp.log_prob(q, tau), lambda q: pp.gradient(q, tau), qc, eps, L,
+                         rng.normal(size=qc.shape), rng.uniform(size=len(qc)))
+    acc_cpu = rc["accepted"].mean()
+    assert 0.5 < acc_cpu < 0.98
+    assert abs(acc_gpu - acc_cpu) < 0.01 + 3 * np.sqrt(0.25 / 12288)
+    # mean Metropolis probability from the device diagnostics agrees with the accept fraction
+    assert abs(r["stats"][3] / r["stats"][1] - acc_gpu) < 0.01
