@@ -14,6 +14,11 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the shared library is a build artefact (git-ignored): compile it when the checkout is fresh
+    # (nvcc cross-compiles sm_100a without a GPU; incremental builds are no-ops)
+    from binf_b200 import _cabi, build
+    if not os.path.exists(_cabi.LIB_PATH):
+        build.build()
 
 
 def load_golden(name):
