@@ -33,6 +33,27 @@ def test_error_reporting_without_gpu():
     assert rc == _cabi.EINVAL and b"null model" in handle.binfb_last_error()
 
 
+def test_argument_validation_needs_no_gpu():
+    import ctypes as C
+    h = _cabi.lib()
+    out = C.c_void_p()
+    xs = np.zeros(4)
+    # more coefficients than the kernels are instantiated for -> EUNSUPPORTED, before any CUDA call
+    rc = h.binfb_model_create_polynomial(_cabi.ptr(xs), _cabi.ptr(xs), 4, 9, None, None, 1.0, 1.0, 0, 0, C.byref(out))
+    assert rc == _cabi.EUNSUPPORTED and b"n_coeff" in h.binfb_last_error()
+    rc = h.binfb_model_create_polynomial(None, _cabi.ptr(xs), 4, 4, None, None, 1.0, 1.0, 0, 0, C.byref(out))
+    assert rc == _cabi.EINVAL
+    rc = h.binfb_model_create_chromatin(1, _cabi.ptr(xs.astype(np.float32)), 2.0, 2.5, 1.0, 1.0, 0.0, 1.0, 1.0, 0, 0, C.byref(out))
+    assert rc == _cabi.EINVAL and b"n_beads" in h.binfb_last_error()
+    assert h.binfb_hmc_run(None, None, None, None, None, 1, None, *([None] * 11)) == _cabi.EINVAL
+    assert h.binfb_chromatin_stream_layout(1000, None, 3, 0, None, 0, None, None) == _cabi.EINVAL   # roles not a power of 2
+    # a structure that cannot fit one chain in shared memory is refused by the plan (chains per CTA = 0)
+    plan = (C.c_int * 8)()
+    nf = C.c_longlong()
+    _cabi.check(h.binfb_chromatin_stream_layout(12000, None, 0, 0, None, 0, C.byref(nf), plan))
+    assert plan[5] == 0
+
+
 def test_launch_plan_heuristic():
     y = np.zeros(1, dtype=np.float32)
     for n, roles, chains in [(64, 1, 16), (500, 1, 16), (1000, 2, 8), (2000, 4, 4), (5000, 8, 1)]:

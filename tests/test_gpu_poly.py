@@ -227,3 +227,48 @@ def test_acceptance_rate_parity_with_reference_sampler(gpu):
     assert abs(acc_gpu - acc_cpu) < 0.01 + 3 * np.sqrt(0.25 / 12288)
     # mean Metropolis probability from the device diagnostics agrees with the accept fraction
     assert abs(r["stats"][3] / r["stats"][1] - acc_gpu) < 0.01
+
+
+def test_error_behaviour_and_edge_shapes(gpu):
+    from binf_b200 import _cabi
+    g = load_golden("poly_n20")
+    m = make_model(g)
+    with pytest.raises(_cabi.BinfB200Error) as e:      # injected momenta need n_traj == 1
+        m.hmc_run(g["q0"], 2.5, 0.02, 5, n_traj=2, p0=g["p0"])
+    assert e.value.code == _cabi.EINVAL
+    with pytest.raises(_cabi.BinfB200Error):
+        m.hmc_run(g["q0"], 2.5, 0.02, 0)               # L >= 1
+    # a single chain, a single datum, chain counts that are not multiples of anything
+    one = m.hmc_run(g["q0"][:1], 2.5, 0.02, 20, p0=g["p0"][:1], u=g["u"][:1], want_end=True)
+    assert np.all(np.abs(one["q_end"][0] - g["q_end"][0]) <= 2e-3 * np.abs(g["q_end"][0]).max())
+    tiny = _cabi.Model.polynomial(np.array([0.5]), np.array([1.0]), 4, np.zeros(4), np.ones(4), 1.0, 1.0)
+    lp, grad, chi2 = tiny.logprob_grad(np.ones((3, 4)), 2.0)
+    mock = 1 + 0.5 + 0.25 + 0.125
+    np.testing.assert_allclose(chi2, (mock - 1.0) ** 2, rtol=1e-6)
+    np.testing.assert_allclose(grad[0], 2.0 * (mock - 1.0) * 0.5 ** np.arange(4), rtol=1e-5)
+    for C in (1, 31, 33, 1023, 4097):
+        rng = np.random.RandomState(C)
+        q = g["q0"][rng.randint(0, len(g["q0"]), size=C)]
+        lp, _, _ = m.logprob_grad(q, 2.5, want_grad=False)
+        pp = port.PolynomialPosterior(g["xs"], g["ys"], g["prior_means"], g["prior_variances"], 1.0, 1.0)
+        np.testing.assert_allclose(lp, pp.log_prob(q, 2.5), rtol=1e-5)
+    # NaN energies reject (hmc.py:151: `u < exp(nan)` is False) and leave the state untouched
+    bad = g["q0"][:4].copy()
+    bad[1, 2] = np.nan
+    r = m.hmc_run(bad, 2.5, 0.02, 5, seed=3)
+    assert not r["accepted"][1] and np.isnan(r["q"][1, 2]) and np.isfinite(r["q"][0]).all()
+    # data sets larger than shared memory are streamed in chunks (N = 20,000 -> 320 KB of rows)
+    rng = np.random.RandomState(0)
+    xs = np.linspace(-1.2, 1.2, 20000)
+    ys = rng.normal(size=20000)
+    big = _cabi.Model.polynomial(xs, ys, 4, np.zeros(4), 5 * np.ones(4), 1.0, 1.0)
+    pb = port.PolynomialPosterior(xs, ys, np.zeros(4), 5 * np.ones(4), 1.0, 1.0)
+    q = rng.normal(size=(70, 4)) * 0.2
+    lp, grad, _ = big.logprob_grad(q, 0.7)
+    np.testing.assert_allclose(lp, pb.log_prob(q, 0.7), rtol=1e-5)
+    ref = pb.gradient(q, 0.7)
+    assert np.all(np.abs(grad - ref) <= 1e-4 * inf_norm(ref))
+    p0, u = rng.normal(size=q.shape), rng.uniform(size=70)
+    r = big.hmc_run(q, 0.7, 0.002, 4, p0=p0, u=u, want_end=True)
+    o = port.hmc_sample(lambda c: pb.log_prob(c, 0.7), lambda c: pb.gradient(c, 0.7), q, 0.002, 4, p0, u)
+    assert np.all(np.abs(r["q_end"] - o["q_end"]) <= 1e-4 * np.maximum(inf_norm(o["q_end"]), 1.0))
