@@ -40,14 +40,27 @@
 
 namespace binfb {
 
+// experiment switches (profiles/experiments/build_variants.py): shape of the pair block
+// (pair_block.cuh: 0 packed (default), 1 hybrid, 2 packed with a shared reciprocal), and whether
+// the special steps are peeled out of the stage loop
+#ifndef BINFB_PAIR_SHAPE
+#define BINFB_PAIR_SHAPE 0
+#endif
+#ifndef BINFB_PEEL
+#define BINFB_PEEL 0
+#endif
+#ifndef BINFB_STS64
+#define BINFB_STS64 0
+#endif
+
 constexpr float CHROM_SOFT = PAIR_SOFT;
 constexpr int STEP_FLOAT4 = 4 * 32;  // float4 per warp-step (16 contacts per lane)
 constexpr int STEP_BYTES = STEP_FLOAT4 * 16;
+constexpr int CHROM_NS = 4;          // ring depth (stages)
 
 struct ChromDev {
     int n, n_pad, Q, KS, NRB, q_even;
     int R, Lr, SS, S_pad;  // roles per chain, slots per row block, steps per stage, padded slots
-    int NS;                // ring depth (power of two)
     const float4 *ystream;
     float A, B;  // exp(alpha (d - d_c)) = 2^(A d + B)
     float alpha, k_bb, l0, inv_s2;
@@ -78,209 +91,304 @@ __device__ __forceinline__ void unpack4(const float4 v, float (&a)[4]) {
     a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w;
 }
 
+// Shared memory of one chain.  Positions and force sums are stored per quad of beads as three
+// consecutive float4 (x0..x3 | y0..y3 | z0..z3): one address register reaches all three with
+// immediate offsets, and the 48-byte lane stride of an LDS.128 / STS.128 over 32 consecutive quads
+// is bank-conflict free (48 = 3 * 16 with 3 odd: 8 consecutive lanes cover all 8 16-byte bank groups).
 struct ChainSmem {
-    float *xs, *ys, *zs, *fx, *fy, *fz;
-    double *red;  // [8] cross-role reduction scratch
+    float *pos, *frc;  // [Q][3][4]
+    double *red;       // [8] cross-role reduction scratch
 };
+__device__ __forceinline__ int qidx(int bead, int comp) { return (bead >> 2) * 12 + comp * 4 + (bead & 3); }
 
+// mbarrier / bulk-copy wrappers on raw 32-bit shared addresses (no generic->shared conversion in
+// the stage loop)
+__device__ __forceinline__ bool bar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    while (!bar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+// The contact ring: CHROM_NS stages of SS warp-steps in shared memory, filled by 1-D bulk async
+// copies (TMA engine) that complete on the `full` mbarrier of the slot.  A slot is handed back
+// through a plain shared-memory counter: the LAST of the n_warps consumers to release stage j is
+// the one that refills the slot with stage j + CHROM_NS -- the refill is issued at the earliest
+// possible moment, nobody ever spins on an "empty" barrier, and a fast warp may run up to
+// CHROM_NS - 1 stages ahead of the slowest one.
 struct Ring {
-    const float4 *ystage;
-    uint64_t *full, *empty;
-    // loader duty (warp 0, lane 0): global source of the pass and stage geometry
-    const unsigned char *src;
-    uint32_t stage_bytes;
+    uint32_t ystage;  // shared address of stage 0
+    const float4 *ystage_ptr;  // the same, as a pointer (consumer loads)
+    uint32_t full;    // shared address of full[0] (8 bytes each)
+    uint32_t cnt;     // shared address of the release counters (4 bytes each)
+    const unsigned char *src;  // global source: the contact stream of one pass
     int n_stage_pass;
-    uint32_t ns_mask, ns_shift;  // ring depth NS = 1 << ns_shift
-    int prefetch;                // stages of lookahead = NS/2: the slot refilled was released NS/2 stages ago
-    bool loader;
+    int n_warps;
 };
 
-// issue the bulk copy of local stage s_local of this pass (global stage index base + s_local)
-__device__ __forceinline__ void ring_issue(const Ring &ring, uint32_t base, int s_local) {
-    const uint32_t gi = base + (uint32_t)s_local;
-    const uint32_t sl = gi & ring.ns_mask;
-    mbar_wait(&ring.empty[sl], ((gi >> ring.ns_shift) & 1u) ^ 1u);
-    mbar_arrive_expect_tx(&ring.full[sl], ring.stage_bytes);
-    bulk_copy_g2s(const_cast<unsigned char *>(reinterpret_cast<const unsigned char *>(ring.ystage)) +
-                      (size_t)sl * ring.stage_bytes,
-                  ring.src + (size_t)s_local * ring.stage_bytes, ring.stage_bytes, &ring.full[sl]);
+template <int STAGE_BYTES>
+__device__ __forceinline__ void ring_issue(const Ring &ring, uint32_t gi, int s_local) {
+    const uint32_t sl = gi & (CHROM_NS - 1);
+    const uint32_t bar = ring.full + sl * 8u;
+    bar_expect_tx(bar, STAGE_BYTES);
+    bulk_g2s(ring.ystage + sl * STAGE_BYTES, ring.src + (size_t)s_local * STAGE_BYTES, STAGE_BYTES, bar);
+}
+
+// release stage (gi, s_local) (lane 0 of every consumer warp; the warp has passed a __syncwarp since
+// its last read of the slot)
+template <int STAGE_BYTES>
+__device__ __forceinline__ void ring_release(const Ring &ring, uint32_t gi, int s_local) {
+    const uint32_t c = ring.cnt + (gi & (CHROM_NS - 1)) * 4u;
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(c) : "memory");
+    if (old == (uint32_t)ring.n_warps - 1u) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(c), "r"(0u) : "memory");
+        if (s_local + CHROM_NS < ring.n_stage_pass) ring_issue<STAGE_BYTES>(ring, gi + CHROM_NS, s_local + CHROM_NS);
+    }
 }
 
 // The pair sweep of one chain, shared by the R warps ("roles") of that chain.  Role r owns the
 // partner steps k in [r*Lr, (r+1)*Lr) of every row block; SPR = SS/R of them per ring stage, and
-// Lr is a multiple of SPR so that a stage never straddles two row blocks.  Fills fx/fy/fz with
+// Lr is a multiple of SPR so that a stage never straddles two row blocks.  Fills frc with
 // sum_j coef_ij (x_i - x_j) (the likelihood force up to the factor -alpha*beta*tau) and returns
 // this lane's share of chi^2.
 //
 // The 4x4 block is evaluated with packed FP32 (FFMA2/FADD2/FMUL2: two partner columns per
-// instruction, see pair_block.cuh): 9.5 FMA-pipe issue slots + 3 MUFU per pair.  The special
-// function unit (16 lanes/clk/SM) is the bounding pipe: 3 MUFU per pair = 24 SMSP-cycles per
-// warp-pair, the FMA pipe needs 19.
+// instruction, see pair_block.cuh): 9.5 FMA-pipe issue slots + 3 MUFU per pair.
 //
 // Race freedom of the partner-force read-modify-write in shared memory: within one warp-step the
 // 32 lanes address 32 distinct quads ((a+k) mod Q is a bijection of a).  Two roles r < r' of
-// one chain work on partner offsets k and k' >= k + Lr - drift, where drift <= NS*SS/R slots is
+// one chain work on partner offsets k and k' >= k + Lr - drift, where drift < CHROM_NS*SPR slots is
 // enforced by the shared stage ring; they can only meet on a quad if k' - k <= 31, which the
-// host-side plan excludes (Lr - NS*SS/R >= 40 whenever R > 1).
-template <bool ENERGY, int SPR>
-__device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSmem &sm,
-                                              const Ring &ring, uint32_t &stage_idx,
-                                              bool chain_valid, int lane, int role, int bar_id) {
-    float4 *xs4 = reinterpret_cast<float4 *>(sm.xs), *ys4 = reinterpret_cast<float4 *>(sm.ys),
-           *zs4 = reinterpret_cast<float4 *>(sm.zs);
-    float4 *fx4 = reinterpret_cast<float4 *>(sm.fx), *fy4 = reinterpret_cast<float4 *>(sm.fy),
-           *fz4 = reinterpret_cast<float4 *>(sm.fz);
+// host-side plan excludes (Lr - CHROM_NS*SPR >= 33 whenever R > 1).
+struct SweepRegs {
+    float2 nx2[4], ny2[4], nz2[4];  // own quad, negated, as broadcast pairs
+    float2 g[4][3];                 // G = -(force sum) of the own quad
+    int k, b;                       // partner offset and partner quad of the next step
+    double chi2;
+};
+
+// one regular step: the 16 pairs (own quad) x (partner quad b), every lane (inactive lanes compute
+// on quad 0 and never store)
+template <bool ENERGY>
+__device__ __forceinline__ void step_fast(SweepRegs &s, float4 *pos4, float4 *frc4, const float4 *yb, float2 A2,
+                                          float2 B2, bool active) {
+    const float4 *pj = pos4 + 3 * s.b;
+    float4 *fj = frc4 + 3 * s.b;
+    const float4 xj = pj[0], yj = pj[1], zj = pj[2];
+    const float4 fx = fj[0], fy = fj[1], fz = fj[2];
+    const float2 xj2[2] = {mk2(xj.x, xj.y), mk2(xj.z, xj.w)}, yj2[2] = {mk2(yj.x, yj.y), mk2(yj.z, yj.w)},
+                 zj2[2] = {mk2(zj.x, zj.y), mk2(zj.z, zj.w)};
+    float2 fx2[2] = {mk2(fx.x, fx.y), mk2(fx.z, fx.w)}, fy2[2] = {mk2(fy.x, fy.y), mk2(fy.z, fy.w)},
+           fz2[2] = {mk2(fz.x, fz.y), mk2(fz.z, fz.w)};
+    float2 c2 = mk2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float4 yv = yb[r * 32];
+#if BINFB_PAIR_SHAPE == 1
+        pair_hybrid<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv.x, yv.y), A2.x,
+                            B2.x, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2);
+        pair_hybrid<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv.z, yv.w), A2.x,
+                            B2.x, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2);
+#elif BINFB_PAIR_SHAPE == 2
+        pair_packed_sr<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv.x, yv.y), A2,
+                               B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2);
+        pair_packed_sr<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv.z, yv.w), A2,
+                               B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2);
+#else
+        pair_packed<ENERGY, false>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv.x, yv.y), A2,
+                                   B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2);
+        pair_packed<ENERGY, false>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv.z, yv.w), A2,
+                                   B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2);
+#endif
+    }
+    if (active) {
+#if BINFB_STS64
+        float2 *f2 = reinterpret_cast<float2 *>(fj);
+        f2[0] = fx2[0], f2[1] = fx2[1], f2[2] = fy2[0], f2[3] = fy2[1], f2[4] = fz2[0], f2[5] = fz2[1];
+#else
+        fj[0] = make_float4(fx2[0].x, fx2[0].y, fx2[1].x, fx2[1].y);
+        fj[1] = make_float4(fy2[0].x, fy2[0].y, fy2[1].x, fy2[1].y);
+        fj[2] = make_float4(fz2[0].x, fz2[0].y, fz2[1].x, fz2[1].y);
+#endif
+        if (ENERGY) s.chi2 += (double)(c2.x + c2.y);
+    }
+}
+
+// the special steps: k == 0 (the 6 pairs inside the lane's own quad), k == KS with an even quad
+// count (only the lower half of the quads owns the (q, q + Q/2) block), k > KS (padding: nothing)
+template <bool ENERGY>
+__device__ __forceinline__ void step_special(SweepRegs &s, float4 *pos4, float4 *frc4, const float4 *yb, float A,
+                                             float B, int KS, bool upper_half) {
+    const int k = s.k;
+    if (k > KS) return;
+    float chi = 0.f;
+    if (k == 0) {
+        float yv[4][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) unpack4(yb[r * 32], yv[r]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = r + 1; c < 4; ++c) {
+                float tx = 0.f, ty = 0.f, tz = 0.f;
+                pair_scalar<ENERGY>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, -s.nx2[c].x, -s.ny2[c].x, -s.nz2[c].x,
+                                    yv[r][c], A, B, s.g[r][0].x, s.g[r][1].x, s.g[r][2].x, tx, ty, tz, chi);
+                s.g[c][0].y -= tx, s.g[c][1].y -= ty, s.g[c][2].y -= tz;
+            }
+    } else if (!upper_half) {
+        const float4 *pj = pos4 + 3 * s.b;
+        float4 *fj = frc4 + 3 * s.b;
+        float xj[4], yj[4], zj[4], fjx[4], fjy[4], fjz[4], yv[4][4];
+        unpack4(pj[0], xj), unpack4(pj[1], yj), unpack4(pj[2], zj);
+        unpack4(fj[0], fjx), unpack4(fj[1], fjy), unpack4(fj[2], fjz);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) unpack4(yb[r * 32], yv[r]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                pair_scalar<ENERGY>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, xj[c], yj[c], zj[c], yv[r][c], A, B,
+                                    s.g[r][0].x, s.g[r][1].x, s.g[r][2].x, fjx[c], fjy[c], fjz[c], chi);
+        fj[0] = make_float4(fjx[0], fjx[1], fjx[2], fjx[3]);
+        fj[1] = make_float4(fjy[0], fjy[1], fjy[2], fjy[3]);
+        fj[2] = make_float4(fjz[0], fjz[1], fjz[2], fjz[3]);
+    }
+    if (ENERGY) s.chi2 += (double)chi;
+}
+
+template <bool ENERGY, int R, int SPR>
+__device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSmem &sm, const Ring &ring,
+                                              uint32_t &stage_idx_io, bool chain_valid, int lane, int role,
+                                              int bar_id) {
+    constexpr int STAGE_BYTES = R * SPR * STEP_BYTES;
+    float4 *pos4 = reinterpret_cast<float4 *>(sm.pos), *frc4 = reinterpret_cast<float4 *>(sm.frc);
     const float A = cd.A, B = cd.B;
     const float2 A2 = mk2(A, A), B2 = mk2(B, B);
-    const int Q = cd.Q, KS = cd.KS, R = cd.R, Lr = cd.Lr, halfQ = cd.Q >> 1;
+    const int Q = cd.Q, KS = cd.KS, Lr = cd.Lr, halfQ = cd.Q >> 1;
     const bool q_even = cd.q_even != 0;
     const int k_fast = q_even ? KS - 1 : KS;  // offsets 1..k_fast need no special handling
-    const int stage_float4 = cd.SS * STEP_FLOAT4;
     const int n_sg = Lr / SPR;                 // stages per row block
-    double chi2 = 0.0;
-    const uint32_t stage_base = stage_idx;
+    const int k0 = role * Lr;
+#if BINFB_PEEL
+    // stages [sg_lo, sg_hi) of this role hold regular steps only
+    const int sg_lo = k0 == 0 ? 1 : 0;
+    int sg_hi = (k_fast - k0 + 1) / SPR;
+    sg_hi = sg_hi < sg_lo ? sg_lo : (sg_hi > n_sg ? n_sg : sg_hi);
+#endif
+    uint32_t stage_idx = stage_idx_io;
     int s_local = 0;
-    if (ring.loader && lane == 0)
-        for (int i = 0; i <= ring.prefetch && i < ring.n_stage_pass; ++i) ring_issue(ring, stage_base, i);
+    const float4 *ylane = ring.ystage_ptr + role * STEP_FLOAT4 + lane;
     bool ready = false;  // the stage about to be consumed was already seen complete (early probe)
+    SweepRegs s;
+    s.chi2 = 0.0;
 
     for (int rb = 0; rb < cd.NRB; ++rb) {
         const int a = rb * 32 + lane;
         const bool active = chain_valid && a < Q;
         const int aa = active ? a : 0;
-        // own quad: negated positions as broadcast pairs, accumulators G = -(force sum)
-        float2 nx2[4], ny2[4], nz2[4], g[4][3];
+        const bool upper_half = q_even && a >= halfQ;
         {
             float xi[4], yi[4], zi[4];
-            unpack4(xs4[aa], xi), unpack4(ys4[aa], yi), unpack4(zs4[aa], zi);
+            unpack4(pos4[3 * aa], xi), unpack4(pos4[3 * aa + 1], yi), unpack4(pos4[3 * aa + 2], zi);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                nx2[r] = mk2(-xi[r], -xi[r]), ny2[r] = mk2(-yi[r], -yi[r]), nz2[r] = mk2(-zi[r], -zi[r]);
-                g[r][0] = g[r][1] = g[r][2] = mk2(0.f, 0.f);
+                s.nx2[r] = mk2(-xi[r], -xi[r]), s.ny2[r] = mk2(-yi[r], -yi[r]), s.nz2[r] = mk2(-zi[r], -zi[r]);
+                s.g[r][0] = s.g[r][1] = s.g[r][2] = mk2(0.f, 0.f);
             }
         }
-        int k = role * Lr;  // partner offset of slot 0
-        int b = aa + k;
-        if (b >= Q) b -= Q;
-        for (int sg = 0; sg < n_sg; ++sg) {
-            const uint32_t slot = stage_idx & ring.ns_mask;
-            if (!ready) mbar_wait(&ring.full[slot], (stage_idx >> ring.ns_shift) & 1u);
-            const float4 *ybase = ring.ystage + (size_t)slot * stage_float4 + role * STEP_FLOAT4 + lane;
+        s.k = k0;  // partner offset of slot 0
+        s.b = aa + s.k;
+        if (s.b >= Q) s.b -= Q;
+#if BINFB_PEEL
+        int sg = 0;
+#pragma unroll 1
+        for (int part = 0; part < 3; ++part) {
+            const int sg_end = part == 0 ? sg_lo : (part == 1 ? sg_hi : n_sg);
+            const bool generic = part != 1;
+#pragma unroll 1
+            for (; sg < sg_end; ++sg) {
+#else
+        {
+            const bool generic = true;
+#pragma unroll 1
+            for (int sg = 0; sg < n_sg; ++sg) {
+#endif
+                const uint32_t slot = stage_idx & (CHROM_NS - 1);
+                if (!ready) bar_wait(ring.full + slot * 8u, (stage_idx >> 2) & 1u);
+                const float4 *ybase = ylane + slot * (STAGE_BYTES / 16);
+                const uint32_t nbar = ring.full + ((stage_idx + 1) & (CHROM_NS - 1)) * 8u;
+                const uint32_t npar = ((stage_idx + 1) >> 2) & 1u;
+                if (!generic) {
 #pragma unroll
-            for (int u = 0; u < SPR; ++u) {
-                const float4 *yb = ybase + u * R * STEP_FLOAT4;
-                if (u == SPR - 1)  // probe the next stage now; the answer is back after this step
-                    ready = mbar_try_wait(&ring.full[(stage_idx + 1) & ring.ns_mask],
-                                          ((stage_idx + 1) >> ring.ns_shift) & 1u);
-                if ((unsigned)(k - 1) < (unsigned)k_fast) {
-                    // ---- regular step: 16 pairs, every lane (inactive lanes compute on quad 0
-                    //      and never store) ------------------------------------------------------
-                    const float4 xj = xs4[b], yj = ys4[b], zj = zs4[b];
-                    const float4 fx = fx4[b], fy = fy4[b], fz = fz4[b];
-                    const float2 xj2[2] = {mk2(xj.x, xj.y), mk2(xj.z, xj.w)},
-                                 yj2[2] = {mk2(yj.x, yj.y), mk2(yj.z, yj.w)},
-                                 zj2[2] = {mk2(zj.x, zj.y), mk2(zj.z, zj.w)};
-                    float2 fx2[2] = {mk2(fx.x, fx.y), mk2(fx.z, fx.w)}, fy2[2] = {mk2(fy.x, fy.y), mk2(fy.z, fy.w)},
-                           fz2[2] = {mk2(fz.x, fz.y), mk2(fz.z, fz.w)};
-                    float2 c2 = mk2(0.f, 0.f);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float4 yv = yb[r * 32];
-                        pair_packed<ENERGY, false>(nx2[r], ny2[r], nz2[r], xj2[0], yj2[0], zj2[0],
-                                                   mk2(yv.x, yv.y), A2, B2, g[r][0], g[r][1], g[r][2],
-                                                   fx2[0], fy2[0], fz2[0], c2);
-                        pair_packed<ENERGY, false>(nx2[r], ny2[r], nz2[r], xj2[1], yj2[1], zj2[1],
-                                                   mk2(yv.z, yv.w), A2, B2, g[r][0], g[r][1], g[r][2],
-                                                   fx2[1], fy2[1], fz2[1], c2);
+                    for (int u = 0; u < SPR; ++u) {
+                        // probe the next stage now; the answer is back after this step
+                        if (u == SPR - 1) ready = bar_try_wait(nbar, npar);
+                        step_fast<ENERGY>(s, pos4, frc4, ybase + u * R * STEP_FLOAT4, A2, B2, active);
+                        ++s.k;
+                        if (++s.b == Q) s.b = 0;
+                        __syncwarp();
                     }
-                    if (active) {
-                        fx4[b] = make_float4(fx2[0].x, fx2[0].y, fx2[1].x, fx2[1].y);
-                        fy4[b] = make_float4(fy2[0].x, fy2[0].y, fy2[1].x, fy2[1].y);
-                        fz4[b] = make_float4(fz2[0].x, fz2[0].y, fz2[1].x, fz2[1].y);
-                        if (ENERGY) chi2 += (double)(c2.x + c2.y);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < SPR; ++u) {
+                        if (u == SPR - 1) ready = bar_try_wait(nbar, npar);
+                        if ((unsigned)(s.k - 1) < (unsigned)k_fast)
+                            step_fast<ENERGY>(s, pos4, frc4, ybase + u * R * STEP_FLOAT4, A2, B2, active);
+                        else if (active)
+                            step_special<ENERGY>(s, pos4, frc4, ybase + u * R * STEP_FLOAT4, A, B, KS, upper_half);
+                        ++s.k;
+                        if (++s.b == Q) s.b = 0;
+                        __syncwarp();
                     }
-                } else if (active && k <= KS) {
-                    float chi = 0.f;
-                    if (k == 0) {
-                        // ---- the 6 pairs inside the lane's own quad --------------------------------
-                        float yv[4][4];
-#pragma unroll
-                        for (int r = 0; r < 3; ++r) unpack4(yb[r * 32], yv[r]);
-#pragma unroll
-                        for (int r = 0; r < 4; ++r)
-#pragma unroll
-                            for (int c = r + 1; c < 4; ++c) {
-                                float tx = 0.f, ty = 0.f, tz = 0.f;
-                                pair_scalar<ENERGY>(nx2[r].x, ny2[r].x, nz2[r].x, -nx2[c].x, -ny2[c].x,
-                                                    -nz2[c].x, yv[r][c], A, B, g[r][0].x, g[r][1].x,
-                                                    g[r][2].x, tx, ty, tz, chi);
-                                g[c][0].y -= tx, g[c][1].y -= ty, g[c][2].y -= tz;
-                            }
-                    } else if (!(q_even && a >= halfQ)) {
-                        // ---- k == KS with an even quad count: only the lower half of the quads owns
-                        //      the (q, q + Q/2) block ------------------------------------------------
-                        float xj[4], yj[4], zj[4], fjx[4], fjy[4], fjz[4], yv[4][4];
-                        unpack4(xs4[b], xj), unpack4(ys4[b], yj), unpack4(zs4[b], zj);
-                        unpack4(fx4[b], fjx), unpack4(fy4[b], fjy), unpack4(fz4[b], fjz);
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) unpack4(yb[r * 32], yv[r]);
-#pragma unroll
-                        for (int r = 0; r < 4; ++r)
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                pair_scalar<ENERGY>(nx2[r].x, ny2[r].x, nz2[r].x, xj[c], yj[c], zj[c],
-                                                    yv[r][c], A, B, g[r][0].x, g[r][1].x, g[r][2].x,
-                                                    fjx[c], fjy[c], fjz[c], chi);
-                        fx4[b] = make_float4(fjx[0], fjx[1], fjx[2], fjx[3]);
-                        fy4[b] = make_float4(fjy[0], fjy[1], fjy[2], fjy[3]);
-                        fz4[b] = make_float4(fjz[0], fjz[1], fjz[2], fjz[3]);
-                    }
-                    if (ENERGY) chi2 += (double)chi;
                 }
-                ++k;
-                if (++b == Q) b = 0;
-                __syncwarp();
+                if (lane == 0) ring_release<STAGE_BYTES>(ring, stage_idx, s_local);
+                ++stage_idx;
+                ++s_local;
             }
-            if (lane == 0) mbar_arrive(&ring.empty[slot]);
-            ++stage_idx;
-            ++s_local;
-            if (ring.loader && lane == 0 && s_local + ring.prefetch < ring.n_stage_pass)
-                ring_issue(ring, stage_base, s_local + ring.prefetch);
         }
         // ---- end of the row block: fold the register-resident accumulators of the own quad into
         //      shared memory (f -= G), one role at a time --------------------------------------------
+#pragma unroll 1
         for (int rr = 0; rr < R; ++rr) {
             if (R > 1) chain_bar(bar_id, R * 32);
             if (rr == role && active) {
-                float4 v = fx4[a];
-                v.x -= g[0][0].x + g[0][0].y, v.y -= g[1][0].x + g[1][0].y;
-                v.z -= g[2][0].x + g[2][0].y, v.w -= g[3][0].x + g[3][0].y;
-                fx4[a] = v;
-                v = fy4[a];
-                v.x -= g[0][1].x + g[0][1].y, v.y -= g[1][1].x + g[1][1].y;
-                v.z -= g[2][1].x + g[2][1].y, v.w -= g[3][1].x + g[3][1].y;
-                fy4[a] = v;
-                v = fz4[a];
-                v.x -= g[0][2].x + g[0][2].y, v.y -= g[1][2].x + g[1][2].y;
-                v.z -= g[2][2].x + g[2][2].y, v.w -= g[3][2].x + g[3][2].y;
-                fz4[a] = v;
+                float4 v = frc4[3 * a];
+                v.x -= s.g[0][0].x + s.g[0][0].y, v.y -= s.g[1][0].x + s.g[1][0].y;
+                v.z -= s.g[2][0].x + s.g[2][0].y, v.w -= s.g[3][0].x + s.g[3][0].y;
+                frc4[3 * a] = v;
+                v = frc4[3 * a + 1];
+                v.x -= s.g[0][1].x + s.g[0][1].y, v.y -= s.g[1][1].x + s.g[1][1].y;
+                v.z -= s.g[2][1].x + s.g[2][1].y, v.w -= s.g[3][1].x + s.g[3][1].y;
+                frc4[3 * a + 1] = v;
+                v = frc4[3 * a + 2];
+                v.x -= s.g[0][2].x + s.g[0][2].y, v.y -= s.g[1][2].x + s.g[1][2].y;
+                v.z -= s.g[2][2].x + s.g[2][2].y, v.w -= s.g[3][2].x + s.g[3][2].y;
+                frc4[3 * a + 2] = v;
             }
         }
         if (R > 1) chain_bar(bar_id, R * 32);
         else __syncwarp();
     }
-    // stages that only pad the stream to a whole number of ring stages
-    while (s_local < ring.n_stage_pass) {
-        const uint32_t slot = stage_idx & ring.ns_mask;
-        mbar_wait(&ring.full[slot], (stage_idx >> ring.ns_shift) & 1u);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ring.empty[slot]);
-        ++stage_idx;
-        ++s_local;
-        if (ring.loader && lane == 0 && s_local + ring.prefetch < ring.n_stage_pass)
-            ring_issue(ring, stage_base, s_local + ring.prefetch);
-    }
-    return chi2;
+    stage_idx_io = stage_idx;
+    return s.chi2;
 }
 
 __device__ __forceinline__ double warp_sum(double v) { return group_allreduce_sum<32>(v); }
@@ -306,39 +414,38 @@ struct ChromCall {
     int n_groups, total_items;
 };
 
+template <int R, int SPR>
 __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall call) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int W = call.W, R = cd.R;
+    constexpr int STAGE_BYTES = R * SPR * STEP_BYTES;
+    const int W = call.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chain_local = warp / R, role = warp % R;
     const int bar_id = 1 + chain_local;
-    const uint32_t stage_bytes = (uint32_t)cd.SS * STEP_BYTES;
-    // ---- shared memory carve-up: [stages][barriers, item][W x (6 n_pad floats + 8 doubles)]
+    // ---- shared memory carve-up: [stages][full barriers, release counters, item][W x chain]
     Ring ring;
-    ring.ystage = reinterpret_cast<const float4 *>(smem_raw);
-    const int NS = cd.NS;
-    ring.full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NS * stage_bytes);
-    ring.empty = ring.full + NS;
-    ring.ns_mask = (uint32_t)NS - 1u;
-    ring.ns_shift = NS == 2 ? 1u : (NS == 4 ? 2u : 3u);
-    ring.prefetch = NS / 2;
+    ring.ystage = smem_u32(smem_raw);
+    ring.ystage_ptr = reinterpret_cast<const float4 *>(smem_raw);
+    ring.full = ring.ystage + CHROM_NS * STAGE_BYTES;
+    ring.cnt = ring.full + CHROM_NS * 8;
     ring.src = reinterpret_cast<const unsigned char *>(cd.ystream);
-    ring.stage_bytes = stage_bytes;
-    ring.n_stage_pass = cd.S_pad * R / cd.SS;
-    ring.loader = warp == 0;
-    int *s_item = reinterpret_cast<int *>(ring.empty + NS);
-    unsigned char *chains = smem_raw + (size_t)NS * stage_bytes + 128;
+    ring.n_stage_pass = cd.S_pad / SPR;
+    ring.n_warps = W * R;
+    unsigned char *ctl = smem_raw + (size_t)CHROM_NS * STAGE_BYTES;
+    uint64_t *full_bars = reinterpret_cast<uint64_t *>(ctl);
+    uint32_t *cnts = reinterpret_cast<uint32_t *>(ctl + CHROM_NS * 8);
+    int *s_item = reinterpret_cast<int *>(ctl + CHROM_NS * 12);
+    unsigned char *chains = ctl + 128;
     const size_t per_chain = (size_t)6 * cd.n_pad * sizeof(float) + 64;
     ChainSmem sm;
     {
         unsigned char *b0 = chains + per_chain * chain_local;
         sm.red = reinterpret_cast<double *>(b0);
-        float *b = reinterpret_cast<float *>(b0 + 64);
-        sm.xs = b, sm.ys = b + cd.n_pad, sm.zs = b + 2 * cd.n_pad;
-        sm.fx = b + 3 * cd.n_pad, sm.fy = b + 4 * cd.n_pad, sm.fz = b + 5 * cd.n_pad;
+        sm.pos = reinterpret_cast<float *>(b0 + 64);
+        sm.frc = sm.pos + 3 * cd.n_pad;
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NS; ++i) mbar_init(&ring.full[i], 1), mbar_init(&ring.empty[i], W * R);
+        for (int i = 0; i < CHROM_NS; ++i) mbar_init(&full_bars[i], 1), cnts[i] = 0u;
         mbar_fence_init();
     }
     __syncthreads();
@@ -353,6 +460,10 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
         if (threadIdx.x == 0) {
             const int it = atomicAdd(cd.counter, 1);
             if (it < call.total_items) {
+                // every warp has released every stage of the previous item (block barrier below):
+                // start streaming the contacts of this pass right away
+                for (int i = 0; i < CHROM_NS && i < ring.n_stage_pass; ++i)
+                    ring_issue<STAGE_BYTES>(ring, stage_idx + (uint32_t)i, i);
                 const int o = it % call.n_groups;
                 const int need = it / call.n_groups;  // passes of this group that must be done
                 if (need > 0)
@@ -396,7 +507,7 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                         __stcg(cd.pw + off + e, pv);
                         kin = fmaf(pv, pv, kin);
                         const int bead = e / 3, comp = e - 3 * bead;
-                        sm.xs[comp * cd.n_pad + bead] = v;
+                        sm.pos[qidx(bead, comp)] = v;
                     }
                 } else {
                     constexpr int U = 8;
@@ -414,31 +525,24 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                             if (e < D) {
                                 const int bead = e / 3, comp = e - 3 * bead;
                                 // q += eps p (hmc.py:119,122)
-                                sm.xs[comp * cd.n_pad + bead] = fmaf(eps_c, pv[uu], v[uu]);
+                                sm.pos[qidx(bead, comp)] = fmaf(eps_c, pv[uu], v[uu]);
                             }
                         }
                     }
                 }
                 for (int i = cd.n + ctid; i < cd.n_pad; i += cthreads) {
                     // padding beads: far away from everything => contact 0, force 0
-                    sm.xs[i] = 1.0e4f * (float)(1 + i - cd.n), sm.ys[i] = 3.0e4f, sm.zs[i] = -2.0e4f;
+                    sm.pos[qidx(i, 0)] = 1.0e4f * (float)(1 + i - cd.n);
+                    sm.pos[qidx(i, 1)] = 3.0e4f, sm.pos[qidx(i, 2)] = -2.0e4f;
                 }
-                for (int i = ctid; i < 3 * cd.n_pad; i += cthreads) sm.fx[i] = 0.f;
+                for (int i = ctid; i < 3 * cd.n_pad; i += cthreads) sm.frc[i] = 0.f;
                 if (hmc && k == 0) kin0 = chain_sum((double)kin, sm, lane, role, R, bar_id);
             }
             if (R > 1) chain_bar(bar_id, cthreads);
             else __syncwarp();
             // ---- phase B: pair sweep -----------------------------------------------------
-            double chi2;
-            if (cd.SS / R == 2)
-                chi2 = energy ? chrom_sweep<true, 2>(cd, sm, ring, stage_idx, valid, lane, role, bar_id)
-                              : chrom_sweep<false, 2>(cd, sm, ring, stage_idx, valid, lane, role, bar_id);
-            else if (cd.SS / R == 4)
-                chi2 = energy ? chrom_sweep<true, 4>(cd, sm, ring, stage_idx, valid, lane, role, bar_id)
-                              : chrom_sweep<false, 4>(cd, sm, ring, stage_idx, valid, lane, role, bar_id);
-            else
-                chi2 = energy ? chrom_sweep<true, 1>(cd, sm, ring, stage_idx, valid, lane, role, bar_id)
-                              : chrom_sweep<false, 1>(cd, sm, ring, stage_idx, valid, lane, role, bar_id);
+            double chi2 = energy ? chrom_sweep<true, R, SPR>(cd, sm, ring, stage_idx, valid, lane, role, bar_id)
+                                 : chrom_sweep<false, R, SPR>(cd, sm, ring, stage_idx, valid, lane, role, bar_id);
             if (R > 1) chain_bar(bar_id, cthreads);
             else __syncwarp();
             if (valid) {
@@ -483,17 +587,20 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                     for (int uu = 0; uu < UC; ++uu) {
                         const int i = i0 + uu * cthreads;
                         if (i >= cd.n) continue;
-                        const float x = sm.xs[i], y = sm.ys[i], z = sm.zs[i];
-                        float gx = scale * sm.fx[i], gy = scale * sm.fy[i], gz = scale * sm.fz[i];
+                        const int ix = qidx(i, 0);
+                        const float x = sm.pos[ix], y = sm.pos[ix + 4], z = sm.pos[ix + 8];
+                        float gx = scale * sm.frc[ix], gy = scale * sm.frc[ix + 4], gz = scale * sm.frc[ix + 8];
                         if (i > 0) {
-                            const float bx = x - sm.xs[i - 1], by = y - sm.ys[i - 1], bz = z - sm.zs[i - 1];
+                            const int im = qidx(i - 1, 0);
+                            const float bx = x - sm.pos[im], by = y - sm.pos[im + 4], bz = z - sm.pos[im + 8];
                             const float r2 = fmaf(bz, bz, fmaf(by, by, fmaf(bx, bx, CHROM_SOFT)));
                             const float inv = rsqrtf(r2), d = r2 * inv;
                             const float cc = cd.k_bb * (d - cd.l0) * inv;
                             gx = fmaf(cc, bx, gx), gy = fmaf(cc, by, gy), gz = fmaf(cc, bz, gz);
                         }
                         if (i < cd.n - 1) {
-                            const float bx = sm.xs[i + 1] - x, by = sm.ys[i + 1] - y, bz = sm.zs[i + 1] - z;
+                            const int ip = qidx(i + 1, 0);
+                            const float bx = sm.pos[ip] - x, by = sm.pos[ip + 4] - y, bz = sm.pos[ip + 8] - z;
                             const float r2 = fmaf(bz, bz, fmaf(by, by, fmaf(bx, bx, CHROM_SOFT)));
                             const float inv = rsqrtf(r2), d = r2 * inv;
                             const float dl = d - cd.l0;
@@ -558,14 +665,14 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                         if (last && (h.q_end || h.p_end)) {
                             for (int e = ctid; e < D; e += cthreads) {
                                 const int bead = e / 3, comp = e - 3 * bead;
-                                if (h.q_end) h.q_end[off + e] = sm.xs[comp * cd.n_pad + bead];
+                                if (h.q_end) h.q_end[off + e] = sm.pos[qidx(bead, comp)];
                                 if (h.p_end) h.p_end[off + e] = __ldcg(cd.pw + off + e);
                             }
                         }
                         if (acc) {
                             for (int e = ctid; e < D; e += cthreads) {
                                 const int bead = e / 3, comp = e - 3 * bead;
-                                __stcg(h.q + off + e, sm.xs[comp * cd.n_pad + bead]);
+                                __stcg(h.q + off + e, sm.pos[qidx(bead, comp)]);
                             }
                         }
                         const double chi2_cur = acc ? chi2 : __ldcg(cd.chi2_0 + c);
@@ -634,21 +741,10 @@ static inline long long tri_index(long long n, long long i, long long j) {  // i
 // R > 1 only when the partner-step ranges of two roles can never overlap within the drift the
 // stage ring allows (see chrom_sweep): Lr - NS*SS/R >= 40.
 // stage size (warp-steps) and ring depth per role count
-static int env_int(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
-// BINFB_CHROM_SS / BINFB_CHROM_NS are tuning knobs for experiments (SS multiple of R, NS in {2,4,8})
-static int chrom_stage_steps(int R) {
-    const int ss = env_int("BINFB_CHROM_SS", 0);
-    if (ss >= R && ss % R == 0 && (ss / R == 1 || ss / R == 2 || ss / R == 4)) return ss;
-    return R <= 4 ? 4 : R;  // measured on B200 at n = 1000: 4-step stages x 4 slots beat 8 x 2
-}
-static int chrom_ring_depth(int R) {
-    const int ns = env_int("BINFB_CHROM_NS", 0);
-    if (ns == 2 || ns == 4 || ns == 8) return ns;
-    return 4;
-}
+// stage size in warp-steps per role count (SPR = SS / R steps per role and stage); the ring has
+// CHROM_NS stages.  Measured on B200 at n = 1000: 4-step stages x 4 slots beat 8 x 2.
+static int chrom_stage_steps(int R) { return R <= 4 ? 4 : R; }
+static int chrom_ring_depth(int) { return CHROM_NS; }
 
 ChromPlan chrom_plan(int n, int smem_optin, int force_roles) {
     ChromPlan pl;
@@ -748,7 +844,7 @@ static ChromDev chrom_dev(const ChromModel &m) {
     const ChromPlan &pl = m.plan;
     d.n = m.n, d.n_pad = pl.n_pad, d.Q = pl.Q, d.KS = pl.KS, d.NRB = pl.NRB;
     d.q_even = (pl.Q % 2) == 0;
-    d.R = pl.R, d.Lr = pl.Lr, d.SS = pl.SS, d.S_pad = pl.S_pad, d.NS = pl.NS;
+    d.R = pl.R, d.Lr = pl.Lr, d.SS = pl.SS, d.S_pad = pl.S_pad;
     d.ystream = reinterpret_cast<const float4 *>(m.ystream);
     const double log2e = 1.4426950408889634;
     d.A = (float)((double)m.alpha * log2e);
@@ -789,9 +885,24 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
     call.total_items = (int)total;
     const size_t smem = pl.fixed_smem + pl.per_chain_smem * W;
     BINFB_CUDA(cudaMemsetAsync(m.sched, 0, (size_t)(1 + call.n_groups) * sizeof(int), s));
-    BINFB_CUDA(cudaFuncSetAttribute(chrom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = call.n_groups < sm_count ? call.n_groups : sm_count;
-    chrom_kernel<<<grid, W * pl.R * 32, smem, s>>>(chrom_dev(m), call);
+    const int threads = W * pl.R * 32;
+    const ChromDev dev = chrom_dev(m);
+#define BINFB_CHROM_LAUNCH(RR, SPR)                                                                            \
+    do {                                                                                                       \
+        BINFB_CUDA(cudaFuncSetAttribute(chrom_kernel<RR, SPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                        (int)smem));                                                           \
+        chrom_kernel<RR, SPR><<<grid, threads, smem, s>>>(dev, call);                                          \
+    } while (0)
+    if (pl.R == 1 && pl.SS == 4) BINFB_CHROM_LAUNCH(1, 4);
+    else if (pl.R == 2 && pl.SS == 4) BINFB_CHROM_LAUNCH(2, 2);
+    else if (pl.R == 4 && pl.SS == 4) BINFB_CHROM_LAUNCH(4, 1);
+    else if (pl.R == 8 && pl.SS == 8) BINFB_CHROM_LAUNCH(8, 1);
+    else {
+        set_error("chromatin model: unsupported launch plan");
+        return BINFB_EUNSUPPORTED;
+    }
+#undef BINFB_CHROM_LAUNCH
     BINFB_CUDA(cudaGetLastError());
     return BINFB_OK;
 }
