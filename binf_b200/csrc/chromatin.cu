@@ -34,6 +34,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "internal.h"
 #include "pair_block.cuh"
@@ -49,8 +51,8 @@ namespace binfb {
 #ifndef BINFB_PEEL
 #define BINFB_PEEL 0
 #endif
-#ifndef BINFB_STS64
-#define BINFB_STS64 0
+#ifndef BINFB_ROTATE
+#define BINFB_ROTATE 1  // start each chain group at a different row block
 #endif
 
 constexpr float CHROM_SOFT = PAIR_SOFT;
@@ -101,8 +103,8 @@ struct ChainSmem {
 };
 __device__ __forceinline__ int qidx(int bead, int comp) { return (bead >> 2) * 12 + comp * 4 + (bead & 3); }
 
-// mbarrier / bulk-copy wrappers on raw 32-bit shared addresses (no generic->shared conversion in
-// the stage loop)
+// mbarrier / bulk-copy / vector load-store wrappers on raw 32-bit shared addresses (no generic->shared
+// conversion and no 64-bit pointer arithmetic in the stage loop)
 __device__ __forceinline__ bool bar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -114,10 +116,6 @@ __device__ __forceinline__ bool bar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
-    while (!bar_try_wait(bar, parity)) {
-    }
-}
 __device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -127,20 +125,50 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
         : "memory");
 }
+// keep a value in a register: the compiler cannot rematerialise it from its inputs (address arithmetic
+// that it would otherwise redo at every use inside the stage loop)
+__device__ __forceinline__ uint32_t pin_reg(uint32_t v) {
+    asm volatile("mov.u32 %0, %0;" : "+r"(v));
+    return v;
+}
+// true in exactly one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(p));
+    return p != 0;
+}
+template <int OFF>
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(addr), "n"(OFF), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
 // The contact ring: CHROM_NS stages of SS warp-steps in shared memory, filled by 1-D bulk async
-// copies (TMA engine) that complete on the `full` mbarrier of the slot.  A slot is handed back
-// through a plain shared-memory counter: the LAST of the n_warps consumers to release stage j is
-// the one that refills the slot with stage j + CHROM_NS -- the refill is issued at the earliest
-// possible moment, nobody ever spins on an "empty" barrier, and a fast warp may run up to
-// CHROM_NS - 1 stages ahead of the slowest one.
+// copies (TMA engine, SASS UBLKCP) that complete on the `full` mbarrier of the slot.  A slot is handed
+// back through a plain shared-memory counter: the LAST of the n_warps consumers to release stage j
+// refills the slot with stage j + CHROM_NS itself.  The refill is issued at the earliest possible
+// moment, nobody ever waits for an "empty" slot, and a fast warp may run up to CHROM_NS - 1 stages
+// ahead of the slowest one.  (Measured alternatives, profiles/README.md: a loader lane that waits on
+// `empty` mbarriers, and a loader lane that polls them once per step -- 7 % and 6 % slower.)
 struct Ring {
     uint32_t ystage;  // shared address of stage 0
-    const float4 *ystage_ptr;  // the same, as a pointer (consumer loads)
-    uint32_t full;    // shared address of full[0] (8 bytes each)
-    uint32_t cnt;     // shared address of the release counters (4 bytes each)
+    uint32_t full;    // shared address of full[0] (8 bytes each); the release counters follow at + 8 * CHROM_NS
     const unsigned char *src;  // global source: the contact stream of one pass
     int n_stage_pass;
     int n_warps;
+    int rot;  // the pass starts at stream stage `rot` and wraps around (see chrom_kernel)
 };
 
 template <int STAGE_BYTES>
@@ -148,16 +176,20 @@ __device__ __forceinline__ void ring_issue(const Ring &ring, uint32_t gi, int s_
     const uint32_t sl = gi & (CHROM_NS - 1);
     const uint32_t bar = ring.full + sl * 8u;
     bar_expect_tx(bar, STAGE_BYTES);
-    bulk_g2s(ring.ystage + sl * STAGE_BYTES, ring.src + (size_t)s_local * STAGE_BYTES, STAGE_BYTES, bar);
+    int st = s_local + ring.rot;
+    if (st >= ring.n_stage_pass) st -= ring.n_stage_pass;
+    bulk_g2s(ring.ystage + sl * STAGE_BYTES, ring.src + (size_t)st * STAGE_BYTES, STAGE_BYTES, bar);
 }
 
-// release stage (gi, s_local) (lane 0 of every consumer warp; the warp has passed a __syncwarp since
-// its last read of the slot)
+// release stage (gi, s_local): called by one elected lane of every consumer warp after the __syncwarp
+// that follows the warp's last read of the slot
 template <int STAGE_BYTES>
 __device__ __forceinline__ void ring_release(const Ring &ring, uint32_t gi, int s_local) {
-    const uint32_t c = ring.cnt + (gi & (CHROM_NS - 1)) * 4u;
+    const uint32_t c = ring.full + CHROM_NS * 8u + (gi & (CHROM_NS - 1)) * 4u;
     uint32_t old;
-    asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(c) : "memory");
+    // the slot's loads have returned (their values were consumed before the __syncwarp in front of this
+    // call), so a relaxed add is enough to order them before the refill the last arriver issues
+    asm volatile("atom.relaxed.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(c) : "memory");
     if (old == (uint32_t)ring.n_warps - 1u) {
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(c), "r"(0u) : "memory");
         if (s_local + CHROM_NS < ring.n_stage_pass) ring_issue<STAGE_BYTES>(ring, gi + CHROM_NS, s_local + CHROM_NS);
@@ -181,53 +213,50 @@ __device__ __forceinline__ void ring_release(const Ring &ring, uint32_t gi, int 
 struct SweepRegs {
     float2 nx2[4], ny2[4], nz2[4];  // own quad, negated, as broadcast pairs
     float2 g[4][3];                 // G = -(force sum) of the own quad
-    int k, b;                       // partner offset and partner quad of the next step
+    int k;                          // partner offset of the next step
+    uint32_t paddr;                 // shared address of the partner quad's positions (48 bytes per quad)
+    int wrap;                       // steps until the partner index wraps from Q - 1 to 0
     double chi2;
 };
 
-// one regular step: the 16 pairs (own quad) x (partner quad b), every lane (inactive lanes compute
-// on quad 0 and never store)
+// one regular step: the 16 pairs (own quad) x (partner quad), every lane (inactive lanes compute on
+// quad 0 and never store).  frc_off = byte distance from a quad's positions to its force sums.
 template <bool ENERGY>
-__device__ __forceinline__ void step_fast(SweepRegs &s, float4 *pos4, float4 *frc4, const float4 *yb, float2 A2,
-                                          float2 B2, bool active) {
-    const float4 *pj = pos4 + 3 * s.b;
-    float4 *fj = frc4 + 3 * s.b;
-    const float4 xj = pj[0], yj = pj[1], zj = pj[2];
-    const float4 fx = fj[0], fy = fj[1], fz = fj[2];
+__device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32_t yaddr, float2 A2, float2 B2,
+                                          bool active) {
+    const uint32_t pa = s.paddr, fa = s.paddr + frc_off;
+    const float4 xj = lds4<0>(pa), yj = lds4<16>(pa), zj = lds4<32>(pa);
+    const float4 fx = lds4<0>(fa), fy = lds4<16>(fa), fz = lds4<32>(fa);
     const float2 xj2[2] = {mk2(xj.x, xj.y), mk2(xj.z, xj.w)}, yj2[2] = {mk2(yj.x, yj.y), mk2(yj.z, yj.w)},
                  zj2[2] = {mk2(zj.x, zj.y), mk2(zj.z, zj.w)};
     float2 fx2[2] = {mk2(fx.x, fx.y), mk2(fx.z, fx.w)}, fy2[2] = {mk2(fy.x, fy.y), mk2(fy.z, fy.w)},
            fz2[2] = {mk2(fz.x, fz.y), mk2(fz.z, fz.w)};
     float2 c2 = mk2(0.f, 0.f);
+    float4 yv[4];
+    yv[0] = lds4<0>(yaddr), yv[1] = lds4<512>(yaddr), yv[2] = lds4<1024>(yaddr), yv[3] = lds4<1536>(yaddr);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const float4 yv = yb[r * 32];
 #if BINFB_PAIR_SHAPE == 1
-        pair_hybrid<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv.x, yv.y), A2.x,
+        pair_hybrid<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y), A2.x,
                             B2.x, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2);
-        pair_hybrid<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv.z, yv.w), A2.x,
+        pair_hybrid<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w), A2.x,
                             B2.x, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2);
 #elif BINFB_PAIR_SHAPE == 2
-        pair_packed_sr<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv.x, yv.y), A2,
+        pair_packed_sr<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y), A2,
                                B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2);
-        pair_packed_sr<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv.z, yv.w), A2,
+        pair_packed_sr<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w), A2,
                                B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2);
 #else
-        pair_packed<ENERGY, false>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv.x, yv.y), A2,
-                                   B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2);
-        pair_packed<ENERGY, false>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv.z, yv.w), A2,
-                                   B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2);
+        pair_packed<ENERGY, false>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y),
+                                   A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2);
+        pair_packed<ENERGY, false>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w),
+                                   A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2);
 #endif
     }
     if (active) {
-#if BINFB_STS64
-        float2 *f2 = reinterpret_cast<float2 *>(fj);
-        f2[0] = fx2[0], f2[1] = fx2[1], f2[2] = fy2[0], f2[3] = fy2[1], f2[4] = fz2[0], f2[5] = fz2[1];
-#else
-        fj[0] = make_float4(fx2[0].x, fx2[0].y, fx2[1].x, fx2[1].y);
-        fj[1] = make_float4(fy2[0].x, fy2[0].y, fy2[1].x, fy2[1].y);
-        fj[2] = make_float4(fz2[0].x, fz2[0].y, fz2[1].x, fz2[1].y);
-#endif
+        sts4<0>(fa, fx2[0].x, fx2[0].y, fx2[1].x, fx2[1].y);
+        sts4<16>(fa, fy2[0].x, fy2[0].y, fy2[1].x, fy2[1].y);
+        sts4<32>(fa, fz2[0].x, fz2[0].y, fz2[1].x, fz2[1].y);
         if (ENERGY) s.chi2 += (double)(c2.x + c2.y);
     }
 }
@@ -235,15 +264,14 @@ __device__ __forceinline__ void step_fast(SweepRegs &s, float4 *pos4, float4 *fr
 // the special steps: k == 0 (the 6 pairs inside the lane's own quad), k == KS with an even quad
 // count (only the lower half of the quads owns the (q, q + Q/2) block), k > KS (padding: nothing)
 template <bool ENERGY>
-__device__ __forceinline__ void step_special(SweepRegs &s, float4 *pos4, float4 *frc4, const float4 *yb, float A,
-                                             float B, int KS, bool upper_half) {
+__device__ __forceinline__ void step_special(SweepRegs &s, uint32_t frc_off, uint32_t yaddr, float A, float B,
+                                             int KS, bool upper_half) {
     const int k = s.k;
     if (k > KS) return;
     float chi = 0.f;
     if (k == 0) {
         float yv[4][4];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) unpack4(yb[r * 32], yv[r]);
+        unpack4(lds4<0>(yaddr), yv[0]), unpack4(lds4<512>(yaddr), yv[1]), unpack4(lds4<1024>(yaddr), yv[2]);
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -254,22 +282,21 @@ __device__ __forceinline__ void step_special(SweepRegs &s, float4 *pos4, float4 
                 s.g[c][0].y -= tx, s.g[c][1].y -= ty, s.g[c][2].y -= tz;
             }
     } else if (!upper_half) {
-        const float4 *pj = pos4 + 3 * s.b;
-        float4 *fj = frc4 + 3 * s.b;
+        const uint32_t pa = s.paddr, fa = s.paddr + frc_off;
         float xj[4], yj[4], zj[4], fjx[4], fjy[4], fjz[4], yv[4][4];
-        unpack4(pj[0], xj), unpack4(pj[1], yj), unpack4(pj[2], zj);
-        unpack4(fj[0], fjx), unpack4(fj[1], fjy), unpack4(fj[2], fjz);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) unpack4(yb[r * 32], yv[r]);
+        unpack4(lds4<0>(pa), xj), unpack4(lds4<16>(pa), yj), unpack4(lds4<32>(pa), zj);
+        unpack4(lds4<0>(fa), fjx), unpack4(lds4<16>(fa), fjy), unpack4(lds4<32>(fa), fjz);
+        unpack4(lds4<0>(yaddr), yv[0]), unpack4(lds4<512>(yaddr), yv[1]);
+        unpack4(lds4<1024>(yaddr), yv[2]), unpack4(lds4<1536>(yaddr), yv[3]);
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int c = 0; c < 4; ++c)
                 pair_scalar<ENERGY>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, xj[c], yj[c], zj[c], yv[r][c], A, B,
                                     s.g[r][0].x, s.g[r][1].x, s.g[r][2].x, fjx[c], fjy[c], fjz[c], chi);
-        fj[0] = make_float4(fjx[0], fjx[1], fjx[2], fjx[3]);
-        fj[1] = make_float4(fjy[0], fjy[1], fjy[2], fjy[3]);
-        fj[2] = make_float4(fjz[0], fjz[1], fjz[2], fjz[3]);
+        sts4<0>(fa, fjx[0], fjx[1], fjx[2], fjx[3]);
+        sts4<16>(fa, fjy[0], fjy[1], fjy[2], fjy[3]);
+        sts4<32>(fa, fjz[0], fjz[1], fjz[2], fjz[3]);
     }
     if (ENERGY) s.chi2 += (double)chi;
 }
@@ -277,9 +304,11 @@ __device__ __forceinline__ void step_special(SweepRegs &s, float4 *pos4, float4 
 template <bool ENERGY, int R, int SPR>
 __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSmem &sm, const Ring &ring,
                                               uint32_t &stage_idx_io, bool chain_valid, int lane, int role,
-                                              int bar_id) {
+                                              int bar_id, int rb0) {
     constexpr int STAGE_BYTES = R * SPR * STEP_BYTES;
     float4 *pos4 = reinterpret_cast<float4 *>(sm.pos), *frc4 = reinterpret_cast<float4 *>(sm.frc);
+    const uint32_t pos_base = smem_u32(sm.pos);
+    const uint32_t frc_off = pin_reg((uint32_t)cd.n_pad * 12u);
     const float A = cd.A, B = cd.B;
     const float2 A2 = mk2(A, A), B2 = mk2(B, B);
     const int Q = cd.Q, KS = cd.KS, Lr = cd.Lr, halfQ = cd.Q >> 1;
@@ -293,14 +322,15 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
     int sg_hi = (k_fast - k0 + 1) / SPR;
     sg_hi = sg_hi < sg_lo ? sg_lo : (sg_hi > n_sg ? n_sg : sg_hi);
 #endif
-    uint32_t stage_idx = stage_idx_io;
-    int s_local = 0;
-    const float4 *ylane = ring.ystage_ptr + role * STEP_FLOAT4 + lane;
-    bool ready = false;  // the stage about to be consumed was already seen complete (early probe)
+    const uint32_t stage_base = stage_idx_io;
+    uint32_t stage_idx = stage_base;
+    const uint32_t ylane = pin_reg(ring.ystage + (uint32_t)role * STEP_BYTES + (uint32_t)lane * 16u);
     SweepRegs s;
     s.chi2 = 0.0;
 
-    for (int rb = 0; rb < cd.NRB; ++rb) {
+    for (int rbi = 0; rbi < cd.NRB; ++rbi) {
+        int rb = rbi + rb0;
+        if (rb >= cd.NRB) rb -= cd.NRB;
         const int a = rb * 32 + lane;
         const bool active = chain_valid && a < Q;
         const int aa = active ? a : 0;
@@ -315,55 +345,50 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
             }
         }
         s.k = k0;  // partner offset of slot 0
-        s.b = aa + s.k;
-        if (s.b >= Q) s.b -= Q;
-#if BINFB_PEEL
-        int sg = 0;
-#pragma unroll 1
-        for (int part = 0; part < 3; ++part) {
-            const int sg_end = part == 0 ? sg_lo : (part == 1 ? sg_hi : n_sg);
-            const bool generic = part != 1;
-#pragma unroll 1
-            for (; sg < sg_end; ++sg) {
-#else
         {
-            const bool generic = true;
+            int b = aa + k0;
+            if (b >= Q) b -= Q;
+            s.paddr = pos_base + (uint32_t)b * 48u;
+            s.wrap = Q - b;
+        }
+        // stages [sg_begin, sg_end) of this row block; GENERIC: a step may be one of the special ones
+        auto run_stages = [&](auto generic_tag, int sg_begin, int sg_end) {
+            constexpr bool GENERIC = decltype(generic_tag)::value;
 #pragma unroll 1
-            for (int sg = 0; sg < n_sg; ++sg) {
-#endif
+            for (int sg = sg_begin; sg < sg_end; ++sg) {
                 const uint32_t slot = stage_idx & (CHROM_NS - 1);
-                if (!ready) bar_wait(ring.full + slot * 8u, (stage_idx >> 2) & 1u);
-                const float4 *ybase = ylane + slot * (STAGE_BYTES / 16);
-                const uint32_t nbar = ring.full + ((stage_idx + 1) & (CHROM_NS - 1)) * 8u;
-                const uint32_t npar = ((stage_idx + 1) >> 2) & 1u;
-                if (!generic) {
-#pragma unroll
-                    for (int u = 0; u < SPR; ++u) {
-                        // probe the next stage now; the answer is back after this step
-                        if (u == SPR - 1) ready = bar_try_wait(nbar, npar);
-                        step_fast<ENERGY>(s, pos4, frc4, ybase + u * R * STEP_FLOAT4, A2, B2, active);
-                        ++s.k;
-                        if (++s.b == Q) s.b = 0;
-                        __syncwarp();
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < SPR; ++u) {
-                        if (u == SPR - 1) ready = bar_try_wait(nbar, npar);
-                        if ((unsigned)(s.k - 1) < (unsigned)k_fast)
-                            step_fast<ENERGY>(s, pos4, frc4, ybase + u * R * STEP_FLOAT4, A2, B2, active);
-                        else if (active)
-                            step_special<ENERGY>(s, pos4, frc4, ybase + u * R * STEP_FLOAT4, A, B, KS, upper_half);
-                        ++s.k;
-                        if (++s.b == Q) s.b = 0;
-                        __syncwarp();
+                {  // (probing the barrier one step early does not pay: the result is consumed at once)
+                    const uint32_t fb = ring.full + slot * 8u, fp = (stage_idx >> 2) & 1u;
+                    while (!bar_try_wait(fb, fp)) {
                     }
                 }
-                if (lane == 0) ring_release<STAGE_BYTES>(ring, stage_idx, s_local);
+                const uint32_t ybase = ylane + slot * STAGE_BYTES;
+#pragma unroll
+                for (int u = 0; u < SPR; ++u) {
+                    if (!GENERIC || (unsigned)(s.k - 1) < (unsigned)k_fast)
+                        step_fast<ENERGY>(s, frc_off, ybase + u * R * STEP_BYTES, A2, B2, active);
+                    else if (active)
+                        step_special<ENERGY>(s, frc_off, ybase + u * R * STEP_BYTES, A, B, KS, upper_half);
+                    if (GENERIC) ++s.k;
+                    s.paddr += 48u;
+                    if (--s.wrap == 0) s.paddr -= (uint32_t)Q * 48u, s.wrap = Q;
+                    __syncwarp();
+                }
+                if (elect_one()) ring_release<STAGE_BYTES>(ring, stage_idx, (int)(stage_idx - stage_base));
                 ++stage_idx;
-                ++s_local;
             }
+            if (!GENERIC) s.k += (sg_end - sg_begin) * SPR;
+        };
+#if BINFB_PEEL
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+            // part 0: generic [0, sg_lo) then regular [sg_lo, sg_hi); part 1: generic [sg_hi, n_sg)
+            run_stages(std::true_type{}, part == 0 ? 0 : sg_hi, part == 0 ? sg_lo : n_sg);
+            if (part == 0) run_stages(std::false_type{}, sg_lo, sg_hi);
         }
+#else
+        run_stages(std::true_type{}, 0, n_sg);
+#endif
         // ---- end of the row block: fold the register-resident accumulators of the own quad into
         //      shared memory (f -= G), one role at a time --------------------------------------------
 #pragma unroll 1
@@ -420,19 +445,19 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
     constexpr int STAGE_BYTES = R * SPR * STEP_BYTES;
     const int W = call.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (warp w runs on SMSP w % 4, so with R = 2 an SMSP hosts one role only; mixing the roles per SMSP
+    // measured 2 % slower)
     const int chain_local = warp / R, role = warp % R;
     const int bar_id = 1 + chain_local;
     // ---- shared memory carve-up: [stages][full barriers, release counters, item][W x chain]
     Ring ring;
     ring.ystage = smem_u32(smem_raw);
-    ring.ystage_ptr = reinterpret_cast<const float4 *>(smem_raw);
     ring.full = ring.ystage + CHROM_NS * STAGE_BYTES;
-    ring.cnt = ring.full + CHROM_NS * 8;
     ring.src = reinterpret_cast<const unsigned char *>(cd.ystream);
     ring.n_stage_pass = cd.S_pad / SPR;
     ring.n_warps = W * R;
     unsigned char *ctl = smem_raw + (size_t)CHROM_NS * STAGE_BYTES;
-    uint64_t *full_bars = reinterpret_cast<uint64_t *>(ctl);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ctl);  // full[NS], then the release counters [NS]
     uint32_t *cnts = reinterpret_cast<uint32_t *>(ctl + CHROM_NS * 8);
     int *s_item = reinterpret_cast<int *>(ctl + CHROM_NS * 12);
     unsigned char *chains = ctl + 128;
@@ -445,7 +470,7 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
         sm.frc = sm.pos + 3 * cd.n_pad;
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < CHROM_NS; ++i) mbar_init(&full_bars[i], 1), cnts[i] = 0u;
+        for (int i = 0; i < CHROM_NS; ++i) mbar_init(&bars[i], 1), cnts[i] = 0u;
         mbar_fence_init();
     }
     __syncthreads();
@@ -461,7 +486,11 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
             const int it = atomicAdd(cd.counter, 1);
             if (it < call.total_items) {
                 // every warp has released every stage of the previous item (block barrier below):
-                // start streaming the contacts of this pass right away
+                // start streaming the contacts of this pass right away.  Chain group o walks the row
+                // blocks starting at block o mod NRB: concurrently running CTAs then read different
+                // parts of the contact stream instead of hammering the same L2 lines in lockstep (the
+                // order is a function of the group, so results do not depend on the CTA schedule).
+                ring.rot = BINFB_ROTATE ? ((it % call.n_groups) % cd.NRB) * (cd.Lr / SPR) : 0;
                 for (int i = 0; i < CHROM_NS && i < ring.n_stage_pass; ++i)
                     ring_issue<STAGE_BYTES>(ring, stage_idx + (uint32_t)i, i);
                 const int o = it % call.n_groups;
@@ -476,6 +505,7 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
         if (item >= call.total_items) break;
         const int o = item % call.n_groups;
         const int seq = item / call.n_groups;  // = tr * passes + k
+        ring.rot = BINFB_ROTATE ? (o % cd.NRB) * (cd.Lr / SPR) : 0;
         const int tr = seq / passes, k = seq % passes;
 
         {
@@ -541,8 +571,9 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
             if (R > 1) chain_bar(bar_id, cthreads);
             else __syncwarp();
             // ---- phase B: pair sweep -----------------------------------------------------
-            double chi2 = energy ? chrom_sweep<true, R, SPR>(cd, sm, ring, stage_idx, valid, lane, role, bar_id)
-                                 : chrom_sweep<false, R, SPR>(cd, sm, ring, stage_idx, valid, lane, role, bar_id);
+            const int rb0 = BINFB_ROTATE ? o % cd.NRB : 0;
+            double chi2 = energy ? chrom_sweep<true, R, SPR>(cd, sm, ring, stage_idx, valid, lane, role, bar_id, rb0)
+                                 : chrom_sweep<false, R, SPR>(cd, sm, ring, stage_idx, valid, lane, role, bar_id, rb0);
             if (R > 1) chain_bar(bar_id, cthreads);
             else __syncwarp();
             if (valid) {
