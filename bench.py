@@ -183,6 +183,96 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------
+# the sample sink (HBM-bound), measured next to the sweep it follows
+# --------------------------------------------------------------------------------------------
+def run_sink(args):
+    """One step = one binfb_sink_push of the configs[2] state (4096 chains x 3000 dof): ring copy
+    (every 2nd sweep) + float64 running moments + MAP tracking.  Roofline: HBM copy bandwidth."""
+    import torch
+    from binf_b200 import _cabi
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    C, D = args.chains or 4096, 3000
+    sink = _cabi.Sink(C, D, capacity=8, burn_in=0, thin=2, track_map=True, device=local)
+    g = torch.Generator(device=dev).manual_seed(args.seed)
+    q = torch.randn(C, D, device=dev, generator=g)
+    tau = torch.rand(C, device=dev, generator=g)
+    logp = torch.randn(C, device=dev, generator=g, dtype=torch.float64)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(max(args.warmup, 3)):
+        sink.push(q, tau, logp, stream)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    # a push is ~100 us: launch it from a CUDA graph so that host-side launch jitter (e.g. the
+    # nvidia-smi clock sampler holding the driver lock) is not mistaken for kernel time
+    steps = max(args.steps, 50)
+    side = torch.cuda.Stream(device=dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for k in range(steps):
+                logp.add_(0.01)                       # every sweep improves: MAP state rewritten each time
+                sink.push(q, tau, logp, side.cuda_stream)
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    with torch.cuda.stream(side):
+        e0.record(side)
+        for _ in range(reps):
+            graph.replay()
+        e1.record(side)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (steps * reps)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.summary() if sampler else None
+    # algorithmic bytes per element and push: read q 4, moments RMW 2 x (8 + 8), MAP state write 4,
+    # ring write 4 on every 2nd sweep
+    bytes_per_push = C * D * (4 + 32 + 4 + 2.0)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = float(peaks.get("hbm_gbs", 6543.7))
+    achieved = bytes_per_push / (ms * 1e-3) / 1e9
+    # e2e: the same push from pinned host memory (H2D inside the timed region)
+    qh = q.cpu().pin_memory()
+    th, lh = tau.cpu().pin_memory(), logp.cpu().pin_memory()
+    t0 = time.perf_counter()
+    n_e2e = 5
+    for _ in range(n_e2e):
+        q.copy_(qh, non_blocking=True), tau.copy_(th, non_blocking=True), logp.copy_(lh, non_blocking=True)
+        sink.push(q, tau, logp, stream)
+        torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+    if rank == 0:
+        print(json.dumps({
+            "metric": "sample-sink state elements absorbed/s (chains x dim per sweep)", "value": world * C * D / (ms * 1e-3),
+            "unit": "elements/s", "n_gpus": world, "steps": steps * reps, "warmup": max(args.warmup, 3) + steps,
+            "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 state, f64 moments",
+            "data": "synthetic",
+            "config": {"workload": "sink_c%d_d%d_thin2_map" % (C, D), "chains_per_gpu": C, "dim": D,
+                       "l2": "working set 295 MB of moments + 49 MB state per push > 126 MB L2"},
+            "e2e": {"value": world * C * D / (e2e_ms * 1e-3), "unit": "elements/s",
+                    "h2d_bytes_per_step": C * D * 4 + C * 12, "d2h_bytes_per_step": 0, "steps": n_e2e,
+                    "api": "Sink.push after an H2D copy of the state from pinned host memory"},
+            "gpu_launches": steps * reps, "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "bytes_per_launch": bytes_per_push,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"},
+            "cpu_baseline": None}))
+
+
 # the product arm
 # --------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -395,7 +485,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="chromatin", choices=sorted(WORKLOADS))  # rex: N >= 2
+    ap.add_argument("--workload", default="chromatin", choices=sorted(WORKLOADS) + ["sink"])  # rex: N >= 2
     ap.add_argument("--chains", type=int, default=0)
     ap.add_argument("--eps", type=float, default=0.0)
     ap.add_argument("--seed", type=int, default=2026)
@@ -405,7 +495,13 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload == "sink":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the sink workload has no reference arm "
+                              "(the reference keeps a Python list of deep copies of one chain)"}))
+        else:
+            run_sink(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -15,6 +15,7 @@ OK, EINVAL, ECUDA, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4
 MODEL_POLYNOMIAL, MODEL_CHROMATIN = 1, 2
 FLAG_PRIOR_GRAD = 1
 GIBBS_NONE, GIBBS_TAU_FIRST, GIBBS_TAU_LAST = 0, 1, 2
+SINK_TRACK_MAP = 1
 
 
 class BinfB200Error(RuntimeError):
@@ -55,6 +56,16 @@ SIGNATURES = {
     "binfb_gibbs_precision_host": (_i, [_vp, _vp, _vp, _vp, _i, _u64, _u64, _u64, _vp, _vp]),
     "binfb_swap_decide": (_i, [_vp, _vp, _d, _d, _i, _u64, _u64, _u64, _u64, _vp, _vp]),
     "binfb_swap_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "binfb_sink_create": (_i, [_i, _i, _i, _i, _i, C.c_uint, _i, C.POINTER(_vp)]),
+    "binfb_sink_destroy": (_i, [_vp]),
+    "binfb_sink_info": (_i, [_vp, _pll, _pll, _pll]),
+    "binfb_sink_push": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "binfb_sink_push_host": (_i, [_vp, _vp, _vp, _vp]),
+    "binfb_sink_summary": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "binfb_sink_summary_host": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "binfb_sink_moments_host": (_i, [_vp, _vp, _vp]),
+    "binfb_sink_read_host": (_i, [_vp, _ll, _ll, _vp, _vp]),
+    "binfb_sink_map_host": (_i, [_vp, _vp, _vp, _vp]),
     "binfb_rng_fill_host": (_i, [_u64, _u64, _u64, _i, _i, _d, _vp, _vp, _vp, _i]),
     "binfb_chromatin_stream_layout": (_i, [_i, _vp, _i, _i, _vp, _ll, _pll, _pi]),
     "binfb_microbench": (_i, [_i, _i, _pd, _pd, _pd, _pd]),
@@ -271,3 +282,72 @@ class Model(object):
         check(lib().binfb_gibbs_precision(self._h, ptr(q), ptr(tau), ptr(beta), q.shape[0], seed,
                                           draw, chain_base, ptr(gamma_draws), ptr(chi2),
                                           ptr(stream)))
+
+
+class Sink(object):
+    """Owning wrapper of a `binfb_sink*` (sample ring, running moments, MAP candidates)."""
+
+    def __init__(self, n_chains, dim, capacity=0, burn_in=0, thin=1, track_map=False, device=0):
+        h = C.c_void_p()
+        check(lib().binfb_sink_create(n_chains, dim, capacity, burn_in, thin,
+                                      SINK_TRACK_MAP if track_map else 0, device, C.byref(h)))
+        self._h = h
+        self.n_chains, self.dim, self.capacity, self.burn_in, self.thin = n_chains, dim, capacity, burn_in, thin
+        self.track_map = track_map
+
+    def close(self):
+        if self._h is not None:
+            lib().binfb_sink_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        a, b, c = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        check(lib().binfb_sink_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(n_pushed=a.value, n_moment=b.value, n_kept=c.value)
+
+    def push(self, q, aux=None, logp=None, stream=None):
+        """q/aux/logp: torch CUDA tensors (device path, asynchronous) or numpy arrays (host path)."""
+        if hasattr(q, "data_ptr"):
+            check(lib().binfb_sink_push(self._h, ptr(q), ptr(aux), ptr(logp), ptr(stream)))
+        else:
+            q = f32(q).reshape(self.n_chains, self.dim)
+            aux = None if aux is None else np.ascontiguousarray(np.broadcast_to(f32(aux), (self.n_chains,)))
+            logp = None if logp is None else np.ascontiguousarray(np.broadcast_to(f64(logp), (self.n_chains,)))
+            check(lib().binfb_sink_push_host(self._h, ptr(q), ptr(aux), ptr(logp)))
+
+    def summary(self):
+        out = [np.empty(self.dim) for _ in range(4)]
+        check(lib().binfb_sink_summary_host(self._h, *[ptr(o) for o in out]))
+        return dict(mean=out[0], var=out[1], rhat=out[2], ess_per_chain=out[3])
+
+    def summary_device(self, mean=None, var=None, rhat=None, ess=None, stream=None):
+        check(lib().binfb_sink_summary(self._h, ptr(mean), ptr(var), ptr(rhat), ptr(ess), ptr(stream)))
+
+    def moments(self):
+        mean, var = np.empty((self.n_chains, self.dim)), np.empty((self.n_chains, self.dim))
+        check(lib().binfb_sink_moments_host(self._h, ptr(mean), ptr(var)))
+        return mean, var
+
+    def read(self, first=None, count=None):
+        """kept samples still in the ring (default: all of them): q [count, C, dim], aux [count, C]"""
+        n_kept = self.info()["n_kept"]
+        oldest = max(0, n_kept - self.capacity)
+        first = oldest if first is None else first
+        count = n_kept - first if count is None else count
+        q = np.empty((count, self.n_chains, self.dim), dtype=np.float32)
+        aux = np.empty((count, self.n_chains), dtype=np.float32)
+        check(lib().binfb_sink_read_host(self._h, first, count, ptr(q), ptr(aux)))
+        return q, aux
+
+    def map_estimate(self):
+        logp = np.empty(self.n_chains)
+        q = np.empty((self.n_chains, self.dim), dtype=np.float32)
+        aux = np.empty(self.n_chains, dtype=np.float32)
+        check(lib().binfb_sink_map_host(self._h, ptr(logp), ptr(q), ptr(aux)))
+        return logp, q, aux

@@ -181,6 +181,9 @@ int binfb_model_create_polynomial(const double *xs, const double *ys, int n_data
     cudaError_t e = cudaMalloc(&pm.rows, rows.size() * sizeof(float));
     if (e == cudaSuccess)
         e = cudaMemcpy(pm.rows, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice);
+    // a cudaMemcpy from pageable memory may return before the DMA has landed, and the kernels run on
+    // non-blocking / caller streams that do not wait for the legacy stream
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         binfb_model_destroy(m);
         return cuda_fail(e, "polynomial data upload");
@@ -228,6 +231,7 @@ int binfb_model_create_chromatin(int n_beads, const float *y_pairs, double alpha
     if (!rc && e == cudaSuccess) e = cudaMalloc(&cm.ypairs, (size_t)cm.M * sizeof(float));
     if (!rc && e == cudaSuccess)
         e = cudaMemcpy(cm.ypairs, y_pairs, (size_t)cm.M * sizeof(float), cudaMemcpyHostToDevice);
+    if (!rc && e == cudaSuccess) e = cudaDeviceSynchronize();  // see binfb_model_create_polynomial
     if (rc || e != cudaSuccess) {
         binfb_model_destroy(m);
         return rc ? rc : cuda_fail(e, "chromatin data upload");

@@ -157,6 +157,42 @@ int binfb_swap_apply(float *q_mine_dev, const float *q_theirs_dev, float *eps_mi
                      const float *eps_theirs_dev, const uint8_t *accept_dev, int n_chains,
                      int dim, void *stream);
 
+/* ---- sample sink ------------------------------------------------------- */
+/* What the reference's driver loop does with every Gibbs sweep, for chains resident in HBM:
+ * `samples.append(deepcopy(gips.sample()))` (example_script.py:32-34), the burn-in/thinning slice
+ * `samples[20000::20]` (example_script.py:41), the MAP estimate = kept sample of maximum
+ * log-probability (binf/example/misc.py:18-22, example_script.py:51) and the posterior summaries
+ * the plots derive from the kept samples (binf/example/plots.py).
+ *   sweep t = 0, 1, ... (one push each).  Sweeps t >= burn_in enter the per-chain running moments
+ *   (Welford, float64); sweeps with (t - burn_in) % thin == 0 are also copied into a ring of
+ *   `capacity` kept samples (the oldest is overwritten); with BINFB_SINK_TRACK_MAP every chain keeps
+ *   its kept sample of maximum logp (ties: the first, like numpy.argmax). */
+#define BINFB_SINK_TRACK_MAP 1u
+typedef struct binfb_sink binfb_sink;
+int binfb_sink_create(int n_chains, int dim, int capacity, int burn_in, int thin, unsigned flags,
+                      int device, binfb_sink **out);
+int binfb_sink_destroy(binfb_sink *s);
+/* sweeps pushed, sweeps in the moments, samples kept so far (the ring holds the last `capacity`) */
+int binfb_sink_info(const binfb_sink *s, long long *n_pushed, long long *n_moment, long long *n_kept);
+/* one sweep: q [C, dim] f32, aux [C] f32 or NULL (e.g. the precision), logp [C] f64 (NULL unless
+ * the sink tracks the MAP).  One fused HBM-bound pass; asynchronous on `stream`. */
+int binfb_sink_push(binfb_sink *s, const float *q_dev, const float *aux_dev, const double *logp_dev,
+                    void *stream);
+int binfb_sink_push_host(binfb_sink *s, const float *q, const float *aux, const double *logp);
+/* per-dimension summaries over all chains, each [dim] f64 or NULL: posterior mean, pooled
+ * within-chain variance W, Gelman-Rubin R-hat sqrt(((n-1)/n W + B/n) / W), and the effective sample
+ * size per chain W / var_c(chain means) (independent chains). */
+int binfb_sink_summary(binfb_sink *s, double *mean_dev, double *var_dev, double *rhat_dev,
+                       double *ess_dev, void *stream);
+int binfb_sink_summary_host(binfb_sink *s, double *mean, double *var, double *rhat, double *ess);
+/* per-chain running mean and unbiased variance, [C, dim] f64 each (either may be NULL) */
+int binfb_sink_moments_host(binfb_sink *s, double *mean, double *var);
+/* kept samples number first .. first+count-1 (0 = the first ever kept) -> q_out [count, C, dim],
+ * aux_out [count, C]; they must still be in the ring */
+int binfb_sink_read_host(binfb_sink *s, long long first, long long count, float *q_out, float *aux_out);
+/* per-chain MAP candidate: logp [C] f64, state [C, dim] f32, aux [C] f32 (any may be NULL) */
+int binfb_sink_map_host(binfb_sink *s, double *logp, float *q_map, float *aux_map);
+
 /* ---- test / measurement helpers ------------------------------------------------------------- */
 /* the device RNG streams, for statistical tests: normals [C, dim] f32 exactly as the momentum
  * draw of trajectory `draw`; uniforms [C]; standard gammas of the given shape [C] f64 */

@@ -116,3 +116,31 @@ def test_contact_stream_covers_every_pair_once(n, roles):
                         np.add.at(seen, (lo, hi), 1)
     assert not s[~used].any()
     assert (seen[iu] == 1).all() and seen.sum() == m
+
+
+def test_sink_argument_validation_needs_no_gpu():
+    import ctypes as C
+    h = _cabi.lib()
+    out = C.c_void_p()
+    for args in [(0, 4, 1, 0, 1), (4, 0, 1, 0, 1), (4, 4, -1, 0, 1), (4, 4, 1, -1, 1), (4, 4, 1, 0, 0)]:
+        assert h.binfb_sink_create(*args, 0, 0, C.byref(out)) == _cabi.EINVAL
+    assert h.binfb_sink_push(None, None, None, None, None) == _cabi.EINVAL
+    assert b"null sink" in h.binfb_last_error()
+    assert h.binfb_sink_destroy(None) == 0
+
+
+def test_list_sink_oracle_matches_reference_slicing():
+    """the oracle's bookkeeping is literally the reference driver's list + slice + argmax"""
+    import sink_port
+    rng = np.random.RandomState(0)
+    ref = sink_port.ListSink(burn_in=5, thin=3)
+    qs, ls = [], []
+    for t in range(20):
+        q, l = rng.normal(size=(2, 3)), rng.normal(size=2)
+        qs.append(q), ls.append(l)
+        ref.append(q, None, l)
+    thin = qs[5::3]                                       # example_script.py:41
+    np.testing.assert_array_equal(np.array(ref.thinned()[0]), np.array(thin))
+    lp = np.array(ls[5::3])
+    for c in range(2):                                    # misc.py:18-22 per chain
+        np.testing.assert_array_equal(ref.get_MAP()[0][c], thin[int(np.argmax(lp[:, c]))][c])
