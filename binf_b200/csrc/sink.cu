@@ -93,31 +93,54 @@ __global__ void __launch_bounds__(256) sink_push_kernel(SinkPush a) {
                 if (better && a.map_aux && a.aux) a.map_aux[c] = a.aux[c];
             }
         }
-        for (int j = tj; j < pc; j += jstep) {
-            const long long i = c * pc + j, e = i * V;
-            float x[V];
-            unpack(__ldcs(reinterpret_cast<const vec *>(a.q) + i), x);
-            if (a.do_moments) {
-                double *mp = a.mean + e, *sp = a.m2 + e;
-                if constexpr (V == 4) {
+        // U groups per thread and trip: all loads are issued before the first dependent instruction, so a
+        // thread keeps U x 80 bytes in flight (the pass has no reuse and is bound by HBM latency x bandwidth)
+        constexpr int U = 3;
+        for (int j0 = tj; j0 < pc; j0 += U * jstep) {
+            float x[U][V];
+            double mu[U][V], m2[U][V];
+            bool on[U];
 #pragma unroll
-                    for (int k = 0; k < 4; k += 2) {
-                        double2 mu = *reinterpret_cast<double2 *>(mp + k), s = *reinterpret_cast<double2 *>(sp + k);
-                        const double d0 = (double)x[k] - mu.x, d1 = (double)x[k + 1] - mu.y;
-                        mu.x += d0 * a.inv_n, mu.y += d1 * a.inv_n;  // Welford
-                        s.x += d0 * ((double)x[k] - mu.x), s.y += d1 * ((double)x[k + 1] - mu.y);
-                        *reinterpret_cast<double2 *>(mp + k) = mu, *reinterpret_cast<double2 *>(sp + k) = s;
+            for (int u = 0; u < U; ++u) {
+                const int j = j0 + u * jstep;
+                on[u] = j < pc;
+                if (!on[u]) continue;
+                const long long i = c * pc + j, e = i * V;
+                unpack(__ldcs(reinterpret_cast<const vec *>(a.q) + i), x[u]);
+                if (a.do_moments) {
+                    if constexpr (V == 4) {
+                        const double2 *mp = reinterpret_cast<const double2 *>(a.mean + e);
+                        const double2 *sp = reinterpret_cast<const double2 *>(a.m2 + e);
+                        const double2 ma = mp[0], mb = mp[1], sa = sp[0], sb = sp[1];
+                        mu[u][0] = ma.x, mu[u][1] = ma.y, mu[u][2] = mb.x, mu[u][3] = mb.y;
+                        m2[u][0] = sa.x, m2[u][1] = sa.y, m2[u][2] = sb.x, m2[u][3] = sb.y;
+                    } else {
+                        mu[u][0] = a.mean[e], m2[u][0] = a.m2[e];
                     }
-                } else {
-                    double mu = mp[0], s = sp[0];
-                    const double d0 = (double)x[0] - mu;
-                    mu += d0 * a.inv_n;
-                    s += d0 * ((double)x[0] - mu);
-                    mp[0] = mu, sp[0] = s;
                 }
             }
-            if (a.ring_q) __stcs(reinterpret_cast<vec *>(a.ring_q) + i, *reinterpret_cast<const vec *>(x));
-            if (better) reinterpret_cast<vec *>(a.map_q)[i] = *reinterpret_cast<const vec *>(x);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!on[u]) continue;
+                const long long i = c * pc + j0 + u * jstep, e = i * V;
+                if (a.do_moments) {
+#pragma unroll
+                    for (int k = 0; k < V; ++k) {  // Welford
+                        const double d0 = (double)x[u][k] - mu[u][k];
+                        mu[u][k] += d0 * a.inv_n;
+                        m2[u][k] += d0 * ((double)x[u][k] - mu[u][k]);
+                    }
+                    if constexpr (V == 4) {
+                        double2 *mp = reinterpret_cast<double2 *>(a.mean + e), *sp = reinterpret_cast<double2 *>(a.m2 + e);
+                        mp[0] = make_double2(mu[u][0], mu[u][1]), mp[1] = make_double2(mu[u][2], mu[u][3]);
+                        sp[0] = make_double2(m2[u][0], m2[u][1]), sp[1] = make_double2(m2[u][2], m2[u][3]);
+                    } else {
+                        a.mean[e] = mu[u][0], a.m2[e] = m2[u][0];
+                    }
+                }
+                if (a.ring_q) __stcs(reinterpret_cast<vec *>(a.ring_q) + i, *reinterpret_cast<const vec *>(x[u]));
+                if (better) reinterpret_cast<vec *>(a.map_q)[i] = *reinterpret_cast<const vec *>(x[u]);
+            }
         }
     }
 }
@@ -290,7 +313,7 @@ int binfb_sink_push(binfb_sink *s, const float *q_dev, const float *aux_dev, con
         const int pc = vec ? s->D / 4 : s->D;
         const int rows = pc >= 256 ? 1 : 256 / pc;
         long long blocks = ((long long)s->C + rows - 1) / rows;
-        const long long cap = (long long)s->sm_count * 8;  // 8 resident CTAs of 256 threads per SM
+        const long long cap = (long long)s->sm_count * 3;  // resident CTAs of 256 threads per SM (80 registers)
         if (blocks > cap) blocks = cap;
         if (vec) sink_push_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
         else sink_push_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
