@@ -166,3 +166,134 @@ class ReplicaExchange(object):
         self.n_attempted += int(mask.numel())
         self.n_swapped += int(mask.sum().item())
         return mask
+
+
+# ------------------------------------------------------------------------------------------------
+# full replica-exchange driver
+# ------------------------------------------------------------------------------------------------
+class RESwapStats(object):
+    """what a replica-exchange scheme logs per attempt (the reference only hints at it in the
+    docstrings of `last_draw_stats`, binf/samplers/hmc.py:171-177, binf/samplers/gibbs.py:117,143)"""
+
+    def __init__(self, attempt, partner, accepted_fraction):
+        self.attempt, self.partner, self.accepted_fraction = attempt, partner, accepted_fraction
+
+    def __repr__(self):
+        return "RESwapStats(attempt=%d, partner=%s, accepted_fraction=%s)" % (
+            self.attempt, self.partner, self.accepted_fraction)
+
+
+def adapt_ladder(betas, pair_rates, gain=1.0, floor=1e-3):
+    """New inverse-temperature ladder with the end points kept: the log-gap between neighbours i and
+    i+1 grows where the measured swap rate is above the mean rate and shrinks where it is below
+    (gap_i *= exp(gain * (p_i - mean p))), then the gaps are rescaled to the original total range.
+    Pure function of its inputs, so every rank that holds the all-gathered rates computes the same
+    ladder."""
+    betas = np.asarray(betas, dtype=np.float64)
+    p = np.clip(np.asarray(pair_rates, dtype=np.float64), 0.0, 1.0)
+    if len(betas) < 3:
+        return betas.copy()
+    gaps = np.log(betas[:-1]) - np.log(betas[1:])
+    total = gaps.sum()
+    gaps = np.maximum(gaps * np.exp(gain * (p - p.mean())), floor * total / len(gaps))
+    gaps *= total / gaps.sum()
+    out = betas.copy()
+    out[1:-1] = np.exp(np.log(betas[0]) - np.cumsum(gaps)[:-1])
+    return out
+
+
+class ReplicaExchangeDriver(object):
+    """Sweeps + neighbour swaps + statistics + ladder adaption for one rank of a tempered ensemble.
+
+    The sampling itself is injected so that the protocol runs on CPU (gloo) in the tests:
+      sweep()              -- advance this rank's chains by one Gibbs/HMC sweep at self.beta
+      log_likelihood()     -- untempered log L per chain, float64 [C]
+      set_beta(beta)       -- called when the ladder changes
+    `ChainShard` provides all three on the GPU (see `for_shard`)."""
+
+    def __init__(self, rank, world, betas, q, tau, sweep, log_likelihood, set_beta=None, seed=0,
+                 chain_base=0, swap_interval=1, decide=None, apply=None, group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.betas = [float(b) for b in betas]
+        assert len(self.betas) == world
+        self.q, self.tau = q, tau
+        self._sweep, self._ll, self._set_beta = sweep, log_likelihood, set_beta
+        self.swap_interval = int(swap_interval)
+        self.rex = ReplicaExchange(rank, world, self.betas[rank], seed=seed, chain_base=chain_base,
+                                   decide=decide, apply=apply, group=group)
+        self.n_sweeps = 0
+        # swap bookkeeping of the pair (rank, rank+1), kept on the lower rank
+        self.pair_attempted = 0
+        self.pair_swapped = 0
+        self._last = None
+
+    @classmethod
+    def for_shard(cls, shard, rank, world, betas, seed=0, swap_interval=1, group=None):
+        import torch
+
+        def set_beta(b):
+            shard.beta = torch.full_like(shard.tau, float(b))
+        set_beta(betas[rank])
+        return cls(rank, world, betas, shard.q, shard.tau, shard.sweep, shard.log_likelihood, set_beta,
+                   seed=seed, chain_base=shard.chain_base, swap_interval=swap_interval, group=group)
+
+    @property
+    def beta(self):
+        return self.betas[self.rank]
+
+    def step(self):
+        """one sweep of every chain, then (every swap_interval sweeps) one swap attempt"""
+        self._sweep()
+        self.n_sweeps += 1
+        if self.world > 1 and self.n_sweeps % self.swap_interval == 0:
+            attempt = self.rex.attempt
+            partner = swap_partner(self.rank, self.world, attempt)
+            mask = self.rex.swap(self.q, self.tau, self._ll(), self.betas)
+            frac = None
+            if mask is not None:
+                n, k = int(mask.numel()), int(mask.sum().item())
+                frac = k / float(n)
+                if partner > self.rank:
+                    self.pair_attempted += n
+                    self.pair_swapped += k
+            self._last = RESwapStats(attempt, partner, frac)
+
+    def run(self, n_sweeps, sink=None, log_prob=None):
+        """n_sweeps steps; after each one the (cold or any) replica's state goes to `sink`
+        (a SampleSink / _cabi.Sink) if given"""
+        for _ in range(n_sweeps):
+            self.step()
+            if sink is not None:
+                sink.push(self.q, self.tau, None if log_prob is None else log_prob())
+
+    @property
+    def last_draw_stats(self):
+        return {"swap": self._last}
+
+    def swap_rates(self):
+        """acceptance rate of every neighbour pair (r, r+1), r = 0..world-2, identical on all ranks
+        (one all-gather of two int64 per rank); NaN where nothing has been attempted yet"""
+        import torch
+        import torch.distributed as dist
+        mine = torch.tensor([self.pair_attempted, self.pair_swapped], dtype=torch.int64, device=self.tau.device)
+        if self.world > 1:
+            allv = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allv, mine, group=self.group)
+        else:
+            allv = [mine]
+        rates = []
+        for r in range(self.world - 1):
+            a, s = int(allv[r][0].item()), int(allv[r][1].item())
+            rates.append(s / float(a) if a else float("nan"))
+        return rates
+
+    def adapt(self, gain=1.0):
+        """re-space the ladder from the swap rates measured since the last call (all ranks must call)"""
+        rates = self.swap_rates()
+        if self.world > 2 and not any(np.isnan(rates)):
+            self.betas = [float(b) for b in adapt_ladder(self.betas, rates, gain)]
+            self.rex.beta = self.betas[self.rank]
+            if self._set_beta is not None:
+                self._set_beta(self.betas[self.rank])
+        self.pair_attempted = self.pair_swapped = 0
+        return rates

@@ -100,3 +100,73 @@ def test_pairing_and_sharding_arithmetic():
         rs = [shard_range(n, r, w) for r in range(w)]
         assert rs[0][0] == 0 and rs[-1][1] == n and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
         assert max(h - l for l, h in rs) - min(h - l for l, h in rs) <= 1
+
+
+# ------------------------------------------------------------------------------------------------
+# full replica-exchange driver: statistics and ladder adaption
+# ------------------------------------------------------------------------------------------------
+def _driver_worker(rank, world, port, out_dir):
+    from binf_b200.distributed import ReplicaExchangeDriver
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # toy tempered target: log L(x) = -0.5 * 40 * |x|^2 in D = 2, exact tempered draws N(0, 1/(40 beta))
+        C, D, k = 256, 2, 40.0
+        betas = [1.0, 0.7, 0.1][:world] if world == 3 else [1.0, 0.5]
+        rng = np.random.RandomState(7 + rank)
+        q = torch.zeros(C, D, dtype=torch.float32)
+        tau = torch.full((C,), float(rank))
+        state = {"beta": betas[rank]}
+
+        def sweep():
+            q.copy_(torch.from_numpy(rng.normal(size=(C, D)) / np.sqrt(k * state["beta"])).float())
+
+        def log_likelihood():
+            return -0.5 * k * (q.double() ** 2).sum(dim=1)
+
+        drv = ReplicaExchangeDriver(rank, world, betas, q, tau, sweep, log_likelihood,
+                                    set_beta=lambda b: state.update(beta=b), seed=3,
+                                    decide=host_decide, apply=host_apply)
+        drv.run(40)
+        assert drv.n_sweeps == 40 and drv.rex.attempt == 40
+        assert drv.last_draw_stats["swap"].attempt == 39
+        rates = drv.swap_rates()                       # identical on every rank
+        gathered = [None] * world
+        dist.all_gather_object(gathered, rates)
+        assert all(g == gathered[0] for g in gathered)
+        assert len(rates) == world - 1 and all(0.0 < r <= 1.0 for r in rates)
+        if world == 3:
+            # the wide gap (0.7 -> 0.1) swaps less often than the narrow one (1.0 -> 0.7)
+            assert rates[1] < rates[0]
+            old = list(drv.betas)
+            drv.adapt(gain=2.0)
+            new = drv.betas
+            assert new[0] == old[0] and new[-1] == old[-1] and old[1] > new[1] > new[2]
+            assert state["beta"] == new[rank] and drv.rex.beta == new[rank]
+            assert drv.pair_attempted == 0
+            drv.run(40)
+            rates2 = drv.swap_rates()
+            assert abs(rates2[0] - rates2[1]) < abs(rates[0] - rates[1])    # more even after adaption
+        with open(os.path.join(out_dir, "ok%d" % rank), "w") as fh:
+            fh.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_replica_exchange_driver(tmp_path, world):
+    mp.spawn(_driver_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
+
+
+def test_adapt_ladder_is_pure_and_keeps_end_points():
+    from binf_b200.distributed import adapt_ladder
+    betas = np.geomspace(1.0, 0.05, 6)
+    even = adapt_ladder(betas, [0.3] * 5)
+    np.testing.assert_allclose(even, betas, rtol=1e-12)          # equal rates: nothing moves
+    new = adapt_ladder(betas, [0.9, 0.9, 0.1, 0.1, 0.5])
+    assert new[0] == betas[0] and new[-1] == betas[-1] and np.all(np.diff(new) < 0)
+    gaps_old, gaps_new = -np.diff(np.log(betas)), -np.diff(np.log(new))
+    assert gaps_new[0] > gaps_old[0] and gaps_new[2] < gaps_old[2]
+    np.testing.assert_allclose(gaps_new.sum(), gaps_old.sum(), rtol=1e-12)
+    assert list(adapt_ladder([1.0, 0.5], [0.2])) == [1.0, 0.5]
