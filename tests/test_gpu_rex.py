@@ -57,3 +57,32 @@ def test_chain_shard_log_likelihood(gpu):
     assert sh.stats[1].item() == 3 * C and not torch.equal(sh.q.cpu(), torch.as_tensor(q0))
     # tempered conjugate update: shape beta*M/2 + a - 1, rate beta*chi2/2 + b
     assert 5.0 < sh.tau.mean().item() < 2000.0
+
+
+def test_driver_for_shard_with_sink(gpu):
+    """single rank: the driver steps the fused kernel at its beta and feeds the sample sink"""
+    import torch
+    import chromatin_port as chrom
+    from binf_b200 import _cabi
+    from binf_b200.distributed import ChainShard, ReplicaExchangeDriver
+    n, C = 40, 12
+    X, y = chrom.synthetic_chromatin(n, seed=5)
+    m = _cabi.Model.chromatin(n, y, 2.0, 2.5, 4.0, 1.0)
+    dev = torch.device("cuda")
+    rng = np.random.RandomState(1)
+    q = torch.as_tensor((X.reshape(-1)[None] + 0.05 * rng.normal(size=(C, 3 * n))).astype(np.float32), device=dev)
+    tau = torch.full((C,), 60.0, device=dev)
+    eps = torch.full((C,), 0.003, device=dev)
+    sh = ChainShard(m, q, tau, eps, 4, gibbs_mode=_cabi.GIBBS_TAU_FIRST, seed=2)
+    drv = ReplicaExchangeDriver.for_shard(sh, 0, 1, [0.25])
+    assert torch.all(sh.beta == 0.25)
+    sink = _cabi.Sink(C, 3 * n, capacity=4, thin=2)
+    drv.run(6, sink=sink)
+    torch.cuda.synchronize()
+    info = sink.info()
+    assert info["n_pushed"] == 6 and info["n_kept"] == 3 and drv.n_sweeps == 6
+    kept, aux = sink.read()
+    assert kept.shape == (3, C, 3 * n) and not np.array_equal(kept[0], kept[-1])
+    assert drv.swap_rates() == [] and drv.last_draw_stats["swap"] is None
+    mean, _ = sink.moments()
+    assert np.all(np.isfinite(mean)) and np.all(aux > 0)
