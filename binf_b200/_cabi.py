@@ -66,6 +66,9 @@ SIGNATURES = {
     "binfb_sink_moments_host": (_i, [_vp, _vp, _vp]),
     "binfb_sink_read_host": (_i, [_vp, _ll, _ll, _vp, _vp]),
     "binfb_sink_map_host": (_i, [_vp, _vp, _vp, _vp]),
+    "binfb_rwmc_run": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _u64, _u64, _u64] + [_vp] * 6),
+    "binfb_rwmc_run_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _u64, _u64, _u64] + [_vp] * 5),
+    "binfb_posterior_predictive_host": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _i, _vp, _i]),
     "binfb_rng_fill_host": (_i, [_u64, _u64, _u64, _i, _i, _d, _vp, _vp, _vp, _i]),
     "binfb_chromatin_stream_layout": (_i, [_i, _vp, _i, _i, _vp, _ll, _pll, _pi]),
     "binfb_microbench": (_i, [_i, _i, _pd, _pd, _pd, _pd]),
@@ -264,6 +267,28 @@ class Model(object):
                                                chain_base, ptr(gamma_draws), ptr(chi2)))
         return tau, chi2
 
+    def rwmc_run(self, q, tau, stepsize, n_moves=1, beta=None, change=None, u=None, seed=0, draw=0,
+                 chain_base=0):
+        """Random-walk Metropolis moves (RWMCSampler.sample); returns a dict, q is not modified."""
+        q = np.array(f32(q).reshape(-1, self.dim))
+        n = q.shape[0]
+        tau = np.ascontiguousarray(np.broadcast_to(f32(tau), (n,)))
+        stepsize = np.ascontiguousarray(np.broadcast_to(f32(stepsize), (n,)))
+        beta = None if beta is None else np.ascontiguousarray(np.broadcast_to(f32(beta), (n,)))
+        change = None if change is None else f32(change).reshape(n, self.dim)
+        u = None if u is None else f32(u).reshape(n)
+        accepted, nacc, logp = np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.int32), np.empty(n)
+        check(lib().binfb_rwmc_run_host(self._h, ptr(q), ptr(tau), ptr(beta), ptr(stepsize), n, n_moves,
+                                        seed, draw, chain_base, ptr(change), ptr(u), ptr(accepted),
+                                        ptr(nacc), ptr(logp)))
+        return dict(q=q, accepted=accepted.astype(bool), n_accepted=nacc, logp=logp)
+
+    def rwmc_run_device(self, q, tau, stepsize, n_moves=1, beta=None, seed=0, draw=0, chain_base=0,
+                        accepted=None, n_accepted=None, logp=None, stream=None):
+        check(lib().binfb_rwmc_run(self._h, ptr(q), ptr(tau), ptr(beta), ptr(stepsize), q.shape[0], n_moves,
+                                   seed, draw, chain_base, None, None, ptr(accepted), ptr(n_accepted),
+                                   ptr(logp), ptr(stream)))
+
     # ---- device-pointer entry points (torch CUDA tensors; asynchronous on `stream`) ----------
     def hmc_run_device(self, q, tau, eps, opts, beta=None, p0=None, u=None, gamma_draws=None,
                        accepted=None, e_before=None, e_after=None, q_end=None, p_end=None,
@@ -282,6 +307,21 @@ class Model(object):
         check(lib().binfb_gibbs_precision(self._h, ptr(q), ptr(tau), ptr(beta), q.shape[0], seed,
                                           draw, chain_base, ptr(gamma_draws), ptr(chi2),
                                           ptr(stream)))
+
+
+def posterior_predictive(coeffs, precision, xs, ys, device=0):
+    """predict (binf/example/misc.py:3-16) for many points at once"""
+    coeffs = f32(coeffs)
+    coeffs = coeffs.reshape(-1, coeffs.shape[-1])
+    precision = f32(precision).reshape(-1)
+    assert len(precision) == len(coeffs)
+    xs, ys = np.atleast_1d(f64(xs)), np.atleast_1d(f64(ys))
+    assert xs.shape == ys.shape
+    out = np.empty(xs.size)
+    check(lib().binfb_posterior_predictive_host(ptr(coeffs), ptr(precision), len(coeffs), coeffs.shape[1],
+                                                ptr(np.ascontiguousarray(xs.ravel())),
+                                                ptr(np.ascontiguousarray(ys.ravel())), xs.size, ptr(out), device))
+    return out.reshape(xs.shape)
 
 
 class Sink(object):

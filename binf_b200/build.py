@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libbinf_b200.so")
-SOURCES = ["capi.cu", "poly.cu", "chromatin.cu", "misc.cu", "sink.cu"]
+SOURCES = ["capi.cu", "poly.cu", "chromatin.cu", "misc.cu", "sink.cu", "rwmc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -244,6 +244,7 @@ int binfb_model_destroy(binfb_model *m) {
     if (!m) return BINFB_OK;
     cudaSetDevice(m->device);
     cudaFree(m->poly.rows);
+    cudaFree(m->rw_prop), cudaFree(m->rw_lp[0]), cudaFree(m->rw_lp[1]), cudaFree(m->rw_lp[2]);
     ChromModel &c = m->chrom;
     cudaFree(c.ystream), cudaFree(c.ypairs), cudaFree(c.qw), cudaFree(c.pw), cudaFree(c.h0);
     cudaFree(c.chi2_0), cudaFree(c.chi2_state), cudaFree(c.tau_w), cudaFree(c.sched);

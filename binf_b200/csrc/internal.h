@@ -126,6 +126,10 @@ struct binfb_model {
     double gamma_shape = 1.0, gamma_rate = 1.0;
     binfb::PolyModel poly;
     binfb::ChromModel chrom;
+    // random-walk Metropolis workspace (rwmc.cu): proposals [cap, dim], log-probs 3 x [cap]
+    float *rw_prop = nullptr;
+    double *rw_lp[3] = {nullptr, nullptr, nullptr};
+    size_t rw_cap = 0;
     // cached device buffers for the *_host entry points
     size_t hb_bytes = 0;
     char *hb = nullptr;

@@ -1,8 +1,84 @@
-"""Conjugate precision sampler and the example's Gibbs wiring
-(reference: binf/example/samplers.py:7-51,94-111).  The reference wires a random-walk Metropolis
-sampler for the coefficients; here `make_sampler` wires the batched device HMCSampler instead (the
-RWMC sampler is outside the hot path)."""
+"""Conjugate precision sampler, random-walk Metropolis sampler and the example's Gibbs wiring
+(reference: binf/example/samplers.py:7-111).  `make_sampler` wires the batched device HMCSampler for
+the coefficients by default; `make_sampler(..., rwmc_stepsize=...)` wires the reference's RWMCSampler
+(also batched on the device, binfb_rwmc_run) exactly as the reference's make_sampler does."""
+from collections import namedtuple
+
 import numpy as np
+
+RWMCSampleStats = namedtuple("RWMCSampleStats", "acceptance_rate")
+
+
+class RWMCSampler(object):
+    """Random-walk Metropolis on the coefficients (samplers.py:54-92): proposal = state +
+    U(-stepsize, stepsize), accept iff u < exp(-(E_new - E_old)).  `state` (D,) is one chain,
+    (C, D) are C chains; a CUDA tensor keeps the chains in HBM."""
+
+    def __init__(self, pdf, state, stepsize, seed=None, chain_base=0):
+        self.pdf = pdf
+        self.state = state
+        self.stepsize = stepsize
+        self._n_moves = 0
+        self._n_accepted_moves = 0
+        self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        self.chain_base = int(chain_base)
+        self._draw = 0
+        self._lowered = None
+        self._dev = None
+
+    @property
+    def last_draw_stats(self):
+        return {"coefficients": RWMCSampleStats(self.acceptance_rate)}
+
+    @property
+    def acceptance_rate(self):
+        if self._n_moves > 0:
+            n = self._n_accepted_moves
+            mean = float(n.double().mean()) if hasattr(n, "data_ptr") else float(np.mean(n))
+            return mean / float(self._n_moves)
+        return 0.0
+
+    def _lower(self):
+        from binf_b200.lowering import lower
+        if self._lowered is None or self._lowered[0] is not self.pdf:
+            low = lower(self.pdf, n_coeff=int(self.state.shape[-1]))
+            if low is None:
+                raise NotImplementedError("RWMCSampler: the pdf is not lowered to the device (no CPU fallback)")
+            self._lowered = (self.pdf, low)
+        self._lowered[1].refresh()
+        return self._lowered[1]
+
+    def sample(self, change=None, u=None, n_moves=1):
+        """`change` / `u` inject the proposal displacement and the uniform (parity tests)."""
+        from binf_b200.lowering import _is_tensor
+        low = self._lower()
+        if _is_tensor(self.state):
+            import torch
+            q = self.state
+            n, dev = q.shape[0], q.device
+            if self._dev is None:
+                self._dev = (torch.zeros(n, dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.int32, device=dev))
+            tau = low.tau(n)
+            tau = tau if _is_tensor(tau) else torch.as_tensor(tau, dtype=torch.float32, device=dev)
+            beta = low.beta(n)
+            beta = None if beta is None else torch.as_tensor(beta, dtype=torch.float32, device=dev)
+            step = torch.as_tensor(np.broadcast_to(np.asarray(self.stepsize, dtype=np.float32), (n,)).copy(), device=dev)
+            low.model.rwmc_run_device(q, tau, step, n_moves, beta=beta, seed=self.seed, draw=self._draw,
+                                      chain_base=self.chain_base, accepted=self._dev[0], n_accepted=self._dev[1],
+                                      stream=torch.cuda.current_stream().cuda_stream)
+            self._n_accepted_moves = self._n_accepted_moves + self._dev[1].to(torch.int64)
+        else:
+            single = np.ndim(self.state) == 1
+            q = np.asarray(self.state, dtype=np.float64).reshape(-1, low.dim)
+            r = low.model.rwmc_run(q, low.tau(len(q)), self.stepsize, n_moves, beta=low.beta(len(q)),
+                                   change=change, u=u, seed=self.seed, draw=self._draw, chain_base=self.chain_base)
+            new = r["q"].astype(np.float64)
+            self.state = new[0] if single else new
+            self._n_accepted_moves = self._n_accepted_moves + (
+                int(r["n_accepted"][0]) if single else r["n_accepted"].astype(np.int64))
+        self._n_moves += n_moves
+        self._draw += n_moves
+        return self.state
 
 
 class GammaSampler(object):
@@ -57,12 +133,19 @@ class GammaSampler(object):
         return self.state
 
 
-def make_sampler(posterior, timestep, start_state, nsteps=20, timestep_adaption_limit=0, seed=None):
-    """GibbsSampler(HMC on the coefficients, conjugate Gamma on the precision)."""
+def make_sampler(posterior, timestep, start_state, nsteps=20, timestep_adaption_limit=0, seed=None,
+                 rwmc_stepsize=None):
+    """GibbsSampler(HMC on the coefficients, conjugate Gamma on the precision); with `rwmc_stepsize`
+    the coefficients are sampled by random-walk Metropolis as in the reference (samplers.py:94-111)."""
     from binf_b200.samplers.gibbs import GibbsSampler
     from binf_b200.samplers.hmc import HMCSampler
     coeffs = start_state.variables["coefficients"]
     precision = start_state.variables["precision"]
+    if rwmc_stepsize is not None:
+        rw = RWMCSampler(posterior.conditional_factory(precision=precision), coeffs, rwmc_stepsize, seed=seed)
+        gam = GammaSampler(posterior.conditional_factory(coefficients=coeffs), precision,
+                           seed=None if seed is None else seed + 1)
+        return GibbsSampler(posterior, start_state, {"coefficients": rw, "precision": gam})
     hmc = HMCSampler(posterior.conditional_factory(precision=precision), coeffs, timestep, nsteps,
                      timestep_adaption_limit=timestep_adaption_limit, variable_name="coefficients",
                      seed=seed)

@@ -193,6 +193,29 @@ int binfb_sink_read_host(binfb_sink *s, long long first, long long count, float 
 /* per-chain MAP candidate: logp [C] f64, state [C, dim] f32, aux [C] f32 (any may be NULL) */
 int binfb_sink_map_host(binfb_sink *s, double *logp, float *q_map, float *aux_map);
 
+/* ---- the shipped example's RWMC sampler and predictive density --------- */
+/* n_moves random-walk Metropolis moves per chain: proposal = state + U(-stepsize, stepsize)^dim,
+ * accept iff u < exp(-(E_new - E_old)), E = -log_prob (RWMCSampler.sample,
+ * binf/example/samplers.py:78-92).  q [C, dim] in/out; stepsize [C]; change [C, dim] / u [C]:
+ * injected proposal displacements / uniforms (parity tests, n_moves == 1) or NULL for Philox draws;
+ * accepted [C] u8 (last move), n_accepted [C] i32 (over the call), logp [C] f64 = log_prob of the
+ * final state; any output may be NULL. */
+int binfb_rwmc_run(binfb_model *m, float *q_dev, const float *tau_dev, const float *beta_dev,
+                   const float *stepsize_dev, int n_chains, int n_moves, uint64_t seed, uint64_t draw,
+                   uint64_t chain_base, const float *change_dev, const float *u_dev,
+                   uint8_t *accepted_dev, int32_t *n_accepted_dev, double *logp_dev, void *stream);
+int binfb_rwmc_run_host(binfb_model *m, float *q, const float *tau, const float *beta,
+                        const float *stepsize, int n_chains, int n_moves, uint64_t seed, uint64_t draw,
+                        uint64_t chain_base, const float *change, const float *u, uint8_t *accepted,
+                        int32_t *n_accepted, double *logp);
+/* posterior-predictive density of new data (x_g, y_g) under the polynomial model: the mean over
+ * the samples of N(y_g; polyval(x_g, coeffs_s), 1/precision_s), summed as a log-sum-exp in
+ * float64 (predict, binf/example/misc.py:3-16).  coeffs [S, n_coeff] f32 (ascending powers),
+ * precision [S] f32, xs/ys [n_points] f64 -> out [n_points] f64.  Host pointers. */
+int binfb_posterior_predictive_host(const float *coeffs, const float *precision, long long n_samples,
+                                    int n_coeff, const double *xs, const double *ys, int n_points,
+                                    double *out, int device);
+
 /* ---- test / measurement helpers ------------------------------------------------------------- */
 /* the device RNG streams, for statistical tests: normals [C, dim] f32 exactly as the momentum
  * draw of trajectory `draw`; uniforms [C]; standard gammas of the given shape [C] f64 */

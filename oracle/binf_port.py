@@ -195,3 +195,26 @@ def gibbs_sweep(state, samplers):
     for var in sorted(state):
         state[var] = samplers[var](state)
     return state
+
+
+def rwmc_sample(log_prob, state, change, u):
+    """RWMCSampler.sample with the randomness injected (binf/example/samplers.py:78-92):
+    `change` replaces np.random.uniform(-stepsize, stepsize, len(state)), `u` np.random.random()."""
+    state = np.asarray(state, dtype=np.float64)
+    e_old = -log_prob(state)                                    # samplers.py:80
+    proposal = state + np.asarray(change, dtype=np.float64)     # samplers.py:81-83
+    e_new = -log_prob(proposal)                                 # samplers.py:84
+    with np.errstate(over="ignore", invalid="ignore"):
+        accepted = bool(u < np.exp(-(e_new - e_old)))           # samplers.py:86
+    return dict(state=proposal if accepted else state, accepted=accepted, e_old=e_old, e_new=e_new)
+
+
+def predict(x, y, coefficients, precisions):
+    """predict (binf/example/misc.py:3-16): exp(log_sum_exp(integrands)) / len(samples) with
+    integrand = -0.5 (polyval(x, c) - y)^2 tau + 0.5 log tau - 0.5 log 2 pi"""
+    c = np.asarray(coefficients, dtype=np.float64)
+    t = np.asarray(precisions, dtype=np.float64)
+    mock = np.polynomial.polynomial.polyval(x, c.T)
+    f = -0.5 * (mock - y) ** 2 * t + 0.5 * np.log(t) - 0.5 * np.log(2.0 * np.pi)
+    m = np.max(f)
+    return np.exp(m + np.log(np.sum(np.exp(f - m)))) / len(t)

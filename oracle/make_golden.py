@@ -238,9 +238,66 @@ def chromatin_case(binf, name, n_beads, n_chains, nsteps, timestep, seed, tau=50
     print(name, "acceptance", np.mean(acc), "max |dH|", np.max(np.abs(np.array(ea) - eb)))
 
 
+def rwmc_predict_case(binf, name, n_data, n_chains, n_moves, stepsize, seed):
+    """RWMCSampler.sample (binf/example/samplers.py:78-92) with the proposal displacement and the
+    uniform injected, chain by chain and move by move; and predict (binf/example/misc.py:3-16) over
+    the visited states."""
+    from binf.example.misc import make_posterior, predict
+    from binf.example.samplers import RWMCSampler
+    from binf.samplers import BinfState
+
+    rng = np.random.RandomState(seed)
+    xs = np.linspace(-2, 2, n_data)
+    ys = rng.normal(polyval(xs, np.array([2.0, -4.0, 1.0, 1.5])), 1.0 / np.sqrt(2.5))
+    tau = 2.5
+    post = make_posterior(xs, ys, polyval)
+    cond = post.conditional_factory(precision=tau)
+    gp = [p for p in cond.priors.values() if "precision" in p._original_variables][0]
+    cprior = [p for p in cond.priors.values() if "coefficients" in p.variables][0]
+    pp = port.PolynomialPosterior(xs, ys, cprior["means"].value, cprior["variances"].value, gp.shape, gp.rate)
+    q0 = np.array([2.0, -4.0, 1.0, 1.5]) + 0.3 * rng.normal(size=(n_chains, 4))
+    change = rng.uniform(-stepsize, stepsize, size=(n_moves, n_chains, 4))
+    u = rng.uniform(size=(n_moves, n_chains))
+    states = np.empty((n_moves + 1, n_chains, 4))
+    states[0] = q0
+    accepted = np.zeros((n_moves, n_chains), dtype=bool)
+    saved = (np.random.uniform, np.random.random)
+    try:
+        for c in range(n_chains):
+            smp = RWMCSampler(cond, q0[c].copy(), stepsize)
+            pstate = q0[c].copy()
+            for k in range(n_moves):
+                np.random.uniform = lambda low=0.0, high=1.0, size=None, v=change[k, c]: np.array(v)
+                np.random.random = lambda v=u[k, c]: float(v)
+                before = smp._n_accepted_moves
+                states[k + 1, c] = smp.sample()
+                accepted[k, c] = smp._n_accepted_moves > before
+                r = port.rwmc_sample(lambda x: pp.log_prob(x, tau), pstate, change[k, c], u[k, c])
+                assert r["accepted"] == accepted[k, c]
+                close(r["state"], states[k + 1, c])
+                pstate = r["state"]
+    finally:
+        np.random.uniform, np.random.random = saved
+    # predictive density over the visited states (each with its own precision draw)
+    taus = rng.gamma(6.0, 0.5, size=(n_moves + 1) * n_chains)
+    flat = states.reshape(-1, 4)
+    samples = [BinfState(dict(coefficients=flat[i], precision=float(taus[i]))) for i in range(len(flat))]
+    gx, gy = np.meshgrid(np.linspace(-2.5, 2.5, 7), np.linspace(-12.0, 12.0, 9))
+    pred = np.array([predict(float(a), float(b), samples, polyval) for a, b in zip(gx.ravel(), gy.ravel())])
+    close(pred, [port.predict(a, b, flat, taus) for a, b in zip(gx.ravel(), gy.ravel())], tol=1e-12)
+    np.savez(os.path.join(GOLDEN, name + ".npz"), xs=xs, ys=ys, tau=tau, stepsize=stepsize, q0=q0,
+             change=change, u=u, states=states, accepted=accepted, gamma_shape=gp.shape,
+             gamma_rate=gp.rate, prior_means=cprior["means"].value, prior_variances=cprior["variances"].value,
+             pred_x=gx.ravel(), pred_y=gy.ravel(), pred_tau=taus, pred=pred)
+    print("wrote", name, "acceptance", accepted.mean())
+
+
 def main():
     binf = ref_import.install()
     os.makedirs(GOLDEN, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "rwmc":     # only the fixtures added with SURVEY 8f rank 4
+        rwmc_predict_case(binf, "poly_rwmc_n20", n_data=20, n_chains=24, n_moves=6, stepsize=0.1, seed=9)
+        return
     # config 1 shape (example_script.py:17-26), seeded
     polynomial_case(binf, "poly_n20", n_data=20, n_chains=16, nsteps=20, timestep=0.02, seed=0)
     # config 2 shape: N = 1000 data points, L = 20
@@ -259,6 +316,7 @@ def main():
                    timestep=0.004, seed=5)
     chromatin_case(binf, "chromatin_n30_big_step", n_beads=30, n_chains=12, nsteps=10,
                    timestep=0.05, seed=8)
+    rwmc_predict_case(binf, "poly_rwmc_n20", n_data=20, n_chains=24, n_moves=6, stepsize=0.1, seed=9)
 
 
 if __name__ == "__main__":

@@ -106,3 +106,23 @@ def test_live_reference_reproduces_golden_vectors():
                              float(gc["k_bb"]), float(gc["l0"]), 0.0, 1.0, 1.0)
     condc = chrom.reference_posterior(binf, m).conditional_factory(precision=float(gc["tau"]))
     np.testing.assert_allclose(condc.gradient(structure=gc["q0"][0].copy()), gc["gradient"][0], rtol=1e-10)
+
+
+def test_rwmc_and_predict_port_vs_reference_outputs():
+    """oracle restatement of RWMCSampler.sample / predict vs the fixture generated by running the
+    reference itself (oracle/make_golden.py rwmc)"""
+    g = load_golden("poly_rwmc_n20")
+    pp = port.PolynomialPosterior(g["xs"], g["ys"], g["prior_means"], g["prior_variances"],
+                                  float(g["gamma_shape"]), float(g["gamma_rate"]))
+    tau = float(g["tau"])
+    n_moves, n_chains = g["u"].shape
+    for c in range(n_chains):
+        state = g["q0"][c]
+        for k in range(n_moves):
+            r = port.rwmc_sample(lambda x: pp.log_prob(x, tau), state, g["change"][k, c], g["u"][k, c])
+            assert r["accepted"] == bool(g["accepted"][k, c])
+            np.testing.assert_allclose(r["state"], g["states"][k + 1, c], rtol=0, atol=1e-12)
+            state = r["state"]
+    flat = g["states"].reshape(-1, 4)
+    pred = [port.predict(a, b, flat, g["pred_tau"]) for a, b in zip(g["pred_x"], g["pred_y"])]
+    np.testing.assert_allclose(pred, g["pred"], rtol=1e-12)
