@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbinf_b200.so")
 
 OK, EINVAL, ECUDA, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4
-MODEL_POLYNOMIAL, MODEL_CHROMATIN = 1, 2
+MODEL_POLYNOMIAL, MODEL_CHROMATIN, MODEL_GENERIC = 1, 2, 3
 FLAG_PRIOR_GRAD = 1
 GIBBS_NONE, GIBBS_TAU_FIRST, GIBBS_TAU_LAST = 0, 1, 2
 SINK_TRACK_MAP = 1
@@ -43,6 +43,9 @@ SIGNATURES = {
                                            C.POINTER(_vp)]),
     "binfb_model_create_chromatin": (_i, [_i, _vp, _d, _d, _d, _d, _d, _d, _d, C.c_uint, _i,
                                           C.POINTER(_vp)]),
+    "binfb_model_create_generic": (_i, [C.c_char_p, _i, _i, _vp, _vp, _i, _vp, _vp, _d, _d, C.c_uint, _i,
+                                        C.POINTER(_vp)]),
+    "binfb_generic_compile_check": (_i, [C.c_char_p, _i, _i, C.c_char_p, _i]),
     "binfb_model_destroy": (_i, [_vp]),
     "binfb_model_info": (_i, [_vp, _pi, _pi, _pll, _pi]),
     "binfb_model_set_gamma_prior": (_i, [_vp, _d, _d]),
@@ -194,6 +197,19 @@ class Model(object):
                                                  C.byref(h)))
         return cls(h)
 
+    @classmethod
+    def generic(cls, device_code, n_params, xs, ys, prior_mean=None, prior_var=None, gamma_shape=1.0,
+                gamma_rate=1.0, flags=0, device=0):
+        """User-defined per-datum forward model given as CUDA device code (compiled with NVRTC)."""
+        xs, ys = f64(xs), f64(ys)
+        xs = xs.reshape(len(ys), -1)
+        pm, pv = f64(prior_mean), f64(prior_var)
+        h = C.c_void_p()
+        check(lib().binfb_model_create_generic(device_code.encode(), n_params, xs.shape[1], ptr(xs), ptr(ys),
+                                               len(ys), ptr(pm), ptr(pv), gamma_shape, gamma_rate, flags,
+                                               device, C.byref(h)))
+        return cls(h)
+
     def close(self):
         if self._h is not None:
             lib().binfb_model_destroy(self._h)
@@ -307,6 +323,16 @@ class Model(object):
         check(lib().binfb_gibbs_precision(self._h, ptr(q), ptr(tau), ptr(beta), q.shape[0], seed,
                                           draw, chain_base, ptr(gamma_draws), ptr(chi2),
                                           ptr(stream)))
+
+
+def generic_compile_check(device_code, n_params, x_dim=1):
+    """(ok, log): run NVRTC on a generic model's device code without touching a GPU"""
+    buf = C.create_string_buffer(1 << 16)
+    rc = lib().binfb_generic_compile_check(device_code.encode(), n_params, x_dim, buf, len(buf))
+    msg = buf.value.decode(errors="replace")
+    if rc != OK and not msg:
+        msg = lib().binfb_last_error().decode(errors="replace")
+    return rc == OK, msg
 
 
 def posterior_predictive(coeffs, precision, xs, ys, device=0):

@@ -192,6 +192,35 @@ int binfb_model_create_polynomial(const double *xs, const double *ys, int n_data
     return BINFB_OK;
 }
 
+int binfb_model_create_generic(const char *device_code, int n_params, int x_dim, const double *xs,
+                               const double *ys, int n_data, const double *prior_mean,
+                               const double *prior_var, double gamma_shape, double gamma_rate,
+                               unsigned flags, int device, binfb_model **out) {
+    if (!device_code || !xs || !ys || !out || n_data < 1 || x_dim < 1) {
+        set_error("model_create_generic: device_code, xs, ys, out required, n_data, x_dim >= 1");
+        return BINFB_EINVAL;
+    }
+    if (n_params < 1 || n_params > 16) {
+        set_error("model_create_generic: n_params must be in 1..16");
+        return BINFB_EUNSUPPORTED;
+    }
+    binfb_model *m = new binfb_model();
+    int rc = model_common_init(m, device);
+    if (rc) {
+        delete m;
+        return rc;
+    }
+    m->kind = BINFB_MODEL_GENERIC, m->dim = n_params, m->n_data = n_data;
+    m->gamma_shape = gamma_shape, m->gamma_rate = gamma_rate;
+    rc = gen_create(m->gen, device_code, n_params, x_dim, xs, ys, n_data, prior_mean, prior_var, flags);
+    if (rc) {
+        binfb_model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return BINFB_OK;
+}
+
 int binfb_model_create_chromatin(int n_beads, const float *y_pairs, double alpha, double d_c,
                                  double k_bb, double l0, double conf_s, double gamma_shape,
                                  double gamma_rate, unsigned flags, int device, binfb_model **out) {
@@ -244,6 +273,7 @@ int binfb_model_destroy(binfb_model *m) {
     if (!m) return BINFB_OK;
     cudaSetDevice(m->device);
     cudaFree(m->poly.rows);
+    gen_destroy(m->gen);
     cudaFree(m->rw_prop), cudaFree(m->rw_lp[0]), cudaFree(m->rw_lp[1]), cudaFree(m->rw_lp[2]);
     ChromModel &c = m->chrom;
     cudaFree(c.ystream), cudaFree(c.ypairs), cudaFree(c.qw), cudaFree(c.pw), cudaFree(c.h0);
@@ -301,6 +331,7 @@ int binfb_logprob_grad(binfb_model *m, const float *q, const float *tau, const f
     a.gamma_shape = m->gamma_shape, a.gamma_rate = m->gamma_rate;
     cudaStream_t s = (cudaStream_t)stream;
     if (m->kind == BINFB_MODEL_POLYNOMIAL) return poly_grad_launch(m->poly, a, m->sm_count, m->smem_optin, s);
+    if (m->kind == BINFB_MODEL_GENERIC) return gen_grad_launch(m->gen, a, s);
     return chrom_grad_launch(m->chrom, a, m->sm_count, m->smem_optin, s);
 }
 
@@ -349,6 +380,7 @@ int binfb_forward_host(binfb_model *m, const float *q, int C, float *mock) {
     cudaStream_t s = m->hstream;
     BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(oq), q, C * D * 4, cudaMemcpyHostToDevice, s));
     if (m->kind == BINFB_MODEL_POLYNOMIAL) rc = poly_forward_launch(m->poly, ar.at<float>(oq), C, ar.at<float>(om), s);
+    else if (m->kind == BINFB_MODEL_GENERIC) rc = gen_forward_launch(m->gen, ar.at<float>(oq), C, ar.at<float>(om), s);
     else rc = chrom_forward_launch(m->chrom, ar.at<float>(oq), C, ar.at<float>(om), s);
     if (rc) return rc;
     BINFB_CUDA(cudaMemcpyAsync(mock, ar.at<float>(om), C * N * 4, cudaMemcpyDeviceToHost, s));
@@ -367,6 +399,7 @@ int binfb_hmc_run(binfb_model *m, float *q, float *tau, const float *beta, float
                                     e_before, e_after, q_end, p_end, n_accepted, stats);
     cudaStream_t s = (cudaStream_t)stream;
     if (m->kind == BINFB_MODEL_POLYNOMIAL) return poly_hmc_launch(m->poly, a, m->sm_count, m->smem_optin, s);
+    if (m->kind == BINFB_MODEL_GENERIC) return gen_hmc_launch(m->gen, a, s);
     return chrom_hmc_launch(m->chrom, a, m->sm_count, m->smem_optin, s);
 }
 

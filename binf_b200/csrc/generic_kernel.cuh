@@ -1,0 +1,209 @@
+// Fused HMC / log-prob+gradient kernels for a USER-DEFINED per-datum forward model -- compiled at run
+// time with NVRTC for sm_100a (not compiled by nvcc).
+//
+// The reference's extension point is AbstractForwardModel._evaluate / _evaluate_jacobi_matrix
+// (binf/model/forwardmodels.py:30-38): mock data f(theta) [N] and its Jacobian [K, N], which
+// Likelihood._evaluate_gradient contracts with the error model's gradient
+// (binf/pdf/likelihoods.py:148-155).  Here the user supplies the same two things as CUDA device code,
+// one datum at a time,
+//
+//     __device__ float binfb_mock(const float *theta, const float *x, float *dmock);
+//         theta[GEN_K]  the sampled variable of one chain
+//         x[GEN_XD]     the abscissae of one datum
+//         returns f_n(theta) and writes dmock[k] = d f_n / d theta_k
+//
+// and this file wraps it into the same fused transition the built-in polynomial model gets: a chain
+// is owned by a group of GEN_G lanes which stride over the data, butterfly-all-reduce the GEN_K
+// gradient sums and chi^2, and keep q, p in registers for the whole trajectory (leapfrog, energies,
+// Metropolis test, step-size adaption, conjugate precision update: binf/samplers/hmc.py:92-125,136-164,
+// 183-191; binf/example/samplers.py:27-51).  Error model: GaussianErrorModel
+// (binf/example/likelihood.py:54-61); priors: Gaussian on theta, Gamma on the precision.
+//
+// Compile-time parameters (-D): GEN_K, GEN_XD, GEN_G (power of two <= 32).
+constexpr int K = GEN_K, XD = GEN_XD, G = GEN_G;
+
+__device__ __forceinline__ void gen_pass(const GenDev &gm, int g, const float (&q)[K], float (&graw)[K],
+                                         double &chi2) {
+    float gacc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) gacc[k] = 0.f;
+    float c32 = 0.f;
+    double c64 = 0.0;
+    int cnt = 0;
+    for (int n = g; n < gm.N; n += G) {
+        const float *row = gm.rows + (size_t)n * gm.stride;
+        float dm[K];
+        const float m = binfb_mock(q, row, dm);
+        const float r = m - __ldg(row + XD);
+#pragma unroll
+        for (int k = 0; k < K; ++k) gacc[k] = fmaf(r, dm[k], gacc[k]);   // J . (mock - y), likelihoods.py:155
+        c32 = fmaf(r, r, c32);
+        if (++cnt == 8) c64 += (double)c32, c32 = 0.f, cnt = 0;
+    }
+    c64 += (double)c32;
+#pragma unroll
+    for (int k = 0; k < K; ++k) graw[k] = group_allreduce_sum<G>(gacc[k]);
+    chi2 = group_allreduce_sum<G>(c64);
+}
+
+// U(q) = -log p(q | tau) in float64 (binf/pdf/posteriors.py:141-151 summed components)
+__device__ __forceinline__ double gen_potential(const GenDev &gm, const float (&q)[K], double chi2, float tau,
+                                                float beta, double ga, double gb) {
+    const double t = (double)tau;
+    double prior = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double d = (double)q[k] - (double)gm.prior_mean[k];
+        prior += d * d * (double)gm.prior_inv_var[k];
+    }
+    const double lt = log(t);
+    return (double)beta * (0.5 * t * chi2 - 0.5 * (double)gm.N * lt) + 0.5 * prior - ((ga - 1.0) * lt - gb * t);
+}
+
+__device__ __forceinline__ void gen_force(const GenDev &gm, const float (&q)[K], const float (&graw)[K], float bt,
+                                          float (&f)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        f[k] = bt * graw[k];
+        if (gm.flags & BINFB_FLAG_PRIOR_GRAD) f[k] = fmaf(q[k] - gm.prior_mean[k], gm.prior_inv_var[k], f[k]);
+    }
+}
+
+__device__ __forceinline__ float gen_draw_tau(const HmcArgs &a, double n_data, double chi2, float beta,
+                                              uint64_t chain, int cid, uint64_t draw) {
+    const double shape = 0.5 * (double)beta * n_data + a.gamma_shape - 1.0;   // samplers.py:32 (quirk Q3)
+    const double rate = 0.5 * (double)beta * chi2 + a.gamma_rate;
+    const double gdraw = a.gamma_draws ? a.gamma_draws[cid] : rng_gamma(a.seed, chain, draw, shape);
+    return (float)(gdraw / rate);
+}
+
+extern "C" __global__ void __launch_bounds__(256) gen_hmc_kernel(GenDev gm, HmcArgs a) {
+    const int g = threadIdx.x % G;
+    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool valid = c < a.C;
+    const int cid = valid ? (int)c : a.C - 1;
+    float q[K], p[K], graw[K], f[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) q[k] = a.q[(size_t)cid * K + k];
+    float tau = a.tau[cid], eps = a.eps[cid];
+    const float beta = a.beta ? a.beta[cid] : 1.0f;
+    int nacc = 0;
+    bool acc = false;
+    double h0 = 0.0, h1 = 0.0, chi2, chi2_cur;
+    double st_acc = 0.0, st_prop = 0.0, st_eps = 0.0, st_pacc = 0.0;
+    for (int tr = 0; tr < a.n_traj; ++tr) {
+        const uint64_t draw = a.draw + (uint64_t)tr;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            p[k] = a.p0 ? a.p0[(size_t)cid * K + k] : rng_normal(a.seed, a.chain_base + cid, draw, k);   // hmc.py:146
+        gen_pass(gm, g, q, graw, chi2);
+        if (a.gibbs_mode == BINFB_GIBBS_TAU_FIRST)
+            tau = gen_draw_tau(a, (double)gm.N, chi2, beta, a.chain_base + cid, cid, draw);
+        chi2_cur = chi2;
+        double kin = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) kin += (double)p[k] * (double)p[k];
+        h0 = gen_potential(gm, q, chi2, tau, beta, a.gamma_shape, a.gamma_rate) + 0.5 * kin;
+        gen_force(gm, q, graw, beta * tau, f);
+#pragma unroll
+        for (int k = 0; k < K; ++k) p[k] = fmaf(-0.5f * eps, f[k], p[k]);             // hmc.py:116
+        for (int s = 1; s < a.L; ++s) {                                              // hmc.py:118-120
+#pragma unroll
+            for (int k = 0; k < K; ++k) q[k] = fmaf(eps, p[k], q[k]);
+            gen_pass(gm, g, q, graw, chi2);
+            gen_force(gm, q, graw, beta * tau, f);
+#pragma unroll
+            for (int k = 0; k < K; ++k) p[k] = fmaf(-eps, f[k], p[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) q[k] = fmaf(eps, p[k], q[k]);                     // hmc.py:122
+        gen_pass(gm, g, q, graw, chi2);
+        gen_force(gm, q, graw, beta * tau, f);
+        kin = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            p[k] = fmaf(-0.5f * eps, f[k], p[k]);                                     // hmc.py:123
+            kin += (double)p[k] * (double)p[k];
+        }
+        h1 = gen_potential(gm, q, chi2, tau, beta, a.gamma_shape, a.gamma_rate) + 0.5 * kin;
+        const float uu = a.u ? a.u[cid] : rng_uniform(a.seed, a.chain_base + cid, draw, RNG_ACCEPT);
+        const double dh = h1 - h0;
+        acc = (double)uu < exp(fmin(709.0, fmax(-308.0, -dh)));                       // hmc.py:151; NaN rejects
+        const bool last = tr == a.n_traj - 1;
+        if (last && valid && g == 0) {
+            if (a.q_end)
+                for (int k = 0; k < K; ++k) a.q_end[(size_t)cid * K + k] = q[k];
+            if (a.p_end)
+                for (int k = 0; k < K; ++k) a.p_end[(size_t)cid * K + k] = p[k];
+        }
+        if (acc) {
+            chi2_cur = chi2;
+            nacc++;
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) q[k] = a.q[(size_t)cid * K + k];
+        }
+        if (valid && g == 0) {
+            st_acc += acc ? 1.0 : 0.0, st_prop += 1.0, st_eps += (double)eps;
+            st_pacc += (dh == dh) ? exp(fmin(0.0, -dh)) : 0.0;
+        }
+        if (tr < a.n_adapt) eps *= acc ? a.adapt_up : a.adapt_down;                   // hmc.py:188-191
+        if (a.gibbs_mode == BINFB_GIBBS_TAU_LAST)
+            tau = gen_draw_tau(a, (double)gm.N, chi2_cur, beta, a.chain_base + cid, cid, draw);
+        if (a.n_traj > 1) {
+            if (valid && g == 0 && acc)
+                for (int k = 0; k < K; ++k) a.q[(size_t)cid * K + k] = q[k];
+            __syncwarp();
+        }
+    }
+    if (valid && g == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) a.q[(size_t)cid * K + k] = q[k];
+        a.tau[cid] = tau, a.eps[cid] = eps;
+        if (a.accepted) a.accepted[cid] = acc ? 1 : 0;
+        if (a.e_before) a.e_before[cid] = h0;
+        if (a.e_after) a.e_after[cid] = h1;
+        if (a.n_accepted) a.n_accepted[cid] = nacc;
+    }
+    if (a.stats) {
+        st_acc = group_allreduce_sum<32>(st_acc), st_prop = group_allreduce_sum<32>(st_prop);
+        st_eps = group_allreduce_sum<32>(st_eps), st_pacc = group_allreduce_sum<32>(st_pacc);
+        if ((threadIdx.x & 31) == 0 && st_prop > 0.0) {
+            atomicAdd(a.stats + 0, st_acc), atomicAdd(a.stats + 1, st_prop);
+            atomicAdd(a.stats + 2, st_eps), atomicAdd(a.stats + 3, st_pacc);
+        }
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(256) gen_grad_kernel(GenDev gm, GradArgs a) {
+    const int g = threadIdx.x % G;
+    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool valid = c < a.C;
+    const int cid = valid ? (int)c : a.C - 1;
+    float q[K], graw[K], f[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) q[k] = a.q[(size_t)cid * K + k];
+    double chi2;
+    gen_pass(gm, g, q, graw, chi2);
+    if (!valid || g != 0) return;
+    const float tau = a.tau[cid];
+    const float beta = a.beta ? a.beta[cid] : 1.0f;
+    if (a.logp) a.logp[cid] = -gen_potential(gm, q, chi2, tau, beta, a.gamma_shape, a.gamma_rate);
+    if (a.chi2) a.chi2[cid] = chi2;
+    if (a.grad) {
+        gen_force(gm, q, graw, beta * tau, f);
+#pragma unroll
+        for (int k = 0; k < K; ++k) a.grad[(size_t)cid * K + k] = f[k];
+    }
+}
+
+// mock data of every chain (AbstractForwardModel.__call__): mock [C, N]
+extern "C" __global__ void gen_forward_kernel(GenDev gm, const float *q, int C, float *mock) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)C * gm.N) return;
+    const int c = (int)(i / gm.N), n = (int)(i - (long long)c * gm.N);
+    float th[K], dm[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) th[k] = q[(size_t)c * K + k];
+    mock[i] = binfb_mock(th, gm.rows + (size_t)n * gm.stride, dm);
+}

@@ -18,6 +18,7 @@ int cuda_fail(cudaError_t e, const char *what);
         if (e__ != cudaSuccess) return ::binfb::cuda_fail(e__, #call); \
     } while (0)
 
+// BEGIN_KERNEL_ARGS  (this block is also compiled by NVRTC as part of the generic-model source)
 // arguments common to every HMC launch (device pointers)
 struct HmcArgs {
     float *q;            // [C, D] state, in/out
@@ -49,6 +50,15 @@ struct GradArgs {
     double *chi2;
     double gamma_shape, gamma_rate;
 };
+
+// generic per-datum model (generic.cu / generic_kernel.cuh): data rows [N, stride] = x[0..XD-1], y, pad
+struct GenDev {
+    const float *rows;
+    int N, stride;
+    float prior_mean[16], prior_inv_var[16];
+    unsigned flags;
+};
+// END_KERNEL_ARGS
 
 // ---- polynomial --------------------------------------------------------------------------
 struct PolyModel {
@@ -99,6 +109,21 @@ int chrom_grad_launch(ChromModel &m, const GradArgs &a, int sm_count, int smem_o
                       cudaStream_t s);
 int chrom_forward_launch(const ChromModel &m, const float *q, int C, float *mock, cudaStream_t s);
 
+// ---- generic per-datum model compiled at run time (NVRTC) ----------------------------------------
+struct GenModel {
+    int K = 0, XD = 0, G = 8;
+    GenDev dev;
+    float *rows = nullptr;
+    void *library = nullptr;                       // cudaLibrary_t
+    void *k_hmc = nullptr, *k_grad = nullptr, *k_fwd = nullptr;  // cudaKernel_t
+};
+int gen_create(GenModel &g, const char *user_code, int n_params, int x_dim, const double *xs, const double *ys,
+               int n_data, const double *prior_mean, const double *prior_var, unsigned flags);
+void gen_destroy(GenModel &g);
+int gen_hmc_launch(const GenModel &g, const HmcArgs &a, cudaStream_t s);
+int gen_grad_launch(const GenModel &g, const GradArgs &a, cudaStream_t s);
+int gen_forward_launch(const GenModel &g, const float *q, int C, float *mock, cudaStream_t s);
+
 // ---- misc ----------------------------------------------------------------------------------
 int gibbs_tau_launch(const double *chi2, float *tau, const float *beta, int C, double n_data,
                      double shape, double rate, uint64_t seed, uint64_t draw, uint64_t chain_base,
@@ -126,6 +151,7 @@ struct binfb_model {
     double gamma_shape = 1.0, gamma_rate = 1.0;
     binfb::PolyModel poly;
     binfb::ChromModel chrom;
+    binfb::GenModel gen;
     // random-walk Metropolis workspace (rwmc.cu): proposals [cap, dim], log-probs 3 x [cap]
     float *rw_prop = nullptr;
     double *rw_lp[3] = {nullptr, nullptr, nullptr};

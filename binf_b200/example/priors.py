@@ -43,25 +43,26 @@ class GaussianPrior(AbstractPrior):
     its force out (quirk Q1); `differentiable=True` includes (c - means)/variances
     (BINFB_FLAG_PRIOR_GRAD on the device)."""
 
-    def __init__(self, means, variances, differentiable=False):
-        AbstractPrior.__init__(self, "coefficients_prior")
+    def __init__(self, means, variances, differentiable=False, variable="coefficients"):
+        AbstractPrior.__init__(self, variable + "_prior")
         for key, value in (("means", means), ("variances", variances)):
             self._register(key)
             self[key] = ArrayParameter(value, key)
         self._differentiable = bool(differentiable)
-        _declare(self, "coefficients", ArrayParameter, self._differentiable)
+        self._variable = variable   # "coefficients" in the reference; user-defined models name their own
+        _declare(self, variable, ArrayParameter, self._differentiable)
 
-    def _z(self, coefficients):
-        return np.asarray(coefficients, dtype=np.float64) - self["means"].value
+    def _z(self, value):
+        return np.asarray(value, dtype=np.float64) - self["means"].value
 
-    def _evaluate_log_prob(self, coefficients):
-        return -0.5 * np.sum(self._z(coefficients) ** 2 / self["variances"].value, axis=-1)
+    def _evaluate_log_prob(self, **variables):
+        return -0.5 * np.sum(self._z(variables[self._variable]) ** 2 / self["variances"].value, axis=-1)
 
-    def _evaluate_gradient(self, coefficients):
-        return self._z(coefficients) / self["variances"].value
+    def _evaluate_gradient(self, **variables):
+        return self._z(variables[self._variable]) / self["variances"].value
 
     def clone(self):
-        return type(self)(self["means"].value, self["variances"].value, self._differentiable)
+        return type(self)(self["means"].value, self["variances"].value, self._differentiable, self._variable)
 
 
 def make_priors():

@@ -116,6 +116,7 @@ def lower(pdf, n_coeff=None):
     from binf_b200.example.likelihood import ForwardModel as PolyForward, GaussianErrorModel
     from binf_b200.example.priors import GammaPrior, GaussianPrior
     from binf_b200.chromatin import ContactForwardModel, BackbonePrior
+    from binf_b200.model.forwardmodels import DeviceForwardModel
 
     if isinstance(pdf, Posterior):
         liks = list(pdf.likelihoods.values())
@@ -179,6 +180,22 @@ def lower(pdf, n_coeff=None):
         model = _cached_model(key, (fwm.xses, em.ys), lambda: _cabi.Model.polynomial(
             fwm.xses, em.ys, n_coeff, means, varis, *gamma(), flags=flags, device=dev))
         return Lowered(model, "coefficients", precision, beta, likelihood_only, gamma)
+    if isinstance(fwm, DeviceForwardModel):
+        # a user-defined per-datum model: kernels compiled at run time from its device code
+        if backbone is not None:
+            return None
+        K = fwm.n_params
+        if gauss_prior is not None:
+            means = np.broadcast_to(np.asarray(gauss_prior["means"].value, dtype=np.float64), (K,))
+            varis = np.broadcast_to(np.asarray(gauss_prior["variances"].value, dtype=np.float64), (K,))
+            flags = _cabi.FLAG_PRIOR_GRAD if fwm.variable in gauss_prior.differentiable_variables else 0
+        else:
+            means, varis, flags = None, None, 0
+        key = ("generic", id(fwm.xses), id(em.ys), fwm.device_code, K,
+               None if means is None else (tuple(means), tuple(varis)), flags, dev)
+        model = _cached_model(key, (fwm.xses, em.ys), lambda: _cabi.Model.generic(
+            fwm.device_code, K, fwm.xses, em.ys, means, varis, *gamma(), flags=flags, device=dev))
+        return Lowered(model, fwm.variable, precision, beta, likelihood_only, gamma)
     if type(fwm) is ContactForwardModel:
         if gauss_prior is not None:
             return None

@@ -39,6 +39,7 @@ extern "C" {
 /* model kinds */
 #define BINFB_MODEL_POLYNOMIAL 1
 #define BINFB_MODEL_CHROMATIN 2
+#define BINFB_MODEL_GENERIC 3
 
 /* model flags */
 #define BINFB_FLAG_PRIOR_GRAD 1u /* polynomial: add the Gaussian-prior force (c-mu)/v that the
@@ -90,6 +91,23 @@ int binfb_model_create_chromatin(int n_beads, const float *y_pairs, double alpha
                                  double k_bb, double l0, double conf_s, double gamma_shape,
                                  double gamma_rate, unsigned flags, int device,
                                  binfb_model **out);
+/* A USER-DEFINED per-datum forward model: the reference's extension point
+ * AbstractForwardModel._evaluate / _evaluate_jacobi_matrix (binf/model/forwardmodels.py:30-38),
+ * given as CUDA device code and compiled at run time (NVRTC, sm_100a) into the same fused
+ * HMC / log-prob kernels the polynomial model has.  device_code must define
+ *     __device__ float binfb_mock(const float *theta, const float *x, float *dmock);
+ * returning f_n(theta) for one datum with abscissae x[x_dim] and writing dmock[k] = d f_n / d theta_k,
+ * k < n_params (<= 16).  Error model: GaussianErrorModel (binf/example/likelihood.py:54-61); priors:
+ * independent Gaussians on theta, Gamma on the precision.  xs: host f64 [n_data, x_dim], ys [n_data].
+ * Compile errors return BINFB_EINVAL with the NVRTC log in binfb_last_error(). */
+int binfb_model_create_generic(const char *device_code, int n_params, int x_dim, const double *xs,
+                               const double *ys, int n_data, const double *prior_mean,
+                               const double *prior_var, double gamma_shape, double gamma_rate,
+                               unsigned flags, int device, binfb_model **out);
+/* compile device_code only (needs libnvrtc, no GPU): 0 if it compiles; the NVRTC log (warnings or
+ * errors) is copied to log_out[log_capacity] if non-NULL */
+int binfb_generic_compile_check(const char *device_code, int n_params, int x_dim, char *log_out,
+                                int log_capacity);
 int binfb_model_destroy(binfb_model *m);
 int binfb_model_info(const binfb_model *m, int *kind, int *dim, long long *n_data, int *device);
 /* update the Gamma prior on the precision (it enters log_prob and the Gibbs update only) */

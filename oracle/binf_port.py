@@ -218,3 +218,34 @@ def predict(x, y, coefficients, precisions):
     f = -0.5 * (mock - y) ** 2 * t + 0.5 * np.log(t) - 0.5 * np.log(2.0 * np.pi)
     m = np.max(f)
     return np.exp(m + np.log(np.sum(np.exp(f - m)))) / len(t)
+
+
+class UserModelPosterior(object):
+    """Posterior over the parameters of a user-defined per-datum forward model, evaluated the way the
+    reference composes it: mock = f(theta) (AbstractForwardModel._evaluate), gradient =
+    J(theta) . tau (mock - y) (binf/pdf/likelihoods.py:148-155 with binf/example/likelihood.py:61),
+    Gaussian prior in log_prob only (quirk Q1), Gamma prior on the precision.
+    f(theta [..., K], x [N]) -> [..., N];  jac(theta, x) -> [..., K, N]."""
+
+    def __init__(self, xs, ys, f, jac, prior_means, prior_variances, gamma_shape, gamma_rate, prior_grad=False):
+        self.xs, self.ys, self.f, self.jac = np.asarray(xs, float), np.asarray(ys, float), f, jac
+        self.mu, self.var = np.asarray(prior_means, float), np.asarray(prior_variances, float)
+        self.a, self.b, self.prior_grad = gamma_shape, gamma_rate, prior_grad
+
+    def chi2(self, q):
+        r = self.f(np.asarray(q, float), self.xs) - self.ys
+        return np.sum(r * r, axis=-1)
+
+    def log_prob(self, q, tau):
+        q = np.asarray(q, float)
+        lik = -0.5 * tau * self.chi2(q) + 0.5 * len(self.ys) * np.log(tau)     # example/likelihood.py:56-57
+        prior = -0.5 * np.sum((q - self.mu) ** 2 / self.var, axis=-1)           # example/priors.py:54
+        return lik + prior + (self.a - 1.0) * np.log(tau) - self.b * tau         # example/priors.py:25
+
+    def gradient(self, q, tau):
+        q = np.asarray(q, float)
+        r = self.f(q, self.xs) - self.ys
+        g = np.einsum("...kn,...n->...k", self.jac(q, self.xs), tau * r)        # likelihoods.py:155
+        if self.prior_grad:
+            g = g + (q - self.mu) / self.var
+        return g

@@ -238,6 +238,87 @@ def chromatin_case(binf, name, n_beads, n_chains, nsteps, timestep, seed, tau=50
     print(name, "acceptance", np.mean(acc), "max |dH|", np.max(np.abs(np.array(ea) - eb)))
 
 
+def user_model_case(binf, name, n_data, n_chains, nsteps, timestep, seed):
+    """A USER-DEFINED forward model written against the reference's own extension point
+    (AbstractForwardModel._evaluate / _evaluate_jacobi_matrix, binf/model/forwardmodels.py:30-38):
+    mock_n = a exp(-k x_n) + c, variables (a, k, c) registered as `coefficients` so that the
+    reference's GaussianPrior / GammaPrior / GaussianErrorModel / Likelihood / Posterior / HMCSampler
+    run it unchanged.  The fixture pins what the NVRTC-lowered device model must reproduce."""
+    from binf import ArrayParameter
+    from binf.model.forwardmodels import AbstractForwardModel
+    from binf.example.likelihood import GaussianErrorModel
+    from binf.example.priors import GammaPrior, GaussianPrior
+    from binf.pdf.likelihoods import Likelihood
+    from binf.pdf.posteriors import Posterior
+    from binf.samplers.hmc import HMCSampler
+
+    class Decay(AbstractForwardModel):
+        def __init__(self, xses):
+            super(Decay, self).__init__("decay")
+            self.xses = xses
+            self._register_variable("coefficients", differentiable=True)
+            self.update_var_param_types(coefficients=ArrayParameter)
+            self._set_original_variables()
+
+        def _evaluate(self, coefficients):
+            a, k, c = coefficients
+            return a * np.exp(-k * self.xses) + c
+
+        def _evaluate_jacobi_matrix(self, coefficients):
+            a, k, c = coefficients
+            e = np.exp(-k * self.xses)
+            return np.vstack([e, -a * self.xses * e, np.ones_like(self.xses)])
+
+        def clone(self):
+            copy = self.__class__(self.xses)
+            self._set_parameters(copy)
+            return copy
+
+    rng = np.random.RandomState(seed)
+    xs = np.linspace(0.0, 4.0, n_data)
+    true = np.array([3.0, 1.2, 0.5])
+    tau = 25.0
+    ys = rng.normal(true[0] * np.exp(-true[1] * xs) + true[2], 1.0 / np.sqrt(tau))
+    lik = Likelihood("points", Decay(xs), GaussianErrorModel(ys))
+    means, variances = np.array([2.0, 1.0, 0.0]), np.array([4.0, 1.0, 2.0])
+    priors = (GammaPrior(1.0, 0.2), GaussianPrior(means=means, variances=variances))
+    post = Posterior({lik.name: lik}, {p.name: p for p in priors})
+    cond = post.conditional_factory(precision=tau)
+    gp = [p for p in cond.priors.values() if "precision" in p._original_variables][0]
+    q0 = true[None] + 0.05 * rng.normal(size=(n_chains, 3))
+    p0 = rng.normal(size=q0.shape)
+    u = rng.uniform(size=n_chains)
+    logp, grad, qe, pe, eb, ea, acc, qn, mock = [], [], [], [], [], [], [], [], []
+    for c in range(n_chains):
+        logp.append(cond.log_prob(coefficients=q0[c].copy()))
+        grad.append(cond.gradient(coefficients=q0[c].copy()))
+        mock.append(lik.forward_model(coefficients=q0[c].copy()))
+        s = HMCSampler(cond, q0[c].copy(), timestep, nsteps, variable_name="coefficients")
+        ql, pl = s._leapfrog(q0[c].copy(), p0[c].copy(), timestep, nsteps)
+        qe.append(ql), pe.append(pl)
+        eb.append(-cond.log_prob(coefficients=q0[c].copy()) + 0.5 * np.sum(p0[c] ** 2))
+        ea.append(-cond.log_prob(coefficients=ql.copy()) + 0.5 * np.sum(pl ** 2))
+        with InjectedRandom(normals=[p0[c]], uniforms=[u[c]]):
+            new = s.sample()
+        acc.append(bool(s.last_move_accepted)), qn.append(new)
+    # the port with the same functor must agree
+    um = port.UserModelPosterior(xs, ys, lambda th, x: th[..., 0:1] * np.exp(-th[..., 1:2] * x) + th[..., 2:3],
+                                 lambda th, x: np.stack([np.exp(-th[..., 1:2] * x),
+                                                         -th[..., 0:1] * x * np.exp(-th[..., 1:2] * x),
+                                                         np.ones_like(th[..., 0:1] * x)], axis=-2),
+                                 means, variances, gp.shape, gp.rate)
+    close(um.log_prob(q0, tau), logp), close(um.gradient(q0, tau), grad)
+    r = port.hmc_sample(lambda q: um.log_prob(q, tau), lambda q: um.gradient(q, tau), q0, timestep, nsteps, p0, u)
+    close(r["q_end"], qe), close(r["p_end"], pe), close(r["e_before"], eb), close(r["e_after"], ea)
+    assert list(r["accepted"]) == acc
+    np.savez(os.path.join(GOLDEN, name + ".npz"), xs=xs, ys=ys, tau=tau, q0=q0, p0=p0, u=u, nsteps=nsteps,
+             timestep=timestep, prior_means=means, prior_variances=variances, gamma_shape=gp.shape,
+             gamma_rate=gp.rate, log_prob=np.array(logp), gradient=np.array(grad), mock=np.array(mock),
+             q_end=np.array(qe), p_end=np.array(pe), e_before=np.array(eb), e_after=np.array(ea),
+             accepted=np.array(acc), q_new=np.array(qn))
+    print(name, "acceptance", np.mean(acc), "max |dH|", np.max(np.abs(np.array(ea) - eb)))
+
+
 def rwmc_predict_case(binf, name, n_data, n_chains, n_moves, stepsize, seed):
     """RWMCSampler.sample (binf/example/samplers.py:78-92) with the proposal displacement and the
     uniform injected, chain by chain and move by move; and predict (binf/example/misc.py:3-16) over
@@ -298,6 +379,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "rwmc":     # only the fixtures added with SURVEY 8f rank 4
         rwmc_predict_case(binf, "poly_rwmc_n20", n_data=20, n_chains=24, n_moves=6, stepsize=0.1, seed=9)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "user":     # the fixture added with SURVEY 8f rank 2
+        user_model_case(binf, "user_decay_n200", n_data=200, n_chains=24, nsteps=10, timestep=0.012, seed=10)
+        return
     # config 1 shape (example_script.py:17-26), seeded
     polynomial_case(binf, "poly_n20", n_data=20, n_chains=16, nsteps=20, timestep=0.02, seed=0)
     # config 2 shape: N = 1000 data points, L = 20
@@ -317,6 +401,7 @@ def main():
     chromatin_case(binf, "chromatin_n30_big_step", n_beads=30, n_chains=12, nsteps=10,
                    timestep=0.05, seed=8)
     rwmc_predict_case(binf, "poly_rwmc_n20", n_data=20, n_chains=24, n_moves=6, stepsize=0.1, seed=9)
+    user_model_case(binf, "user_decay_n200", n_data=200, n_chains=24, nsteps=10, timestep=0.012, seed=10)
 
 
 if __name__ == "__main__":

@@ -144,3 +144,38 @@ def test_list_sink_oracle_matches_reference_slicing():
     lp = np.array(ls[5::3])
     for c in range(2):                                    # misc.py:18-22 per chain
         np.testing.assert_array_equal(ref.get_MAP()[0][c], thin[int(np.argmax(lp[:, c]))][c])
+
+
+DECAY_CODE = """
+__device__ float binfb_mock(const float *theta, const float *x, float *dmock) {
+    const float e = expf(-theta[1] * x[0]);
+    dmock[0] = e; dmock[1] = -theta[0] * x[0] * e; dmock[2] = 1.0f;
+    return theta[0] * e + theta[2];
+}
+"""
+
+
+def test_generic_model_device_code_compiles_without_gpu():
+    """NVRTC runs on the host: user code + the generic fused kernels compile for sm_100a here"""
+    ok, log = _cabi.generic_compile_check(DECAY_CODE, 3, 1)
+    assert ok, log
+    ok, log = _cabi.generic_compile_check("__device__ float binfb_mock(const float *t, const float *x, float *d)"
+                                          " { return nope(t[0]); }", 2, 1)
+    assert not ok and "user_model.cu(1)" in log and "nope" in log      # the log points into the user's code
+    h = _cabi.lib()
+    assert h.binfb_generic_compile_check(None, 3, 1, None, 0) == _cabi.EINVAL
+    assert h.binfb_generic_compile_check(DECAY_CODE.encode(), 17, 1, None, 0) == _cabi.EINVAL
+
+
+def test_device_forward_model_descriptor():
+    from binf_b200.model.forwardmodels import DeviceForwardModel
+    xs = np.linspace(0, 1, 8)
+    m = DeviceForwardModel("decay", xs, "rates", 3, DECAY_CODE)
+    assert "rates" in m.variables and m.check_device_code() == ""
+    twin = m.clone()
+    assert twin.device_code == m.device_code and twin.n_params == 3
+    with pytest.raises(ValueError):
+        DeviceForwardModel("bad", xs, "rates", 3, "int x;")
+    with pytest.raises(ValueError):
+        DeviceForwardModel("bad", xs, "rates", 3, "__device__ float binfb_mock(const float*a,const float*b,float*c){return q;}"
+                           ).check_device_code()

@@ -126,3 +126,23 @@ def test_rwmc_and_predict_port_vs_reference_outputs():
     flat = g["states"].reshape(-1, 4)
     pred = [port.predict(a, b, flat, g["pred_tau"]) for a, b in zip(g["pred_x"], g["pred_y"])]
     np.testing.assert_allclose(pred, g["pred"], rtol=1e-12)
+
+
+DECAY_F = staticmethod(lambda th, x: th[..., 0:1] * np.exp(-th[..., 1:2] * x) + th[..., 2:3])
+DECAY_J = staticmethod(lambda th, x: np.stack([np.exp(-th[..., 1:2] * x), -th[..., 0:1] * x * np.exp(-th[..., 1:2] * x),
+                                               np.ones_like(th[..., 0:1] * x)], axis=-2))
+
+
+def test_user_model_port_vs_reference_outputs():
+    """a user-defined AbstractForwardModel run by the reference itself (oracle/make_golden.py user)"""
+    g = load_golden("user_decay_n200")
+    um = port.UserModelPosterior(g["xs"], g["ys"], DECAY_F.__func__, DECAY_J.__func__, g["prior_means"],
+                                 g["prior_variances"], float(g["gamma_shape"]), float(g["gamma_rate"]))
+    tau = float(g["tau"])
+    np.testing.assert_allclose(um.log_prob(g["q0"], tau), g["log_prob"], rtol=1e-12)
+    np.testing.assert_allclose(um.gradient(g["q0"], tau), g["gradient"], rtol=1e-10, atol=1e-9)
+    r = port.hmc_sample(lambda q: um.log_prob(q, tau), lambda q: um.gradient(q, tau), g["q0"],
+                        float(g["timestep"]), int(g["nsteps"]), g["p0"], g["u"])
+    np.testing.assert_allclose(r["q_end"], g["q_end"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(r["e_after"], g["e_after"], rtol=1e-10)
+    assert np.array_equal(r["accepted"], g["accepted"]) and not g["accepted"].all()
