@@ -58,7 +58,13 @@ namespace binfb {
 constexpr float CHROM_SOFT = PAIR_SOFT;
 constexpr int STEP_FLOAT4 = 4 * 32;  // float4 per warp-step (16 contacts per lane)
 constexpr int STEP_BYTES = STEP_FLOAT4 * 16;
-constexpr int CHROM_NS = 4;          // ring depth (stages)
+#ifndef BINFB_CHROM_NS
+#define BINFB_CHROM_NS 4
+#endif
+#ifndef BINFB_CHROM_SS
+#define BINFB_CHROM_SS 4
+#endif
+constexpr int CHROM_NS = BINFB_CHROM_NS;  // ring depth (stages)
 
 struct ChromDev {
     int n, n_pad, Q, KS, NRB, q_even;
@@ -358,7 +364,7 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
             for (int sg = sg_begin; sg < sg_end; ++sg) {
                 const uint32_t slot = stage_idx & (CHROM_NS - 1);
                 {  // (probing the barrier one step early does not pay: the result is consumed at once)
-                    const uint32_t fb = ring.full + slot * 8u, fp = (stage_idx >> 2) & 1u;
+                    const uint32_t fb = ring.full + slot * 8u, fp = (stage_idx / CHROM_NS) & 1u;
                     while (!bar_try_wait(fb, fp)) {
                     }
                 }
@@ -774,7 +780,7 @@ static inline long long tri_index(long long n, long long i, long long j) {  // i
 // stage size (warp-steps) and ring depth per role count
 // stage size in warp-steps per role count (SPR = SS / R steps per role and stage); the ring has
 // CHROM_NS stages.  Measured on B200 at n = 1000: 4-step stages x 4 slots beat 8 x 2.
-static int chrom_stage_steps(int R) { return R <= 4 ? 4 : R; }
+static int chrom_stage_steps(int R) { return R <= BINFB_CHROM_SS ? BINFB_CHROM_SS : R; }
 static int chrom_ring_depth(int) { return CHROM_NS; }
 
 ChromPlan chrom_plan(int n, int smem_optin, int force_roles) {
@@ -926,6 +932,11 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
         chrom_kernel<RR, SPR><<<grid, threads, smem, s>>>(dev, call);                                          \
     } while (0)
     if (pl.R == 1 && pl.SS == 4) BINFB_CHROM_LAUNCH(1, 4);
+#if BINFB_CHROM_SS == 8
+    else if (pl.R == 2 && pl.SS == 8) BINFB_CHROM_LAUNCH(2, 4);
+#elif BINFB_CHROM_SS == 2
+    else if (pl.R == 2 && pl.SS == 2) BINFB_CHROM_LAUNCH(2, 1);
+#endif
     else if (pl.R == 2 && pl.SS == 4) BINFB_CHROM_LAUNCH(2, 2);
     else if (pl.R == 4 && pl.SS == 4) BINFB_CHROM_LAUNCH(4, 1);
     else if (pl.R == 8 && pl.SS == 8) BINFB_CHROM_LAUNCH(8, 1);
