@@ -257,6 +257,17 @@ int binfb_model_create_chromatin(int n_beads, const float *y_pairs, double alpha
     if (!rc) e = cudaMalloc(&cm.ystream, (size_t)n_floats * sizeof(float));
     if (!rc && e == cudaSuccess)
         e = cudaMemcpy(cm.ystream, stream.data(), (size_t)n_floats * sizeof(float), cudaMemcpyHostToDevice);
+    // small-batch alternative plan with its own stream layout (not when the role count is forced)
+    if (!rc && e == cudaSuccess && force_roles == 0) {
+        cm.plan_alt = chrom_plan_small_batch(n_beads, m->smem_optin, cm.plan);
+        if (cm.plan_alt.W >= 1) {
+            std::vector<float> alt((size_t)cm.plan_alt.stream_floats);
+            rc = chrom_build_stream(n_beads, y_pairs, cm.plan_alt, alt.data());
+            if (!rc) e = cudaMalloc(&cm.ystream_alt, alt.size() * sizeof(float));
+            if (!rc && e == cudaSuccess)
+                e = cudaMemcpy(cm.ystream_alt, alt.data(), alt.size() * sizeof(float), cudaMemcpyHostToDevice);
+        }
+    }
     if (!rc && e == cudaSuccess) e = cudaMalloc(&cm.ypairs, (size_t)cm.M * sizeof(float));
     if (!rc && e == cudaSuccess)
         e = cudaMemcpy(cm.ypairs, y_pairs, (size_t)cm.M * sizeof(float), cudaMemcpyHostToDevice);
@@ -276,7 +287,7 @@ int binfb_model_destroy(binfb_model *m) {
     gen_destroy(m->gen);
     cudaFree(m->rw_prop), cudaFree(m->rw_lp[0]), cudaFree(m->rw_lp[1]), cudaFree(m->rw_lp[2]);
     ChromModel &c = m->chrom;
-    cudaFree(c.ystream), cudaFree(c.ypairs), cudaFree(c.qw), cudaFree(c.pw), cudaFree(c.h0);
+    cudaFree(c.ystream), cudaFree(c.ystream_alt), cudaFree(c.ypairs), cudaFree(c.qw), cudaFree(c.pw), cudaFree(c.h0);
     cudaFree(c.chi2_0), cudaFree(c.chi2_state), cudaFree(c.tau_w), cudaFree(c.sched);
     if (m->hb) cudaFree(m->hb);
     if (m->hstream) cudaStreamDestroy(m->hstream);

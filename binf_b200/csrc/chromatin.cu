@@ -307,7 +307,7 @@ __device__ __forceinline__ void step_special(SweepRegs &s, uint32_t frc_off, uin
     if (ENERGY) s.chi2 += (double)chi;
 }
 
-template <bool ENERGY, int R, int SPR>
+template <bool ENERGY, int R, int SPR, bool LOCKSTEP>
 __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSmem &sm, const Ring &ring,
                                               uint32_t &stage_idx_io, bool chain_valid, int lane, int role,
                                               int bar_id, int rb0) {
@@ -378,7 +378,10 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
                     if (GENERIC) ++s.k;
                     s.paddr += 48u;
                     if (--s.wrap == 0) s.paddr -= (uint32_t)Q * 48u, s.wrap = Q;
-                    __syncwarp();
+                    // LOCKSTEP: all roles of the chain finish step s before any starts s + 1, so their
+                    // partner offsets always differ by exactly a multiple of Lr >= 32 (see chrom_plan)
+                    if (LOCKSTEP) chain_bar(bar_id, R * 32);
+                    else __syncwarp();
                 }
                 if (elect_one()) ring_release<STAGE_BYTES>(ring, stage_idx, (int)(stage_idx - stage_base));
                 ++stage_idx;
@@ -445,7 +448,7 @@ struct ChromCall {
     int n_groups, total_items;
 };
 
-template <int R, int SPR>
+template <int R, int SPR, bool LOCKSTEP>
 __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall call) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int STAGE_BYTES = R * SPR * STEP_BYTES;
@@ -578,8 +581,8 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
             else __syncwarp();
             // ---- phase B: pair sweep -----------------------------------------------------
             const int rb0 = BINFB_ROTATE ? o % cd.NRB : 0;
-            double chi2 = energy ? chrom_sweep<true, R, SPR>(cd, sm, ring, stage_idx, valid, lane, role, bar_id, rb0)
-                                 : chrom_sweep<false, R, SPR>(cd, sm, ring, stage_idx, valid, lane, role, bar_id, rb0);
+            double chi2 = energy ? chrom_sweep<true, R, SPR, LOCKSTEP>(cd, sm, ring, stage_idx, valid, lane, role, bar_id, rb0)
+                                 : chrom_sweep<false, R, SPR, LOCKSTEP>(cd, sm, ring, stage_idx, valid, lane, role, bar_id, rb0);
             if (R > 1) chain_bar(bar_id, cthreads);
             else __syncwarp();
             if (valid) {
@@ -774,48 +777,62 @@ static inline long long tri_index(long long n, long long i, long long j) {  // i
     return i * n - i * (i + 1) / 2 + (j - i - 1);
 }
 
-// Launch geometry: W chains per CTA, R warps ("roles") per chain, W*R <= 16 consumer warps.
-// R > 1 only when the partner-step ranges of two roles can never overlap within the drift the
-// stage ring allows (see chrom_sweep): Lr - NS*SS/R >= 40.
-// stage size (warp-steps) and ring depth per role count
 // stage size in warp-steps per role count (SPR = SS / R steps per role and stage); the ring has
 // CHROM_NS stages.  Measured on B200 at n = 1000: 4-step stages x 4 slots beat 8 x 2.
 static int chrom_stage_steps(int R) { return R <= BINFB_CHROM_SS ? BINFB_CHROM_SS : R; }
 static int chrom_ring_depth(int) { return CHROM_NS; }
 
-ChromPlan chrom_plan(int n, int smem_optin, int force_roles) {
+// the plan for a fixed role count R; W = 0 if it cannot run.  Two roles of a chain may only touch the
+// same partner quad if their offsets differ by <= 31.  Free-running roles drift by up to NS*spr - 1
+// slots (the ring holds NS stages of spr slots per role), which needs Lr - drift >= 34; roles in
+// LOCKSTEP (a chain barrier after every step) always differ by exactly a multiple of Lr, which needs
+// Lr >= 32 only.
+static ChromPlan chrom_plan_for(int n, int smem_optin, int R, bool allow_lockstep) {
     ChromPlan pl;
     pl.n_pad = (n + 3) / 4 * 4, pl.Q = pl.n_pad / 4, pl.KS = pl.Q / 2, pl.NRB = (pl.Q + 31) / 32;
     const size_t per_chain = (size_t)6 * pl.n_pad * sizeof(float) + 64;
-    int best_R = 1;
-    for (int R = 2; R <= 8; R *= 2) {  // 16 roles (32 KiB stages, 2 slots) measured slower at n = 5000
-        const int SS = chrom_stage_steps(R), NS = chrom_ring_depth(R);
-        const size_t fixed = (size_t)NS * SS * STEP_BYTES + 128;
-        if ((size_t)smem_optin < fixed + per_chain) break;
-        const int wmax = (int)(((size_t)smem_optin - fixed) / per_chain);
-        const int spr = SS / R;
-        const int Lr = ((pl.KS + 1 + R - 1) / R + spr - 1) / spr * spr;
-        // two roles of a chain are at most NS*spr - 1 slots apart (the ring holds NS stages of spr
-        // slots per role); they can only meet on a partner quad if their offsets differ by <= 31
-        const bool safe = Lr - (NS * spr - 1) >= 34;
-        // more roles only pay off while the chains alone cannot fill 16 warps
-        if (safe && wmax * (R / 2) < 16) best_R = R;
-    }
-    if (force_roles > 0) best_R = force_roles;
-    pl.R = best_R;
-    pl.SS = chrom_stage_steps(pl.R), pl.NS = chrom_ring_depth(pl.R);
-    const int NS = pl.NS;
-    const int spr = pl.SS / pl.R;  // slots per stage and role
-    pl.Lr = ((pl.KS + 1 + pl.R - 1) / pl.R + spr - 1) / spr * spr;  // stages never straddle row blocks
+    pl.R = R;
+    pl.SS = chrom_stage_steps(R), pl.NS = chrom_ring_depth(R);
+    const int spr = pl.SS / R;  // slots per stage and role
+    pl.Lr = ((pl.KS + 1 + R - 1) / R + spr - 1) / spr * spr;  // stages never straddle row blocks
     pl.S_pad = pl.NRB * pl.Lr;
-    pl.fixed_smem = (size_t)NS * pl.SS * STEP_BYTES + 128;
+    pl.fixed_smem = (size_t)pl.NS * pl.SS * STEP_BYTES + 128;
     pl.per_chain_smem = per_chain;
+    const bool safe_free = R == 1 || pl.Lr - (pl.NS * spr - 1) >= 34;
+    const bool safe_lock = pl.Lr >= 32;
+    pl.lockstep = !safe_free && safe_lock && allow_lockstep;
     int W = (size_t)smem_optin > pl.fixed_smem ? (int)(((size_t)smem_optin - pl.fixed_smem) / per_chain) : 0;
-    if (W > 16 / pl.R) W = 16 / pl.R;
-    if (W < 1 && (size_t)smem_optin >= pl.fixed_smem + per_chain) W = 1;
+    if (W > 16 / R) W = 16 / R;
+    if (!safe_free && !pl.lockstep) W = 0;
     pl.W = W;
-    pl.stream_floats = (long long)pl.S_pad * pl.R * STEP_FLOAT4 * 4;
+    pl.stream_floats = (long long)pl.S_pad * R * STEP_FLOAT4 * 4;
     return pl;
+}
+
+// Launch geometry: W chains per CTA, R warps ("roles") per chain, W*R <= 16 consumer warps.  More roles
+// only pay off while the chains alone cannot fill 16 warps; free-running roles are preferred.
+ChromPlan chrom_plan(int n, int smem_optin, int force_roles) {
+    if (force_roles > 0) return chrom_plan_for(n, smem_optin, force_roles, true);
+    ChromPlan best = chrom_plan_for(n, smem_optin, 1, false);
+    for (int R = 2; R <= 8; R *= 2) {  // 16 roles (32 KiB stages, 2 slots) measured slower at n = 5000
+        const ChromPlan pl = chrom_plan_for(n, smem_optin, R, false);
+        const size_t per_chain = pl.per_chain_smem;
+        if ((size_t)smem_optin < pl.fixed_smem + per_chain) break;
+        const int wmax = (int)(((size_t)smem_optin - pl.fixed_smem) / per_chain);
+        if (pl.W >= 1 && wmax * (R / 2) < 16) best = pl;
+    }
+    return best;
+}
+
+// Small batches (fewer chains than the primary plan needs to give every SM 16 warps): twice the roles
+// per chain, in lockstep if necessary.  W = 0 if there is no such plan.
+ChromPlan chrom_plan_small_batch(int n, int smem_optin, const ChromPlan &primary) {
+    ChromPlan none;
+    none.W = 0;
+    const int R = primary.R * 2;
+    if (R > 8) return none;
+    const ChromPlan pl = chrom_plan_for(n, smem_optin, R, true);
+    return pl.W >= 1 ? pl : none;
 }
 
 // Contact stream in consumption order: step t' = (rb*Lr + s)*R + role holds, for lane l and row r,
@@ -876,13 +893,12 @@ int chrom_reserve(ChromModel &m, int C) {
     return BINFB_OK;
 }
 
-static ChromDev chrom_dev(const ChromModel &m) {
+static ChromDev chrom_dev(const ChromModel &m, const ChromPlan &pl, const float *ystream) {
     ChromDev d;
-    const ChromPlan &pl = m.plan;
     d.n = m.n, d.n_pad = pl.n_pad, d.Q = pl.Q, d.KS = pl.KS, d.NRB = pl.NRB;
     d.q_even = (pl.Q % 2) == 0;
     d.R = pl.R, d.Lr = pl.Lr, d.SS = pl.SS, d.S_pad = pl.S_pad;
-    d.ystream = reinterpret_cast<const float4 *>(m.ystream);
+    d.ystream = reinterpret_cast<const float4 *>(ystream);
     const double log2e = 1.4426950408889634;
     d.A = (float)((double)m.alpha * log2e);
     d.B = (float)(-(double)m.alpha * (double)m.d_c * log2e);
@@ -898,13 +914,24 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
                         cudaStream_t s) {
     int rc = chrom_reserve(m, C);
     if (rc) return rc;
-    const ChromPlan &pl = m.plan;
-    int W = pl.W;
-    // small batches: rather fewer chains per CTA than idle SMs
-    if ((C + W - 1) / W < sm_count) W = (C + sm_count - 1) / sm_count;
-    if (W > pl.W) W = pl.W;
-    if (m.opt_warps > 0 && m.opt_warps < W) W = m.opt_warps;
-    if (W > C) W = C;
+    // chains per CTA for a plan: rather fewer chains per CTA than idle SMs
+    auto chains_per_cta = [&](const ChromPlan &p) {
+        int w = p.W;
+        if (w >= 1 && (C + w - 1) / w < sm_count) w = (C + sm_count - 1) / sm_count;
+        if (w > p.W) w = p.W;
+        if (m.opt_warps > 0 && m.opt_warps < w) w = m.opt_warps;
+        if (w > C) w = C;
+        return w;
+    };
+    const ChromPlan *plp = &m.plan;
+    const float *ystream = m.ystream;
+    int W = chains_per_cta(m.plan);
+    // a batch that leaves the SMs half empty with the primary plan runs with twice the warps per chain
+    if (m.ystream_alt && W >= 1 && W * m.plan.R <= 8) {
+        const int wa = chains_per_cta(m.plan_alt);
+        if (wa >= 1 && wa * m.plan_alt.R > W * m.plan.R) plp = &m.plan_alt, ystream = m.ystream_alt, W = wa;
+    }
+    const ChromPlan &pl = *plp;
     if (W < 1) {
         set_error("chromatin model: one chain does not fit in shared memory (n_beads too large for "
                   "this kernel)");
@@ -924,14 +951,21 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
     BINFB_CUDA(cudaMemsetAsync(m.sched, 0, (size_t)(1 + call.n_groups) * sizeof(int), s));
     const int grid = call.n_groups < sm_count ? call.n_groups : sm_count;
     const int threads = W * pl.R * 32;
-    const ChromDev dev = chrom_dev(m);
-#define BINFB_CHROM_LAUNCH(RR, SPR)                                                                            \
+    const ChromDev dev = chrom_dev(m, pl, ystream);
+#define BINFB_CHROM_LAUNCH_L(RR, SPR, LOCK)                                                                    \
     do {                                                                                                       \
-        BINFB_CUDA(cudaFuncSetAttribute(chrom_kernel<RR, SPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                        (int)smem));                                                           \
-        chrom_kernel<RR, SPR><<<grid, threads, smem, s>>>(dev, call);                                          \
+        BINFB_CUDA(cudaFuncSetAttribute(chrom_kernel<RR, SPR, LOCK>,                                           \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        chrom_kernel<RR, SPR, LOCK><<<grid, threads, smem, s>>>(dev, call);                                    \
     } while (0)
-    if (pl.R == 1 && pl.SS == 4) BINFB_CHROM_LAUNCH(1, 4);
+#define BINFB_CHROM_LAUNCH(RR, SPR) BINFB_CHROM_LAUNCH_L(RR, SPR, false)
+    if (pl.lockstep && pl.R == 2 && pl.SS == 4) BINFB_CHROM_LAUNCH_L(2, 2, true);
+    else if (pl.lockstep && pl.R == 4 && pl.SS == 4) BINFB_CHROM_LAUNCH_L(4, 1, true);
+    else if (pl.lockstep && pl.R == 8 && pl.SS == 8) BINFB_CHROM_LAUNCH_L(8, 1, true);
+    else if (pl.lockstep) {
+        set_error("chromatin model: unsupported lockstep launch plan");
+        return BINFB_EUNSUPPORTED;
+    } else if (pl.R == 1 && pl.SS == 4) BINFB_CHROM_LAUNCH(1, 4);
 #if BINFB_CHROM_SS == 8
     else if (pl.R == 2 && pl.SS == 8) BINFB_CHROM_LAUNCH(2, 4);
 #elif BINFB_CHROM_SS == 2
@@ -945,6 +979,7 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
         return BINFB_EUNSUPPORTED;
     }
 #undef BINFB_CHROM_LAUNCH
+#undef BINFB_CHROM_LAUNCH_L
     BINFB_CUDA(cudaGetLastError());
     return BINFB_OK;
 }

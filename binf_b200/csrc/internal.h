@@ -80,6 +80,7 @@ struct ChromPlan {
     int R = 1, W = 1;                       // warps per chain, chains per CTA
     int Lr = 0, SS = 4, S_pad = 0;          // slots per row block, steps per stage, padded slots
     int NS = 4;                             // ring depth
+    int lockstep = 0;                       // the roles of a chain advance step by step together
     size_t fixed_smem = 0, per_chain_smem = 0;
     long long stream_floats = 0;
 };
@@ -88,6 +89,10 @@ struct ChromModel {
     ChromPlan plan;
     long long M = 0;
     float *ystream = nullptr;      // device [S_pad * R][4][32] float4
+    // small-batch alternative: twice the warps per chain in lockstep (own stream layout), used when the
+    // batch cannot fill the SMs with the primary plan
+    ChromPlan plan_alt;
+    float *ystream_alt = nullptr;
     float *ypairs = nullptr;       // device [M] (triu order; forward/mock kernel only)
     float alpha = 0, d_c = 0, k_bb = 0, l0 = 0, inv_s2 = 0;
     unsigned flags = 0;
@@ -101,6 +106,7 @@ struct ChromModel {
     int sched_len = 0;
 };
 ChromPlan chrom_plan(int n, int smem_optin, int force_roles);
+ChromPlan chrom_plan_small_batch(int n, int smem_optin, const ChromPlan &primary);
 int chrom_build_stream(int n, const float *y_pairs, const ChromPlan &pl, float *out);
 int chrom_reserve(ChromModel &m, int C);
 int chrom_hmc_launch(ChromModel &m, const HmcArgs &a, int sm_count, int smem_optin,

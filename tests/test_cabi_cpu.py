@@ -179,3 +179,15 @@ def test_device_forward_model_descriptor():
     with pytest.raises(ValueError):
         DeviceForwardModel("bad", xs, "rates", 3, "__device__ float binfb_mock(const float*a,const float*b,float*c){return q;}"
                            ).check_device_code()
+
+
+def test_lockstep_plans_are_reported_and_unsafe_role_counts_refused():
+    import ctypes as C
+    h = _cabi.lib()
+    nf, plan = C.c_longlong(), (C.c_int * 8)()
+    # n = 1000, 4 roles: role ranges of 32 slots -> only safe in lockstep; the layout pass still plans it
+    _cabi.check(h.binfb_chromatin_stream_layout(1000, None, 4, 0, None, 0, C.byref(nf), plan))
+    assert list(plan)[3] == 4 and list(plan)[4] == 32 and list(plan)[5] == 4
+    # n = 1000, 8 roles: ranges of 16 slots can collide even in lockstep -> no chains per CTA
+    _cabi.check(h.binfb_chromatin_stream_layout(1000, None, 8, 0, None, 0, C.byref(nf), plan))
+    assert list(plan)[5] == 0

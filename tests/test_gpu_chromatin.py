@@ -68,9 +68,11 @@ def test_ragged_sizes_vs_oracle(gpu, n):
         assert chi2[c] == pytest.approx(o.chi2(q[c]), rel=1e-5)
 
 
-@pytest.mark.parametrize("n,roles", [(2000, 0), (2000, 2), (700, 2)])
+@pytest.mark.parametrize("n,roles", [(2000, 0), (2000, 2), (700, 2), (1000, 4), (500, 2), (1000, 0)])
 def test_multi_warp_chains_vs_oracle(gpu, n, roles):
-    """2 and 4 warps per chain (partner-step ranges split between the warps of a chain)"""
+    """2 and 4 warps per chain (partner-step ranges split between the warps of a chain); (1000, 4) and
+    (500, 2) need the LOCKSTEP kernels (role ranges of exactly 32 slots), and (1000, 0) with 9 chains
+    takes the small-batch route (the alternative 4-role lockstep plan and its own contact stream)"""
     from binf_b200 import _cabi
     X, y = chrom.synthetic_chromatin(n, seed=n)
     o = chrom.ChromatinModel(n, y, 2.0, 2.5, 4.0, 1.0)
