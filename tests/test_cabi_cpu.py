@@ -191,3 +191,38 @@ def test_lockstep_plans_are_reported_and_unsafe_role_counts_refused():
     # n = 1000, 8 roles: ranges of 16 slots can collide even in lockstep -> no chains per CTA
     _cabi.check(h.binfb_chromatin_stream_layout(1000, None, 8, 0, None, 0, C.byref(nf), plan))
     assert list(plan)[5] == 0
+
+
+@pytest.mark.parametrize("n,roles", [(1000, 2), (1000, 4), (500, 2), (700, 2), (2000, 4), (5000, 8), (1400, 4)])
+def test_roles_never_touch_the_same_partner_quad(n, roles):
+    """Host replay of the race-freedom argument of the pair sweep (compute-sanitizer's racecheck is not
+    available on the GPU pool).  Within a row block, role r at slot s read-modify-writes the partner
+    quads {(a + r*Lr + s) mod Q : a in the row block}.  Free-running roles may be up to
+    NS*SPR - 1 slots apart, LOCKSTEP roles are always at the same slot: no two roles may ever address
+    the same quad within that window."""
+    import ctypes as C
+    h = _cabi.lib()
+    nf, plan = C.c_longlong(), (C.c_int * 8)()
+    _cabi.check(h.binfb_chromatin_stream_layout(n, None, roles, 0, None, 0, C.byref(nf), plan))
+    q, ks, nrb, R, lr, W, ss, ns = list(plan)
+    assert R == roles and W >= 1
+    spr = ss // R
+    free_ok = lr - (ns * spr - 1) >= 34
+    drift = ns * spr - 1 if free_ok else 0             # lockstep plans: the roles move together
+    assert free_ok or lr >= 32
+    for rb in (0, nrb - 1):
+        a = rb * 32 + np.arange(32)
+        a = a[a < q]
+        for s in range(0, lr, max(1, lr // 7)):
+            touched = {}
+            for role in range(R):
+                for ds in range(-drift, drift + 1):     # every slot the other roles can be at meanwhile
+                    sl = s + (ds if role else 0)
+                    if not 0 <= sl < lr:
+                        continue
+                    k = role * lr + sl
+                    if k > ks:
+                        continue
+                    for b in (a + k) % q:
+                        owner = touched.setdefault(int(b), role)
+                        assert owner == role, "roles %d and %d meet on quad %d (n=%d)" % (owner, role, b, n)
