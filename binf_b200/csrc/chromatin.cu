@@ -22,10 +22,14 @@
 //   * within a step the 32 lanes address 32 distinct partner quads, so the read-modify-write of the
 //     partner forces in shared memory is conflict- and race-free without atomics.
 //   * contacts are pre-laid-out on the host in exactly the order the lanes consume them
-//     ([row block][slot][role][row r][lane] float4).  Lane 0 of warp 0 streams that array through
-//     a 4-stage shared-memory ring with 1-D bulk async copies (TMA engine, UBLKCP) completing on
-//     mbarriers, two stages ahead of the consumers; all warps read the same stage, so L2->SM
+//     ([row block][slot][role][row r][lane] float4) and streamed through a 4-stage shared-memory
+//     ring with 1-D bulk async copies (TMA engine, UBLKCP) completing on mbarriers; the last warp to
+//     release a stage issues its refill (see `Ring`); all warps read the same stage, so L2->SM
 //     traffic is 1/W of naive.
+//   * shared memory per chain: positions and force sums per quad as [x0..x3 | y0..y3 | z0..z3]
+//     (48-byte lane stride: one address register, no bank conflicts).
+//   * small batches switch to an alternative plan with twice the roles per chain, kept race-free by
+//     a per-step chain barrier (LOCKSTEP); see chrom_plan / chrom_launch.
 //   * scheduling: a work item is (trajectory, leapfrog pass, group of W chains).  CTAs are
 //     persistent and claim items from an atomic counter; a per-group pass counter (release/acquire)
 //     orders the passes of one group.  Between passes q and p round-trip through L2 (24 KB per
