@@ -111,6 +111,34 @@ __device__ __forceinline__ void pair_packed(float2 nx2, float2 ny2, float2 nz2, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// packed shape with SCALAR row accumulators: the three row accumulations (coef*d + G, three distinct
+// register pairs = 3 dispatch cycles each as FFMA2) become six scalar FFMA into one scalar G per
+// component (1.15 cycles each), which also halves the registers the row accumulators occupy
+// (12 instead of 24 per lane).
+// ---------------------------------------------------------------------------------------------
+template <bool ENERGY>
+__device__ __forceinline__ void pair_packed_gs(float2 nx2, float2 ny2, float2 nz2, float2 xj2, float2 yj2,
+                                               float2 zj2, float2 y2, float2 A2, float2 B2, float &gx, float &gy,
+                                               float &gz, float2 &fx2, float2 &fy2, float2 &fz2, float2 &chi2) {
+    const float2 dx = add2(xj2, nx2), dy = add2(yj2, ny2), dz = add2(zj2, nz2);
+    const float2 r2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, mk2(PAIR_SOFT, PAIR_SOFT))));
+    const float2 inv = mk2(mufu_rsqrt(r2.x), mufu_rsqrt(r2.y));
+    const float2 d = mul2(r2, inv);
+    const float2 t = fma2(d, A2, B2);
+    const float2 e = mk2(mufu_ex2(t.x), mufu_ex2(t.y));
+    const float2 sn = fma2(e, mk2(-1.f, -1.f), mk2(-1.f, -1.f));
+    const float2 mn = mk2(mufu_rcp(sn.x), mufu_rcp(sn.y));
+    const float2 rs = add2(mn, y2);
+    const float2 wn = fma2(mn, mn, mn);
+    const float2 coef = mul2(mul2(rs, wn), inv);
+    gx = fmaf(coef.y, dx.y, fmaf(coef.x, dx.x, gx));
+    gy = fmaf(coef.y, dy.y, fmaf(coef.x, dy.x, gy));
+    gz = fmaf(coef.y, dz.y, fmaf(coef.x, dz.x, gz));
+    fx2 = fma2(coef, dx, fx2), fy2 = fma2(coef, dy, fy2), fz2 = fma2(coef, dz, fz2);
+    if (ENERGY) chi2 = fma2(rs, rs, chi2);
+}
+
+// ---------------------------------------------------------------------------------------------
 // hybrid shape.  Measured on B200 (profiles/microbench/ffma2_operands.cu): FFMA2 with three distinct
 // register operands occupies the FMA pipe 3.04 cycles (register-bank reads), two-operand packed ops
 // 2.04, a scalar FFMA with three distinct registers 1.15.  So two-operand work stays packed (half
