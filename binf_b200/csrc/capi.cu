@@ -556,8 +556,8 @@ int binfb_rng_fill_host(uint64_t seed, uint64_t draw, uint64_t chain_base, int C
 
 int binfb_chromatin_stream_layout(int n_beads, const float *y_pairs, int roles, int smem_bytes,
                                   float *out, long long capacity, long long *n_floats, int *plan6) {
-    if (n_beads < 2 || roles < 0 || roles > 8 || (roles & (roles - 1))) {
-        set_error("chromatin_stream_layout: n_beads >= 2, roles in {0 (auto),1,2,4,8}");
+    if (n_beads < 2 || roles < 0 || roles > 16 || (roles & (roles - 1))) {
+        set_error("chromatin_stream_layout: n_beads >= 2, roles in {0 (auto),1,2,4,8,16}");
         return BINFB_EINVAL;
     }
     const ChromPlan pl = chrom_plan(n_beads, smem_bytes > 0 ? smem_bytes : 232448, roles);

@@ -63,6 +63,7 @@ namespace binfb {
 constexpr float CHROM_SOFT = PAIR_SOFT;
 constexpr int STEP_FLOAT4 = 4 * 32;  // float4 per warp-step (16 contacts per lane)
 constexpr int STEP_BYTES = STEP_FLOAT4 * 16;
+constexpr int CHAIN_SCRATCH_BYTES = 128;  // per chain, in front of its positions: one double per role (<= 16)
 #ifndef BINFB_CHROM_NS
 #define BINFB_CHROM_NS 4
 #endif
@@ -110,7 +111,7 @@ __device__ __forceinline__ void unpack4(const float4 v, float (&a)[4]) {
 // is bank-conflict free (48 = 3 * 16 with 3 odd: 8 consecutive lanes cover all 8 16-byte bank groups).
 struct ChainSmem {
     float *pos, *frc;  // [Q][3][4]
-    double *red;       // [8] cross-role reduction scratch
+    double *red;       // [16] cross-role reduction scratch (CHAIN_SCRATCH_BYTES)
 };
 __device__ __forceinline__ int qidx(int bead, int comp) { return (bead >> 2) * 12 + comp * 4 + (bead & 3); }
 
@@ -182,9 +183,9 @@ struct Ring {
     int rot;  // the pass starts at stream stage `rot` and wraps around (see chrom_kernel)
 };
 
-template <int STAGE_BYTES>
+template <int STAGE_BYTES, int NS>
 __device__ __forceinline__ void ring_issue(const Ring &ring, uint32_t gi, int s_local) {
-    const uint32_t sl = gi & (CHROM_NS - 1);
+    const uint32_t sl = gi & (NS - 1);
     const uint32_t bar = ring.full + sl * 8u;
     bar_expect_tx(bar, STAGE_BYTES);
     int st = s_local + ring.rot;
@@ -194,16 +195,16 @@ __device__ __forceinline__ void ring_issue(const Ring &ring, uint32_t gi, int s_
 
 // release stage (gi, s_local): called by one elected lane of every consumer warp after the __syncwarp
 // that follows the warp's last read of the slot
-template <int STAGE_BYTES>
+template <int STAGE_BYTES, int NS>
 __device__ __forceinline__ void ring_release(const Ring &ring, uint32_t gi, int s_local) {
-    const uint32_t c = ring.full + CHROM_NS * 8u + (gi & (CHROM_NS - 1)) * 4u;
+    const uint32_t c = ring.full + NS * 8u + (gi & (NS - 1)) * 4u;
     uint32_t old;
     // the slot's loads have returned (their values were consumed before the __syncwarp in front of this
     // call), so a relaxed add is enough to order them before the refill the last arriver issues
     asm volatile("atom.relaxed.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(c) : "memory");
     if (old == (uint32_t)ring.n_warps - 1u) {
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(c), "r"(0u) : "memory");
-        if (s_local + CHROM_NS < ring.n_stage_pass) ring_issue<STAGE_BYTES>(ring, gi + CHROM_NS, s_local + CHROM_NS);
+        if (s_local + NS < ring.n_stage_pass) ring_issue<STAGE_BYTES, NS>(ring, gi + NS, s_local + NS);
     }
 }
 
@@ -332,7 +333,7 @@ __device__ __forceinline__ void step_special(SweepRegs &s, uint32_t frc_off, uin
     if (ENERGY) s.chi2 += (double)chi;
 }
 
-template <bool ENERGY, int R, int SPR, bool LOCKSTEP>
+template <bool ENERGY, int R, int SPR, bool LOCKSTEP, int NS>
 __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSmem &sm, const Ring &ring,
                                               uint32_t &stage_idx_io, bool chain_valid, int lane, int role,
                                               int bar_id, int rb0) {
@@ -387,9 +388,9 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
             constexpr bool GENERIC = decltype(generic_tag)::value;
 #pragma unroll 1
             for (int sg = sg_begin; sg < sg_end; ++sg) {
-                const uint32_t slot = stage_idx & (CHROM_NS - 1);
+                const uint32_t slot = stage_idx & (NS - 1);
                 {  // (probing the barrier one step early does not pay: the result is consumed at once)
-                    const uint32_t fb = ring.full + slot * 8u, fp = (stage_idx / CHROM_NS) & 1u;
+                    const uint32_t fb = ring.full + slot * 8u, fp = (stage_idx / NS) & 1u;
                     while (!bar_try_wait(fb, fp)) {
                     }
                 }
@@ -408,7 +409,7 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
                     if (LOCKSTEP) chain_bar(bar_id, R * 32);
                     else __syncwarp();
                 }
-                if (elect_one()) ring_release<STAGE_BYTES>(ring, stage_idx, (int)(stage_idx - stage_base));
+                if (elect_one()) ring_release<STAGE_BYTES, NS>(ring, stage_idx, (int)(stage_idx - stage_base));
                 ++stage_idx;
             }
             if (!GENERIC) s.k += (sg_end - sg_begin) * SPR;
@@ -473,7 +474,7 @@ struct ChromCall {
     int n_groups, total_items;
 };
 
-template <int R, int SPR, bool LOCKSTEP>
+template <int R, int SPR, bool LOCKSTEP, int NS>
 __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall call) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int STAGE_BYTES = R * SPR * STEP_BYTES;
@@ -486,25 +487,25 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
     // ---- shared memory carve-up: [stages][full barriers, release counters, item][W x chain]
     Ring ring;
     ring.ystage = smem_u32(smem_raw);
-    ring.full = ring.ystage + CHROM_NS * STAGE_BYTES;
+    ring.full = ring.ystage + NS * STAGE_BYTES;
     ring.src = reinterpret_cast<const unsigned char *>(cd.ystream);
     ring.n_stage_pass = cd.S_pad / SPR;
     ring.n_warps = W * R;
-    unsigned char *ctl = smem_raw + (size_t)CHROM_NS * STAGE_BYTES;
+    unsigned char *ctl = smem_raw + (size_t)NS * STAGE_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(ctl);  // full[NS], then the release counters [NS]
-    uint32_t *cnts = reinterpret_cast<uint32_t *>(ctl + CHROM_NS * 8);
-    int *s_item = reinterpret_cast<int *>(ctl + CHROM_NS * 12);
+    uint32_t *cnts = reinterpret_cast<uint32_t *>(ctl + NS * 8);
+    int *s_item = reinterpret_cast<int *>(ctl + NS * 12);
     unsigned char *chains = ctl + 128;
-    const size_t per_chain = (size_t)6 * cd.n_pad * sizeof(float) + 64;
+    const size_t per_chain = (size_t)6 * cd.n_pad * sizeof(float) + CHAIN_SCRATCH_BYTES;
     ChainSmem sm;
     {
         unsigned char *b0 = chains + per_chain * chain_local;
         sm.red = reinterpret_cast<double *>(b0);
-        sm.pos = reinterpret_cast<float *>(b0 + 64);
+        sm.pos = reinterpret_cast<float *>(b0 + CHAIN_SCRATCH_BYTES);
         sm.frc = sm.pos + 3 * cd.n_pad;
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < CHROM_NS; ++i) mbar_init(&bars[i], 1), cnts[i] = 0u;
+        for (int i = 0; i < NS; ++i) mbar_init(&bars[i], 1), cnts[i] = 0u;
         mbar_fence_init();
     }
     __syncthreads();
@@ -525,8 +526,8 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                 // parts of the contact stream instead of hammering the same L2 lines in lockstep (the
                 // order is a function of the group, so results do not depend on the CTA schedule).
                 ring.rot = BINFB_ROTATE ? ((it % call.n_groups) % cd.NRB) * (cd.Lr / SPR) : 0;
-                for (int i = 0; i < CHROM_NS && i < ring.n_stage_pass; ++i)
-                    ring_issue<STAGE_BYTES>(ring, stage_idx + (uint32_t)i, i);
+                for (int i = 0; i < NS && i < ring.n_stage_pass; ++i)
+                    ring_issue<STAGE_BYTES, NS>(ring, stage_idx + (uint32_t)i, i);
                 const int o = it % call.n_groups;
                 const int need = it / call.n_groups;  // passes of this group that must be done
                 if (need > 0)
@@ -606,8 +607,8 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
             else __syncwarp();
             // ---- phase B: pair sweep -----------------------------------------------------
             const int rb0 = BINFB_ROTATE ? o % cd.NRB : 0;
-            double chi2 = energy ? chrom_sweep<true, R, SPR, LOCKSTEP>(cd, sm, ring, stage_idx, valid, lane, role, bar_id, rb0)
-                                 : chrom_sweep<false, R, SPR, LOCKSTEP>(cd, sm, ring, stage_idx, valid, lane, role, bar_id, rb0);
+            double chi2 = energy ? chrom_sweep<true, R, SPR, LOCKSTEP, NS>(cd, sm, ring, stage_idx, valid, lane, role, bar_id, rb0)
+                                 : chrom_sweep<false, R, SPR, LOCKSTEP, NS>(cd, sm, ring, stage_idx, valid, lane, role, bar_id, rb0);
             if (R > 1) chain_bar(bar_id, cthreads);
             else __syncwarp();
             if (valid) {
@@ -805,7 +806,8 @@ static inline long long tri_index(long long n, long long i, long long j) {  // i
 // stage size in warp-steps per role count (SPR = SS / R steps per role and stage); the ring has
 // CHROM_NS stages.  Measured on B200 at n = 1000: 4-step stages x 4 slots beat 8 x 2.
 static int chrom_stage_steps(int R) { return R <= BINFB_CHROM_SS ? BINFB_CHROM_SS : R; }
-static int chrom_ring_depth(int) { return CHROM_NS; }
+// 16 roles: 32 KiB stages, two of them (the shared memory left next to a 5000-bead chain)
+static int chrom_ring_depth(int R) { return R >= 16 ? 2 : CHROM_NS; }
 
 // the plan for a fixed role count R; W = 0 if it cannot run.  Two roles of a chain may only touch the
 // same partner quad if their offsets differ by <= 31.  Free-running roles drift by up to NS*spr - 1
@@ -815,7 +817,7 @@ static int chrom_ring_depth(int) { return CHROM_NS; }
 static ChromPlan chrom_plan_for(int n, int smem_optin, int R, bool allow_lockstep) {
     ChromPlan pl;
     pl.n_pad = (n + 3) / 4 * 4, pl.Q = pl.n_pad / 4, pl.KS = pl.Q / 2, pl.NRB = (pl.Q + 31) / 32;
-    const size_t per_chain = (size_t)6 * pl.n_pad * sizeof(float) + 64;
+    const size_t per_chain = (size_t)6 * pl.n_pad * sizeof(float) + CHAIN_SCRATCH_BYTES;
     pl.R = R;
     pl.SS = chrom_stage_steps(R), pl.NS = chrom_ring_depth(R);
     const int spr = pl.SS / R;  // slots per stage and role
@@ -839,7 +841,7 @@ static ChromPlan chrom_plan_for(int n, int smem_optin, int R, bool allow_lockste
 ChromPlan chrom_plan(int n, int smem_optin, int force_roles) {
     if (force_roles > 0) return chrom_plan_for(n, smem_optin, force_roles, true);
     ChromPlan best = chrom_plan_for(n, smem_optin, 1, false);
-    for (int R = 2; R <= 8; R *= 2) {  // 16 roles (32 KiB stages, 2 slots) measured slower at n = 5000
+    for (int R = 2; R <= 16; R *= 2) {
         const ChromPlan pl = chrom_plan_for(n, smem_optin, R, false);
         const size_t per_chain = pl.per_chain_smem;
         if ((size_t)smem_optin < pl.fixed_smem + per_chain) break;
@@ -977,14 +979,16 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
     const int grid = call.n_groups < sm_count ? call.n_groups : sm_count;
     const int threads = W * pl.R * 32;
     const ChromDev dev = chrom_dev(m, pl, ystream);
-#define BINFB_CHROM_LAUNCH_L(RR, SPR, LOCK)                                                                    \
+#define BINFB_CHROM_LAUNCH_N(RR, SPR, LOCK, NSS)                                                               \
     do {                                                                                                       \
-        BINFB_CUDA(cudaFuncSetAttribute(chrom_kernel<RR, SPR, LOCK>,                                           \
+        BINFB_CUDA(cudaFuncSetAttribute(chrom_kernel<RR, SPR, LOCK, NSS>,                                      \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-        chrom_kernel<RR, SPR, LOCK><<<grid, threads, smem, s>>>(dev, call);                                    \
+        chrom_kernel<RR, SPR, LOCK, NSS><<<grid, threads, smem, s>>>(dev, call);                               \
     } while (0)
+#define BINFB_CHROM_LAUNCH_L(RR, SPR, LOCK) BINFB_CHROM_LAUNCH_N(RR, SPR, LOCK, CHROM_NS)
 #define BINFB_CHROM_LAUNCH(RR, SPR) BINFB_CHROM_LAUNCH_L(RR, SPR, false)
-    if (pl.lockstep && pl.R == 2 && pl.SS == 4) BINFB_CHROM_LAUNCH_L(2, 2, true);
+    if (pl.R == 16 && pl.SS == 16 && pl.NS == 2 && !pl.lockstep) BINFB_CHROM_LAUNCH_N(16, 1, false, 2);
+    else if (pl.lockstep && pl.R == 2 && pl.SS == 4) BINFB_CHROM_LAUNCH_L(2, 2, true);
     else if (pl.lockstep && pl.R == 4 && pl.SS == 4) BINFB_CHROM_LAUNCH_L(4, 1, true);
     else if (pl.lockstep && pl.R == 8 && pl.SS == 8) BINFB_CHROM_LAUNCH_L(8, 1, true);
     else if (pl.lockstep) {
@@ -1005,6 +1009,7 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
     }
 #undef BINFB_CHROM_LAUNCH
 #undef BINFB_CHROM_LAUNCH_L
+#undef BINFB_CHROM_LAUNCH_N
     BINFB_CUDA(cudaGetLastError());
     return BINFB_OK;
 }

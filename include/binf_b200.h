@@ -241,7 +241,7 @@ int binfb_rng_fill_host(uint64_t seed, uint64_t draw, uint64_t chain_base, int n
                         double gamma_shape, float *normals, float *uniforms, double *gammas,
                         int device);
 /* host-side layout pass of the chromatin contact stream (no GPU needed).  roles = warps per
- * chain (0 = the heuristic for smem_bytes of opt-in shared memory, 0 = 227 KiB).  Writes the number
+ * chain (0 = the heuristic for smem_bytes of opt-in shared memory, 0 = 227 KiB; else 1..16, a power of 2).  Writes the number
  * of float32 the kernel streams per force evaluation and plan6[8] = {quads, partner steps, row
  * blocks, roles, slots per row block, chains per CTA, warp-steps per ring stage, ring depth}; if
  * out != NULL (capacity floats) fills it. */

@@ -56,7 +56,7 @@ def test_argument_validation_needs_no_gpu():
 
 def test_launch_plan_heuristic():
     y = np.zeros(1, dtype=np.float32)
-    for n, roles, chains in [(64, 1, 16), (500, 1, 16), (1000, 2, 8), (2000, 4, 4), (5000, 8, 1)]:
+    for n, roles, chains in [(64, 1, 16), (500, 1, 16), (1000, 2, 8), (2000, 4, 4), (5000, 16, 1)]:
         h = _cabi.lib()
         import ctypes as C
         plan = (C.c_int * 8)()
@@ -193,7 +193,7 @@ def test_lockstep_plans_are_reported_and_unsafe_role_counts_refused():
     assert list(plan)[5] == 0
 
 
-@pytest.mark.parametrize("n,roles", [(1000, 2), (1000, 4), (500, 2), (700, 2), (2000, 4), (5000, 8), (1400, 4)])
+@pytest.mark.parametrize("n,roles", [(1000, 2), (1000, 4), (500, 2), (700, 2), (2000, 4), (5000, 8), (5000, 16), (1400, 4)])
 def test_roles_never_touch_the_same_partner_quad(n, roles):
     """Host replay of the race-freedom argument of the pair sweep (compute-sanitizer's racecheck is not
     available on the GPU pool).  Within a row block, role r at slot s read-modify-writes the partner
