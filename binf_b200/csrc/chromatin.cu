@@ -56,6 +56,9 @@ namespace binfb {
 #ifndef BINFB_PEEL
 #define BINFB_PEEL 0
 #endif
+#ifndef BINFB_PREFETCH
+#define BINFB_PREFETCH 0  // load the next step's partner positions one step ahead
+#endif
 #ifndef BINFB_ROTATE
 #define BINFB_ROTATE 1  // start each chain group at a different row block
 #endif
@@ -242,7 +245,12 @@ struct SweepRegs {
 #endif
     int k;                          // partner offset of the next step
     uint32_t paddr;                 // shared address of the partner quad's positions (48 bytes per quad)
+    uint32_t pwrap;                 // shared address of quad 0's positions
     int wrap;                       // steps until the partner index wraps from Q - 1 to 0
+#if BINFB_PREFETCH
+    float4 nxt[3];                  // positions of the NEXT step's partner quad (read-only data: safe to
+                                    // load across the __syncwarp that orders the force updates)
+#endif
     double chi2;
 };
 
@@ -252,7 +260,15 @@ template <bool ENERGY>
 __device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32_t yaddr, float2 A2, float2 B2,
                                           bool active) {
     const uint32_t pa = s.paddr, fa = s.paddr + frc_off;
+#if BINFB_PREFETCH
+    const float4 xj = s.nxt[0], yj = s.nxt[1], zj = s.nxt[2];
+    {
+        const uint32_t pn = s.wrap == 1 ? s.pwrap : pa + 48u;
+        s.nxt[0] = lds4<0>(pn), s.nxt[1] = lds4<16>(pn), s.nxt[2] = lds4<32>(pn);
+    }
+#else
     const float4 xj = lds4<0>(pa), yj = lds4<16>(pa), zj = lds4<32>(pa);
+#endif
     const float4 fx = lds4<0>(fa), fy = lds4<16>(fa), fz = lds4<32>(fa);
     const float2 xj2[2] = {mk2(xj.x, xj.y), mk2(xj.z, xj.w)}, yj2[2] = {mk2(yj.x, yj.y), mk2(yj.z, yj.w)},
                  zj2[2] = {mk2(zj.x, zj.y), mk2(zj.z, zj.w)};
@@ -381,7 +397,11 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
             int b = aa + k0;
             if (b >= Q) b -= Q;
             s.paddr = pos_base + (uint32_t)b * 48u;
+            s.pwrap = pos_base;
             s.wrap = Q - b;
+#if BINFB_PREFETCH
+            s.nxt[0] = lds4<0>(s.paddr), s.nxt[1] = lds4<16>(s.paddr), s.nxt[2] = lds4<32>(s.paddr);
+#endif
         }
         // stages [sg_begin, sg_end) of this row block; GENERIC: a step may be one of the special ones
         auto run_stages = [&](auto generic_tag, int sg_begin, int sg_end) {
@@ -399,8 +419,13 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
                 for (int u = 0; u < SPR; ++u) {
                     if (!GENERIC || (unsigned)(s.k - 1) < (unsigned)k_fast)
                         step_fast<ENERGY>(s, frc_off, ybase + u * R * STEP_BYTES, A2, B2, active);
-                    else if (active)
-                        step_special<ENERGY>(s, frc_off, ybase + u * R * STEP_BYTES, A, B, KS, upper_half);
+                    else {
+                        if (active) step_special<ENERGY>(s, frc_off, ybase + u * R * STEP_BYTES, A, B, KS, upper_half);
+#if BINFB_PREFETCH
+                        const uint32_t pn = s.wrap == 1 ? s.pwrap : s.paddr + 48u;
+                        s.nxt[0] = lds4<0>(pn), s.nxt[1] = lds4<16>(pn), s.nxt[2] = lds4<32>(pn);
+#endif
+                    }
                     if (GENERIC) ++s.k;
                     s.paddr += 48u;
                     if (--s.wrap == 0) s.paddr -= (uint32_t)Q * 48u, s.wrap = Q;
