@@ -1,5 +1,6 @@
 import sys, json, subprocess
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from binf_b200 import _cabi
 xs = np.linspace(-2, 2, 1000); rng = np.random.RandomState(0)
@@ -7,7 +8,7 @@ ys = rng.normal(np.polynomial.polynomial.polyval(xs, [2., -4., 1., 1.5]), 1/np.s
 C = 65536
 q0 = (np.ones((C, 4)) + 0.1*np.random.RandomState(1).normal(size=(C, 4))).astype(np.float32)
 dev = torch.device('cuda')
-for (J, G, blk) in [(2, 4, -1), (4, 4, -1), (4, 8, -1), (4, 4, 448), (2, 8, -1), (4, 8, 768)]:
+for (J, G, blk) in [(2, 4, -1), (1, 2, -1), (4, 4, -1), (4, 8, -1), (2, 8, -1)]:
     m = _cabi.Model.polynomial(xs, ys, 4, np.zeros(4), 5*np.ones(4), 1.0, 1.0)
     m.set_option('poly.chains_per_thread', J); m.set_option('poly.group', G); m.set_option('poly.block', blk)
     q = torch.from_numpy(q0).to(dev); tau = torch.full((C,), 2.5, device=dev); eps = torch.full((C,), 0.009, device=dev)
