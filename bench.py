@@ -300,7 +300,7 @@ def run_ours(args):
     if args.workload in ("chromatin", "rex", "chromatin5k"):
         y, q_host = chromatin_inputs(w, C, rank)
         model = _cabi.Model.chromatin(w["n_beads"], y, w["alpha"], w["d_c"], w["k_bb"], w["l0"], 0.0,
-                                      1.0, 1.0, device=local, roles=args.roles)
+                                      1.0, 1.0, device=local, roles=args.roles, ev_k=args.ev_k, ev_d=1.5)
         tau0, gibbs = 100.0, _cabi.GIBBS_TAU_FIRST
         units = float(model.n_data)            # pairs per force evaluation
         flop_per_launch = FLOP_PER_PAIR * units * (L + 1) * C
@@ -494,6 +494,7 @@ def main():
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--roles", type=int, default=0, help="chromatin: force the warps per chain (experiments)")
+    ap.add_argument("--ev-k", type=float, default=0.0, help="chromatin: excluded-volume strength (0 = off)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

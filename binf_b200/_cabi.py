@@ -186,8 +186,9 @@ class Model(object):
 
     @classmethod
     def chromatin(cls, n_beads, y_pairs, alpha, d_c, k_bb, l0, conf_s=0.0, gamma_shape=1.0,
-                  gamma_rate=1.0, flags=0, device=0, roles=0):
-        """roles: warps per chain (0 = heuristic; forcing it is a test hook, flags bits 8..11)."""
+                  gamma_rate=1.0, flags=0, device=0, roles=0, ev_k=0.0, ev_d=0.0):
+        """roles: warps per chain (0 = heuristic; forcing it is a test hook, flags bits 8..12);
+        ev_k, ev_d: excluded-volume prior -ev_k sum max(0, ev_d - d_ij)^4 (0 = off)."""
         flags |= (roles & 0x1f) << 8
         y = f32(y_pairs)
         assert y.shape == (n_beads * (n_beads - 1) // 2,)
@@ -195,7 +196,11 @@ class Model(object):
         check(lib().binfb_model_create_chromatin(n_beads, ptr(y), alpha, d_c, k_bb, l0, conf_s,
                                                  gamma_shape, gamma_rate, flags, device,
                                                  C.byref(h)))
-        return cls(h)
+        model = cls(h)
+        if ev_k > 0.0:
+            model.set_option("chrom.ev_k", ev_k)
+            model.set_option("chrom.ev_d", ev_d)
+        return model
 
     @classmethod
     def generic(cls, device_code, n_params, xs, ys, prior_mean=None, prior_var=None, gamma_shape=1.0,

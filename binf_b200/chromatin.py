@@ -65,10 +65,32 @@ class BackbonePrior(AbstractPrior):
         return copy
 
 
+class ExcludedVolumePrior(AbstractPrior):
+    """-k_ev sum_{i<j} max(0, d_ev - |x_i - x_j|)^4: a quartic repulsion between beads closer than d_ev
+    (SURVEY.md 8f rank 2).  Its force is fused into the pair loop of the chromatin kernel."""
+
+    def __init__(self, n_beads, k_ev, d_ev):
+        super(ExcludedVolumePrior, self).__init__("excluded_volume")
+        self.n_beads, self.k_ev, self.d_ev = int(n_beads), float(k_ev), float(d_ev)
+        self._register_variable("structure", differentiable=True)
+        self.update_var_param_types(structure=ArrayParameter)
+        self._set_original_variables()
+
+    def _evaluate_log_prob(self, structure):
+        raise NotImplementedError("ExcludedVolumePrior is evaluated inside the fused chromatin kernel")
+
+    _evaluate_gradient = _evaluate_log_prob
+
+    def clone(self):
+        copy = self.__class__(self.n_beads, self.k_ev, self.d_ev)
+        copy.set_fixed_variables_from_pdf(self)
+        return copy
+
+
 def make_chromatin_posterior(n_beads, y_pairs, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, conf_s=0.0,
-                             gamma_shape=1.0, gamma_rate=1.0):
-    """Posterior({contacts likelihood}, {backbone prior, Gamma precision prior}) over the
-    variables `structure` and `precision`."""
+                             gamma_shape=1.0, gamma_rate=1.0, ev_k=0.0, ev_d=0.0):
+    """Posterior({contacts likelihood}, {backbone prior, Gamma precision prior[, excluded volume]}) over
+    the variables `structure` and `precision`."""
     from binf_b200.pdf.likelihoods import Likelihood
     from binf_b200.pdf.posteriors import Posterior
     from binf_b200.example.likelihood import GaussianErrorModel
@@ -77,4 +99,6 @@ def make_chromatin_posterior(n_beads, y_pairs, alpha=2.0, d_c=2.5, k_bb=4.0, l0=
     lik = Likelihood("points", ContactForwardModel(n_beads, alpha, d_c), GaussianErrorModel(y))
     priors = {"structure_prior": BackbonePrior(n_beads, k_bb, l0, conf_s),
               "precision_prior": GammaPrior(gamma_shape, gamma_rate)}
+    if ev_k > 0.0:
+        priors["excluded_volume"] = ExcludedVolumePrior(n_beads, ev_k, ev_d)
     return Posterior({lik.name: lik}, priors)

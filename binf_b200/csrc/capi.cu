@@ -321,7 +321,14 @@ int binfb_model_set_option(binfb_model *m, const char *key, double value) {
     else if (!strcmp(key, "poly.chains_per_thread")) m->poly.opt_jchains = v;
     else if (!strcmp(key, "poly.block")) m->poly.opt_block = v;
     else if (!strcmp(key, "chrom.warps")) m->chrom.opt_warps = v;
-    else {
+    else if (!strcmp(key, "chrom.ev_k") || !strcmp(key, "chrom.ev_d")) {
+        // excluded-volume prior k_ev sum_{i<j} max(0, d_ev - d_ij)^4 of the chromatin model (0 = off)
+        if (m->kind != BINFB_MODEL_CHROMATIN || value < 0) {
+            set_error("chrom.ev_k / chrom.ev_d: chromatin models only, value >= 0");
+            return BINFB_EINVAL;
+        }
+        (key[9] == 'k' ? m->chrom.ev_k : m->chrom.ev_d) = (float)value;
+    } else {
         set_error(std::string("unknown option: ") + key);
         return BINFB_EINVAL;
     }

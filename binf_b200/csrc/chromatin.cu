@@ -81,6 +81,7 @@ struct ChromDev {
     const float4 *ystream;
     float A, B;  // exp(alpha (d - d_c)) = 2^(A d + B)
     float alpha, k_bb, l0, inv_s2;
+    float ev_k, ev_d;  // excluded volume: k_ev (0 = off) and d_ev
     double M;
     // workspace
     float *qw, *pw;
@@ -252,11 +253,13 @@ struct SweepRegs {
                                     // load across the __syncwarp that orders the force updates)
 #endif
     double chi2;
+    double ev;                      // sum of max(0, d_ev - d)^4 over this lane's pairs (EV energy passes)
+    float dev, cev;                 // excluded volume: d_ev and 4 k_ev / (alpha beta tau)
 };
 
 // one regular step: the 16 pairs (own quad) x (partner quad), every lane (inactive lanes compute on
 // quad 0 and never store).  frc_off = byte distance from a quad's positions to its force sums.
-template <bool ENERGY>
+template <bool ENERGY, bool EV>
 __device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32_t yaddr, float2 A2, float2 B2,
                                           bool active) {
     const uint32_t pa = s.paddr, fa = s.paddr + frc_off;
@@ -274,7 +277,8 @@ __device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32
                  zj2[2] = {mk2(zj.x, zj.y), mk2(zj.z, zj.w)};
     float2 fx2[2] = {mk2(fx.x, fx.y), mk2(fx.z, fx.w)}, fy2[2] = {mk2(fy.x, fy.y), mk2(fy.z, fy.w)},
            fz2[2] = {mk2(fz.x, fz.y), mk2(fz.z, fz.w)};
-    float2 c2 = mk2(0.f, 0.f);
+    float2 c2 = mk2(0.f, 0.f), ev2 = mk2(0.f, 0.f);
+    static_assert(!EV || BINFB_PAIR_SHAPE == 3, "the excluded-volume term is implemented for pair shape 3");
     float4 yv[4];
     yv[0] = lds4<0>(yaddr), yv[1] = lds4<512>(yaddr), yv[2] = lds4<1024>(yaddr), yv[3] = lds4<1536>(yaddr);
 #pragma unroll
@@ -290,10 +294,12 @@ __device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32
         pair_packed_sr<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w), A2,
                                B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2);
 #elif BINFB_PAIR_SHAPE == 3
-        pair_packed_gs<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y), A2,
-                               B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2);
-        pair_packed_gs<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w), A2,
-                               B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2);
+        pair_packed_gs<ENERGY, EV>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y),
+                                   A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2, s.dev,
+                                   s.cev, &ev2);
+        pair_packed_gs<ENERGY, EV>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w),
+                                   A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2, s.dev,
+                                   s.cev, &ev2);
 #else
         pair_packed<ENERGY, false>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y),
                                    A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2);
@@ -306,17 +312,18 @@ __device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32
         sts4<16>(fa, fy2[0].x, fy2[0].y, fy2[1].x, fy2[1].y);
         sts4<32>(fa, fz2[0].x, fz2[0].y, fz2[1].x, fz2[1].y);
         if (ENERGY) s.chi2 += (double)(c2.x + c2.y);
+        if (ENERGY && EV) s.ev += (double)(ev2.x + ev2.y);
     }
 }
 
 // the special steps: k == 0 (the 6 pairs inside the lane's own quad), k == KS with an even quad
 // count (only the lower half of the quads owns the (q, q + Q/2) block), k > KS (padding: nothing)
-template <bool ENERGY>
+template <bool ENERGY, bool EV>
 __device__ __forceinline__ void step_special(SweepRegs &s, uint32_t frc_off, uint32_t yaddr, float A, float B,
                                              int KS, bool upper_half) {
     const int k = s.k;
     if (k > KS) return;
-    float chi = 0.f;
+    float chi = 0.f, evs = 0.f;
     if (k == 0) {
         float yv[4][4];
         unpack4(lds4<0>(yaddr), yv[0]), unpack4(lds4<512>(yaddr), yv[1]), unpack4(lds4<1024>(yaddr), yv[2]);
@@ -325,8 +332,9 @@ __device__ __forceinline__ void step_special(SweepRegs &s, uint32_t frc_off, uin
 #pragma unroll
             for (int c = r + 1; c < 4; ++c) {
                 float tx = 0.f, ty = 0.f, tz = 0.f;
-                pair_scalar<ENERGY>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, -s.nx2[c].x, -s.ny2[c].x, -s.nz2[c].x,
-                                    yv[r][c], A, B, G_LO(s.g[r][0]), G_LO(s.g[r][1]), G_LO(s.g[r][2]), tx, ty, tz, chi);
+                pair_scalar<ENERGY, EV>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, -s.nx2[c].x, -s.ny2[c].x, -s.nz2[c].x,
+                                        yv[r][c], A, B, G_LO(s.g[r][0]), G_LO(s.g[r][1]), G_LO(s.g[r][2]), tx, ty,
+                                        tz, chi, s.dev, s.cev, &evs);
                 G_HI(s.g[c][0]) -= tx, G_HI(s.g[c][1]) -= ty, G_HI(s.g[c][2]) -= tz;
             }
     } else if (!upper_half) {
@@ -340,19 +348,21 @@ __device__ __forceinline__ void step_special(SweepRegs &s, uint32_t frc_off, uin
         for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                pair_scalar<ENERGY>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, xj[c], yj[c], zj[c], yv[r][c], A, B,
-                                    G_LO(s.g[r][0]), G_LO(s.g[r][1]), G_LO(s.g[r][2]), fjx[c], fjy[c], fjz[c], chi);
+                pair_scalar<ENERGY, EV>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, xj[c], yj[c], zj[c], yv[r][c], A, B,
+                                        G_LO(s.g[r][0]), G_LO(s.g[r][1]), G_LO(s.g[r][2]), fjx[c], fjy[c], fjz[c],
+                                        chi, s.dev, s.cev, &evs);
         sts4<0>(fa, fjx[0], fjx[1], fjx[2], fjx[3]);
         sts4<16>(fa, fjy[0], fjy[1], fjy[2], fjy[3]);
         sts4<32>(fa, fjz[0], fjz[1], fjz[2], fjz[3]);
     }
     if (ENERGY) s.chi2 += (double)chi;
+    if (ENERGY && EV) s.ev += (double)evs;
 }
 
-template <bool ENERGY, int R, int SPR, bool LOCKSTEP, int NS>
+template <bool ENERGY, int R, int SPR, bool LOCKSTEP, int NS, bool EV>
 __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSmem &sm, const Ring &ring,
                                               uint32_t &stage_idx_io, bool chain_valid, int lane, int role,
-                                              int bar_id, int rb0) {
+                                              int bar_id, int rb0, float cev, double &ev_out) {
     constexpr int STAGE_BYTES = R * SPR * STEP_BYTES;
     float4 *pos4 = reinterpret_cast<float4 *>(sm.pos), *frc4 = reinterpret_cast<float4 *>(sm.frc);
     const uint32_t pos_base = smem_u32(sm.pos);
@@ -374,7 +384,8 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
     uint32_t stage_idx = stage_base;
     const uint32_t ylane = pin_reg(ring.ystage + (uint32_t)role * STEP_BYTES + (uint32_t)lane * 16u);
     SweepRegs s;
-    s.chi2 = 0.0;
+    s.chi2 = 0.0, s.ev = 0.0;
+    s.dev = cd.ev_d, s.cev = cev;
 
     for (int rbi = 0; rbi < cd.NRB; ++rbi) {
         int rb = rbi + rb0;
@@ -418,9 +429,9 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
 #pragma unroll
                 for (int u = 0; u < SPR; ++u) {
                     if (!GENERIC || (unsigned)(s.k - 1) < (unsigned)k_fast)
-                        step_fast<ENERGY>(s, frc_off, ybase + u * R * STEP_BYTES, A2, B2, active);
+                        step_fast<ENERGY, EV>(s, frc_off, ybase + u * R * STEP_BYTES, A2, B2, active);
                     else {
-                        if (active) step_special<ENERGY>(s, frc_off, ybase + u * R * STEP_BYTES, A, B, KS, upper_half);
+                        if (active) step_special<ENERGY, EV>(s, frc_off, ybase + u * R * STEP_BYTES, A, B, KS, upper_half);
 #if BINFB_PREFETCH
                         const uint32_t pn = s.wrap == 1 ? s.pwrap : s.paddr + 48u;
                         s.nxt[0] = lds4<0>(pn), s.nxt[1] = lds4<16>(pn), s.nxt[2] = lds4<32>(pn);
@@ -473,6 +484,7 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
         else __syncwarp();
     }
     stage_idx_io = stage_idx;
+    ev_out = s.ev;
     return s.chi2;
 }
 
@@ -499,7 +511,7 @@ struct ChromCall {
     int n_groups, total_items;
 };
 
-template <int R, int SPR, bool LOCKSTEP, int NS>
+template <int R, int SPR, bool LOCKSTEP, int NS, bool EV>
 __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall call) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int STAGE_BYTES = R * SPR * STEP_BYTES;
@@ -630,17 +642,47 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
             }
             if (R > 1) chain_bar(bar_id, cthreads);
             else __syncwarp();
+            // ---- the precision of this pass.  With the excluded-volume term it must be known BEFORE the
+            //      sweep (the EV force is folded into the pair coefficients relative to alpha beta tau),
+            //      so a fused precision-first Gibbs update draws tau here from chi^2 of the current state,
+            //      which the host launcher (first trajectory) or the previous trajectory left in
+            //      chi2_state; without EV it is drawn after pass 0 from the chi^2 that pass computes.
+            float tau_pre = 1.f, cev = 0.f;
+            if (EV && valid) {
+                if (!hmc) tau_pre = call.g.tau[c];
+                else if (k > 0) tau_pre = __ldcg(cd.tau_w + c);
+                else {
+                    tau_pre = __ldcg(h.tau + c);
+                    if (h.gibbs_mode == BINFB_GIBBS_TAU_FIRST) {
+                        const double shape = 0.5 * (double)beta_c * cd.M + h.gamma_shape - 1.0;
+                        const double rate = 0.5 * (double)beta_c * __ldcg(cd.chi2_state + c) + h.gamma_rate;
+                        const double gd = h.gamma_draws ? h.gamma_draws[c]
+                                                        : rng_gamma(h.seed, h.chain_base + c, h.draw + (uint64_t)tr, shape);
+                        tau_pre = (float)(gd / rate);
+                    }
+                }
+                cev = 4.0f * cd.ev_k / (cd.alpha * beta_c * tau_pre);
+            }
             // ---- phase B: pair sweep -----------------------------------------------------
             const int rb0 = BINFB_ROTATE ? o % cd.NRB : 0;
-            double chi2 = energy ? chrom_sweep<true, R, SPR, LOCKSTEP, NS>(cd, sm, ring, stage_idx, valid, lane, role, bar_id, rb0)
-                                 : chrom_sweep<false, R, SPR, LOCKSTEP, NS>(cd, sm, ring, stage_idx, valid, lane, role, bar_id, rb0);
+            double ev_sum = 0.0;
+            double chi2 = energy ? chrom_sweep<true, R, SPR, LOCKSTEP, NS, EV>(cd, sm, ring, stage_idx, valid, lane, role,
+                                                                              bar_id, rb0, cev, ev_sum)
+                                 : chrom_sweep<false, R, SPR, LOCKSTEP, NS, EV>(cd, sm, ring, stage_idx, valid, lane, role,
+                                                                               bar_id, rb0, cev, ev_sum);
             if (R > 1) chain_bar(bar_id, cthreads);
             else __syncwarp();
             if (valid) {
                 // ---- phase C: forces, kick, energies ----------------------------------------
                 if (energy) chi2 = chain_sum(chi2, sm, lane, role, R, bar_id);
                 float tau_c;
-                if (hmc) {
+                if (EV) {
+                    tau_c = tau_pre;
+                    if (hmc && k == 0 && ctid == 0) {
+                        __stcg(cd.tau_w + c, tau_c);
+                        if (h.gibbs_mode == BINFB_GIBBS_TAU_FIRST) __stcg(h.tau + c, tau_c);
+                    }
+                } else if (hmc) {
                     if (k == 0) {
                         tau_c = __ldcg(h.tau + c);
                         if (h.gibbs_mode == BINFB_GIBBS_TAU_FIRST) {
@@ -720,7 +762,8 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                     }
                 }
                 if (energy) {
-                    const double ep = chain_sum((double)e_prior, sm, lane, role, R, bar_id);
+                    double ep = chain_sum((double)e_prior, sm, lane, role, R, bar_id);
+                    if (EV) ep += (double)cd.ev_k * chain_sum(ev_sum, sm, lane, role, R, bar_id);
                     const double t = (double)tau_c, lt = log(t);
                     const double ga = hmc ? h.gamma_shape : call.g.gamma_shape;
                     const double gb = hmc ? h.gamma_rate : call.g.gamma_rate;
@@ -955,6 +998,7 @@ static ChromDev chrom_dev(const ChromModel &m, const ChromPlan &pl, const float 
     d.A = (float)((double)m.alpha * log2e);
     d.B = (float)(-(double)m.alpha * (double)m.d_c * log2e);
     d.alpha = m.alpha, d.k_bb = m.k_bb, d.l0 = m.l0, d.inv_s2 = m.inv_s2;
+    d.ev_k = m.ev_k, d.ev_d = m.ev_d;
     d.M = (double)m.M;
     d.qw = m.qw, d.pw = m.pw, d.h0 = m.h0, d.chi2_0 = m.chi2_0, d.chi2_state = m.chi2_state;
     d.tau_w = m.tau_w;
@@ -1004,11 +1048,16 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
     const int grid = call.n_groups < sm_count ? call.n_groups : sm_count;
     const int threads = W * pl.R * 32;
     const ChromDev dev = chrom_dev(m, pl, ystream);
+#define BINFB_CHROM_LAUNCH_E(RR, SPR, LOCK, NSS, EVV)                                                          \
+    do {                                                                                                       \
+        BINFB_CUDA(cudaFuncSetAttribute(chrom_kernel<RR, SPR, LOCK, NSS, EVV>,                                 \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        chrom_kernel<RR, SPR, LOCK, NSS, EVV><<<grid, threads, smem, s>>>(dev, call);                          \
+    } while (0)
 #define BINFB_CHROM_LAUNCH_N(RR, SPR, LOCK, NSS)                                                               \
     do {                                                                                                       \
-        BINFB_CUDA(cudaFuncSetAttribute(chrom_kernel<RR, SPR, LOCK, NSS>,                                      \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-        chrom_kernel<RR, SPR, LOCK, NSS><<<grid, threads, smem, s>>>(dev, call);                               \
+        if (m.ev_k > 0.f) BINFB_CHROM_LAUNCH_E(RR, SPR, LOCK, NSS, true);                                      \
+        else BINFB_CHROM_LAUNCH_E(RR, SPR, LOCK, NSS, false);                                                  \
     } while (0)
 #define BINFB_CHROM_LAUNCH_L(RR, SPR, LOCK) BINFB_CHROM_LAUNCH_N(RR, SPR, LOCK, CHROM_NS)
 #define BINFB_CHROM_LAUNCH(RR, SPR) BINFB_CHROM_LAUNCH_L(RR, SPR, false)
@@ -1035,6 +1084,7 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
 #undef BINFB_CHROM_LAUNCH
 #undef BINFB_CHROM_LAUNCH_L
 #undef BINFB_CHROM_LAUNCH_N
+#undef BINFB_CHROM_LAUNCH_E
     BINFB_CUDA(cudaGetLastError());
     return BINFB_OK;
 }
@@ -1045,6 +1095,17 @@ int chrom_hmc_launch(ChromModel &m, const HmcArgs &a, int sm_count, int smem_opt
     call.h = a;
     call.g = GradArgs();
     if (a.n_accepted) BINFB_CUDA(cudaMemsetAsync(a.n_accepted, 0, (size_t)a.C * sizeof(int32_t), s));
+    if (m.ev_k > 0.f && a.gibbs_mode == BINFB_GIBBS_TAU_FIRST) {
+        // excluded volume + precision-first Gibbs: tau must be drawn before the first sweep, from
+        // chi^2 of the incoming state (see chrom_kernel): one energy-only pass fills chi2_state
+        int rc = chrom_reserve(m, a.C);
+        if (rc) return rc;
+        GradArgs g = GradArgs();
+        g.q = a.q, g.tau = a.tau, g.beta = a.beta, g.C = a.C, g.logp = nullptr, g.grad = nullptr;
+        g.chi2 = m.chi2_state, g.gamma_shape = a.gamma_shape, g.gamma_rate = a.gamma_rate;
+        rc = chrom_grad_launch(m, g, sm_count, smem_optin, s);
+        if (rc) return rc;
+    }
     return chrom_launch(m, call, a.C, sm_count, smem_optin, s);
 }
 

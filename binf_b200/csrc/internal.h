@@ -95,6 +95,7 @@ struct ChromModel {
     float *ystream_alt = nullptr;
     float *ypairs = nullptr;       // device [M] (triu order; forward/mock kernel only)
     float alpha = 0, d_c = 0, k_bb = 0, l0 = 0, inv_s2 = 0;
+    float ev_k = 0, ev_d = 0;      // excluded-volume prior k_ev sum max(0, d_ev - d_ij)^4 (0 = off)
     unsigned flags = 0;
     int opt_warps = -1;
     // per-launch workspace (grown on demand)

@@ -63,11 +63,15 @@ __device__ __forceinline__ float2 poly_ex2_2(float2 t) {
 // ---------------------------------------------------------------------------------------------
 // scalar reference shape (one pair at a time; the compiler interleaves)
 // ---------------------------------------------------------------------------------------------
-template <bool ENERGY>
+// Excluded-volume prior (EV): E_ev = k_ev sum_{i<j} max(0, d_ev - d_ij)^4 (a quartic repulsion between
+// beads closer than d_ev).  Its force -4 k_ev s^3 (x_i - x_j)/d has the same geometry as the
+// likelihood force, so it rides on the same accumulators: coef += cev * s^3 / d with
+// cev = 4 k_ev / (alpha beta tau) cancelling the factor -alpha beta tau the caller applies to the sums.
+template <bool ENERGY, bool EV = false>
 __device__ __forceinline__ void pair_scalar(float nxi, float nyi, float nzi, float xj, float yj,
                                             float zj, float y, float A, float B, float &gx,
                                             float &gy, float &gz, float &fx, float &fy, float &fz,
-                                            float &chi) {
+                                            float &chi, float dev = 0.f, float cev = 0.f, float *ev = nullptr) {
     const float dx = xj + nxi, dy = yj + nyi, dz = zj + nzi;
     const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, PAIR_SOFT)));
     const float inv = mufu_rsqrt(r2);
@@ -76,7 +80,12 @@ __device__ __forceinline__ void pair_scalar(float nxi, float nyi, float nzi, flo
     const float mn = mufu_rcp(fmaf(e, -1.0f, -1.0f));  // -m
     const float rs = mn + y;                            // -(m - y)
     const float wn = fmaf(mn, mn, mn);                  // -(m - m^2)
-    const float coef = rs * wn * inv;
+    float coef = rs * wn * inv;
+    if (EV) {
+        const float s = fmaxf(dev - d, 0.f), s2 = s * s;
+        coef = fmaf(s2 * s * cev, inv, coef);
+        if (ENERGY) *ev = fmaf(s2, s2, *ev);
+    }
     gx = fmaf(coef, dx, gx), gy = fmaf(coef, dy, gy), gz = fmaf(coef, dz, gz);
     fx = fmaf(coef, dx, fx), fy = fmaf(coef, dy, fy), fz = fmaf(coef, dz, fz);
     if (ENERGY) chi = fmaf(rs, rs, chi);
@@ -116,10 +125,11 @@ __device__ __forceinline__ void pair_packed(float2 nx2, float2 ny2, float2 nz2, 
 // component (1.15 cycles each), which also halves the registers the row accumulators occupy
 // (12 instead of 24 per lane).
 // ---------------------------------------------------------------------------------------------
-template <bool ENERGY>
+template <bool ENERGY, bool EV = false>
 __device__ __forceinline__ void pair_packed_gs(float2 nx2, float2 ny2, float2 nz2, float2 xj2, float2 yj2,
                                                float2 zj2, float2 y2, float2 A2, float2 B2, float &gx, float &gy,
-                                               float &gz, float2 &fx2, float2 &fy2, float2 &fz2, float2 &chi2) {
+                                               float &gz, float2 &fx2, float2 &fy2, float2 &fz2, float2 &chi2,
+                                               float dev = 0.f, float cev = 0.f, float2 *ev2 = nullptr) {
     const float2 dx = add2(xj2, nx2), dy = add2(yj2, ny2), dz = add2(zj2, nz2);
     const float2 r2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, mk2(PAIR_SOFT, PAIR_SOFT))));
     const float2 inv = mk2(mufu_rsqrt(r2.x), mufu_rsqrt(r2.y));
@@ -130,7 +140,14 @@ __device__ __forceinline__ void pair_packed_gs(float2 nx2, float2 ny2, float2 nz
     const float2 mn = mk2(mufu_rcp(sn.x), mufu_rcp(sn.y));
     const float2 rs = add2(mn, y2);
     const float2 wn = fma2(mn, mn, mn);
-    const float2 coef = mul2(mul2(rs, wn), inv);
+    float2 coef = mul2(mul2(rs, wn), inv);
+    if (EV) {
+        float2 s = fma2(d, mk2(-1.f, -1.f), mk2(dev, dev));   // d_ev - d
+        s = mk2(fmaxf(s.x, 0.f), fmaxf(s.y, 0.f));
+        const float2 s2 = mul2(s, s);
+        coef = fma2(mul2(mul2(s2, s), mk2(cev, cev)), inv, coef);
+        if (ENERGY) *ev2 = fma2(s2, s2, *ev2);
+    }
     gx = fmaf(coef.y, dx.y, fmaf(coef.x, dx.x, gx));
     gy = fmaf(coef.y, dy.y, fmaf(coef.x, dy.x, gy));
     gz = fmaf(coef.y, dz.y, fmaf(coef.x, dz.x, gz));

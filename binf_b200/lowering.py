@@ -115,7 +115,7 @@ def lower(pdf, n_coeff=None):
     from binf_b200.pdf.posteriors import Posterior
     from binf_b200.example.likelihood import ForwardModel as PolyForward, GaussianErrorModel
     from binf_b200.example.priors import GammaPrior, GaussianPrior
-    from binf_b200.chromatin import ContactForwardModel, BackbonePrior
+    from binf_b200.chromatin import ContactForwardModel, BackbonePrior, ExcludedVolumePrior
     from binf_b200.model.forwardmodels import DeviceForwardModel
 
     if isinstance(pdf, Posterior):
@@ -135,6 +135,7 @@ def lower(pdf, n_coeff=None):
     gamma_prior = None
     gauss_prior = None
     backbone = None
+    exvol = None
     for pr in priors:
         if type(pr) is GammaPrior:
             gamma_prior = pr
@@ -142,6 +143,8 @@ def lower(pdf, n_coeff=None):
             gauss_prior = pr
         elif type(pr) is BackbonePrior:
             backbone = pr
+        elif type(pr) is ExcludedVolumePrior:
+            exvol = pr
         else:
             return None
 
@@ -155,6 +158,8 @@ def lower(pdf, n_coeff=None):
         return getattr(pdf, "beta", None)
 
     dev = get_device()
+    if exvol is not None and type(fwm) is not ContactForwardModel:
+        return None
     if type(fwm) is PolyForward:
         if backbone is not None:
             return None
@@ -200,8 +205,9 @@ def lower(pdf, n_coeff=None):
         if gauss_prior is not None:
             return None
         k_bb, l0, conf = (backbone.k_bb, backbone.l0, backbone.conf_s) if backbone is not None else (0.0, 1.0, 0.0)
-        key = ("chrom", id(em.ys), fwm.n_beads, fwm.alpha, fwm.d_c, k_bb, l0, conf, dev)
+        ev_k, ev_d = (exvol.k_ev, exvol.d_ev) if exvol is not None else (0.0, 0.0)
+        key = ("chrom", id(em.ys), fwm.n_beads, fwm.alpha, fwm.d_c, k_bb, l0, conf, ev_k, ev_d, dev)
         model = _cached_model(key, (em.ys,), lambda: _cabi.Model.chromatin(
-            fwm.n_beads, em.ys, fwm.alpha, fwm.d_c, k_bb, l0, conf, *gamma(), device=dev))
+            fwm.n_beads, em.ys, fwm.alpha, fwm.d_c, k_bb, l0, conf, *gamma(), device=dev, ev_k=ev_k, ev_d=ev_d))
         return Lowered(model, "structure", precision, beta, likelihood_only, gamma)
     return None

@@ -112,8 +112,10 @@ int binfb_model_destroy(binfb_model *m);
 int binfb_model_info(const binfb_model *m, int *kind, int *dim, long long *n_data, int *device);
 /* update the Gamma prior on the precision (it enters log_prob and the Gibbs update only) */
 int binfb_model_set_gamma_prior(binfb_model *m, double shape, double rate);
-/* tuning knobs ("poly.group", "poly.chains_per_thread", "poly.block", "chrom.warps", ...);
- * value < 0 restores the heuristic */
+/* tuning knobs ("poly.group", "poly.chains_per_thread", "poly.block", "chrom.warps"; value < 0 restores
+ * the heuristic) and model extras: "chrom.ev_k", "chrom.ev_d" switch on the excluded-volume prior
+ * -k_ev sum_{i<j} max(0, d_ev - d_ij)^4 of the chromatin model, whose force is
+ * fused into the pair loop */
 int binfb_model_set_option(binfb_model *m, const char *key, double value);
 
 /* ---- pdf seam: AbstractBinfPDF.log_prob / gradient ------------------------------------------ */

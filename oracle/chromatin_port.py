@@ -20,6 +20,8 @@ Model (float64 here, float32 on the device):
   error model: the reference's GaussianErrorModel (example/likelihood.py:40-68)
   prior on structure: backbone  -1/2 k_bb sum_i (|x_{i+1}-x_i|_soft - l0)^2
                       optional confinement  -1/2 |X|^2 / s^2   (conf_s = 0 disables)
+                      optional excluded volume  -k_ev sum_{i<j} max(0, d_ev - d_ij)^4  (ev_k = 0 disables;
+                      the quartic repulsion of the ISD chromatin models the README's paper describes)
   tempering: log p_beta = beta * log L + log prior            
 """
 import numpy as np
@@ -29,7 +31,7 @@ SOFT = 1e-12
 
 class ChromatinModel(object):
     def __init__(self, n_beads, y_pairs, alpha, d_c, k_bb, l0, conf_s=0.0,
-                 gamma_shape=1.0, gamma_rate=1.0):
+                 gamma_shape=1.0, gamma_rate=1.0, ev_k=0.0, ev_d=0.0):
         self.n = int(n_beads)
         self.iu = np.triu_indices(self.n, 1)
         self.y = np.asarray(y_pairs, dtype=np.float64)
@@ -37,6 +39,7 @@ class ChromatinModel(object):
         self.alpha, self.d_c = float(alpha), float(d_c)
         self.k_bb, self.l0, self.conf_s = float(k_bb), float(l0), float(conf_s)
         self.gamma_shape, self.gamma_rate = float(gamma_shape), float(gamma_rate)
+        self.ev_k, self.ev_d = float(ev_k), float(ev_d)
         self.Y = np.zeros((self.n, self.n))
         self.Y[self.iu] = self.y
         self.Y += self.Y.T
@@ -103,6 +106,9 @@ class ChromatinModel(object):
         lp = -0.5 * self.k_bb * np.sum((d - self.l0) ** 2)
         if self.conf_s > 0.0:
             lp += -0.5 * np.sum(X * X) / self.conf_s ** 2
+        if self.ev_k > 0.0:
+            dp = np.sqrt(np.sum((X[self.iu[0]] - X[self.iu[1]]) ** 2, axis=-1) + SOFT)
+            lp += -self.ev_k * np.sum(np.maximum(self.ev_d - dp, 0.0) ** 4)
         return lp
 
     def prior_gradient(self, q):
@@ -116,6 +122,11 @@ class ChromatinModel(object):
         g[:-1] -= c
         if self.conf_s > 0.0:
             g += X / self.conf_s ** 2
+        if self.ev_k > 0.0:
+            diff, dd = self._dist_full(X)
+            w = -4.0 * self.ev_k * np.maximum(self.ev_d - dd, 0.0) ** 3 / dd
+            np.fill_diagonal(w, 0.0)
+            g += np.einsum("ij,ija->ia", w, diff)
         return g.reshape(-1)
 
     # ---- posterior over the structure at fixed precision --------------------------

@@ -184,7 +184,7 @@ def polynomial_gibbs_case(binf, name, n_sweeps, seed):
     print(name, "acceptance", np.mean(accs), "tau", taus[-1], "dt", steps[-1])
 
 
-def chromatin_case(binf, name, n_beads, n_chains, nsteps, timestep, seed, tau=50.0):
+def chromatin_case(binf, name, n_beads, n_chains, nsteps, timestep, seed, tau=50.0, ev_k=0.0, ev_d=0.0):
     """The reference's Posterior / Likelihood (dense J.dot(g)) / HMCSampler driving the
     build-defined chromatin model at small n."""
     from binf.samplers.hmc import HMCSampler
@@ -192,7 +192,7 @@ def chromatin_case(binf, name, n_beads, n_chains, nsteps, timestep, seed, tau=50
     alpha, d_c, k_bb, l0 = 2.0, 2.5, 4.0, 1.0
     X, y = chrom.synthetic_chromatin(n_beads, alpha, d_c, l0, 0.05, seed)
     model = chrom.ChromatinModel(n_beads, y, alpha, d_c, k_bb, l0, conf_s=0.0,
-                                 gamma_shape=1.0, gamma_rate=1.0)
+                                 gamma_shape=1.0, gamma_rate=1.0, ev_k=ev_k, ev_d=ev_d)
     post = chrom.reference_posterior(binf, model)
     cond = post.conditional_factory(precision=tau)
     rng = np.random.RandomState(seed + 1)
@@ -214,7 +214,7 @@ def chromatin_case(binf, name, n_beads, n_chains, nsteps, timestep, seed, tau=50
     gp = [p for p in cond.priors.values() if "precision" in p._original_variables][0]
 
     # ---- matrix-free port vs the reference's dense-Jacobian path ----
-    m2 = chrom.ChromatinModel(n_beads, y, alpha, d_c, k_bb, l0, 0.0, gp.shape, gp.rate)
+    m2 = chrom.ChromatinModel(n_beads, y, alpha, d_c, k_bb, l0, 0.0, gp.shape, gp.rate, ev_k, ev_d)
     for c in range(n_chains):
         close(m2.log_prob(q0[c], tau), logp[c]), close(m2.gradient(q0[c], tau), grad[c], 1e-9)
         r = port.hmc_sample(lambda q: m2.log_prob(q, tau), lambda q: m2.gradient(q, tau),
@@ -230,7 +230,7 @@ def chromatin_case(binf, name, n_beads, n_chains, nsteps, timestep, seed, tau=50
         g_fd[k] = -(m2.log_prob(q0[0] + e, tau) - m2.log_prob(q0[0] - e, tau)) / (2 * h)
     close(g_fd, grad[0], 1e-6)
     np.savez(os.path.join(GOLDEN, name + ".npz"), n_beads=n_beads, y=y, alpha=alpha, d_c=d_c,
-             k_bb=k_bb, l0=l0, tau=tau, gamma_shape=gp.shape, gamma_rate=gp.rate,
+             k_bb=k_bb, l0=l0, tau=tau, gamma_shape=gp.shape, gamma_rate=gp.rate, ev_k=ev_k, ev_d=ev_d,
              q0=q0, p0=p0, u=u, nsteps=nsteps, timestep=timestep, log_prob=np.array(logp),
              gradient=np.array(grad), q_end=np.array(qe), p_end=np.array(pe),
              e_before=np.array(eb), e_after=np.array(ea), accepted=np.array(acc),
@@ -379,6 +379,10 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "rwmc":     # only the fixtures added with SURVEY 8f rank 4
         rwmc_predict_case(binf, "poly_rwmc_n20", n_data=20, n_chains=24, n_moves=6, stepsize=0.1, seed=9)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "ev":       # the fixture added with the excluded-volume prior
+        chromatin_case(binf, "chromatin_ev_n28", n_beads=28, n_chains=8, nsteps=6, timestep=0.004, seed=11,
+                       ev_k=5.0, ev_d=1.6)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "user":     # the fixture added with SURVEY 8f rank 2
         user_model_case(binf, "user_decay_n200", n_data=200, n_chains=24, nsteps=10, timestep=0.012, seed=10)
         return
@@ -400,6 +404,8 @@ def main():
                    timestep=0.004, seed=5)
     chromatin_case(binf, "chromatin_n30_big_step", n_beads=30, n_chains=12, nsteps=10,
                    timestep=0.05, seed=8)
+    chromatin_case(binf, "chromatin_ev_n28", n_beads=28, n_chains=8, nsteps=6, timestep=0.004, seed=11,
+                   ev_k=5.0, ev_d=1.6)
     rwmc_predict_case(binf, "poly_rwmc_n20", n_data=20, n_chains=24, n_moves=6, stepsize=0.1, seed=9)
     user_model_case(binf, "user_decay_n200", n_data=200, n_chains=24, nsteps=10, timestep=0.012, seed=10)
 

@@ -9,14 +9,15 @@ import binf_port as port
 import chromatin_port as chrom
 
 pytestmark = pytest.mark.gpu
-CASES = ["chromatin_n24", "chromatin_n37_L20", "chromatin_n30_big_step"]
+CASES = ["chromatin_n24", "chromatin_n37_L20", "chromatin_n30_big_step", "chromatin_ev_n28"]
 
 
 def make_model(g):
     from binf_b200 import _cabi
     return _cabi.Model.chromatin(int(g["n_beads"]), g["y"], float(g["alpha"]), float(g["d_c"]),
                                  float(g["k_bb"]), float(g["l0"]), 0.0, float(g["gamma_shape"]),
-                                 float(g["gamma_rate"]))
+                                 float(g["gamma_rate"]), ev_k=float(g.get("ev_k", 0.0)),
+                                 ev_d=float(g.get("ev_d", 0.0)))
 
 
 def inf_norm(a):
@@ -237,3 +238,66 @@ def test_fused_gibbs_sweeps_and_multi_trajectory(gpu):
     r = m.hmc_run(q0, 100.0, 0.002, 5, n_traj=3, n_adapt=3, seed=6)
     expect = 0.002 * 1.05 ** r["n_accepted"] * 0.95 ** (3 - r["n_accepted"])
     np.testing.assert_allclose(r["eps"], expect, rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,roles,C", [(61, 0, 5), (300, 0, 3), (1000, 0, 3), (1000, 2, 2), (1000, 0, 1300)])
+def test_excluded_volume_prior_vs_oracle(gpu, n, roles, C):
+    """the quartic excluded-volume repulsion fused into the pair loop: log_prob, gradient, a short
+    trajectory, for every kernel shape (1 / 2 / 4 lockstep roles, small-batch and full-batch plans)"""
+    from binf_b200 import _cabi
+    X, y = chrom.synthetic_chromatin(n, seed=n + 1)
+    ev_k, ev_d, tau = 4.0, 1.8, 60.0
+    o = chrom.ChromatinModel(n, y, 2.0, 2.5, 4.0, 1.0, ev_k=ev_k, ev_d=ev_d)
+    plain = chrom.ChromatinModel(n, y, 2.0, 2.5, 4.0, 1.0)
+    m = _cabi.Model.chromatin(n, y, 2.0, 2.5, 4.0, 1.0, roles=roles, ev_k=ev_k, ev_d=ev_d)
+    rng = np.random.RandomState(n)
+    q = (X.reshape(-1)[None] + 0.1 * rng.normal(size=(C, 3 * n))).astype(np.float32).astype(np.float64)
+    beta = np.linspace(1.0, 0.5, C)
+    logp, grad, chi2 = m.logprob_grad(q, tau, beta=beta)
+    for c in sorted({0, C - 1, C // 2}):
+        assert o.prior_log_prob(q[c]) < plain.prior_log_prob(q[c]) - 1.0     # the term is active
+        assert logp[c] == pytest.approx(o.log_prob(q[c], tau, beta[c]), rel=1e-5)
+        ref = o.gradient(q[c], tau, beta[c])
+        assert np.all(np.abs(grad[c] - ref) <= 1e-4 * np.max(np.abs(ref)))
+    p0, u = rng.normal(size=(C, 3 * n)), np.full(C, 0.5)
+    r = m.hmc_run(q, tau, 0.002, 3, beta=beta, p0=p0, u=u, want_end=True)
+    c = C // 2
+    ref = port.hmc_sample(lambda x: o.log_prob(x, tau, beta[c]), lambda x: o.gradient(x, tau, beta[c]), q[c],
+                          0.002, 3, p0[c], 0.5)
+    assert np.max(np.abs(r["q_end"][c] - ref["q_end"])) <= 1e-4 * np.max(np.abs(ref["q_end"]))
+    assert r["e_before"][c] == pytest.approx(ref["e_before"], rel=1e-5)
+    assert (r["e_after"][c] - r["e_before"][c]) == pytest.approx(ref["e_after"] - ref["e_before"], abs=3e-2)
+
+
+def test_excluded_volume_with_fused_gibbs_sweep(gpu):
+    """precision-first fused sweep with the excluded-volume term == precision update, then trajectory
+    (the kernel draws tau before the first sweep from chi^2 of the incoming state)"""
+    from binf_b200 import _cabi
+    n, C = 120, 6
+    X, y = chrom.synthetic_chromatin(n, seed=4)
+    m = _cabi.Model.chromatin(n, y, 2.0, 2.5, 4.0, 1.0, ev_k=3.0, ev_d=1.7)
+    rng = np.random.RandomState(2)
+    q = X.reshape(-1)[None] + 0.1 * rng.normal(size=(C, 3 * n))
+    p0, u, gd = rng.normal(size=q.shape), rng.uniform(size=C), rng.gamma(3000.0, size=C)
+    fused = m.hmc_run(q, 55.0, 0.002, 4, p0=p0, u=u, gamma_draws=gd, gibbs_mode=_cabi.GIBBS_TAU_FIRST, want_end=True)
+    tau1, _ = m.gibbs_precision(q, 55.0, gamma_draws=gd)
+    split = m.hmc_run(q, tau1, 0.002, 4, p0=p0, u=u, want_end=True)
+    np.testing.assert_allclose(fused["tau"], tau1, rtol=1e-6)
+    np.testing.assert_allclose(fused["q_end"], split["q_end"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(fused["e_after"], split["e_after"], rtol=1e-9)
+    # several fused sweeps on Philox streams: tau stays where the data put it, chains keep moving
+    r = m.hmc_run(q, 55.0, 0.002, 4, n_traj=5, gibbs_mode=_cabi.GIBBS_TAU_FIRST, seed=3)
+    assert np.all(r["tau"] > 5.0) and np.all(r["tau"] < 5000.0) and r["n_accepted"].min() >= 3
+
+
+def test_excluded_volume_through_the_python_api(gpu):
+    from binf_b200.chromatin import make_chromatin_posterior
+    n = 48
+    X, y = chrom.synthetic_chromatin(n, seed=9)
+    post = make_chromatin_posterior(n, y, ev_k=2.0, ev_d=1.5)
+    o = chrom.ChromatinModel(n, y, 2.0, 2.5, 4.0, 1.0, ev_k=2.0, ev_d=1.5)
+    q = X.reshape(-1) + 0.05 * np.random.RandomState(1).normal(size=3 * n)
+    cond = post.conditional_factory(precision=40.0)
+    assert cond.log_prob(structure=q) == pytest.approx(o.log_prob(q, 40.0), rel=1e-5)
+    ref = o.gradient(q, 40.0)
+    assert np.max(np.abs(cond.gradient(structure=q) - ref)) <= 1e-4 * np.max(np.abs(ref))

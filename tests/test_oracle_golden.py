@@ -9,7 +9,7 @@ import chromatin_port as chrom
 import ref_import
 
 POLY_CASES = ["poly_n20", "poly_n1000", "poly_n1000_L5", "poly_n1000_mode", "poly_n77_mode"]
-CHROM_CASES = ["chromatin_n24", "chromatin_n37_L20", "chromatin_n30_big_step"]
+CHROM_CASES = ["chromatin_n24", "chromatin_n37_L20", "chromatin_n30_big_step", "chromatin_ev_n28"]
 
 
 def _poly(g):
@@ -78,7 +78,7 @@ def test_chromatin_port_matches_reference_vectors(name):
     g = load_golden(name)
     m = chrom.ChromatinModel(int(g["n_beads"]), g["y"], float(g["alpha"]), float(g["d_c"]),
                              float(g["k_bb"]), float(g["l0"]), 0.0, float(g["gamma_shape"]),
-                             float(g["gamma_rate"]))
+                             float(g["gamma_rate"]), float(g.get("ev_k", 0.0)), float(g.get("ev_d", 0.0)))
     tau = float(g["tau"])
     for c in range(g["q0"].shape[0]):
         assert m.log_prob(g["q0"][c], tau) == pytest.approx(float(g["log_prob"][c]), rel=1e-12)
