@@ -9,7 +9,7 @@ samplers of the same kinds.
 
     save("run.npz", gibbs)                      # or an HMCSampler / RWMCSampler / GammaSampler
     ...
-    gibbs = make_sampler(posterior, 0.02, start_state)   # same construction as the original run
+    gibbs = make_sampler(posterior, 0.02, start_state, nsteps=20)   # same construction as the original run
     load("run.npz", gibbs)
 """
 import numpy as np

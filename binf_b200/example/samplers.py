@@ -1,7 +1,7 @@
 """Conjugate precision sampler, random-walk Metropolis sampler and the example's Gibbs wiring
-(reference: binf/example/samplers.py:7-111).  `make_sampler` wires the batched device HMCSampler for
-the coefficients by default; `make_sampler(..., rwmc_stepsize=...)` wires the reference's RWMCSampler
-(also batched on the device, binfb_rwmc_run) exactly as the reference's make_sampler does."""
+(reference: binf/example/samplers.py:7-111).  `make_sampler(posterior, rwmc_stepsize, start_state)` wires
+the reference's RWMCSampler + GammaSampler exactly as the reference does (both batched on the device);
+`make_sampler(posterior, timestep, start_state, nsteps=L)` wires the fused device HMCSampler instead."""
 from collections import namedtuple
 
 import numpy as np
@@ -133,22 +133,22 @@ class GammaSampler(object):
         return self.state
 
 
-def make_sampler(posterior, timestep, start_state, nsteps=20, timestep_adaption_limit=0, seed=None,
-                 rwmc_stepsize=None):
-    """GibbsSampler(HMC on the coefficients, conjugate Gamma on the precision); with `rwmc_stepsize`
-    the coefficients are sampled by random-walk Metropolis as in the reference (samplers.py:94-111)."""
+def make_sampler(posterior, rwmc_stepsize, start_state, nsteps=None, timestep_adaption_limit=0, seed=None):
+    """GibbsSampler over (coefficients, precision) exactly as the reference wires it
+    (samplers.py:94-111): random-walk Metropolis with `rwmc_stepsize` on the coefficients, the conjugate
+    Gamma sampler on the precision.  With `nsteps` given, the coefficients are sampled by HMC instead
+    (leapfrog time step = the second argument, `nsteps` steps per trajectory) and a sweep is ONE launch
+    of the fused kernel."""
     from binf_b200.samplers.gibbs import GibbsSampler
     from binf_b200.samplers.hmc import HMCSampler
     coeffs = start_state.variables["coefficients"]
     precision = start_state.variables["precision"]
-    if rwmc_stepsize is not None:
-        rw = RWMCSampler(posterior.conditional_factory(precision=precision), coeffs, rwmc_stepsize, seed=seed)
-        gam = GammaSampler(posterior.conditional_factory(coefficients=coeffs), precision,
-                           seed=None if seed is None else seed + 1)
-        return GibbsSampler(posterior, start_state, {"coefficients": rw, "precision": gam})
-    hmc = HMCSampler(posterior.conditional_factory(precision=precision), coeffs, timestep, nsteps,
-                     timestep_adaption_limit=timestep_adaption_limit, variable_name="coefficients",
-                     seed=seed)
+    if nsteps is None:
+        sub = RWMCSampler(posterior.conditional_factory(precision=precision), coeffs, rwmc_stepsize, seed=seed)
+    else:
+        sub = HMCSampler(posterior.conditional_factory(precision=precision), coeffs, rwmc_stepsize, nsteps,
+                         timestep_adaption_limit=timestep_adaption_limit, variable_name="coefficients",
+                         seed=seed)
     gam = GammaSampler(posterior.conditional_factory(coefficients=coeffs), precision,
                        seed=None if seed is None else seed + 1)
-    return GibbsSampler(posterior, start_state, {"coefficients": hmc, "precision": gam})
+    return GibbsSampler(posterior, start_state, {"coefficients": sub, "precision": gam})

@@ -207,3 +207,21 @@ def test_fused_gibbs_on_device_resident_state_matches_host_path(gpu):
     assert hh.acceptance_rate == pytest.approx(hd.acceptance_rate)
     np.testing.assert_allclose(hd.timestep, hh.timestep, rtol=1e-6)
     assert 100.0 < np.median(sh.variables["precision"]) < 1000.0     # noise sd 0.05 => tau ~ 400
+
+
+@pytest.mark.parametrize("argv", [["--sweeps", "900"], ["--sweeps", "300", "--chains", "64", "--hmc", "--sink"]])
+def test_reference_example_script_runs_on_the_device(gpu, argv, capsys):
+    """BASELINE configs[0]: the reference's example_script.py flow (make_posterior, make_sampler, the
+    sample loop, thinning, get_MAP, predict) unchanged, through install_as_binf()"""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("example_script", os.path.join(ROOT, "examples", "example_script.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    coeffs, precisions, dens = mod.main(argv)
+    assert np.all(np.abs(coeffs.mean(axis=0) - [2.0, -4.0, 1.0, 1.5]) < [1.2, 1.2, 0.6, 0.6])
+    assert 0.5 < precisions.mean() < 8.0
+    assert np.all(dens >= 0) and dens.max() > 0.05
+    out = capsys.readouterr().out
+    assert "posterior mean" in out and (int(argv[1]) <= 500 or "acceptance rate" in out)

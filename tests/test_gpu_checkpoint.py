@@ -17,8 +17,9 @@ def _make(seed=7, rwmc=False):
     C = 200
     start = BinfState(dict(coefficients=np.array([2.0, -4.0, 1.0, 1.5]) + 0.05 * rng.normal(size=(C, 4)),
                            precision=np.full(C, 2.0)))
-    return make_sampler(post, 0.01, start, nsteps=8, timestep_adaption_limit=6, seed=seed,
-                        rwmc_stepsize=0.03 if rwmc else None)
+    if rwmc:
+        return make_sampler(post, 0.03, start, seed=seed)
+    return make_sampler(post, 0.01, start, nsteps=8, timestep_adaption_limit=6, seed=seed)
 
 
 @pytest.mark.parametrize("rwmc", [False, True])
