@@ -66,6 +66,7 @@ SIGNATURES = {
     "binfb_sink_push_host": (_i, [_vp, _vp, _vp, _vp]),
     "binfb_sink_summary": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "binfb_sink_summary_host": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "binfb_sink_sums_host": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "binfb_sink_moments_host": (_i, [_vp, _vp, _vp]),
     "binfb_sink_read_host": (_i, [_vp, _ll, _ll, _vp, _vp]),
     "binfb_sink_map_host": (_i, [_vp, _vp, _vp, _vp]),
@@ -396,6 +397,13 @@ class Sink(object):
         out = [np.empty(self.dim) for _ in range(4)]
         check(lib().binfb_sink_summary_host(self._h, *[ptr(o) for o in out]))
         return dict(mean=out[0], var=out[1], rhat=out[2], ess_per_chain=out[3])
+
+    def sums(self):
+        """raw per-dimension sums of the summary (see binf_b200.distributed.merge_sink_sums)"""
+        out = [np.empty(self.dim) for _ in range(4)]
+        check(lib().binfb_sink_sums_host(self._h, *[ptr(o) for o in out]))
+        return dict(pivot=out[0], s1=out[1], s2=out[2], s3=out[3], n_chains=self.n_chains,
+                    n=self.info()["n_moment"])
 
     def summary_device(self, mean=None, var=None, rhat=None, ess=None, stream=None):
         check(lib().binfb_sink_summary(self._h, ptr(mean), ptr(var), ptr(rhat), ptr(ess), ptr(stream)))

@@ -382,6 +382,26 @@ int binfb_sink_summary(binfb_sink *s, double *mean_dev, double *var_dev, double 
     return BINFB_OK;
 }
 
+int binfb_sink_sums_host(binfb_sink *s, double *pivot, double *sum_dev, double *sum_dev2, double *sum_m2) {
+    int rc = check_sink(s);
+    if (rc) return rc;
+    if (s->n_moment < 2) {
+        set_error("sink_sums: needs at least 2 post-burn-in sweeps");
+        return BINFB_EINVAL;
+    }
+    BINFB_CUDA(cudaSetDevice(s->device));
+    // same reduction as binfb_sink_summary, without the finalisation
+    rc = binfb_sink_summary(s, nullptr, nullptr, nullptr, nullptr, s->hstream);
+    if (rc) return rc;
+    BINFB_CUDA(cudaStreamSynchronize(s->hstream));
+    const size_t D = s->D;
+    if (pivot) BINFB_CUDA(cudaMemcpy(pivot, s->mean, D * sizeof(double), cudaMemcpyDeviceToHost));
+    if (sum_dev) BINFB_CUDA(cudaMemcpy(sum_dev, s->acc, D * sizeof(double), cudaMemcpyDeviceToHost));
+    if (sum_dev2) BINFB_CUDA(cudaMemcpy(sum_dev2, s->acc + D, D * sizeof(double), cudaMemcpyDeviceToHost));
+    if (sum_m2) BINFB_CUDA(cudaMemcpy(sum_m2, s->acc + 2 * D, D * sizeof(double), cudaMemcpyDeviceToHost));
+    return BINFB_OK;
+}
+
 int binfb_sink_summary_host(binfb_sink *s, double *mean, double *var, double *rhat, double *ess) {
     int rc = check_sink(s);
     if (rc) return rc;

@@ -297,3 +297,45 @@ class ReplicaExchangeDriver(object):
                 self._set_beta(self.betas[self.rank])
         self.pair_attempted = self.pair_swapped = 0
         return rates
+
+
+# ------------------------------------------------------------------------------------------------
+# posterior summaries over the chains of ALL ranks
+# ------------------------------------------------------------------------------------------------
+def merge_sink_sums(parts):
+    """Combine the per-rank sums of `Sink.sums()` into the global per-dimension summary (mean, pooled
+    within-chain variance, Gelman-Rubin R-hat, effective sample size per chain) -- what `Sink.summary()`
+    returns for one GPU, over the chains of every rank.  Each part carries its own pivot (the running
+    mean of its chain 0); the sums are re-centred on the first part's pivot before they are added:
+        sum (m - p0)^2 = sum (m - p)^2 + 2 (p - p0) sum (m - p) + C (p - p0)^2."""
+    p0 = np.asarray(parts[0]["pivot"], dtype=np.float64)
+    n = parts[0]["n"]
+    C, s1, s2, s3 = 0, 0.0, 0.0, 0.0
+    for part in parts:
+        if part["n"] != n:
+            raise ValueError("ranks hold different numbers of sweeps (%d vs %d)" % (part["n"], n))
+        d = np.asarray(part["pivot"], dtype=np.float64) - p0
+        c = part["n_chains"]
+        s2 = s2 + part["s2"] + 2.0 * d * part["s1"] + c * d * d
+        s1 = s1 + part["s1"] + c * d
+        s3 = s3 + part["s3"]
+        C += c
+    mu = s1 / C
+    W = s3 / ((n - 1.0) * C)
+    var_means = (s2 - C * mu * mu) / (C - 1.0) if C > 1 else np.zeros_like(W)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rhat = np.sqrt(((n - 1.0) / n * W + var_means) / W)
+        ess = W / var_means
+    return dict(mean=p0 + mu, var=W, rhat=rhat, ess_per_chain=ess, n_chains=C)
+
+
+def sink_summary_all_ranks(sink, group=None):
+    """`Sink.summary()` over the chains of all ranks: one all-gather of 4 x dim doubles per rank
+    (a diagnostics exchange, once per reporting interval)."""
+    import torch.distributed as dist
+    mine = getattr(sink, "_sink", sink).sums()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return merge_sink_sums([mine])
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, mine, group=group)
+    return merge_sink_sums(parts)

@@ -205,6 +205,10 @@ int binfb_sink_push_host(binfb_sink *s, const float *q, const float *aux, const 
 int binfb_sink_summary(binfb_sink *s, double *mean_dev, double *var_dev, double *rhat_dev,
                        double *ess_dev, void *stream);
 int binfb_sink_summary_host(binfb_sink *s, double *mean, double *var, double *rhat, double *ess);
+/* the raw per-dimension sums behind the summary, for merging across GPUs (binf_b200.distributed.
+ * merge_sink_sums): pivot[d] = running mean of chain 0, sum_c (mean_c - pivot), sum_c (mean_c - pivot)^2,
+ * sum_c M2_c; each [dim] f64, any may be NULL */
+int binfb_sink_sums_host(binfb_sink *s, double *pivot, double *sum_dev, double *sum_dev2, double *sum_m2);
 /* per-chain running mean and unbiased variance, [C, dim] f64 each (either may be NULL) */
 int binfb_sink_moments_host(binfb_sink *s, double *mean, double *var);
 /* kept samples number first .. first+count-1 (0 = the first ever kept) -> q_out [count, C, dim],

@@ -170,3 +170,32 @@ def test_adapt_ladder_is_pure_and_keeps_end_points():
     assert gaps_new[0] > gaps_old[0] and gaps_new[2] < gaps_old[2]
     np.testing.assert_allclose(gaps_new.sum(), gaps_old.sum(), rtol=1e-12)
     assert list(adapt_ladder([1.0, 0.5], [0.2])) == [1.0, 0.5]
+
+
+def test_merge_sink_sums_equals_one_big_sink():
+    """the cross-rank merge of per-GPU sink sums == the summary over all chains at once (numpy stand-in
+    for Sink.sums(): same definitions as binfb_sink_sums_host)"""
+    from binf_b200.distributed import merge_sink_sums
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import sink_port
+    rng = np.random.RandomState(5)
+    n, D = 40, 6
+    shards = [30.0 + rng.normal(size=(n, C, D)) + rng.normal(size=(1, C, 1)) for C in (7, 12, 5)]
+
+    def sums(x):
+        mean, m2 = x.mean(axis=0), x.var(axis=0, ddof=0) * x.shape[0]
+        pivot = mean[0]
+        dev = mean - pivot
+        return dict(pivot=pivot, s1=dev.sum(0), s2=(dev * dev).sum(0), s3=m2.sum(0), n_chains=x.shape[1], n=n)
+
+    merged = merge_sink_sums([sums(x) for x in shards])
+    ref = sink_port.ListSink()
+    for t in range(n):
+        ref.append(np.concatenate([x[t] for x in shards], axis=0))
+    r = ref.summary()
+    assert merged["n_chains"] == 24
+    for k in ("mean", "var", "rhat", "ess_per_chain"):
+        np.testing.assert_allclose(merged[k], r[k], rtol=1e-9, err_msg=k)
+    with pytest.raises(ValueError):
+        merge_sink_sums([sums(shards[0]), dict(sums(shards[1]), n=n + 1)])

@@ -114,3 +114,20 @@ def test_device_tensors_and_errors(gpu):
         sink.get_MAP()                          # created without track_map
     with pytest.raises(_cabi.BinfB200Error):
         _cabi.Sink(4, 4).summary()              # fewer than 2 sweeps
+
+
+def test_sums_merge_across_sinks_equals_one_sink(gpu):
+    """two sinks holding disjoint chain ranges (as two ranks would) merge to the summary of one sink
+    over all chains"""
+    from binf_b200 import _cabi
+    from binf_b200.distributed import merge_sink_sums
+    rng = np.random.RandomState(8)
+    C, D, n = 96, 12, 30
+    a, b, whole = _cabi.Sink(40, D), _cabi.Sink(C - 40, D), _cabi.Sink(C, D)
+    drift = rng.normal(size=(C, D))
+    for t in range(n):
+        x = (10.0 + drift + rng.normal(size=(C, D))).astype(np.float32)
+        a.push(x[:40]), b.push(x[40:]), whole.push(x)
+    merged, ref = merge_sink_sums([a.sums(), b.sums()]), whole.summary()
+    for k in ("mean", "var", "rhat", "ess_per_chain"):
+        np.testing.assert_allclose(merged[k], ref[k], rtol=1e-9, err_msg=k)
