@@ -24,9 +24,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0 prints exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# rank 0 prints exactly ONE line on stdout: keep NCCL's version banner off it (NCCL prints it to stdout at
+# every debug level from VERSION up; unset = silent)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    del os.environ["NCCL_DEBUG"]
 
 FLOP_PER_PAIR = 31.0          # per unordered bead pair and force evaluation
 FLOP_PER_DATUM = 14.0         # per chain, datum and force evaluation (K = 4)
