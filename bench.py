@@ -24,10 +24,24 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0 prints exactly ONE line on stdout: keep NCCL's version banner off it (NCCL prints it to stdout at
-# every debug level from VERSION up; unset = silent)
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
-    del os.environ["NCCL_DEBUG"]
+# rank 0 prints exactly ONE line on stdout.  Libraries write there too (NCCL's "NCCL version ..." banner at
+# communicator creation), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes
+# to a saved copy of the real stdout.
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
+def _capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
 
 FLOP_PER_PAIR = 31.0          # per unordered bead pair and force evaluation
 FLOP_PER_DATUM = 14.0         # per chain, datum and force evaluation (K = 4)
@@ -183,7 +197,7 @@ def run_reference(args):
                 e2e=dict(value=best["value"], unit="leapfrog steps/s", h2d_bytes_per_step=0,
                          d2h_bytes_per_step=0),
                 wall_s=time.perf_counter() - t0)
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------
@@ -259,7 +273,7 @@ def run_sink(args):
         torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
     if rank == 0:
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "sample-sink state elements absorbed/s (chains x dim per sweep)", "value": world * C * D / (ms * 1e-3),
             "unit": "elements/s", "n_gpus": world, "steps": steps * reps, "warmup": max(args.warmup, 3) + steps,
             "ms_per_step": ms,
@@ -478,7 +492,7 @@ def run_ours(args):
                 acceptance_rate=float(st[0] / st[1]) if st[1] else None,
                 e2e=e2e, gpu_launches=launches[0], wall_ms=wall_ms, clocks=clocks, roofline=roofline,
                 cpu_baseline=cpu)
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -499,11 +513,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    _capture_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.workload == "sink":
         if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "the sink workload has no reference arm "
+            emit(json.dumps({"impl": "reference", "unavailable": "the sink workload has no reference arm "
                               "(the reference keeps a Python list of deep copies of one chain)"}))
         else:
             run_sink(args)
