@@ -66,7 +66,8 @@ namespace binfb {
 constexpr float CHROM_SOFT = PAIR_SOFT;
 constexpr int STEP_FLOAT4 = 4 * 32;  // float4 per warp-step (16 contacts per lane)
 constexpr int STEP_BYTES = STEP_FLOAT4 * 16;
-constexpr int CHAIN_SCRATCH_BYTES = 128;  // per chain, in front of its positions: one double per role (<= 16)
+constexpr int CHAIN_SCRATCH_BYTES = 144;  // per chain, in front of its positions: one double per role (<= 16)
+                                          // and the mbarrier of the position copy
 #ifndef BINFB_CHROM_NS
 #define BINFB_CHROM_NS 4
 #endif
@@ -116,6 +117,7 @@ __device__ __forceinline__ void unpack4(const float4 v, float (&a)[4]) {
 struct ChainSmem {
     float *pos, *frc;  // [Q][3][4]
     double *red;       // [16] cross-role reduction scratch (CHAIN_SCRATCH_BYTES)
+    uint32_t pos_bar;  // shared address of the mbarrier the bulk copy of the positions completes on
 };
 __device__ __forceinline__ int qidx(int bead, int comp) { return (bead >> 2) * 12 + comp * 4 + (bead & 3); }
 
@@ -538,11 +540,13 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
     {
         unsigned char *b0 = chains + per_chain * chain_local;
         sm.red = reinterpret_cast<double *>(b0);
+        sm.pos_bar = smem_u32(b0 + 128);
         sm.pos = reinterpret_cast<float *>(b0 + CHAIN_SCRATCH_BYTES);
         sm.frc = sm.pos + 3 * cd.n_pad;
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; ++i) mbar_init(&bars[i], 1), cnts[i] = 0u;
+        for (int w = 0; w < W; ++w) mbar_init(reinterpret_cast<uint64_t *>(chains + per_chain * w + 128), 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -551,6 +555,7 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
     const int passes = call.mode == CHROM_MODE_HMC ? call.h.L + 1 : 1;
     const int cthreads = R * 32, ctid = role * 32 + lane;  // threads of this chain
     uint32_t stage_idx = 0;  // running stage counter, identical in every warp
+    uint32_t pos_copies = 0; // bulk copies of positions this chain slot has received (mbarrier phase)
 
     for (;;) {
         // ---- claim a work item and wait for the previous pass of its chain group ----------
@@ -611,33 +616,45 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                         const int bead = e / 3, comp = e - 3 * bead;
                         sm.pos[qidx(bead, comp)] = v;
                     }
+                } else if (hmc) {
+                    // passes k > 0: the previous pass left the drifted positions q + eps p (hmc.py:119,122)
+                    // in the working copy, already in the shared-memory layout: one bulk async copy
+                    // (TMA engine) brings them in while the forces are zeroed
+                    if (ctid == 0) {
+                        const uint32_t bytes = (uint32_t)cd.n_pad * 12u;
+                        bar_expect_tx(sm.pos_bar, bytes);
+                        bulk_g2s(smem_u32(sm.pos), cd.qw + (size_t)c * 3 * cd.n_pad, bytes, sm.pos_bar);
+                    }
                 } else {
                     constexpr int U = 8;
                     for (int e0 = ctid; e0 < D; e0 += cthreads * U) {
-                        float v[U], pv[U];
+                        float v[U];
 #pragma unroll
                         for (int uu = 0; uu < U; ++uu) {
                             const int e = e0 + uu * cthreads;
                             v[uu] = e < D ? __ldcg(src + off + e) : 0.f;
-                            pv[uu] = (hmc && e < D) ? __ldcg(cd.pw + off + e) : 0.f;
                         }
 #pragma unroll
                         for (int uu = 0; uu < U; ++uu) {
                             const int e = e0 + uu * cthreads;
                             if (e < D) {
                                 const int bead = e / 3, comp = e - 3 * bead;
-                                // q += eps p (hmc.py:119,122)
-                                sm.pos[qidx(bead, comp)] = fmaf(eps_c, pv[uu], v[uu]);
+                                sm.pos[qidx(bead, comp)] = v[uu];
                             }
                         }
                     }
+                }
+                for (int i = ctid; i < 3 * cd.n_pad; i += cthreads) sm.frc[i] = 0.f;
+                if (hmc && k > 0) {
+                    while (!bar_try_wait(sm.pos_bar, pos_copies & 1u)) {
+                    }
+                    ++pos_copies;
                 }
                 for (int i = cd.n + ctid; i < cd.n_pad; i += cthreads) {
                     // padding beads: far away from everything => contact 0, force 0
                     sm.pos[qidx(i, 0)] = 1.0e4f * (float)(1 + i - cd.n);
                     sm.pos[qidx(i, 1)] = 3.0e4f, sm.pos[qidx(i, 2)] = -2.0e4f;
                 }
-                for (int i = ctid; i < 3 * cd.n_pad; i += cthreads) sm.frc[i] = 0.f;
                 if (hmc && k == 0) kin0 = chain_sum((double)kin, sm, lane, role, R, bar_id);
             }
             if (R > 1) chain_bar(bar_id, cthreads);
@@ -752,8 +769,10 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                             __stcg(pp, px), __stcg(pp + 1, py), __stcg(pp + 2, pz);
                             kin = fmaf(px, px, fmaf(py, py, fmaf(pz, pz, kin)));
                             if (k < h.L) {
-                                float *qq = cd.qw + off + 3 * i;
-                                __stcg(qq, x), __stcg(qq + 1, y), __stcg(qq + 2, z);
+                                // the next pass's positions, drift included, in the shared-memory layout
+                                float *qq = cd.qw + (size_t)c * 3 * cd.n_pad + ix;
+                                __stcg(qq, fmaf(eps_c, px, x)), __stcg(qq + 4, fmaf(eps_c, py, y));
+                                __stcg(qq + 8, fmaf(eps_c, pz, z));
                             }
                         } else if (call.g.grad) {
                             float *gg = call.g.grad + off + 3 * i;
@@ -969,7 +988,7 @@ int chrom_reserve(ChromModel &m, int C) {
         m.qw = m.pw = m.tau_w = nullptr;
         m.h0 = m.chi2_0 = m.chi2_state = nullptr;
         m.ws_chains = 0;
-        BINFB_CUDA(cudaMalloc(&m.qw, (size_t)C * D * sizeof(float)));
+        BINFB_CUDA(cudaMalloc(&m.qw, (size_t)C * 3 * m.plan.n_pad * sizeof(float)));
         BINFB_CUDA(cudaMalloc(&m.pw, (size_t)C * D * sizeof(float)));
         BINFB_CUDA(cudaMalloc(&m.h0, (size_t)C * sizeof(double)));
         BINFB_CUDA(cudaMalloc(&m.chi2_0, (size_t)C * sizeof(double)));
