@@ -262,6 +262,11 @@ def run_sink(args):
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak = float(peaks.get("hbm_gbs", 6543.7))
     achieved = bytes_per_push / (ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["sink"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     # e2e: the same push from pinned host memory (H2D inside the timed region)
     qh = q.cpu().pin_memory()
     th, lh = tau.cpu().pin_memory(), logp.cpu().pin_memory()
@@ -286,7 +291,7 @@ def run_sink(args):
                     "api": "Sink.push after an H2D copy of the state from pinned host memory"},
             "gpu_launches": steps * reps, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "bytes_per_launch": bytes_per_push,
+                         "traffic": traffic, "bytes_per_launch": bytes_per_push,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"},
             "cpu_baseline": None}))
 
