@@ -46,13 +46,9 @@
 
 namespace binfb {
 
-// experiment switches (profiles/experiments/build_variants.py): shape of the pair block
-// (pair_block.cuh: 0 packed, 1 hybrid, 2 packed with a shared reciprocal, 3 packed with scalar row
-// accumulators (default: 0.5 % faster than 0 and 12 registers fewer)), and whether the special steps
-// are peeled out of the stage loop
-#ifndef BINFB_PAIR_SHAPE
-#define BINFB_PAIR_SHAPE 3
-#endif
+// experiment switches (profiles/experiments/build_variants.py).  The pair block is pair_packed_gs of
+// pair_block.cuh (packed columns, scalar row accumulators); the other shapes measured there and in
+// profiles/README.md (plain packed, hybrid, shared reciprocal) were 0.5-2 % slower in this kernel.
 #ifndef BINFB_PEEL
 #define BINFB_PEEL 0
 #endif
@@ -228,24 +224,9 @@ __device__ __forceinline__ void ring_release(const Ring &ring, uint32_t gi, int 
 // one chain work on partner offsets k and k' >= k + Lr - drift, where drift < CHROM_NS*SPR slots is
 // enforced by the shared stage ring; they can only meet on a quad if k' - k <= 31, which the
 // host-side plan excludes (Lr - CHROM_NS*SPR >= 33 whenever R > 1).
-#if BINFB_PAIR_SHAPE == 3
-#define G_LO(v) (v)
-#define G_HI(v) (v)
-#define G_SUM(v) (v)
-#define G_ZERO 0.f
-#else
-#define G_LO(v) ((v).x)
-#define G_HI(v) ((v).y)
-#define G_SUM(v) ((v).x + (v).y)
-#define G_ZERO mk2(0.f, 0.f)
-#endif
 struct SweepRegs {
     float2 nx2[4], ny2[4], nz2[4];  // own quad, negated, as broadcast pairs
-#if BINFB_PAIR_SHAPE == 3
-    float g[4][3];                  // G = -(force sum) of the own quad (scalar accumulators)
-#else
-    float2 g[4][3];                 // G = -(force sum) of the own quad
-#endif
+    float g[4][3];                  // G = -(force sum) of the own quad
     int k;                          // partner offset of the next step
     uint32_t paddr;                 // shared address of the partner quad's positions (48 bytes per quad)
     uint32_t pwrap;                 // shared address of quad 0's positions
@@ -280,34 +261,16 @@ __device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32
     float2 fx2[2] = {mk2(fx.x, fx.y), mk2(fx.z, fx.w)}, fy2[2] = {mk2(fy.x, fy.y), mk2(fy.z, fy.w)},
            fz2[2] = {mk2(fz.x, fz.y), mk2(fz.z, fz.w)};
     float2 c2 = mk2(0.f, 0.f), ev2 = mk2(0.f, 0.f);
-    static_assert(!EV || BINFB_PAIR_SHAPE == 3, "the excluded-volume term is implemented for pair shape 3");
     float4 yv[4];
     yv[0] = lds4<0>(yaddr), yv[1] = lds4<512>(yaddr), yv[2] = lds4<1024>(yaddr), yv[3] = lds4<1536>(yaddr);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-#if BINFB_PAIR_SHAPE == 1
-        pair_hybrid<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y), A2.x,
-                            B2.x, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2);
-        pair_hybrid<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w), A2.x,
-                            B2.x, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2);
-#elif BINFB_PAIR_SHAPE == 2
-        pair_packed_sr<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y), A2,
-                               B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2);
-        pair_packed_sr<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w), A2,
-                               B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2);
-#elif BINFB_PAIR_SHAPE == 3
         pair_packed_gs<ENERGY, EV>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y),
                                    A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2, s.dev,
                                    s.cev, &ev2);
         pair_packed_gs<ENERGY, EV>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w),
                                    A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2, s.dev,
                                    s.cev, &ev2);
-#else
-        pair_packed<ENERGY, false>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y),
-                                   A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2);
-        pair_packed<ENERGY, false>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w),
-                                   A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2);
-#endif
     }
     if (active) {
         sts4<0>(fa, fx2[0].x, fx2[0].y, fx2[1].x, fx2[1].y);
@@ -335,9 +298,9 @@ __device__ __forceinline__ void step_special(SweepRegs &s, uint32_t frc_off, uin
             for (int c = r + 1; c < 4; ++c) {
                 float tx = 0.f, ty = 0.f, tz = 0.f;
                 pair_scalar<ENERGY, EV>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, -s.nx2[c].x, -s.ny2[c].x, -s.nz2[c].x,
-                                        yv[r][c], A, B, G_LO(s.g[r][0]), G_LO(s.g[r][1]), G_LO(s.g[r][2]), tx, ty,
+                                        yv[r][c], A, B, s.g[r][0], s.g[r][1], s.g[r][2], tx, ty,
                                         tz, chi, s.dev, s.cev, &evs);
-                G_HI(s.g[c][0]) -= tx, G_HI(s.g[c][1]) -= ty, G_HI(s.g[c][2]) -= tz;
+                s.g[c][0] -= tx, s.g[c][1] -= ty, s.g[c][2] -= tz;
             }
     } else if (!upper_half) {
         const uint32_t pa = s.paddr, fa = s.paddr + frc_off;
@@ -351,7 +314,7 @@ __device__ __forceinline__ void step_special(SweepRegs &s, uint32_t frc_off, uin
 #pragma unroll
             for (int c = 0; c < 4; ++c)
                 pair_scalar<ENERGY, EV>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, xj[c], yj[c], zj[c], yv[r][c], A, B,
-                                        G_LO(s.g[r][0]), G_LO(s.g[r][1]), G_LO(s.g[r][2]), fjx[c], fjy[c], fjz[c],
+                                        s.g[r][0], s.g[r][1], s.g[r][2], fjx[c], fjy[c], fjz[c],
                                         chi, s.dev, s.cev, &evs);
         sts4<0>(fa, fjx[0], fjx[1], fjx[2], fjx[3]);
         sts4<16>(fa, fjy[0], fjy[1], fjy[2], fjy[3]);
@@ -402,7 +365,7 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 s.nx2[r] = mk2(-xi[r], -xi[r]), s.ny2[r] = mk2(-yi[r], -yi[r]), s.nz2[r] = mk2(-zi[r], -zi[r]);
-                s.g[r][0] = s.g[r][1] = s.g[r][2] = G_ZERO;
+                s.g[r][0] = s.g[r][1] = s.g[r][2] = 0.f;
             }
         }
         s.k = k0;  // partner offset of slot 0
@@ -469,16 +432,16 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
             if (R > 1) chain_bar(bar_id, R * 32);
             if (rr == role && active) {
                 float4 v = frc4[3 * a];
-                v.x -= G_SUM(s.g[0][0]), v.y -= G_SUM(s.g[1][0]);
-                v.z -= G_SUM(s.g[2][0]), v.w -= G_SUM(s.g[3][0]);
+                v.x -= s.g[0][0], v.y -= s.g[1][0];
+                v.z -= s.g[2][0], v.w -= s.g[3][0];
                 frc4[3 * a] = v;
                 v = frc4[3 * a + 1];
-                v.x -= G_SUM(s.g[0][1]), v.y -= G_SUM(s.g[1][1]);
-                v.z -= G_SUM(s.g[2][1]), v.w -= G_SUM(s.g[3][1]);
+                v.x -= s.g[0][1], v.y -= s.g[1][1];
+                v.z -= s.g[2][1], v.w -= s.g[3][1];
                 frc4[3 * a + 1] = v;
                 v = frc4[3 * a + 2];
-                v.x -= G_SUM(s.g[0][2]), v.y -= G_SUM(s.g[1][2]);
-                v.z -= G_SUM(s.g[2][2]), v.w -= G_SUM(s.g[3][2]);
+                v.x -= s.g[0][2], v.y -= s.g[1][2];
+                v.z -= s.g[2][2], v.w -= s.g[3][2];
                 frc4[3 * a + 2] = v;
             }
         }
