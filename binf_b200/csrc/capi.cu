@@ -228,6 +228,12 @@ int binfb_model_create_chromatin(int n_beads, const float *y_pairs, double alpha
         set_error("model_create_chromatin: y_pairs, out required, n_beads >= 2");
         return BINFB_EINVAL;
     }
+    // the pair loop works on positions scaled by the exponent slope alpha*log2(e) and folds 2^(-alpha d_c log2 e)
+    // into a multiplier (pair_block.cuh, SCALED): the slope must be positive and the multiplier a normal float
+    if (!(alpha > 0.0) || !(fabs(alpha * d_c) <= 80.0)) {
+        set_error("model_create_chromatin: alpha > 0 and |alpha * d_c| <= 80 required");
+        return BINFB_EINVAL;
+    }
     binfb_model *m = new binfb_model();
     int rc = model_common_init(m, device);
     if (rc) {

@@ -77,6 +77,10 @@ struct ChromDev {
     int R, Lr, SS, S_pad;  // roles per chain, slots per row block, steps per stage, padded slots
     const float4 *ystream;
     float A, B;  // exp(alpha (d - d_c)) = 2^(A d + B)
+    // The kernel keeps positions multiplied by S = A (> 0) in shared memory and in the working copy qw, so
+    // that the scaled distance IS the exponent (pair_block.cuh, SCALED): e = 2^B 2^(S d).
+    float S, invS;      // A and 1 / A
+    float softS, nC;    // A^2 * soft and -2^B
     float alpha, k_bb, l0, inv_s2;
     float ev_k, ev_d;  // excluded volume: k_ev (0 = off) and d_ev
     double M;
@@ -265,10 +269,10 @@ __device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32
     yv[0] = lds4<0>(yaddr), yv[1] = lds4<512>(yaddr), yv[2] = lds4<1024>(yaddr), yv[3] = lds4<1536>(yaddr);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        pair_packed_gs<ENERGY, EV>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y),
+        pair_packed_gs<ENERGY, EV, true>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y),
                                    A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2, s.dev,
                                    s.cev, &ev2);
-        pair_packed_gs<ENERGY, EV>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w),
+        pair_packed_gs<ENERGY, EV, true>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w),
                                    A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2, s.dev,
                                    s.cev, &ev2);
     }
@@ -297,7 +301,7 @@ __device__ __forceinline__ void step_special(SweepRegs &s, uint32_t frc_off, uin
 #pragma unroll
             for (int c = r + 1; c < 4; ++c) {
                 float tx = 0.f, ty = 0.f, tz = 0.f;
-                pair_scalar<ENERGY, EV>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, -s.nx2[c].x, -s.ny2[c].x, -s.nz2[c].x,
+                pair_scalar<ENERGY, EV, true>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, -s.nx2[c].x, -s.ny2[c].x, -s.nz2[c].x,
                                         yv[r][c], A, B, s.g[r][0], s.g[r][1], s.g[r][2], tx, ty,
                                         tz, chi, s.dev, s.cev, &evs);
                 s.g[c][0] -= tx, s.g[c][1] -= ty, s.g[c][2] -= tz;
@@ -313,7 +317,7 @@ __device__ __forceinline__ void step_special(SweepRegs &s, uint32_t frc_off, uin
         for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                pair_scalar<ENERGY, EV>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, xj[c], yj[c], zj[c], yv[r][c], A, B,
+                pair_scalar<ENERGY, EV, true>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, xj[c], yj[c], zj[c], yv[r][c], A, B,
                                         s.g[r][0], s.g[r][1], s.g[r][2], fjx[c], fjy[c], fjz[c],
                                         chi, s.dev, s.cev, &evs);
         sts4<0>(fa, fjx[0], fjx[1], fjx[2], fjx[3]);
@@ -332,7 +336,8 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
     float4 *pos4 = reinterpret_cast<float4 *>(sm.pos), *frc4 = reinterpret_cast<float4 *>(sm.frc);
     const uint32_t pos_base = smem_u32(sm.pos);
     const uint32_t frc_off = pin_reg((uint32_t)cd.n_pad * 12u);
-    const float A = cd.A, B = cd.B;
+    // scaled positions: the "A" slot of the pair block carries the scaled softening, the "B" slot -2^B
+    const float A = cd.softS, B = cd.nC;
     const float2 A2 = mk2(A, A), B2 = mk2(B, B);
     const int Q = cd.Q, KS = cd.KS, Lr = cd.Lr, halfQ = cd.Q >> 1;
     const bool q_even = cd.q_even != 0;
@@ -350,7 +355,7 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
     const uint32_t ylane = pin_reg(ring.ystage + (uint32_t)role * STEP_BYTES + (uint32_t)lane * 16u);
     SweepRegs s;
     s.chi2 = 0.0, s.ev = 0.0;
-    s.dev = cd.ev_d, s.cev = cev;
+    s.dev = cd.ev_d * cd.S, s.cev = cev * (cd.invS * cd.invS * cd.invS);  // scaled units (pair_block.cuh)
 
     for (int rbi = 0; rbi < cd.NRB; ++rbi) {
         int rb = rbi + rb0;
@@ -577,7 +582,7 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                         __stcg(cd.pw + off + e, pv);
                         kin = fmaf(pv, pv, kin);
                         const int bead = e / 3, comp = e - 3 * bead;
-                        sm.pos[qidx(bead, comp)] = v;
+                        sm.pos[qidx(bead, comp)] = v * cd.S;
                     }
                 } else if (hmc) {
                     // passes k > 0: the previous pass left the drifted positions q + eps p (hmc.py:119,122)
@@ -602,7 +607,7 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                             const int e = e0 + uu * cthreads;
                             if (e < D) {
                                 const int bead = e / 3, comp = e - 3 * bead;
-                                sm.pos[qidx(bead, comp)] = v[uu];
+                                sm.pos[qidx(bead, comp)] = v[uu] * cd.S;
                             }
                         }
                     }
@@ -614,7 +619,7 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                     ++pos_copies;
                 }
                 for (int i = cd.n + ctid; i < cd.n_pad; i += cthreads) {
-                    // padding beads: far away from everything => contact 0, force 0
+                    // padding beads: far away from everything (scaled distance = exponent > 128) => contact 0, force 0
                     sm.pos[qidx(i, 0)] = 1.0e4f * (float)(1 + i - cd.n);
                     sm.pos[qidx(i, 1)] = 3.0e4f, sm.pos[qidx(i, 2)] = -2.0e4f;
                 }
@@ -701,29 +706,32 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                         const int i = i0 + uu * cthreads;
                         if (i >= cd.n) continue;
                         const int ix = qidx(i, 0);
+                        // x, y, z and the bond vectors are in scaled units (S x); a bond force
+                        // k_bb (d - l0) b / d is the same in both units up to d = d' / S
                         const float x = sm.pos[ix], y = sm.pos[ix + 4], z = sm.pos[ix + 8];
                         float gx = scale * sm.frc[ix], gy = scale * sm.frc[ix + 4], gz = scale * sm.frc[ix + 8];
                         if (i > 0) {
                             const int im = qidx(i - 1, 0);
                             const float bx = x - sm.pos[im], by = y - sm.pos[im + 4], bz = z - sm.pos[im + 8];
-                            const float r2 = fmaf(bz, bz, fmaf(by, by, fmaf(bx, bx, CHROM_SOFT)));
+                            const float r2 = fmaf(bz, bz, fmaf(by, by, fmaf(bx, bx, cd.softS)));
                             const float inv = rsqrtf(r2), d = r2 * inv;
-                            const float cc = cd.k_bb * (d - cd.l0) * inv;
+                            const float cc = cd.k_bb * fmaf(d, cd.invS, -cd.l0) * inv;
                             gx = fmaf(cc, bx, gx), gy = fmaf(cc, by, gy), gz = fmaf(cc, bz, gz);
                         }
                         if (i < cd.n - 1) {
                             const int ip = qidx(i + 1, 0);
                             const float bx = sm.pos[ip] - x, by = sm.pos[ip + 4] - y, bz = sm.pos[ip + 8] - z;
-                            const float r2 = fmaf(bz, bz, fmaf(by, by, fmaf(bx, bx, CHROM_SOFT)));
+                            const float r2 = fmaf(bz, bz, fmaf(by, by, fmaf(bx, bx, cd.softS)));
                             const float inv = rsqrtf(r2), d = r2 * inv;
-                            const float dl = d - cd.l0;
+                            const float dl = fmaf(d, cd.invS, -cd.l0);
                             const float cc = cd.k_bb * dl * inv;
                             gx = fmaf(-cc, bx, gx), gy = fmaf(-cc, by, gy), gz = fmaf(-cc, bz, gz);
                             e_prior = fmaf(0.5f * cd.k_bb * dl, dl, e_prior);
                         }
                         if (cd.inv_s2 > 0.f) {
-                            gx = fmaf(cd.inv_s2, x, gx), gy = fmaf(cd.inv_s2, y, gy), gz = fmaf(cd.inv_s2, z, gz);
-                            e_prior = fmaf(0.5f * cd.inv_s2, fmaf(x, x, fmaf(y, y, z * z)), e_prior);
+                            const float w = cd.inv_s2 * cd.invS;
+                            gx = fmaf(w, x, gx), gy = fmaf(w, y, gy), gz = fmaf(w, z, gz);
+                            e_prior = fmaf(0.5f * w * cd.invS, fmaf(x, x, fmaf(y, y, z * z)), e_prior);
                         }
                         if (hmc) {
                             float *pp = cd.pw + off + 3 * i;
@@ -734,8 +742,9 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                             if (k < h.L) {
                                 // the next pass's positions, drift included, in the shared-memory layout
                                 float *qq = cd.qw + (size_t)c * 3 * cd.n_pad + ix;
-                                __stcg(qq, fmaf(eps_c, px, x)), __stcg(qq + 4, fmaf(eps_c, py, y));
-                                __stcg(qq + 8, fmaf(eps_c, pz, z));
+                                const float es = eps_c * cd.S;  // the drift in scaled units
+                                __stcg(qq, fmaf(es, px, x)), __stcg(qq + 4, fmaf(es, py, y));
+                                __stcg(qq + 8, fmaf(es, pz, z));
                             }
                         } else if (call.g.grad) {
                             float *gg = call.g.grad + off + 3 * i;
@@ -745,7 +754,8 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                 }
                 if (energy) {
                     double ep = chain_sum((double)e_prior, sm, lane, role, R, bar_id);
-                    if (EV) ep += (double)cd.ev_k * chain_sum(ev_sum, sm, lane, role, R, bar_id);
+                    if (EV) ep += (double)cd.ev_k * ((double)cd.invS * cd.invS * cd.invS * cd.invS) *
+                                  chain_sum(ev_sum, sm, lane, role, R, bar_id);
                     const double t = (double)tau_c, lt = log(t);
                     const double ga = hmc ? h.gamma_shape : call.g.gamma_shape;
                     const double gb = hmc ? h.gamma_rate : call.g.gamma_rate;
@@ -781,14 +791,14 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                         if (last && (h.q_end || h.p_end)) {
                             for (int e = ctid; e < D; e += cthreads) {
                                 const int bead = e / 3, comp = e - 3 * bead;
-                                if (h.q_end) h.q_end[off + e] = sm.pos[qidx(bead, comp)];
+                                if (h.q_end) h.q_end[off + e] = sm.pos[qidx(bead, comp)] * cd.invS;
                                 if (h.p_end) h.p_end[off + e] = __ldcg(cd.pw + off + e);
                             }
                         }
                         if (acc) {
                             for (int e = ctid; e < D; e += cthreads) {
                                 const int bead = e / 3, comp = e - 3 * bead;
-                                __stcg(h.q + off + e, sm.pos[qidx(bead, comp)]);
+                                __stcg(h.q + off + e, sm.pos[qidx(bead, comp)] * cd.invS);
                             }
                         }
                         const double chi2_cur = acc ? chi2 : __ldcg(cd.chi2_0 + c);
@@ -979,6 +989,9 @@ static ChromDev chrom_dev(const ChromModel &m, const ChromPlan &pl, const float 
     const double log2e = 1.4426950408889634;
     d.A = (float)((double)m.alpha * log2e);
     d.B = (float)(-(double)m.alpha * (double)m.d_c * log2e);
+    d.S = d.A, d.invS = (float)(1.0 / ((double)m.alpha * log2e));
+    d.softS = (float)((double)d.A * (double)d.A * (double)CHROM_SOFT);
+    d.nC = (float)(-exp2(-(double)m.alpha * (double)m.d_c * log2e));
     d.alpha = m.alpha, d.k_bb = m.k_bb, d.l0 = m.l0, d.inv_s2 = m.inv_s2;
     d.ev_k = m.ev_k, d.ev_d = m.ev_d;
     d.M = (double)m.M;

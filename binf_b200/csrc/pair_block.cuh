@@ -67,17 +67,19 @@ __device__ __forceinline__ float2 poly_ex2_2(float2 t) {
 // beads closer than d_ev).  Its force -4 k_ev s^3 (x_i - x_j)/d has the same geometry as the
 // likelihood force, so it rides on the same accumulators: coef += cev * s^3 / d with
 // cev = 4 k_ev / (alpha beta tau) cancelling the factor -alpha beta tau the caller applies to the sums.
-template <bool ENERGY, bool EV = false>
+// SCALED: see pair_packed_gs (positions pre-multiplied by the slope of the exponent; A carries the scaled
+// softening, B carries -2^B, dev / cev the scaled excluded-volume constants).
+template <bool ENERGY, bool EV = false, bool SCALED = false>
 __device__ __forceinline__ void pair_scalar(float nxi, float nyi, float nzi, float xj, float yj,
                                             float zj, float y, float A, float B, float &gx,
                                             float &gy, float &gz, float &fx, float &fy, float &fz,
                                             float &chi, float dev = 0.f, float cev = 0.f, float *ev = nullptr) {
     const float dx = xj + nxi, dy = yj + nyi, dz = zj + nzi;
-    const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, PAIR_SOFT)));
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, SCALED ? A : PAIR_SOFT)));
     const float inv = mufu_rsqrt(r2);
     const float d = r2 * inv;
-    const float e = mufu_ex2(fmaf(d, A, B));
-    const float mn = mufu_rcp(fmaf(e, -1.0f, -1.0f));  // -m
+    const float sn = SCALED ? fmaf(mufu_ex2(d), B, -1.0f) : fmaf(mufu_ex2(fmaf(d, A, B)), -1.0f, -1.0f);
+    const float mn = mufu_rcp(sn);  // -m
     const float rs = mn + y;                            // -(m - y)
     const float wn = fmaf(mn, mn, mn);                  // -(m - m^2)
     float coef = rs * wn * inv;
@@ -125,18 +127,30 @@ __device__ __forceinline__ void pair_packed(float2 nx2, float2 ny2, float2 nz2, 
 // component (1.15 cycles each), which also halves the registers the row accumulators occupy
 // (12 instead of 24 per lane).
 // ---------------------------------------------------------------------------------------------
-template <bool ENERGY, bool EV = false>
+// SCALED: the positions arrive multiplied by A (the slope of the exponent, A > 0), so that the distance
+// itself is the exponent: d' = A d, e = 2^B 2^d'.  The FMA that formed A d + B disappears (2^B rides on
+// the FMA that forms -(1 + e)) and nothing else changes: coef' = coef / A and dx' = A dx, so the force sums
+// coef' dx' come out in the original units.  In this mode A2 carries the scaled softening (A^2 soft) and B2
+// carries -2^B; dev / cev are the scaled excluded-volume constants (A d_ev, cev / A^3; the energy sum
+// comes out multiplied by A^4).
+template <bool ENERGY, bool EV = false, bool SCALED = false>
 __device__ __forceinline__ void pair_packed_gs(float2 nx2, float2 ny2, float2 nz2, float2 xj2, float2 yj2,
                                                float2 zj2, float2 y2, float2 A2, float2 B2, float &gx, float &gy,
                                                float &gz, float2 &fx2, float2 &fy2, float2 &fz2, float2 &chi2,
                                                float dev = 0.f, float cev = 0.f, float2 *ev2 = nullptr) {
     const float2 dx = add2(xj2, nx2), dy = add2(yj2, ny2), dz = add2(zj2, nz2);
-    const float2 r2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, mk2(PAIR_SOFT, PAIR_SOFT))));
+    const float2 r2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, SCALED ? A2 : mk2(PAIR_SOFT, PAIR_SOFT))));
     const float2 inv = mk2(mufu_rsqrt(r2.x), mufu_rsqrt(r2.y));
     const float2 d = mul2(r2, inv);
-    const float2 t = fma2(d, A2, B2);
-    const float2 e = mk2(mufu_ex2(t.x), mufu_ex2(t.y));
-    const float2 sn = fma2(e, mk2(-1.f, -1.f), mk2(-1.f, -1.f));
+    float2 sn;
+    if (SCALED) {
+        const float2 e = mk2(mufu_ex2(d.x), mufu_ex2(d.y));
+        sn = fma2(e, B2, mk2(-1.f, -1.f));
+    } else {
+        const float2 t = fma2(d, A2, B2);
+        const float2 e = mk2(mufu_ex2(t.x), mufu_ex2(t.y));
+        sn = fma2(e, mk2(-1.f, -1.f), mk2(-1.f, -1.f));
+    }
     const float2 mn = mk2(mufu_rcp(sn.x), mufu_rcp(sn.y));
     const float2 rs = add2(mn, y2);
     const float2 wn = fma2(mn, mn, mn);

@@ -207,6 +207,45 @@ __global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) chi_tot += g[r][0].x + g[r][0].y + g[r][1].x + g[r][1].y + g[r][2].x + g[r][2].y;
+    } else if (VAR == 9 || VAR == 10) {
+        // the kernel's shape: packed columns, scalar row accumulators; VAR 10: positions pre-scaled by A
+        float2 nx2[4], ny2[4], nz2[4];
+        float g[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            nx2[r] = mk2(-xi[r], -xi[r]), ny2[r] = mk2(-yi[r], -yi[r]), nz2[r] = mk2(-zi[r], -zi[r]);
+            g[r][0] = g[r][1] = g[r][2] = 0.f;
+        }
+        const float2 A2 = VAR == 10 ? mk2(A * A * PAIR_SOFT, A * A * PAIR_SOFT) : mk2(A, A);
+        const float2 B2 = VAR == 10 ? mk2(-exp2f(B), -exp2f(B)) : mk2(B, B);
+        for (int st = 0; st < steps; ++st) {
+            const float4 xj = xs4[b], yj = ys4[b], zj = zs4[b];
+            float4 fx = fx4[b], fy = fy4[b], fz = fz4[b];
+            float2 xj2[2] = {mk2(xj.x, xj.y), mk2(xj.z, xj.w)}, yj2[2] = {mk2(yj.x, yj.y), mk2(yj.z, yj.w)},
+                   zj2[2] = {mk2(zj.x, zj.y), mk2(zj.z, zj.w)};
+            float2 fx2[2] = {mk2(fx.x, fx.y), mk2(fx.z, fx.w)}, fy2[2] = {mk2(fy.x, fy.y), mk2(fy.z, fy.w)},
+                   fz2[2] = {mk2(fz.x, fz.y), mk2(fz.z, fz.w)};
+            const float4 *yb = (const float4 *)ybuf + (st & 3) * 128 + lane;
+            float2 chi2 = mk2(0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float4 yv = yb[r * 32];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float2 y2 = h ? mk2(yv.z, yv.w) : mk2(yv.x, yv.y);
+                    pair_packed_gs<false, false, VAR == 10>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2,
+                                                            g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
+                }
+            }
+            fx4[b] = make_float4(fx2[0].x, fx2[0].y, fx2[1].x, fx2[1].y);
+            fy4[b] = make_float4(fy2[0].x, fy2[0].y, fy2[1].x, fy2[1].y);
+            fz4[b] = make_float4(fz2[0].x, fz2[0].y, fz2[1].x, fz2[1].y);
+            chi_tot += chi2.x + chi2.y;
+            if (++b >= Q) b = 0;
+            __syncwarp();
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) chi_tot += g[r][0] + g[r][1] + g[r][2];
     } else {
         float2 nx2[4], ny2[4], nz2[4], g[4][3];
 #pragma unroll
@@ -287,9 +326,8 @@ int main() {
     float *init, *out; cudaMalloc(&init, 4096 * 4); cudaMalloc(&out, (1 + 148 * 64) * 4);
     cudaMemcpy(init, h.data(), 4096 * 4, cudaMemcpyHostToDevice);
     const int sms = p.multiProcessorCount; const double g = clk / 1e6;
-    run<0, 0, 512>("scalar", init, out, sms, g);
     run<1, 0, 512>("packed 4x4", init, out, sms, g);
-    run<8, 0, 512>("hybrid: packed 2-operand ops, scalar FMAs", init, out, sms, g);
-    run<8, 0, 384>("hybrid: packed 2-operand ops, scalar FMAs", init, out, sms, g);
+    run<9, 0, 512>("packed 4x4, scalar row sums (kernel shape)", init, out, sms, g);
+    run<10, 0, 512>("same, positions pre-scaled by A", init, out, sms, g);
     return 0;
 }
