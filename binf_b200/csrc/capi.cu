@@ -1,5 +1,7 @@
 // C ABI of libbinf_b200.so (declared in include/binf_b200.h).
 #include <math.h>
+
+#include <atomic>
 #include <string.h>
 
 #include <string>
@@ -163,6 +165,10 @@ int binfb_model_create_polynomial(const double *xs, const double *ys, int n_data
     m->gamma_shape = gamma_shape, m->gamma_rate = gamma_rate;
     PolyModel &pm = m->poly;
     pm.N = n_data, pm.K = n_coeff, pm.stride = (n_coeff + 3) / 4 * 4, pm.flags = flags;
+    {
+        static std::atomic<unsigned long long> next_uid{1};
+        pm.uid = next_uid.fetch_add(1);
+    }
     for (int k = 0; k < 8; ++k) {
         pm.prior_mean[k] = (k < n_coeff && prior_mean) ? (float)prior_mean[k] : 0.f;
         pm.prior_inv_var[k] = (k < n_coeff && prior_var) ? (float)(1.0 / prior_var[k]) : 0.f;
@@ -324,6 +330,7 @@ int binfb_model_set_option(binfb_model *m, const char *key, double value) {
     if (!key) return BINFB_EINVAL;
     const int v = value < 0 ? -1 : (int)value;
     if (!strcmp(key, "poly.group")) m->poly.opt_group = v;
+    else if (!strcmp(key, "poly.uniform_rows")) m->poly.opt_ur = v;
     else if (!strcmp(key, "poly.chains_per_thread")) m->poly.opt_jchains = v;
     else if (!strcmp(key, "poly.block")) m->poly.opt_block = v;
     else if (!strcmp(key, "chrom.warps")) m->chrom.opt_warps = v;

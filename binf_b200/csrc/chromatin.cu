@@ -55,6 +55,9 @@ namespace binfb {
 #ifndef BINFB_PREFETCH
 #define BINFB_PREFETCH 0  // load the next step's partner positions one step ahead
 #endif
+#ifndef BINFB_YJIT
+#define BINFB_YJIT 0  // load each row's contacts right before its two packs instead of all 16 up front
+#endif
 #ifndef BINFB_ROTATE
 #define BINFB_ROTATE 1  // start each chain group at a different row block
 #endif
@@ -252,10 +255,12 @@ __device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32
     const uint32_t pa = s.paddr, fa = s.paddr + frc_off;
 #if BINFB_PREFETCH
     const float4 xj = s.nxt[0], yj = s.nxt[1], zj = s.nxt[2];
+#if BINFB_PREFETCH == 1
     {
         const uint32_t pn = s.wrap == 1 ? s.pwrap : pa + 48u;
         s.nxt[0] = lds4<0>(pn), s.nxt[1] = lds4<16>(pn), s.nxt[2] = lds4<32>(pn);
     }
+#endif
 #else
     const float4 xj = lds4<0>(pa), yj = lds4<16>(pa), zj = lds4<32>(pa);
 #endif
@@ -266,9 +271,14 @@ __device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32
            fz2[2] = {mk2(fz.x, fz.y), mk2(fz.z, fz.w)};
     float2 c2 = mk2(0.f, 0.f), ev2 = mk2(0.f, 0.f);
     float4 yv[4];
+#if !BINFB_YJIT
     yv[0] = lds4<0>(yaddr), yv[1] = lds4<512>(yaddr), yv[2] = lds4<1024>(yaddr), yv[3] = lds4<1536>(yaddr);
+#endif
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
+#if BINFB_YJIT
+        yv[r] = r == 0 ? lds4<0>(yaddr) : r == 1 ? lds4<512>(yaddr) : r == 2 ? lds4<1024>(yaddr) : lds4<1536>(yaddr);
+#endif
         pair_packed_gs<ENERGY, EV, true>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y),
                                    A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2, s.dev,
                                    s.cev, &ev2);
@@ -276,6 +286,14 @@ __device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32
                                    A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2, s.dev,
                                    s.cev, &ev2);
     }
+#if BINFB_PREFETCH == 2
+    {   // positions are read-only during the sweep: the next step's partner may be loaded across the
+        // __syncwarp that orders the force updates; issued here, in the tail of the step, the 12 registers
+        // are only live across the step boundary
+        const uint32_t pn = s.wrap == 1 ? s.pwrap : pa + 48u;
+        s.nxt[0] = lds4<0>(pn), s.nxt[1] = lds4<16>(pn), s.nxt[2] = lds4<32>(pn);
+    }
+#endif
     if (active) {
         sts4<0>(fa, fx2[0].x, fx2[0].y, fx2[1].x, fx2[1].y);
         sts4<16>(fa, fy2[0].x, fy2[0].y, fy2[1].x, fy2[1].y);

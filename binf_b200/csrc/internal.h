@@ -67,6 +67,8 @@ struct PolyModel {
     float prior_mean[8], prior_inv_var[8];
     unsigned flags = 0;
     int opt_group = -1, opt_jchains = -1, opt_block = -1;
+    int opt_ur = -1;                // 0 disables the uniform-row mapping (poly.cu)
+    unsigned long long uid = 0;     // unique per model: owner tag of the constant-bank copy of the rows
 };
 int poly_hmc_launch(const PolyModel &m, const HmcArgs &a, int sm_count, int smem_optin,
                     cudaStream_t s);

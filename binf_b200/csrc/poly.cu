@@ -14,6 +14,9 @@
 // [x, x^2, .., x^(K-1), y] live in shared memory for the whole launch.
 #include <math.h>
 
+#include <mutex>
+#include <type_traits>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -210,6 +213,120 @@ __device__ __forceinline__ void poly_grad_pass(const PolyDev &pm, float *srows, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// "uniform-row" mapping (UR).  Measured on B200 (profiles/microbench/ffma2_operands.cu, poly_ur.cu): an
+// FFMA2 whose broadcast operand sits in a vector register occupies the FMA pipe 3 cycles, the same FFMA2
+// with the broadcast operand in a UNIFORM register 2 cycles.  A data row lands in uniform registers when
+// the whole warp reads the same row from constant memory (LDCU).  So here the 32 lanes of a warp own 32
+// different chain pairs and all walk the same rows; the W warps of a "set" own the same 32 chain pairs and
+// split the rows into W contiguous ranges; the K gradient sums (and chi^2) of a pass are combined through
+// shared memory in a fixed order, so that all W warps hold bitwise identical q, p.  No LDS in the row loop.
+// ---------------------------------------------------------------------------------------------
+constexpr int POLY_CROWS_BYTES = 48 * 1024;
+__constant__ float4 c_poly_rows[POLY_CROWS_BYTES / 16];
+
+__device__ __forceinline__ void set_bar(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// scratch of one set: [2 buffers][J*K sums][W warps][32 lanes] float, then [2][J][W][32] double
+template <int K, int W, int J>
+struct PolyUrScratch {
+    static constexpr int F = 2 * J * K * W * 32;  // floats
+    static constexpr int D = 2 * J * W * 32;      // doubles
+    static constexpr size_t BYTES = (size_t)F * 4 + (size_t)D * 8;
+};
+
+template <int K, int W, int J, bool ENERGY>
+__device__ __forceinline__ void poly_grad_pass_ur(const PolyDev &pm, unsigned char *set_scratch, int buf, int w,
+                                                  int lane, int bar_id, const float (&cs)[J][K],
+                                                  float (&graw)[J][K], double (&chi2)[J]) {
+    static_assert(J % 2 == 0, "UR mapping packs chain pairs");
+    constexpr int S4 = PolyRow<K>::STRIDE / 4, JP = J / 2, U = 8;
+    float2 c[JP][K], acc[JP][K];
+    double chi[J];
+#pragma unroll
+    for (int j = 0; j < JP; ++j)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            c[j][k] = make_float2(cs[2 * j][k], cs[2 * j + 1][k]);
+            acc[j][k] = make_float2(0.f, 0.f);
+        }
+#pragma unroll
+    for (int j = 0; j < J; ++j) chi[j] = 0.0;
+    const int rpw = (pm.N + W - 1) / W;
+    int i = w * rpw;  // w is warp-uniform (broadcast by the caller): the row index stays in the uniform datapath
+    const int i_end = min(pm.N, i + rpw);
+    for (; i + U <= i_end; i += U) {
+        float2 part[JP];
+#pragma unroll
+        for (int j = 0; j < JP; ++j) part[j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int uu = 0; uu < U; ++uu)
+            poly_row2<K, JP, ENERGY>(reinterpret_cast<const float *>(c_poly_rows + (size_t)(i + uu) * S4), c, acc, part);
+        if (ENERGY) {
+#pragma unroll
+            for (int j = 0; j < JP; ++j) chi[2 * j] += (double)part[j].x, chi[2 * j + 1] += (double)part[j].y;
+        }
+    }
+    if (i < i_end) {
+        float2 part[JP];
+#pragma unroll
+        for (int j = 0; j < JP; ++j) part[j] = make_float2(0.f, 0.f);
+        for (; i < i_end; ++i)
+            poly_row2<K, JP, ENERGY>(reinterpret_cast<const float *>(c_poly_rows + (size_t)i * S4), c, acc, part);
+        if (ENERGY) {
+#pragma unroll
+            for (int j = 0; j < JP; ++j) chi[2 * j] += (double)part[j].x, chi[2 * j + 1] += (double)part[j].y;
+        }
+    }
+    if (W == 1) {
+#pragma unroll
+        for (int j = 0; j < JP; ++j)
+#pragma unroll
+            for (int k = 0; k < K; ++k) graw[2 * j][k] = acc[j][k].x, graw[2 * j + 1][k] = acc[j][k].y;
+#pragma unroll
+        for (int j = 0; j < J; ++j) chi2[j] = chi[j];
+        return;
+    }
+    // combine the W row ranges: every warp writes its partial sums, one barrier, every warp adds all W
+    // partials in the same order.  Buffer `buf` of pass e is rewritten by pass e + 2, i.e. after the barrier
+    // of pass e + 1, which every warp reaches only after it has read pass e.
+    using Sc = PolyUrScratch<K, W, J>;
+    float *sf = reinterpret_cast<float *>(set_scratch) + (size_t)buf * (Sc::F / 2);
+    double *sd = reinterpret_cast<double *>(set_scratch + (size_t)Sc::F * 4) + (size_t)buf * (Sc::D / 2);
+#pragma unroll
+    for (int j = 0; j < JP; ++j)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            sf[(((2 * j) * K + k) * W + w) * 32 + lane] = acc[j][k].x;
+            sf[(((2 * j + 1) * K + k) * W + w) * 32 + lane] = acc[j][k].y;
+        }
+    if (ENERGY) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) sd[(j * W + w) * 32 + lane] = chi[j];
+    }
+    set_bar(bar_id, W * 32);
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float t = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < W; ++ww) t += sf[((j * K + k) * W + ww) * 32 + lane];
+            graw[j][k] = t;
+        }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        double t = 0.0;
+        if (ENERGY) {
+#pragma unroll
+            for (int ww = 0; ww < W; ++ww) t += sd[(j * W + ww) * 32 + lane];
+        }
+        chi2[j] = t;
+    }
+}
+
 // U(q) = -log p(q | tau) in float64 (binf/pdf/posteriors.py:141-151 summed components)
 template <int K>
 __device__ __forceinline__ double poly_potential(const PolyDev &pm, const float (&q)[K], double chi2,
@@ -250,18 +367,54 @@ __device__ __forceinline__ float draw_tau(const HmcArgs &a, double n_data, doubl
 // (4 chains with 4 lanes per chain: 16 warps, no register limit that matters)
 constexpr int poly_max_block(int G, int J) { return J == 1 ? 1024 : (J == 4 && G <= 4 ? 512 : 896); }
 
-template <int K, int G, int J>
+// thread -> (chain tuple, share of the rows).  Regular mapping: G consecutive lanes per tuple, lane g walks
+// rows g, g+G, ...  UR mapping: lane l of the G warps of set s owns tuple (s, l); "g" is the warp's index in
+// its set, broadcast from lane 0 so that the compiler keeps everything derived from it in uniform registers.
+template <int G, bool UR>
+struct PolyMap {
+    int g, lane, bar_id;
+    long long group, n_groups;
+    unsigned char *scratch;
+    template <int K, int J>
+    __device__ __forceinline__ void init(float *smem) {
+        if (UR) {
+            const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+            const int set = warp / G, sets = (int)(blockDim.x >> 5) / G;
+            g = warp % G, lane = threadIdx.x & 31, bar_id = 1 + set;
+            group = ((long long)blockIdx.x * sets + set) * 32 + lane;
+            n_groups = (long long)gridDim.x * sets * 32;
+            scratch = reinterpret_cast<unsigned char *>(smem) + (size_t)set * PolyUrScratch<K, G, J>::BYTES;
+        } else {
+            g = threadIdx.x % G, lane = 0, bar_id = 0, scratch = nullptr;
+            group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+            n_groups = ((long long)gridDim.x * blockDim.x) / G;
+        }
+    }
+};
+
+template <int K, int G, int J, bool UR = false>
 __global__ void __launch_bounds__(poly_max_block(G, J), 1)
     poly_hmc_kernel(PolyDev pm, HmcArgs a, int iters, int rows_per_chunk, int n_chunks) {
     extern __shared__ __align__(16) float srows[];
     constexpr int S = PolyRow<K>::STRIDE;
-    if (n_chunks == 1) {
+    if (!UR && n_chunks == 1) {
         poly_load_rows(srows, pm.rows, pm.N * S);
         __syncthreads();
     }
-    const int g = threadIdx.x % G;
-    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const long long n_groups = ((long long)gridDim.x * blockDim.x) / G;
+    PolyMap<G, UR> map;
+    map.template init<K, J>(srows);
+    const int g = map.g;
+    const long long group = map.group, n_groups = map.n_groups;
+    int pass = 0;  // UR: running count of gradient passes (scratch buffer parity)
+    auto grad_pass = [&](auto energy_tag, const float (&qq)[J][K], float (&gg)[J][K], double (&cc)[J]) {
+        constexpr bool EN = decltype(energy_tag)::value;
+        if constexpr (UR) {
+            poly_grad_pass_ur<K, G, J, EN>(pm, map.scratch, pass & 1, g, map.lane, map.bar_id, qq, gg, cc);
+            ++pass;
+        } else {
+            poly_grad_pass<K, G, J, EN>(pm, srows, rows_per_chunk, n_chunks, g, qq, gg, cc);
+        }
+    };
     double st_acc = 0.0, st_prop = 0.0, st_eps = 0.0, st_pacc = 0.0;
 
     for (int it = 0; it < iters; ++it) {
@@ -296,7 +449,7 @@ __global__ void __launch_bounds__(poly_max_block(G, J), 1)
                     p[j][k] = a.p0 ? a.p0[(size_t)cid[j] * K + k]
                                    : rng_normal(a.seed, a.chain_base + cid[j], draw, k);
             // ---- force evaluation 0 (+ energy at q0) -----------------------------------
-            poly_grad_pass<K, G, J, true>(pm, srows, rows_per_chunk, n_chunks, g, q, graw, chi2);
+            grad_pass(std::true_type{}, q, graw, chi2);
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 if (a.gibbs_mode == BINFB_GIBBS_TAU_FIRST)
@@ -319,7 +472,7 @@ __global__ void __launch_bounds__(poly_max_block(G, J), 1)
                 for (int j = 0; j < J; ++j)
 #pragma unroll
                     for (int k = 0; k < K; ++k) q[j][k] = fmaf(eps[j], p[j][k], q[j][k]);
-                poly_grad_pass<K, G, J, false>(pm, srows, rows_per_chunk, n_chunks, g, q, graw, chi2);
+                grad_pass(std::false_type{}, q, graw, chi2);
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
                     poly_force<K>(pm, q[j], graw[j], beta[j] * tau[j], f);
@@ -332,7 +485,7 @@ __global__ void __launch_bounds__(poly_max_block(G, J), 1)
             for (int j = 0; j < J; ++j)
 #pragma unroll
                 for (int k = 0; k < K; ++k) q[j][k] = fmaf(eps[j], p[j][k], q[j][k]);
-            poly_grad_pass<K, G, J, true>(pm, srows, rows_per_chunk, n_chunks, g, q, graw, chi2);
+            grad_pass(std::true_type{}, q, graw, chi2);
             const bool last = tr == a.n_traj - 1;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
@@ -383,7 +536,8 @@ __global__ void __launch_bounds__(poly_max_block(G, J), 1)
                 for (int j = 0; j < J; ++j)
                     if (valid[j] && g == 0 && acc[j])
                         for (int k = 0; k < K; ++k) a.q[(size_t)cid[j] * K + k] = q[j][k];
-                __syncwarp();
+                if (UR && G > 1) set_bar(map.bar_id, G * 32);  // the tuple's other lanes sit in other warps
+                else __syncwarp();
             }
         }
 #pragma unroll
@@ -414,18 +568,19 @@ __global__ void __launch_bounds__(poly_max_block(G, J), 1)
     }
 }
 
-template <int K, int G, int J>
+template <int K, int G, int J, bool UR = false>
 __global__ void __launch_bounds__(poly_max_block(G, J), 1)
     poly_grad_kernel(PolyDev pm, GradArgs a, int iters, int rows_per_chunk, int n_chunks) {
     extern __shared__ __align__(16) float srows[];
     constexpr int S = PolyRow<K>::STRIDE;
-    if (n_chunks == 1) {
+    if (!UR && n_chunks == 1) {
         poly_load_rows(srows, pm.rows, pm.N * S);
         __syncthreads();
     }
-    const int g = threadIdx.x % G;
-    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const long long n_groups = ((long long)gridDim.x * blockDim.x) / G;
+    PolyMap<G, UR> map;
+    map.template init<K, J>(srows);
+    const int g = map.g;
+    const long long group = map.group, n_groups = map.n_groups;
     for (int it = 0; it < iters; ++it) {
         const long long tuple = (long long)it * n_groups + group;
         int cid[J];
@@ -440,7 +595,10 @@ __global__ void __launch_bounds__(poly_max_block(G, J), 1)
 #pragma unroll
             for (int k = 0; k < K; ++k) q[j][k] = a.q[(size_t)cid[j] * K + k];
         }
-        poly_grad_pass<K, G, J, true>(pm, srows, rows_per_chunk, n_chunks, g, q, graw, chi2);
+        if constexpr (UR)
+            poly_grad_pass_ur<K, G, J, true>(pm, map.scratch, it & 1, g, map.lane, map.bar_id, q, graw, chi2);
+        else
+            poly_grad_pass<K, G, J, true>(pm, srows, rows_per_chunk, n_chunks, g, q, graw, chi2);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             if (!valid[j] || g != 0) continue;
@@ -478,6 +636,7 @@ __global__ void poly_forward_kernel(const float *__restrict__ rows, int N, const
 // ---------------------------------------------------------------------------------------------
 struct PolyPlan {
     int G, J, grid, block, iters, rows_per_chunk, n_chunks;
+    int ur;  // uniform-row mapping: G = warps per set
     size_t smem;
 };
 
@@ -504,6 +663,24 @@ static PolyPlan poly_plan(const PolyModel &m, int C, int sm_count, int smem_opti
         max_block = poly_max_block(G, 4);
     }
     pl.G = G;
+    // uniform-row mapping (see poly_grad_pass_ur): K = 4, packed chain pairs, the rows fit the constant bank
+    pl.ur = m.K == 4 && pl.J == 2 && G <= 8 && m.opt_ur != 0 &&
+            (size_t)m.N * m.stride * sizeof(float) <= (size_t)POLY_CROWS_BYTES;
+    if (pl.ur) {
+        const int unit = 32 * G;  // threads of one set
+        max_block = (max_block / unit) * unit;
+        const long long sets = (tuples + 31) / 32;
+        long long grid = sets >= sm_count ? sm_count : sets;
+        long long spc = (sets + grid - 1) / grid;  // sets per CTA
+        if (spc * unit > max_block) spc = max_block / unit;
+        if (m.opt_block > 0 && m.opt_block % unit == 0 && m.opt_block <= max_block) spc = m.opt_block / unit;
+        pl.grid = (int)grid, pl.block = (int)(spc * unit);
+        const long long n_groups = grid * spc * 32;
+        pl.iters = (int)((tuples + n_groups - 1) / n_groups);
+        pl.rows_per_chunk = m.N, pl.n_chunks = 1;
+        pl.smem = G > 1 ? (size_t)spc * PolyUrScratch<4, 8, 2>::BYTES * G / 8 : 0;
+        return pl;
+    }
     const long long threads = tuples * G;
     long long grid = threads >= 32LL * sm_count ? sm_count : (threads + 31) / 32;
     long long block = (threads + grid - 1) / grid;
@@ -536,10 +713,31 @@ static PolyDev poly_dev(const PolyModel &m) {
     return d;
 }
 
+// The constant bank holds the rows of ONE polynomial model per device.  A launch of another model rebinds
+// it after a device-wide synchronize (kernels of the previous owner may still be reading); the mutex is held
+// across the launch so that a concurrent caller cannot rebind between the check and the launch.  A sampler
+// that keeps using one model never pays for this.
+static std::mutex g_crow_mutex;
+static unsigned long long g_crow_owner[64];
+
 template <typename Kern, typename Args>
 static int poly_launch_one(Kern kern, const PolyModel &m, const Args &a, const PolyPlan &pl,
                            cudaStream_t s) {
     BINFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    if (pl.ur) {
+        int dev = 0;
+        BINFB_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(g_crow_mutex);
+        if (g_crow_owner[dev & 63] != m.uid) {
+            BINFB_CUDA(cudaDeviceSynchronize());
+            BINFB_CUDA(cudaMemcpyToSymbol(c_poly_rows, m.rows, (size_t)m.N * m.stride * sizeof(float), 0,
+                                          cudaMemcpyDeviceToDevice));
+            g_crow_owner[dev & 63] = m.uid;
+        }
+        kern<<<pl.grid, pl.block, pl.smem, s>>>(poly_dev(m), a, pl.iters, pl.rows_per_chunk, pl.n_chunks);
+        BINFB_CUDA(cudaGetLastError());
+        return BINFB_OK;
+    }
     kern<<<pl.grid, pl.block, pl.smem, s>>>(poly_dev(m), a, pl.iters, pl.rows_per_chunk, pl.n_chunks);
     BINFB_CUDA(cudaGetLastError());
     return BINFB_OK;
@@ -573,6 +771,14 @@ static int poly_launch_one(Kern kern, const PolyModel &m, const Args &a, const P
             if (pl.J == 4) {                                                                \
                 if (pl.G == 8) return poly_launch_one(KERNEL<4, 8, 4>, m, a, pl, s);         \
                 return poly_launch_one(KERNEL<4, 4, 4>, m, a, pl, s);                        \
+            } else if (pl.J == 2 && pl.ur) {                                                \
+                switch (pl.G) {                                                             \
+                    case 1: return poly_launch_one(KERNEL<4, 1, 2, true>, m, a, pl, s);      \
+                    case 2: return poly_launch_one(KERNEL<4, 2, 2, true>, m, a, pl, s);      \
+                    case 4: return poly_launch_one(KERNEL<4, 4, 2, true>, m, a, pl, s);      \
+                    case 8: return poly_launch_one(KERNEL<4, 8, 2, true>, m, a, pl, s);      \
+                    default: break;                                                         \
+                }                                                                           \
             } else if (pl.J == 2) {                                                         \
                 POLY_DISPATCH_G_FULL(KERNEL, 4, 2)                                           \
             } else {                                                                        \

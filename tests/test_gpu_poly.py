@@ -67,12 +67,56 @@ def test_all_template_shapes_agree(gpu):
             if j == 4 and grp not in (4, 8):
                 continue
             m = make_model(g)
-            m.set_option("poly.group", grp), m.set_option("poly.chains_per_thread", j)
-            r = m.hmc_run(g["q0"], 2.5, float(g["timestep"]), 20, p0=g["p0"], u=g["u"], want_end=True)
-            if base is None:
-                base = r
-            assert np.all(np.abs(r["q_end"] - base["q_end"]) <= 2e-3 * inf_norm(base["q_end"]))
-            np.testing.assert_allclose(r["e_before"], base["e_before"], rtol=1e-6)
+            for ur in ((1, 0) if (j == 2 and grp <= 8) else (1,)):   # uniform-row mapping on / off
+                m.set_option("poly.group", grp), m.set_option("poly.chains_per_thread", j)
+                m.set_option("poly.uniform_rows", ur)
+                r = m.hmc_run(g["q0"], 2.5, float(g["timestep"]), 20, p0=g["p0"], u=g["u"], want_end=True)
+                if base is None:
+                    base = r
+                assert np.all(np.abs(r["q_end"] - base["q_end"]) <= 2e-3 * inf_norm(base["q_end"]))
+                np.testing.assert_allclose(r["e_before"], base["e_before"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["poly_n1000_L5", "poly_n77_mode", "poly_n20"])
+@pytest.mark.parametrize("warps", [1, 2, 4, 8])
+def test_uniform_row_mapping(gpu, name, warps):
+    """the uniform-row mapping (rows in constant memory, W warps per chain set, cross-warp reduction in
+    shared memory) against the golden vectors: log-prob / gradient, trajectories, several trajectories
+    per launch with rejections (the state array is the rejection fallback across warps), ragged chain
+    counts, row counts that do not divide by W, and two models taking turns on the constant bank"""
+    g = load_golden(name)
+    m = make_model(g)
+    m.set_option("poly.chains_per_thread", 2), m.set_option("poly.group", warps)
+    logp, grad, chi2 = m.logprob_grad(g["q0"], float(g["tau"]))
+    np.testing.assert_allclose(logp, g["log_prob"], rtol=1e-5)
+    assert np.all(np.abs(grad - g["gradient"]) <= 1e-4 * inf_norm(g["gradient"]))
+    L = int(g["nsteps"])
+    r = m.hmc_run(g["q0"], float(g["tau"]), float(g["timestep"]), L, p0=g["p0"], u=g["u"], want_end=True)
+    tol = 1e-4 if L <= 7 else 2e-3
+    assert np.all(np.abs(r["q_end"] - g["q_end"]) <= tol * inf_norm(g["q_end"]))
+    np.testing.assert_allclose(r["e_before"], g["e_before"], rtol=1e-5)
+    margin = np.abs(np.log(g["u"]) + g["e_after"] - g["e_before"])
+    assert np.array_equal(r["accepted"][margin > 0.05], g["accepted"][margin > 0.05])
+    # a second model with other data in between, then the same runs with the regular mapping: a ragged
+    # number of chains (not a multiple of 64), 3 trajectories per launch with a step size that rejects a lot
+    other = make_model(dict(g, ys=g["ys"][::-1].copy()))
+    other.set_option("poly.chains_per_thread", 2), other.set_option("poly.group", warps)
+    rng = np.random.RandomState(5)
+    C = 203
+    q0 = g["q0"][0] + 0.05 * rng.normal(size=(C, 4))
+    ref = make_model(g)
+    ref.set_option("poly.chains_per_thread", 2), ref.set_option("poly.group", warps)
+    ref.set_option("poly.uniform_rows", 0)
+    eps = 4.0 * float(g["timestep"])
+    outs = []
+    for model in (m, ref):
+        other.logprob_grad(q0, 1.0)
+        outs.append(model.hmc_run(q0, float(g["tau"]), eps, 6, n_traj=3, seed=11, want_end=True))
+    a, b = outs
+    same = a["n_accepted"] == b["n_accepted"]
+    assert same.mean() > 0.95 and 0.02 < (a["n_accepted"] < 3).mean()
+    assert np.all(np.abs(a["q"][same] - b["q"][same]) <= 2e-3 * inf_norm(b["q"][same]))
+    np.testing.assert_allclose(a["e_before"][same], b["e_before"][same], rtol=1e-4)
 
 
 @pytest.mark.parametrize("k", [1, 2, 3, 5, 6, 8])
