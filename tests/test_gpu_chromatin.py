@@ -301,3 +301,45 @@ def test_excluded_volume_through_the_python_api(gpu):
     assert cond.log_prob(structure=q) == pytest.approx(o.log_prob(q, 40.0), rel=1e-5)
     ref = o.gradient(q, 40.0)
     assert np.max(np.abs(cond.gradient(structure=q) - ref)) <= 1e-4 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("alpha,d_c", [(0.35, 6.0), (1.0, 2.0), (6.5, 1.2), (12.0, 3.0)])
+def test_other_exponent_slopes_vs_oracle(gpu, alpha, d_c):
+    """the pair loop works on positions scaled by alpha*log2(e) (pair_block.cuh, SCALED): every constant
+    that carries a length (softening, backbone, conformational prior, excluded volume, drift) has to follow"""
+    from binf_b200 import _cabi
+    n, C, L = 70, 7, 4
+    rng = np.random.RandomState(3)
+    X = np.cumsum(rng.normal(size=(n, 3)), axis=0)
+    iu = np.triu_indices(n, 1)
+    d = np.sqrt(((X[iu[0]] - X[iu[1]]) ** 2).sum(-1))
+    y = (1.0 / (1.0 + np.exp(np.minimum(alpha * (d - d_c), 60.0))) + 0.05 * rng.normal(size=d.shape)).astype(np.float32)
+    kw = dict(conf_s=15.0, gamma_shape=2.0, gamma_rate=0.5, ev_k=1.5, ev_d=1.4)
+    o = chrom.ChromatinModel(n, y, alpha, d_c, 3.0, 1.1, **kw)
+    m = _cabi.Model.chromatin(n, y, alpha, d_c, 3.0, 1.1, **kw)
+    q = X.reshape(-1)[None] + 0.1 * rng.normal(size=(C, 3 * n))
+    tau, beta = rng.uniform(20, 60, size=C), rng.uniform(0.3, 1.0, size=C)
+    logp, grad, chi2 = m.logprob_grad(q, tau, beta)
+    for c in range(C):
+        assert logp[c] == pytest.approx(o.log_prob(q[c], tau[c], beta[c]), rel=1e-5)
+        ref = o.gradient(q[c], tau[c], beta[c])
+        assert np.all(np.abs(grad[c] - ref) <= 1e-4 * np.max(np.abs(ref)))
+        assert chi2[c] == pytest.approx(o.chi2(q[c]), rel=1e-5)
+    p0, u = rng.normal(size=q.shape), rng.uniform(size=C)
+    eps = 2e-3
+    r = m.hmc_run(q, tau, eps, L, beta=beta, p0=p0, u=u, want_end=True)
+    for c in range(C):
+        ref = port.hmc_sample(lambda x: o.log_prob(x, tau[c], beta[c]), lambda x: o.gradient(x, tau[c], beta[c]),
+                              q[c], eps, L, p0[c], u[c])
+        assert np.max(np.abs(r["q_end"][c] - ref["q_end"])) <= 1e-4 * np.max(np.abs(ref["q_end"]))
+        assert np.max(np.abs(r["p_end"][c] - ref["p_end"])) <= 1e-4 * max(1.0, np.max(np.abs(ref["p_end"])))
+        assert r["e_before"][c] == pytest.approx(ref["e_before"], rel=1e-5)
+        assert abs((r["e_after"][c] - r["e_before"][c]) - (ref["e_after"] - ref["e_before"])) <= 5e-3
+
+
+def test_exponent_slope_limits_are_checked(gpu):
+    from binf_b200 import _cabi
+    y = np.zeros(10 * 9 // 2, dtype=np.float32)
+    for alpha, d_c in [(0.0, 2.5), (-2.0, 2.5), (50.0, 2.5), (float("nan"), 2.5)]:
+        with pytest.raises((_cabi.BinfB200Error, ValueError)):
+            _cabi.Model.chromatin(10, y, alpha, d_c, 3.0, 1.0)
