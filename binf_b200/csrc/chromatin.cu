@@ -55,6 +55,12 @@ namespace binfb {
 #ifndef BINFB_PREFETCH
 #define BINFB_PREFETCH 0  // load the next step's partner positions one step ahead
 #endif
+#ifndef BINFB_WRAP2
+#define BINFB_WRAP2 0  // partner address wraps by comparing with the end address (no step counter)
+#endif
+#ifndef BINFB_DEFER
+#define BINFB_DEFER 0  // consume the ticket of a stage release one stage later (hides the shared-memory atomic's latency)
+#endif
 #ifndef BINFB_YJIT
 #define BINFB_YJIT 0  // load each row's contacts right before its two packs instead of all 16 up front
 #endif
@@ -217,6 +223,23 @@ __device__ __forceinline__ void ring_release(const Ring &ring, uint32_t gi, int 
     }
 }
 
+// the two halves of ring_release, for callers that look at the ticket one stage later (BINFB_DEFER)
+template <int NS>
+__device__ __forceinline__ uint32_t ring_arrive(const Ring &ring, uint32_t gi) {
+    const uint32_t c = ring.full + NS * 8u + (gi & (NS - 1)) * 4u;
+    uint32_t old;
+    asm volatile("atom.relaxed.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(c) : "memory");
+    return old;
+}
+template <int STAGE_BYTES, int NS>
+__device__ __forceinline__ void ring_finish(const Ring &ring, uint32_t gi, int s_local, uint32_t old) {
+    if (old == (uint32_t)ring.n_warps - 1u) {
+        const uint32_t c = ring.full + NS * 8u + (gi & (NS - 1)) * 4u;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(c), "r"(0u) : "memory");
+        if (s_local + NS < ring.n_stage_pass) ring_issue<STAGE_BYTES, NS>(ring, gi + NS, s_local + NS);
+    }
+}
+
 // The pair sweep of one chain, shared by the R warps ("roles") of that chain.  Role r owns the
 // partner steps k in [r*Lr, (r+1)*Lr) of every row block; SPR = SS/R of them per ring stage, and
 // Lr is a multiple of SPR so that a stage never straddles two row blocks.  Fills frc with
@@ -372,6 +395,7 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
     uint32_t stage_idx = stage_base;
     const uint32_t ylane = pin_reg(ring.ystage + (uint32_t)role * STEP_BYTES + (uint32_t)lane * 16u);
     SweepRegs s;
+    uint32_t ticket = 0xffffffffu;  // BINFB_DEFER: result of the previous stage's release (none yet)
     s.chi2 = 0.0, s.ev = 0.0;
     s.dev = cd.ev_d * cd.S, s.cev = cev * (cd.invS * cd.invS * cd.invS);  // scaled units (pair_block.cuh)
 
@@ -397,7 +421,11 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
             if (b >= Q) b -= Q;
             s.paddr = pos_base + (uint32_t)b * 48u;
             s.pwrap = pos_base;
+#if BINFB_WRAP2
+            s.wrap = (int)(pos_base + (uint32_t)Q * 48u);  // end address
+#else
             s.wrap = Q - b;
+#endif
 #if BINFB_PREFETCH
             s.nxt[0] = lds4<0>(s.paddr), s.nxt[1] = lds4<16>(s.paddr), s.nxt[2] = lds4<32>(s.paddr);
 #endif
@@ -427,13 +455,24 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
                     }
                     if (GENERIC) ++s.k;
                     s.paddr += 48u;
+#if BINFB_WRAP2
+                    if (s.paddr == (uint32_t)s.wrap) s.paddr = s.pwrap;
+#else
                     if (--s.wrap == 0) s.paddr -= (uint32_t)Q * 48u, s.wrap = Q;
+#endif
                     // LOCKSTEP: all roles of the chain finish step s before any starts s + 1, so their
                     // partner offsets always differ by exactly a multiple of Lr >= 32 (see chrom_plan)
                     if (LOCKSTEP) chain_bar(bar_id, R * 32);
                     else __syncwarp();
                 }
+#if BINFB_DEFER
+                if (elect_one()) {
+                    ring_finish<STAGE_BYTES, NS>(ring, stage_idx - 1u, (int)(stage_idx - stage_base) - 1, ticket);
+                    ticket = ring_arrive<NS>(ring, stage_idx);
+                }
+#else
                 if (elect_one()) ring_release<STAGE_BYTES, NS>(ring, stage_idx, (int)(stage_idx - stage_base));
+#endif
                 ++stage_idx;
             }
             if (!GENERIC) s.k += (sg_end - sg_begin) * SPR;
@@ -471,6 +510,10 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
         if (R > 1) chain_bar(bar_id, R * 32);
         else __syncwarp();
     }
+#if BINFB_DEFER
+    if (elect_one())
+        ring_finish<STAGE_BYTES, NS>(ring, stage_idx - 1u, (int)(stage_idx - stage_base) - 1, ticket);
+#endif
     stage_idx_io = stage_idx;
     ev_out = s.ev;
     return s.chi2;

@@ -207,6 +207,40 @@ __global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) chi_tot += g[r][0].x + g[r][0].y + g[r][1].x + g[r][1].y + g[r][2].x + g[r][2].y;
+    } else if (VAR == 11) {
+        // 4 x 2 tile (own quad x half a partner quad) at positions pre-scaled by A: half the registers for
+        // partner data, so that 24 warps fit the register file (80 registers per thread)
+        float2 nx2[4], ny2[4], nz2[4];
+        float g[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            nx2[r] = mk2(-xi[r], -xi[r]), ny2[r] = mk2(-yi[r], -yi[r]), nz2[r] = mk2(-zi[r], -zi[r]);
+            g[r][0] = g[r][1] = g[r][2] = 0.f;
+        }
+        const float2 A2 = mk2(A * A * PAIR_SOFT, A * A * PAIR_SOFT);
+        const float2 B2 = mk2(-exp2f(B), -exp2f(B));
+        float2 *xs2 = (float2 *)xs4, *ys2 = (float2 *)ys4, *zs2 = (float2 *)zs4;
+        float2 *fx2p = (float2 *)fx4, *fy2p = (float2 *)fy4, *fz2p = (float2 *)fz4;
+        int hb = 2 * b;
+        for (int st = 0; st < 2 * steps; ++st) {
+            const float2 xj = xs2[hb], yj = ys2[hb], zj = zs2[hb];
+            float2 fx = fx2p[hb], fy = fy2p[hb], fz = fz2p[hb];
+            const float4 *yb = (const float4 *)ybuf + (st & 7) * 64 + lane;
+            float2 chi2 = mk2(0.f, 0.f);
+            const float4 ya = yb[0], ybb = yb[32];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float2 y2 = r == 0 ? mk2(ya.x, ya.y) : r == 1 ? mk2(ya.z, ya.w) : r == 2 ? mk2(ybb.x, ybb.y) : mk2(ybb.z, ybb.w);
+                pair_packed_gs<false, false, true>(nx2[r], ny2[r], nz2[r], xj, yj, zj, y2, A2, B2,
+                                                   g[r][0], g[r][1], g[r][2], fx, fy, fz, chi2);
+            }
+            fx2p[hb] = fx, fy2p[hb] = fy, fz2p[hb] = fz;
+            chi_tot += chi2.x + chi2.y;
+            if (++hb >= 2 * Q) hb = 0;
+            __syncwarp();
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) chi_tot += g[r][0] + g[r][1] + g[r][2];
     } else if (VAR == 9 || VAR == 10) {
         // the kernel's shape: packed columns, scalar row accumulators; VAR 10: positions pre-scaled by A
         float2 nx2[4], ny2[4], nz2[4];
@@ -294,9 +328,9 @@ __global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float
     if (threadIdx.x < 64) out[1 + blockIdx.x * 64 + threadIdx.x] = base[3 * n_pad + threadIdx.x];
 }
 
-template <int VAR, int NPOLY, int THREADS, int PAIRS = 16>
+template <int VAR, int NPOLY, int THREADS, int PAIRS = 16, int QQ = 250>
 void run(const char *name, const float *init, float *out, int sms, double clk) {
-    const int Q = 250, steps = 4000;
+    const int Q = QQ, steps = 4000;
     const int chains = THREADS / 64;
     const size_t smem = (2048 + (size_t)chains * 6 * 4 * Q) * sizeof(float);
     cudaFuncSetAttribute(pairbench<VAR, NPOLY, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -326,8 +360,10 @@ int main() {
     float *init, *out; cudaMalloc(&init, 4096 * 4); cudaMalloc(&out, (1 + 148 * 64) * 4);
     cudaMemcpy(init, h.data(), 4096 * 4, cudaMemcpyHostToDevice);
     const int sms = p.multiProcessorCount; const double g = clk / 1e6;
-    run<1, 0, 512>("packed 4x4", init, out, sms, g);
-    run<9, 0, 512>("packed 4x4, scalar row sums (kernel shape)", init, out, sms, g);
-    run<10, 0, 512>("same, positions pre-scaled by A", init, out, sms, g);
+    run<10, 0, 512>("4x4 tile, scaled positions, 16 warps", init, out, sms, g);
+    run<10, 0, 512, 16, 160>("4x4 tile, scaled, 16 warps, Q=160", init, out, sms, g);
+    run<11, 0, 512, 16, 160>("4x2 tile, scaled, 16 warps, Q=160", init, out, sms, g);
+    run<11, 0, 768, 16, 160>("4x2 tile, scaled, 24 warps, Q=160", init, out, sms, g);
+    run<11, 0, 640, 16, 160>("4x2 tile, scaled, 20 warps, Q=160", init, out, sms, g);
     return 0;
 }

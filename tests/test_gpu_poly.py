@@ -316,3 +316,21 @@ def test_error_behaviour_and_edge_shapes(gpu):
     r = big.hmc_run(q, 0.7, 0.002, 4, p0=p0, u=u, want_end=True)
     o = port.hmc_sample(lambda c: pb.log_prob(c, 0.7), lambda c: pb.gradient(c, 0.7), q, 0.002, 4, p0, u)
     assert np.all(np.abs(r["q_end"] - o["q_end"]) <= 1e-4 * np.maximum(inf_norm(o["q_end"]), 1.0))
+
+
+def test_uniform_row_mapping_many_chains(gpu):
+    """more chains than one wave of chain sets (several iterations per thread, one warp per set): the
+    uniform-row and the regular mapping agree chain by chain"""
+    g = load_golden("poly_n1000_L5")
+    C = 600001
+    rng = np.random.RandomState(2)
+    q0 = g["q0"][0] + 0.05 * rng.normal(size=(C, 4))
+    outs = []
+    for ur in (1, 0):
+        m = make_model(g)
+        m.set_option("poly.uniform_rows", ur)
+        outs.append(m.hmc_run(q0, float(g["tau"]), float(g["timestep"]), 3, seed=3, want_end=True))
+    a, b = outs
+    assert np.all(np.abs(a["q_end"] - b["q_end"]) <= 1e-4 * inf_norm(b["q_end"]))
+    np.testing.assert_allclose(a["e_before"], b["e_before"], rtol=1e-5)
+    assert (a["accepted"] == b["accepted"]).mean() > 0.999
