@@ -169,6 +169,30 @@ __device__ __forceinline__ void pair_packed_gs(float2 nx2, float2 ny2, float2 nz
     if (ENERGY) chi2 = fma2(rs, rs, chi2);
 }
 
+// scaled positions + scalar row accumulators + ONE reciprocal per pack (1/a = b/(ab), 1/b = a/(ab)): 2.5 MUFU
+// per pair.  The exponent is clamped to 30 so that (1 + C 2^d)^2 cannot overflow (m < 2^-30/C there).
+template <bool ENERGY>
+__device__ __forceinline__ void pair_packed_gs_sr(float2 nx2, float2 ny2, float2 nz2, float2 xj2, float2 yj2,
+                                                  float2 zj2, float2 y2, float2 A2, float2 B2, float &gx, float &gy,
+                                                  float &gz, float2 &fx2, float2 &fy2, float2 &fz2, float2 &chi2) {
+    const float2 dx = add2(xj2, nx2), dy = add2(yj2, ny2), dz = add2(zj2, nz2);
+    const float2 r2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, A2)));
+    const float2 inv = mk2(mufu_rsqrt(r2.x), mufu_rsqrt(r2.y));
+    const float2 d = mul2(r2, inv);
+    const float2 e = mk2(mufu_ex2(fminf(d.x, 40.0f)), mufu_ex2(fminf(d.y, 40.0f)));
+    const float2 sn = fma2(e, B2, mk2(-1.f, -1.f));  // -(1 + e)
+    const float ip = mufu_rcp(sn.x * sn.y);          // 1 / ((1+e_x)(1+e_y)) > 0
+    const float2 mn = mul2(mk2(sn.y, sn.x), mk2(ip, ip));
+    const float2 rs = add2(mn, y2);
+    const float2 wn = fma2(mn, mn, mn);
+    const float2 coef = mul2(mul2(rs, wn), inv);
+    gx = fmaf(coef.y, dx.y, fmaf(coef.x, dx.x, gx));
+    gy = fmaf(coef.y, dy.y, fmaf(coef.x, dy.x, gy));
+    gz = fmaf(coef.y, dz.y, fmaf(coef.x, dz.x, gz));
+    fx2 = fma2(coef, dx, fx2), fy2 = fma2(coef, dy, fy2), fz2 = fma2(coef, dz, fz2);
+    if (ENERGY) chi2 = fma2(rs, rs, chi2);
+}
+
 // ---------------------------------------------------------------------------------------------
 // hybrid shape.  Measured on B200 (profiles/microbench/ffma2_operands.cu): FFMA2 with three distinct
 // register operands occupies the FMA pipe 3.04 cycles (register-bank reads), two-operand packed ops

@@ -86,7 +86,9 @@ int binfb_model_create_polynomial(const double *xs, const double *ys, int n_data
 /* Chromatin bead chain with a logistic contact forward model behind the reference's
  * AbstractForwardModel / GaussianErrorModel / AbstractPrior API (build-defined, SURVEY.md A.2;
  * the reference's Likelihood._evaluate_gradient, binf/pdf/likelihoods.py:148-155, is what the
- * pair kernel fuses).  y_pairs: host float32 [n(n-1)/2] in numpy.triu_indices(n, 1) order. */
+ * pair kernel fuses).  y_pairs: host float32 [n(n-1)/2] in numpy.triu_indices(n, 1) order.
+ * alpha > 0 and |alpha * d_c| <= 80 (BINFB_EINVAL otherwise): the pair loop works on positions scaled by
+ * alpha*log2(e) and folds 2^(-alpha d_c log2 e) into a multiplier that has to stay a normal float. */
 int binfb_model_create_chromatin(int n_beads, const float *y_pairs, double alpha, double d_c,
                                  double k_bb, double l0, double conf_s, double gamma_shape,
                                  double gamma_rate, unsigned flags, int device,
@@ -113,7 +115,7 @@ int binfb_model_info(const binfb_model *m, int *kind, int *dim, long long *n_dat
 /* update the Gamma prior on the precision (it enters log_prob and the Gibbs update only) */
 int binfb_model_set_gamma_prior(binfb_model *m, double shape, double rate);
 /* tuning knobs ("poly.group", "poly.chains_per_thread", "poly.block", "chrom.warps"; value < 0 restores
- * the heuristic) and model extras: "chrom.ev_k", "chrom.ev_d" switch on the excluded-volume prior
+ * the heuristic; "poly.uniform_rows" = 0 keeps the data rows in shared memory instead of the constant bank) and model extras: "chrom.ev_k", "chrom.ev_d" switch on the excluded-volume prior
  * -k_ev sum_{i<j} max(0, d_ev - d_ij)^4 of the chromatin model, whose force is
  * fused into the pair loop */
 int binfb_model_set_option(binfb_model *m, const char *key, double value);

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) chi_tot += g[r][0] + g[r][1] + g[r][2];
-    } else if (VAR == 9 || VAR == 10) {
+    } else if (VAR == 9 || VAR == 10 || VAR == 12) {
         // the kernel's shape: packed columns, scalar row accumulators; VAR 10: positions pre-scaled by A
         float2 nx2[4], ny2[4], nz2[4];
         float g[4][3];
@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float
             nx2[r] = mk2(-xi[r], -xi[r]), ny2[r] = mk2(-yi[r], -yi[r]), nz2[r] = mk2(-zi[r], -zi[r]);
             g[r][0] = g[r][1] = g[r][2] = 0.f;
         }
-        const float2 A2 = VAR == 10 ? mk2(A * A * PAIR_SOFT, A * A * PAIR_SOFT) : mk2(A, A);
-        const float2 B2 = VAR == 10 ? mk2(-exp2f(B), -exp2f(B)) : mk2(B, B);
+        const float2 A2 = VAR >= 10 ? mk2(A * A * PAIR_SOFT, A * A * PAIR_SOFT) : mk2(A, A);
+        const float2 B2 = VAR >= 10 ? mk2(-exp2f(B), -exp2f(B)) : mk2(B, B);
         for (int st = 0; st < steps; ++st) {
             const float4 xj = xs4[b], yj = ys4[b], zj = zs4[b];
             float4 fx = fx4[b], fy = fy4[b], fz = fz4[b];
@@ -267,8 +267,12 @@ __global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const float2 y2 = h ? mk2(yv.z, yv.w) : mk2(yv.x, yv.y);
-                    pair_packed_gs<false, false, VAR == 10>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2,
-                                                            g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
+                    if (VAR == 12)
+                        pair_packed_gs_sr<false>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2,
+                                                 g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
+                    else
+                        pair_packed_gs<false, false, VAR == 10>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2,
+                                                                g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
                 }
             }
             fx4[b] = make_float4(fx2[0].x, fx2[0].y, fx2[1].x, fx2[1].y);
@@ -361,9 +365,7 @@ int main() {
     cudaMemcpy(init, h.data(), 4096 * 4, cudaMemcpyHostToDevice);
     const int sms = p.multiProcessorCount; const double g = clk / 1e6;
     run<10, 0, 512>("4x4 tile, scaled positions, 16 warps", init, out, sms, g);
-    run<10, 0, 512, 16, 160>("4x4 tile, scaled, 16 warps, Q=160", init, out, sms, g);
-    run<11, 0, 512, 16, 160>("4x2 tile, scaled, 16 warps, Q=160", init, out, sms, g);
-    run<11, 0, 768, 16, 160>("4x2 tile, scaled, 24 warps, Q=160", init, out, sms, g);
-    run<11, 0, 640, 16, 160>("4x2 tile, scaled, 20 warps, Q=160", init, out, sms, g);
+    run<12, 0, 512>("same + one rcp per pack (2.5 MUFU per pair)", init, out, sms, g);
+    run<12, 0, 384>("same + one rcp per pack, 12 warps", init, out, sms, g);
     return 0;
 }
