@@ -730,8 +730,12 @@ static int poly_launch_one(Kern kern, const PolyModel &m, const Args &a, const P
         std::lock_guard<std::mutex> lock(g_crow_mutex);
         if (g_crow_owner[dev & 63] != m.uid) {
             BINFB_CUDA(cudaDeviceSynchronize());
-            BINFB_CUDA(cudaMemcpyToSymbol(c_poly_rows, m.rows, (size_t)m.N * m.stride * sizeof(float), 0,
-                                          cudaMemcpyDeviceToDevice));
+            // device-to-device copies do not synchronize with the host and the legacy stream does not order
+            // with the (non-blocking) caller streams: copy on the launch stream and wait for it, so that a
+            // later launch of this model on any other stream finds the rows in place
+            BINFB_CUDA(cudaMemcpyToSymbolAsync(c_poly_rows, m.rows, (size_t)m.N * m.stride * sizeof(float), 0,
+                                               cudaMemcpyDeviceToDevice, s));
+            BINFB_CUDA(cudaStreamSynchronize(s));
             g_crow_owner[dev & 63] = m.uid;
         }
         kern<<<pl.grid, pl.block, pl.smem, s>>>(poly_dev(m), a, pl.iters, pl.rows_per_chunk, pl.n_chunks);
