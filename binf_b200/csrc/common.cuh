@@ -52,16 +52,21 @@ __host__ __device__ __forceinline__ double u64_to_unit_open0(uint32_t hi, uint32
     return ((double)v + 1.0) * (1.0 / 9007199254740992.0);
 }
 
-// standard normal for (chain, draw, element e) -- the momentum stream
+// standard normal for (chain, draw, element e) -- the momentum stream.  One Philox block serves the four
+// elements 4b .. 4b+3 (two Box-Muller pairs, cosine and sine branch of each), so a caller that draws
+// consecutive elements with compile-time indices (the K coefficients of a chain) pays for one block, one
+// logarithm / square root and one sincos per two normals; a caller with a run-time index pays what a private
+// block per element would cost.
 __device__ __forceinline__ float rng_normal(uint64_t seed, uint64_t chain, uint64_t draw,
                                             uint32_t elem) {
     const u32x4 r = philox4x32_10(seed ^ (draw >> 32) * 0x9E3779B97F4A7C15ull, chain,
-                                  (uint32_t)draw, ((uint32_t)RNG_MOMENTUM << 24) | elem);
-    const float u1 = u32_to_unit_open0(r.x);
-    const float u2 = u32_to_unit(r.y);
+                                  (uint32_t)draw, ((uint32_t)RNG_MOMENTUM << 24) | (elem >> 2));
+    const bool second = (elem & 2u) != 0u;
+    const float u1 = u32_to_unit_open0(second ? r.z : r.x);
+    const float u2 = u32_to_unit(second ? r.w : r.y);
     float s, c;
     sincospif(2.0f * u2, &s, &c);
-    return sqrtf(-2.0f * logf(u1)) * c;
+    return sqrtf(-2.0f * logf(u1)) * ((elem & 1u) ? s : c);
 }
 
 __device__ __forceinline__ float rng_uniform(uint64_t seed, uint64_t chain, uint64_t draw,
