@@ -19,11 +19,131 @@
 // 183-191; binf/example/samplers.py:27-51).  Error model: GaussianErrorModel
 // (binf/example/likelihood.py:54-61); priors: Gaussian on theta, Gamma on the precision.
 //
-// Compile-time parameters (-D): GEN_K, GEN_XD, GEN_G (power of two <= 32).
+// Compile-time parameters (-D): GEN_K, GEN_XD, GEN_G (power of two <= 32), GEN_UR.
+//
+// GEN_UR = 1, the uniform-row mapping (like poly.cu): the data rows sit in this module's own constant bank,
+// lane l of a warp owns chain l of its set and every lane walks the same rows, so that a row arrives through
+// the uniform datapath (LDCU, no per-lane loads) and enters the user's arithmetic as uniform-register
+// operands; the G warps of a set own the same 32 chains and split the rows into G contiguous ranges, and the
+// K gradient sums (+ chi^2) of a pass are combined through shared memory in a fixed order, so that all G
+// warps keep bitwise identical q, p.  GEN_UR = 0: a chain is owned by G lanes that stride over rows in
+// global memory (data sets that do not fit the constant bank).
 constexpr int K = GEN_K, XD = GEN_XD, G = GEN_G;
+#ifndef GEN_UR
+#define GEN_UR 0
+#endif
+constexpr bool UR = GEN_UR != 0;
+constexpr int GEN_CROW_FLOATS = 12288;  // 48 KiB of the constant bank
+#if GEN_UR
+__constant__ float gen_crows[GEN_CROW_FLOATS];
+#endif
+constexpr int GEN_BLOCK = 256;
+constexpr int GEN_SETS = UR ? (GEN_BLOCK / 32) / G : 1;  // chain sets per block
 
-__device__ __forceinline__ void gen_pass(const GenDev &gm, int g, const float (&q)[K], float (&graw)[K],
-                                         double &chi2) {
+// who am I: g = share of the rows (lane in the group, or warp in the set), c = chain, leader = g == 0
+struct GenMap {
+    int g, lane, bar_id, set;
+    long long c;
+    __device__ __forceinline__ void init() {
+        if (UR) {
+            // broadcast from lane 0: the compiler keeps everything derived from it in uniform registers
+            const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+            set = warp / G, g = warp % G, lane = threadIdx.x & 31, bar_id = 1 + set;
+            c = ((long long)blockIdx.x * GEN_SETS + set) * 32 + lane;
+        } else {
+            g = threadIdx.x % G, lane = 0, bar_id = 0, set = 0;
+            c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+        }
+    }
+};
+
+__device__ __forceinline__ void gen_set_bar(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(G * 32) : "memory");
+}
+
+#if GEN_UR
+// one pass over this warp's share of the rows; `buf` alternates between passes (one barrier per pass: a
+// buffer is rewritten two passes later, after the barrier of the pass in between)
+// the scratch of the cross-warp reduction: ONE instance per kernel (static shared memory of a plain function,
+// not of the ENERGY template)
+typedef float GenSum[2][K][G][32];
+typedef double GenChi[2][G][32];
+__device__ __forceinline__ GenSum *gen_s_sum() {
+    __shared__ float s[GEN_SETS][2][K][G][32];
+    return s;
+}
+__device__ __forceinline__ GenChi *gen_s_chi() {
+    __shared__ double s[GEN_SETS][2][G][32];
+    return s;
+}
+// (ENERGY = false: chi^2 is not needed -- the L - 1 interior leapfrog steps -- and is returned as 0)
+template <bool ENERGY>
+__device__ __forceinline__ void gen_pass(const GenDev &gm, const GenMap &mp, int buf, const float (&q)[K],
+                                         float (&graw)[K], double &chi2) {
+    float (*s_sum)[2][K][G][32] = gen_s_sum();
+    double (*s_chi)[2][G][32] = gen_s_chi();
+    float gacc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) gacc[k] = 0.f;
+    float c32 = 0.f;
+    double c64 = 0.0;
+    const int rpw = (gm.N + G - 1) / G;
+    const int n0 = mp.g * rpw, n1 = min(gm.N, n0 + rpw);
+    int n = n0;
+    for (; n + 8 <= n1; n += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float xr[XD], dm[K];
+#pragma unroll
+            for (int j = 0; j < XD; ++j) xr[j] = gen_crows[(n + u) * gm.stride + j];
+            const float m = binfb_mock(q, xr, dm);
+            const float r = m - gen_crows[(n + u) * gm.stride + XD];
+#pragma unroll
+            for (int k = 0; k < K; ++k) gacc[k] = fmaf(r, dm[k], gacc[k]);   // J . (mock - y), likelihoods.py:155
+            if (ENERGY) c32 = fmaf(r, r, c32);
+        }
+        if (ENERGY) c64 += (double)c32, c32 = 0.f;
+    }
+    for (; n < n1; ++n) {
+        float xr[XD], dm[K];
+#pragma unroll
+        for (int j = 0; j < XD; ++j) xr[j] = gen_crows[n * gm.stride + j];
+        const float m = binfb_mock(q, xr, dm);
+        const float r = m - gen_crows[n * gm.stride + XD];
+#pragma unroll
+        for (int k = 0; k < K; ++k) gacc[k] = fmaf(r, dm[k], gacc[k]);
+        if (ENERGY) c32 = fmaf(r, r, c32);
+    }
+    if (ENERGY) c64 += (double)c32;
+    if (G == 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) graw[k] = gacc[k];
+        chi2 = c64;
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) s_sum[mp.set][buf][k][mp.g][mp.lane] = gacc[k];
+    if (ENERGY) s_chi[mp.set][buf][mp.g][mp.lane] = c64;
+    gen_set_bar(mp.bar_id);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < G; ++w) t += s_sum[mp.set][buf][k][w][mp.lane];
+        graw[k] = t;
+    }
+    double t = 0.0;
+    if (ENERGY) {
+#pragma unroll
+        for (int w = 0; w < G; ++w) t += s_chi[mp.set][buf][w][mp.lane];
+    }
+    chi2 = t;
+}
+#else
+template <bool ENERGY>
+__device__ __forceinline__ void gen_pass(const GenDev &gm, const GenMap &mp, int, const float (&q)[K],
+                                         float (&graw)[K], double &chi2) {
+    const int g = mp.g;
     float gacc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) gacc[k] = 0.f;
@@ -45,6 +165,7 @@ __device__ __forceinline__ void gen_pass(const GenDev &gm, int g, const float (&
     for (int k = 0; k < K; ++k) graw[k] = group_allreduce_sum<G>(gacc[k]);
     chi2 = group_allreduce_sum<G>(c64);
 }
+#endif
 
 // U(q) = -log p(q | tau) in float64 (binf/pdf/posteriors.py:141-151 summed components)
 __device__ __forceinline__ double gen_potential(const GenDev &gm, const float (&q)[K], double chi2, float tau,
@@ -77,9 +198,12 @@ __device__ __forceinline__ float gen_draw_tau(const HmcArgs &a, double n_data, d
     return (float)(gdraw / rate);
 }
 
-extern "C" __global__ void __launch_bounds__(256) gen_hmc_kernel(GenDev gm, HmcArgs a) {
-    const int g = threadIdx.x % G;
-    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_hmc_kernel(GenDev gm, HmcArgs a) {
+    GenMap mp;
+    mp.init();
+    const int g = mp.g;
+    const long long c = mp.c;
+    int pass = 0;
     const bool valid = c < a.C;
     const int cid = valid ? (int)c : a.C - 1;
     float q[K], p[K], graw[K], f[K];
@@ -96,7 +220,7 @@ extern "C" __global__ void __launch_bounds__(256) gen_hmc_kernel(GenDev gm, HmcA
 #pragma unroll
         for (int k = 0; k < K; ++k)
             p[k] = a.p0 ? a.p0[(size_t)cid * K + k] : rng_normal(a.seed, a.chain_base + cid, draw, k);   // hmc.py:146
-        gen_pass(gm, g, q, graw, chi2);
+        gen_pass<true>(gm, mp, pass++ & 1, q, graw, chi2);
         if (a.gibbs_mode == BINFB_GIBBS_TAU_FIRST)
             tau = gen_draw_tau(a, (double)gm.N, chi2, beta, a.chain_base + cid, cid, draw);
         chi2_cur = chi2;
@@ -110,14 +234,14 @@ extern "C" __global__ void __launch_bounds__(256) gen_hmc_kernel(GenDev gm, HmcA
         for (int s = 1; s < a.L; ++s) {                                              // hmc.py:118-120
 #pragma unroll
             for (int k = 0; k < K; ++k) q[k] = fmaf(eps, p[k], q[k]);
-            gen_pass(gm, g, q, graw, chi2);
+            gen_pass<false>(gm, mp, pass++ & 1, q, graw, chi2);
             gen_force(gm, q, graw, beta * tau, f);
 #pragma unroll
             for (int k = 0; k < K; ++k) p[k] = fmaf(-eps, f[k], p[k]);
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) q[k] = fmaf(eps, p[k], q[k]);                     // hmc.py:122
-        gen_pass(gm, g, q, graw, chi2);
+        gen_pass<true>(gm, mp, pass++ & 1, q, graw, chi2);
         gen_force(gm, q, graw, beta * tau, f);
         kin = 0.0;
 #pragma unroll
@@ -153,7 +277,8 @@ extern "C" __global__ void __launch_bounds__(256) gen_hmc_kernel(GenDev gm, HmcA
         if (a.n_traj > 1) {
             if (valid && g == 0 && acc)
                 for (int k = 0; k < K; ++k) a.q[(size_t)cid * K + k] = q[k];
-            __syncwarp();
+            if (UR && G > 1) gen_set_bar(mp.bar_id);  // the chain's other owners sit in other warps
+            else __syncwarp();
         }
     }
     if (valid && g == 0) {
@@ -175,16 +300,18 @@ extern "C" __global__ void __launch_bounds__(256) gen_hmc_kernel(GenDev gm, HmcA
     }
 }
 
-extern "C" __global__ void __launch_bounds__(256) gen_grad_kernel(GenDev gm, GradArgs a) {
-    const int g = threadIdx.x % G;
-    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_grad_kernel(GenDev gm, GradArgs a) {
+    GenMap mp;
+    mp.init();
+    const int g = mp.g;
+    const long long c = mp.c;
     const bool valid = c < a.C;
     const int cid = valid ? (int)c : a.C - 1;
     float q[K], graw[K], f[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) q[k] = a.q[(size_t)cid * K + k];
     double chi2;
-    gen_pass(gm, g, q, graw, chi2);
+    gen_pass<true>(gm, mp, 0, q, graw, chi2);
     if (!valid || g != 0) return;
     const float tau = a.tau[cid];
     const float beta = a.beta ? a.beta[cid] : 1.0f;

@@ -121,6 +121,7 @@ int chrom_forward_launch(const ChromModel &m, const float *q, int C, float *mock
 // ---- generic per-datum model compiled at run time (NVRTC) ----------------------------------------
 struct GenModel {
     int K = 0, XD = 0, G = 8;
+    int ur = 0;  // uniform-row mapping: rows in the module's constant bank, G warps per chain set
     GenDev dev;
     float *rows = nullptr;
     void *library = nullptr;                       // cudaLibrary_t

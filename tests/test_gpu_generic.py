@@ -126,3 +126,38 @@ def test_compile_error_is_reported(gpu):
         _cabi.Model.generic("__device__ float binfb_mock(const float *t, const float *x, float *d) { return zz; }",
                             2, np.zeros(4), np.zeros(4))
     assert "zz" in str(e.value) and "user_model.cu" in str(e.value)
+
+
+@pytest.mark.parametrize("n_data", [100, 1000, 3001, 5000])
+def test_generic_polynomial_row_mappings_vs_oracle(gpu, n_data):
+    """short data sets take the uniform-row mapping (rows in the module's constant bank: one warp per set
+    below 128 rows, four above), long ones (> 48 KiB of rows) the lanes-per-chain mapping over global
+    memory; ragged chain and row counts; several trajectories per launch with rejections"""
+    from binf_b200 import _cabi
+    rng = np.random.RandomState(n_data)
+    xs = np.sort(rng.uniform(-2, 2, size=n_data))
+    ys = rng.normal(np.polynomial.polynomial.polyval(xs, [2.0, -4.0, 1.0, 1.5]), 1 / np.sqrt(2.5))
+    pm, pv = np.zeros(4), 5.0 * np.ones(4)
+    m = _cabi.Model.generic(POLY_CODE, 4, xs[:, None].copy(), ys, pm, pv, 1.0, 0.2)
+    pp = port.PolynomialPosterior(xs, ys, pm, pv, 1.0, 0.2)
+    C = 77
+    q0 = np.array([2.0, -4.0, 1.0, 1.5]) + 0.02 * rng.normal(size=(C, 4))
+    logp, grad, chi2 = m.logprob_grad(q0, 2.5)
+    np.testing.assert_allclose(logp, pp.log_prob(q0, 2.5), rtol=1e-5)
+    ref = pp.gradient(q0, 2.5)
+    assert np.all(np.abs(grad - ref) <= 1e-4 * np.max(np.abs(ref), axis=-1, keepdims=True))
+    np.testing.assert_allclose(chi2, pp.chi2(q0), rtol=1e-5)
+    eps, L = 0.2 / n_data ** 0.5, 6
+    p0, u = rng.normal(size=q0.shape), rng.uniform(size=C)
+    r = m.hmc_run(q0, 2.5, eps, L, p0=p0, u=u, want_end=True)
+    o = port.hmc_sample(lambda c: pp.log_prob(c, 2.5), lambda c: pp.gradient(c, 2.5), q0, eps, L, p0, u)
+    assert np.all(np.abs(r["q_end"] - o["q_end"]) <= 1e-4 * np.max(np.abs(o["q_end"])))
+    np.testing.assert_allclose(r["e_after"], o["e_after"], rtol=1e-5)
+    # Philox momenta, three trajectories per launch, a step size that rejects often: the same chains on the
+    # built-in polynomial kernel (same streams, same arithmetic up to summation order)
+    b = _cabi.Model.polynomial(xs, ys, 4, pm, pv, 1.0, 0.2)
+    ra = m.hmc_run(q0, 2.5, 4 * eps, L, n_traj=3, seed=5, want_end=True)
+    rb = b.hmc_run(q0, 2.5, 4 * eps, L, n_traj=3, seed=5, want_end=True)
+    same = ra["n_accepted"] == rb["n_accepted"]
+    assert same.mean() > 0.9 and (ra["n_accepted"] < 3).any()
+    assert np.all(np.abs(ra["q"][same] - rb["q"][same]) <= 2e-3 * np.max(np.abs(rb["q"][same])))
