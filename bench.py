@@ -434,7 +434,10 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             el = float(t.item())
         e2e = dict(value=world * C * L * n_e2e / el, unit="leapfrog steps/s",
-                   h2d_bytes_per_step=int(4 * C * D + 8 * C), d2h_bytes_per_step=int(4 * C * D + 9 * C),
+                   h2d_bytes_per_step=int(4 * C * D + 8 * C),
+                   # back: the state, the accept flags, the precision when the sweep updates it (the step sizes
+                   # only while they adapt)
+                   d2h_bytes_per_step=int(4 * C * D + C + (4 * C if gibbs else 0)),
                    steps=n_e2e, api="binfb_hmc_run_host (pinned host buffers in, synchronous)")
 
     if rank != 0:

@@ -469,8 +469,11 @@ int binfb_hmc_run_host(binfb_model *m, float *q, float *tau, const float *beta, 
                        stats ? ar.at<double>(os) : nullptr, s);
     if (rc) return rc;
     BINFB_CUDA(cudaMemcpyAsync(q, ar.at<float>(oq), C * D * 4, cudaMemcpyDeviceToHost, s));
-    BINFB_CUDA(cudaMemcpyAsync(tau, ar.at<float>(ot), C * 4, cudaMemcpyDeviceToHost, s));
-    BINFB_CUDA(cudaMemcpyAsync(eps, ar.at<float>(oe), C * 4, cudaMemcpyDeviceToHost, s));
+    // tau only changes under a fused Gibbs update, eps only while the step size adapts
+    if (opts->gibbs_mode != BINFB_GIBBS_NONE)
+        BINFB_CUDA(cudaMemcpyAsync(tau, ar.at<float>(ot), C * 4, cudaMemcpyDeviceToHost, s));
+    if (opts->n_adapt > 0)
+        BINFB_CUDA(cudaMemcpyAsync(eps, ar.at<float>(oe), C * 4, cudaMemcpyDeviceToHost, s));
     if (accepted) BINFB_CUDA(cudaMemcpyAsync(accepted, ar.at<uint8_t>(oa), C, cudaMemcpyDeviceToHost, s));
     if (e_before) BINFB_CUDA(cudaMemcpyAsync(e_before, ar.at<double>(o0), C * 8, cudaMemcpyDeviceToHost, s));
     if (e_after) BINFB_CUDA(cudaMemcpyAsync(e_after, ar.at<double>(o1), C * 8, cudaMemcpyDeviceToHost, s));
