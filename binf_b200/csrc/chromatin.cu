@@ -71,6 +71,7 @@ namespace binfb {
 constexpr float CHROM_SOFT = PAIR_SOFT;
 constexpr int STEP_FLOAT4 = 4 * 32;  // float4 per warp-step (16 contacts per lane)
 constexpr int STEP_BYTES = STEP_FLOAT4 * 16;
+constexpr int FLUSH_ROLE_BYTES = 12 * 32 * 4;  // one role's row sums of a row block: [r*3+comp][lane] float
 constexpr int CHAIN_SCRATCH_BYTES = 144;  // per chain, in front of its positions: one double per role (<= 16)
                                           // and the mbarrier of the position copy
 #ifndef BINFB_CHROM_NS
@@ -126,6 +127,7 @@ __device__ __forceinline__ void unpack4(const float4 v, float (&a)[4]) {
 struct ChainSmem {
     float *pos, *frc;  // [Q][3][4]
     double *red;       // [16] cross-role reduction scratch (CHAIN_SCRATCH_BYTES)
+    float *flush;      // [R][12][32] row sums of all roles (nullptr: the roles fold them in one after the other)
     uint32_t pos_bar;  // shared address of the mbarrier the bulk copy of the positions completes on
 };
 __device__ __forceinline__ int qidx(int bead, int comp) { return (bead >> 2) * 12 + comp * 4 + (bead & 3); }
@@ -488,32 +490,49 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
         run_stages(std::true_type{}, 0, n_sg);
 #endif
         // ---- end of the row block: fold the register-resident accumulators of the own quad into
-        //      shared memory (f -= G), one role at a time --------------------------------------------
+        //      shared memory (f -= G).  All R roles hold sums for the SAME 32 quads.  With scratch space
+        //      (many roles per chain: n = 5000 runs 16) every role parks its 12 sums per lane, and the chain's
+        //      threads then add up the R contributions of one (quad, component) each: 3 barriers per row
+        //      block instead of R + 1.  Without it the roles take turns. --------------------------------
+        if (R >= 4 && sm.flush != nullptr) {  // (R is a template parameter)
+            chain_bar(bar_id, R * 32);  // no partner update of this row block is in flight any more
+            float *mine = sm.flush + (size_t)role * (12 * 32) + lane;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) mine[(c * 4 + r) * 32] = active ? s.g[r][c] : 0.f;
+            chain_bar(bar_id, R * 32);
+            for (int v = role * 32 + lane; v < 12 * 32; v += R * 32) {
+                const int ql = v & 31, idx = v >> 5;  // idx = comp * 4 + r: the offset inside a quad's 12 floats
+                float t = 0.f;
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) t += sm.flush[(size_t)rr * (12 * 32) + idx * 32 + ql];
+                const int aq = rb * 32 + ql;
+                if (chain_valid && aq < Q) sm.frc[aq * 12 + idx] -= t;
+            }
+        } else {
 #pragma unroll 1
-        for (int rr = 0; rr < R; ++rr) {
-            if (R > 1) chain_bar(bar_id, R * 32);
-            if (rr == role && active) {
-                float4 v = frc4[3 * a];
-                v.x -= s.g[0][0], v.y -= s.g[1][0];
-                v.z -= s.g[2][0], v.w -= s.g[3][0];
-                frc4[3 * a] = v;
-                v = frc4[3 * a + 1];
-                v.x -= s.g[0][1], v.y -= s.g[1][1];
-                v.z -= s.g[2][1], v.w -= s.g[3][1];
-                frc4[3 * a + 1] = v;
-                v = frc4[3 * a + 2];
-                v.x -= s.g[0][2], v.y -= s.g[1][2];
-                v.z -= s.g[2][2], v.w -= s.g[3][2];
-                frc4[3 * a + 2] = v;
+            for (int rr = 0; rr < R; ++rr) {
+                if (R > 1) chain_bar(bar_id, R * 32);
+                if (rr == role && active) {
+                    float4 v = frc4[3 * a];
+                    v.x -= s.g[0][0], v.y -= s.g[1][0];
+                    v.z -= s.g[2][0], v.w -= s.g[3][0];
+                    frc4[3 * a] = v;
+                    v = frc4[3 * a + 1];
+                    v.x -= s.g[0][1], v.y -= s.g[1][1];
+                    v.z -= s.g[2][1], v.w -= s.g[3][1];
+                    frc4[3 * a + 1] = v;
+                    v = frc4[3 * a + 2];
+                    v.x -= s.g[0][2], v.y -= s.g[1][2];
+                    v.z -= s.g[2][2], v.w -= s.g[3][2];
+                    frc4[3 * a + 2] = v;
+                }
             }
         }
         if (R > 1) chain_bar(bar_id, R * 32);
         else __syncwarp();
     }
-#if BINFB_DEFER
-    if (elect_one())
-        ring_finish<STAGE_BYTES, NS>(ring, stage_idx - 1u, (int)(stage_idx - stage_base) - 1, ticket);
-#endif
     stage_idx_io = stage_idx;
     ev_out = s.ev;
     return s.chi2;
@@ -572,6 +591,17 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
         sm.pos_bar = smem_u32(b0 + 128);
         sm.pos = reinterpret_cast<float *>(b0 + CHAIN_SCRATCH_BYTES);
         sm.frc = sm.pos + 3 * cd.n_pad;
+        sm.flush = nullptr;
+        if constexpr (R >= 4) {
+            // the launcher appends W * R * FLUSH_ROLE_BYTES behind the chains where that fits (chrom_launch);
+            // the kernel sees it in the size of its dynamic shared memory (no extra kernel parameter: the
+            // kernels with fewer roles stay exactly as they were)
+            uint32_t dyn;
+            asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+            const size_t need = (size_t)NS * STAGE_BYTES + 128 + per_chain * W;
+            if ((size_t)dyn >= need + (size_t)W * R * FLUSH_ROLE_BYTES)
+                sm.flush = reinterpret_cast<float *>(chains + per_chain * W + (size_t)chain_local * R * FLUSH_ROLE_BYTES);
+        }
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; ++i) mbar_init(&bars[i], 1), cnts[i] = 0u;
@@ -1099,7 +1129,11 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
         return BINFB_EUNSUPPORTED;
     }
     call.total_items = (int)total;
-    const size_t smem = pl.fixed_smem + pl.per_chain_smem * W;
+    size_t smem = pl.fixed_smem + pl.per_chain_smem * W;
+    // scratch for the parallel fold of the row sums (chrom_sweep), where it fits next to the chains
+    const size_t flush_bytes = (size_t)W * pl.R * FLUSH_ROLE_BYTES;
+    const bool flush_scratch = pl.R >= 4 && smem + flush_bytes <= (size_t)smem_optin;
+    if (flush_scratch) smem += flush_bytes;
     BINFB_CUDA(cudaMemsetAsync(m.sched, 0, (size_t)(1 + call.n_groups) * sizeof(int), s));
     const int grid = call.n_groups < sm_count ? call.n_groups : sm_count;
     const int threads = W * pl.R * 32;
