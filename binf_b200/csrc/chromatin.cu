@@ -127,7 +127,8 @@ __device__ __forceinline__ void unpack4(const float4 v, float (&a)[4]) {
 struct ChainSmem {
     float *pos, *frc;  // [Q][3][4]
     double *red;       // [16] cross-role reduction scratch (CHAIN_SCRATCH_BYTES)
-    float *flush;      // [R][12][32] row sums of all roles (nullptr: the roles fold them in one after the other)
+    float *flush;      // [F][12][32] row sums of F roles at a time (nullptr: the roles fold them in one after the other)
+    int flush_roles;   // F: a power of two <= R
     uint32_t pos_bar;  // shared address of the mbarrier the bulk copy of the positions completes on
 };
 __device__ __forceinline__ int qidx(int bead, int comp) { return (bead >> 2) * 12 + comp * 4 + (bead & 3); }
@@ -200,9 +201,16 @@ struct Ring {
     int rot;  // the pass starts at stream stage `rot` and wraps around (see chrom_kernel)
 };
 
+// ring slot of stage gi (the ring depth is a power of two except for the 3-stage ring of the 16-role kernel)
+template <int NS>
+__device__ __forceinline__ uint32_t ring_slot(uint32_t gi) {
+    if constexpr ((NS & (NS - 1)) == 0) return gi & (NS - 1);
+    else return gi % NS;
+}
+
 template <int STAGE_BYTES, int NS>
 __device__ __forceinline__ void ring_issue(const Ring &ring, uint32_t gi, int s_local) {
-    const uint32_t sl = gi & (NS - 1);
+    const uint32_t sl = ring_slot<NS>(gi);
     const uint32_t bar = ring.full + sl * 8u;
     bar_expect_tx(bar, STAGE_BYTES);
     int st = s_local + ring.rot;
@@ -214,7 +222,7 @@ __device__ __forceinline__ void ring_issue(const Ring &ring, uint32_t gi, int s_
 // that follows the warp's last read of the slot
 template <int STAGE_BYTES, int NS>
 __device__ __forceinline__ void ring_release(const Ring &ring, uint32_t gi, int s_local) {
-    const uint32_t c = ring.full + NS * 8u + (gi & (NS - 1)) * 4u;
+    const uint32_t c = ring.full + NS * 8u + ring_slot<NS>(gi) * 4u;
     uint32_t old;
     // the slot's loads have returned (their values were consumed before the __syncwarp in front of this
     // call), so a relaxed add is enough to order them before the refill the last arriver issues
@@ -228,7 +236,7 @@ __device__ __forceinline__ void ring_release(const Ring &ring, uint32_t gi, int 
 // the two halves of ring_release, for callers that look at the ticket one stage later (BINFB_DEFER)
 template <int NS>
 __device__ __forceinline__ uint32_t ring_arrive(const Ring &ring, uint32_t gi) {
-    const uint32_t c = ring.full + NS * 8u + (gi & (NS - 1)) * 4u;
+    const uint32_t c = ring.full + NS * 8u + ring_slot<NS>(gi) * 4u;
     uint32_t old;
     asm volatile("atom.relaxed.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(c) : "memory");
     return old;
@@ -236,7 +244,7 @@ __device__ __forceinline__ uint32_t ring_arrive(const Ring &ring, uint32_t gi) {
 template <int STAGE_BYTES, int NS>
 __device__ __forceinline__ void ring_finish(const Ring &ring, uint32_t gi, int s_local, uint32_t old) {
     if (old == (uint32_t)ring.n_warps - 1u) {
-        const uint32_t c = ring.full + NS * 8u + (gi & (NS - 1)) * 4u;
+        const uint32_t c = ring.full + NS * 8u + ring_slot<NS>(gi) * 4u;
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(c), "r"(0u) : "memory");
         if (s_local + NS < ring.n_stage_pass) ring_issue<STAGE_BYTES, NS>(ring, gi + NS, s_local + NS);
     }
@@ -437,7 +445,7 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
             constexpr bool GENERIC = decltype(generic_tag)::value;
 #pragma unroll 1
             for (int sg = sg_begin; sg < sg_end; ++sg) {
-                const uint32_t slot = stage_idx & (NS - 1);
+                const uint32_t slot = ring_slot<NS>(stage_idx);
                 {  // (probing the barrier one step early does not pay: the result is consumed at once)
                     const uint32_t fb = ring.full + slot * 8u, fp = (stage_idx / NS) & 1u;
                     while (!bar_try_wait(fb, fp)) {
@@ -495,20 +503,26 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
         //      threads then add up the R contributions of one (quad, component) each: 3 barriers per row
         //      block instead of R + 1.  Without it the roles take turns. --------------------------------
         if (R >= 4 && sm.flush != nullptr) {  // (R is a template parameter)
+            const int F = sm.flush_roles;
             chain_bar(bar_id, R * 32);  // no partner update of this row block is in flight any more
-            float *mine = sm.flush + (size_t)role * (12 * 32) + lane;
+#pragma unroll 1
+            for (int round = 0; round * F < R; ++round) {
+                if (round > 0) chain_bar(bar_id, R * 32);  // the previous round has been read
+                if (role / F == round) {
+                    float *mine = sm.flush + (size_t)(role % F) * (12 * 32) + lane;
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+                    for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) mine[(c * 4 + r) * 32] = active ? s.g[r][c] : 0.f;
-            chain_bar(bar_id, R * 32);
-            for (int v = role * 32 + lane; v < 12 * 32; v += R * 32) {
-                const int ql = v & 31, idx = v >> 5;  // idx = comp * 4 + r: the offset inside a quad's 12 floats
-                float t = 0.f;
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr) t += sm.flush[(size_t)rr * (12 * 32) + idx * 32 + ql];
-                const int aq = rb * 32 + ql;
-                if (chain_valid && aq < Q) sm.frc[aq * 12 + idx] -= t;
+                        for (int c = 0; c < 3; ++c) mine[(c * 4 + r) * 32] = active ? s.g[r][c] : 0.f;
+                }
+                chain_bar(bar_id, R * 32);
+                for (int v = role * 32 + lane; v < 12 * 32; v += R * 32) {
+                    const int ql = v & 31, idx = v >> 5;  // idx = comp * 4 + r: the offset inside a quad's 12 floats
+                    float t = 0.f;
+                    for (int rr = 0; rr < F; ++rr) t += sm.flush[(size_t)rr * (12 * 32) + idx * 32 + ql];
+                    const int aq = rb * 32 + ql;
+                    if (chain_valid && aq < Q) sm.frc[aq * 12 + idx] -= t;
+                }
             }
         } else {
 #pragma unroll 1
@@ -591,7 +605,7 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
         sm.pos_bar = smem_u32(b0 + 128);
         sm.pos = reinterpret_cast<float *>(b0 + CHAIN_SCRATCH_BYTES);
         sm.frc = sm.pos + 3 * cd.n_pad;
-        sm.flush = nullptr;
+        sm.flush = nullptr, sm.flush_roles = 0;
         if constexpr (R >= 4) {
             // the launcher appends W * R * FLUSH_ROLE_BYTES behind the chains where that fits (chrom_launch);
             // the kernel sees it in the size of its dynamic shared memory (no extra kernel parameter: the
@@ -599,8 +613,12 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
             uint32_t dyn;
             asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
             const size_t need = (size_t)NS * STAGE_BYTES + 128 + per_chain * W;
-            if ((size_t)dyn >= need + (size_t)W * R * FLUSH_ROLE_BYTES)
-                sm.flush = reinterpret_cast<float *>(chains + per_chain * W + (size_t)chain_local * R * FLUSH_ROLE_BYTES);
+            int F = (size_t)dyn > need ? (int)(((size_t)dyn - need) / ((size_t)W * FLUSH_ROLE_BYTES)) : 0;
+            if (F > R) F = R;
+            while (F & (F - 1)) F &= F - 1;  // round down to a power of two
+            sm.flush_roles = F;
+            if (F >= 2)
+                sm.flush = reinterpret_cast<float *>(chains + per_chain * W + (size_t)chain_local * F * FLUSH_ROLE_BYTES);
         }
     }
     if (threadIdx.x == 0) {
@@ -957,8 +975,8 @@ static inline long long tri_index(long long n, long long i, long long j) {  // i
 // stage size in warp-steps per role count (SPR = SS / R steps per role and stage); the ring has
 // CHROM_NS stages.  Measured on B200 at n = 1000: 4-step stages x 4 slots beat 8 x 2.
 static int chrom_stage_steps(int R) { return R <= BINFB_CHROM_SS ? BINFB_CHROM_SS : R; }
-// 16 roles: 32 KiB stages, two of them (the shared memory left next to a 5000-bead chain)
-static int chrom_ring_depth(int R) { return R >= 16 ? 2 : CHROM_NS; }
+// 16 roles: 32 KiB stages, three of them where a chain leaves room (n <= 5576), else two
+static int chrom_ring_depth(int R) { return R >= 16 ? 3 : CHROM_NS; }
 
 // the plan for a fixed role count R; W = 0 if it cannot run.  Two roles of a chain may only touch the
 // same partner quad if their offsets differ by <= 31.  Free-running roles drift by up to NS*spr - 1
@@ -984,6 +1002,14 @@ static ChromPlan chrom_plan_for(int n, int smem_optin, int R, bool allow_lockste
     if (!safe_free && !pl.lockstep) W = 0;
     pl.W = W;
     pl.stream_floats = (long long)pl.S_pad * R * STEP_FLOAT4 * 4;
+    if (W < 1 && pl.NS == 3) {  // no room for the third stage of the 16-role ring: two stages
+        pl.NS = 2;
+        pl.fixed_smem = (size_t)pl.NS * pl.SS * STEP_BYTES + 128;
+        W = (size_t)smem_optin > pl.fixed_smem ? (int)(((size_t)smem_optin - pl.fixed_smem) / per_chain) : 0;
+        if (W > 16 / R) W = 16 / R;
+        if (!(R == 1 || pl.Lr - (pl.NS * spr - 1) >= 34) && !pl.lockstep) W = 0;
+        pl.W = W;
+    }
     return pl;
 }
 
@@ -1131,9 +1157,12 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
     call.total_items = (int)total;
     size_t smem = pl.fixed_smem + pl.per_chain_smem * W;
     // scratch for the parallel fold of the row sums (chrom_sweep), where it fits next to the chains
-    const size_t flush_bytes = (size_t)W * pl.R * FLUSH_ROLE_BYTES;
-    const bool flush_scratch = pl.R >= 4 && smem + flush_bytes <= (size_t)smem_optin;
-    if (flush_scratch) smem += flush_bytes;
+    // (F roles at a time, F the largest power of two <= R that fits; the kernel derives F from the size)
+    if (pl.R >= 4) {
+        int F = pl.R;
+        while (F >= 2 && smem + (size_t)W * F * FLUSH_ROLE_BYTES > (size_t)smem_optin) F /= 2;
+        if (F >= 2) smem += (size_t)W * F * FLUSH_ROLE_BYTES;
+    }
     BINFB_CUDA(cudaMemsetAsync(m.sched, 0, (size_t)(1 + call.n_groups) * sizeof(int), s));
     const int grid = call.n_groups < sm_count ? call.n_groups : sm_count;
     const int threads = W * pl.R * 32;
@@ -1151,7 +1180,8 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
     } while (0)
 #define BINFB_CHROM_LAUNCH_L(RR, SPR, LOCK) BINFB_CHROM_LAUNCH_N(RR, SPR, LOCK, CHROM_NS)
 #define BINFB_CHROM_LAUNCH(RR, SPR) BINFB_CHROM_LAUNCH_L(RR, SPR, false)
-    if (pl.R == 16 && pl.SS == 16 && pl.NS == 2 && !pl.lockstep) BINFB_CHROM_LAUNCH_N(16, 1, false, 2);
+    if (pl.R == 16 && pl.SS == 16 && pl.NS == 3 && !pl.lockstep) BINFB_CHROM_LAUNCH_N(16, 1, false, 3);
+    else if (pl.R == 16 && pl.SS == 16 && pl.NS == 2 && !pl.lockstep) BINFB_CHROM_LAUNCH_N(16, 1, false, 2);
     else if (pl.lockstep && pl.R == 2 && pl.SS == 4) BINFB_CHROM_LAUNCH_L(2, 2, true);
     else if (pl.lockstep && pl.R == 4 && pl.SS == 4) BINFB_CHROM_LAUNCH_L(4, 1, true);
     else if (pl.lockstep && pl.R == 8 && pl.SS == 8) BINFB_CHROM_LAUNCH_L(8, 1, true);

@@ -343,3 +343,40 @@ def test_exponent_slope_limits_are_checked(gpu):
     for alpha, d_c in [(0.0, 2.5), (-2.0, 2.5), (50.0, 2.5), (float("nan"), 2.5)]:
         with pytest.raises((_cabi.BinfB200Error, ValueError)):
             _cabi.Model.chromatin(10, y, alpha, d_c, 3.0, 1.0)
+
+
+def test_n6000_two_stage_ring_fallback(gpu):
+    """beyond ~5576 beads a chain leaves no room for the third stage of the 16-role contact ring: the plan
+    falls back to two stages.  Size-independent properties (the full oracle is checked at n = 5000): chi^2
+    against float64 on a row subset is replaced by Newton's third law, translation invariance, agreement of
+    energy-only and energy+gradient passes, and a reversible trajectory"""
+    from binf_b200 import _cabi
+    n, alpha, d_c, k_bb, l0, tau = 6000, 2.0, 2.5, 4.0, 1.0, 120.0
+    X, y = chrom.synthetic_chromatin(n, alpha, d_c, l0, 0.05, seed=11)
+    m = _cabi.Model.chromatin(n, y, alpha, d_c, k_bb, l0)
+    rng = np.random.RandomState(4)
+    C = 2
+    q = X.reshape(-1)[None] + 0.1 * rng.normal(size=(C, 3 * n))
+    logp, grad, chi2 = m.logprob_grad(q, tau)
+    # chi^2 of chain 0 in float64, chunked over rows
+    Xc = q[0].reshape(n, 3)
+    iu = np.triu_indices(n, 1)
+    Y = np.zeros((n, n), dtype=np.float32)
+    Y[iu] = y
+    chi2_ref = 0.0
+    for lo in range(0, n, 500):
+        blk = np.arange(lo, min(n, lo + 500))
+        d = np.sqrt(np.sum((Xc[blk][:, None, :] - Xc[None, :, :]) ** 2, axis=-1) + 1e-12)
+        with np.errstate(over="ignore"):
+            res = 1.0 / (1.0 + np.exp(alpha * (d - d_c))) - Y[blk]
+        res[np.arange(n)[None, :] <= blk[:, None]] = 0.0     # pairs i < j only
+        chi2_ref += np.sum(res * res)
+    assert chi2[0] == pytest.approx(chi2_ref, rel=1e-5)
+    assert np.all(np.abs(grad.reshape(C, n, 3).sum(axis=1)) <= 1e-3 * np.max(np.abs(grad)))
+    logp2, _, _ = m.logprob_grad(q + np.tile([1.0, 2.0, -3.0], n)[None], tau, want_grad=False)
+    np.testing.assert_allclose(logp2, logp, rtol=2e-6)
+    p0 = rng.normal(size=q.shape)
+    u = np.full(C, 1e-30)
+    fwd = m.hmc_run(q, tau, 0.001, 2, p0=p0, u=u, want_end=True)
+    back = m.hmc_run(fwd["q_end"], tau, 0.001, 2, p0=-fwd["p_end"], u=u, want_end=True)
+    assert np.max(np.abs(back["q_end"] - q)) < 2e-4 * np.max(np.abs(q))
