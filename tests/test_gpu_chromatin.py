@@ -134,7 +134,7 @@ def test_n1000_vs_matrix_free_oracle(gpu, roles):
 @pytest.mark.parametrize("roles", [0, 8])
 def test_n5000_many_warps_per_chain(gpu, roles):
     """Config-4 size: 5000 beads (12,497,500 pairs per force evaluation), one chain per CTA, 16 warps
-    per chain (the plan's choice: two 32 KiB ring stages) or 8.  Oracle: float64 forces on a subset of beads (chunked), chi^2 over all pairs."""
+    per chain (the plan's choice: three 32 KiB ring stages) or 8.  Oracle: float64 forces on a subset of beads (chunked), chi^2 over all pairs."""
     from binf_b200 import _cabi
     n, alpha, d_c, k_bb, l0, tau = 5000, 2.0, 2.5, 4.0, 1.0, 120.0
     X, y = chrom.synthetic_chromatin(n, alpha, d_c, l0, 0.05, seed=7)
