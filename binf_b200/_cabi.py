@@ -118,6 +118,29 @@ def f32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
 
 
+_TORCH_NAMES = {"float32": "torch.float32", "float64": "torch.float64", "int32": "torch.int32",
+                "uint8": "torch.uint8"}
+
+
+def dev_arg(name, t, device, dtype, shape):
+    """Validate one tensor argument of a device entry point and return it.  The kernels take raw pointers, so
+    a float64, non-contiguous, wrong-device or wrongly shaped tensor would be silently reinterpreted (or read
+    out of bounds); `None` passes through (optional outputs)."""
+    if t is None:
+        return None
+    if not hasattr(t, "data_ptr"):
+        raise ValueError("%s: expected a CUDA torch tensor, got %s" % (name, type(t).__name__))
+    if not t.is_cuda or t.device.index != device:
+        raise ValueError("%s: tensor lives on %s, the model on cuda:%d" % (name, t.device, device))
+    if str(t.dtype) != _TORCH_NAMES[dtype]:
+        raise ValueError("%s: dtype %s, expected %s" % (name, t.dtype, _TORCH_NAMES[dtype]))
+    if not t.is_contiguous():
+        raise ValueError("%s: tensor is not contiguous" % name)
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError("%s: shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+    return t
+
+
 def f64(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
 
@@ -305,8 +328,21 @@ class Model(object):
                                         ptr(nacc), ptr(logp)))
         return dict(q=q, accepted=accepted.astype(bool), n_accepted=nacc, logp=logp)
 
+    def _chains_of(self, q):
+        """number of chains of a device state [C, dim] (validated)"""
+        if not hasattr(q, "data_ptr") or q.dim() != 2 or q.shape[1] != self.dim:
+            raise ValueError("q: expected a CUDA tensor of shape [n_chains, %d], got %s"
+                             % (self.dim, tuple(getattr(q, "shape", ())) or type(q).__name__))
+        n = int(q.shape[0])
+        dev_arg("q", q, self.device, "float32", (n, self.dim))
+        return n
+
     def rwmc_run_device(self, q, tau, stepsize, n_moves=1, beta=None, seed=0, draw=0, chain_base=0,
                         accepted=None, n_accepted=None, logp=None, stream=None):
+        n, d = self._chains_of(q), self.device
+        dev_arg("tau", tau, d, "float32", (n,)), dev_arg("stepsize", stepsize, d, "float32", (n,))
+        dev_arg("beta", beta, d, "float32", (n,)), dev_arg("accepted", accepted, d, "uint8", (n,))
+        dev_arg("n_accepted", n_accepted, d, "int32", (n,)), dev_arg("logp", logp, d, "float64", (n,))
         check(lib().binfb_rwmc_run(self._h, ptr(q), ptr(tau), ptr(beta), ptr(stepsize), q.shape[0], n_moves,
                                    seed, draw, chain_base, None, None, ptr(accepted), ptr(n_accepted),
                                    ptr(logp), ptr(stream)))
@@ -315,17 +351,32 @@ class Model(object):
     def hmc_run_device(self, q, tau, eps, opts, beta=None, p0=None, u=None, gamma_draws=None,
                        accepted=None, e_before=None, e_after=None, q_end=None, p_end=None,
                        n_accepted=None, stats=None, stream=None):
+        n, d = self._chains_of(q), self.device
+        dev_arg("tau", tau, d, "float32", (n,)), dev_arg("eps", eps, d, "float32", (n,))
+        dev_arg("beta", beta, d, "float32", (n,)), dev_arg("p0", p0, d, "float32", (n, self.dim))
+        dev_arg("u", u, d, "float32", (n,)), dev_arg("gamma_draws", gamma_draws, d, "float64", (n,))
+        dev_arg("accepted", accepted, d, "uint8", (n,)), dev_arg("e_before", e_before, d, "float64", (n,))
+        dev_arg("e_after", e_after, d, "float64", (n,)), dev_arg("q_end", q_end, d, "float32", (n, self.dim))
+        dev_arg("p_end", p_end, d, "float32", (n, self.dim)), dev_arg("n_accepted", n_accepted, d, "int32", (n,))
+        dev_arg("stats", stats, d, "float64", (4,))
         check(lib().binfb_hmc_run(self._h, ptr(q), ptr(tau), ptr(beta), ptr(eps), q.shape[0],
                                   C.byref(opts), ptr(p0), ptr(u), ptr(gamma_draws), ptr(accepted),
                                   ptr(e_before), ptr(e_after), ptr(q_end), ptr(p_end),
                                   ptr(n_accepted), ptr(stats), ptr(stream)))
 
     def logprob_grad_device(self, q, tau, beta=None, logp=None, grad=None, chi2=None, stream=None):
+        n, d = self._chains_of(q), self.device
+        dev_arg("tau", tau, d, "float32", (n,)), dev_arg("beta", beta, d, "float32", (n,))
+        dev_arg("logp", logp, d, "float64", (n,)), dev_arg("grad", grad, d, "float32", (n, self.dim))
+        dev_arg("chi2", chi2, d, "float64", (n,))
         check(lib().binfb_logprob_grad(self._h, ptr(q), ptr(tau), ptr(beta), q.shape[0], ptr(logp),
                                        ptr(grad), ptr(chi2), ptr(stream)))
 
     def gibbs_precision_device(self, q, tau, chi2, beta=None, gamma_draws=None, seed=0, draw=0,
                                chain_base=0, stream=None):
+        n, d = self._chains_of(q), self.device
+        dev_arg("tau", tau, d, "float32", (n,)), dev_arg("chi2", chi2, d, "float64", (n,))
+        dev_arg("beta", beta, d, "float32", (n,)), dev_arg("gamma_draws", gamma_draws, d, "float64", (n,))
         check(lib().binfb_gibbs_precision(self._h, ptr(q), ptr(tau), ptr(beta), q.shape[0], seed,
                                           draw, chain_base, ptr(gamma_draws), ptr(chi2),
                                           ptr(stream)))
@@ -364,6 +415,7 @@ class Sink(object):
         check(lib().binfb_sink_create(n_chains, dim, capacity, burn_in, thin,
                                       SINK_TRACK_MAP if track_map else 0, device, C.byref(h)))
         self._h = h
+        self.device = device
         self.n_chains, self.dim, self.capacity, self.burn_in, self.thin = n_chains, dim, capacity, burn_in, thin
         self.track_map = track_map
 
@@ -386,6 +438,9 @@ class Sink(object):
     def push(self, q, aux=None, logp=None, stream=None):
         """q/aux/logp: torch CUDA tensors (device path, asynchronous) or numpy arrays (host path)."""
         if hasattr(q, "data_ptr"):
+            dev_arg("q", q, self.device, "float32", (self.n_chains, self.dim))
+            dev_arg("aux", aux, self.device, "float32", (self.n_chains,))
+            dev_arg("logp", logp, self.device, "float64", (self.n_chains,))
             check(lib().binfb_sink_push(self._h, ptr(q), ptr(aux), ptr(logp), ptr(stream)))
         else:
             q = f32(q).reshape(self.n_chains, self.dim)

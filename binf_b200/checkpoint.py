@@ -31,6 +31,17 @@ def _like(template, value):
     return np.array(value)
 
 
+def _counter_like(state, value):
+    """acceptance counters in the kind the sampler's own update produces: a python int for one chain, an int64
+    CUDA tensor next to a device-resident state (hmc.py / example/samplers.py add `_nacc_dev` to it), else numpy"""
+    if not np.ndim(value):
+        return int(value)
+    if hasattr(state, "detach"):
+        import torch
+        return torch.as_tensor(np.asarray(value), dtype=torch.int64, device=state.device)
+    return np.array(value)
+
+
 def _sampler_state(s):
     from binf_b200.example.samplers import GammaSampler, RWMCSampler
     from binf_b200.samplers.hmc import HMCSampler
@@ -52,13 +63,13 @@ def _restore_sampler(s, d):
         s.timestep = d["eps"] if np.ndim(d["eps"]) else float(d["eps"])
         s.counter, s._draw = int(d["counter"]), int(d["draw"])
         s.seed, s.chain_base = int(d["seed"]), int(d["chain_base"])
-        s.n_accepted = d["n_accepted"] if np.ndim(d["n_accepted"]) else int(d["n_accepted"])
+        s.n_accepted = _counter_like(s.state, d["n_accepted"])
     elif kind == "rwmc":
         s.state = _like(s.state, d["state"])
         s.stepsize = d["stepsize"] if np.ndim(d["stepsize"]) else float(d["stepsize"])
         s._n_moves, s._draw = int(d["n_moves"]), int(d["draw"])
         s.seed, s.chain_base = int(d["seed"]), int(d["chain_base"])
-        s._n_accepted_moves = d["n_accepted"] if np.ndim(d["n_accepted"]) else int(d["n_accepted"])
+        s._n_accepted_moves = _counter_like(s.state, d["n_accepted"])
     elif kind == "gamma":
         s.state = _like(s.state, d["state"])
         s._draw, s.seed, s.chain_base = int(d["draw"]), int(d["seed"]), int(d["chain_base"])

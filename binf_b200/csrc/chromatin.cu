@@ -155,6 +155,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
         : "memory");
 }
+// Orders generic-proxy accesses to global memory (ordinary ld/st) against async-proxy accesses (the bulk copies
+// of the TMA engine) to the same locations.  The working positions qw are written with __stcg by one CTA and
+// fetched with cp.async.bulk by another CTA of the same launch; release/acquire on pass_done orders the two
+// CTAs, but the PTX memory model additionally requires a proxy fence on the generic -> async edge.
+__device__ __forceinline__ void fence_proxy_async_global() {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 // keep a value in a register: the compiler cannot rematerialise it from its inputs (address arithmetic
 // that it would otherwise redo at every use inside the stage loop)
 __device__ __forceinline__ uint32_t pin_reg(uint32_t v) {
@@ -699,6 +706,7 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                     // (TMA engine) brings them in while the forces are zeroed
                     if (ctid == 0) {
                         const uint32_t bytes = (uint32_t)cd.n_pad * 12u;
+                        fence_proxy_async_global();  // reader side of the generic -> async edge on qw
                         bar_expect_tx(sm.pos_bar, bytes);
                         bulk_g2s(smem_u32(sm.pos), cd.qw + (size_t)c * 3 * cd.n_pad, bytes, sm.pos_bar);
                     }
@@ -939,6 +947,7 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
             }
         }
         // ---- publish the pass ---------------------------------------------------------------
+        fence_proxy_async_global();  // writer side: this thread's __stcg stores to qw vs the next pass's bulk copy
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) st_release(cd.pass_done + o, seq + 1);

@@ -252,7 +252,7 @@ extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_hmc_kernel(GenDev gm
         h1 = gen_potential(gm, q, chi2, tau, beta, a.gamma_shape, a.gamma_rate) + 0.5 * kin;
         const float uu = a.u ? a.u[cid] : rng_uniform(a.seed, a.chain_base + cid, draw, RNG_ACCEPT);
         const double dh = h1 - h0;
-        acc = (double)uu < exp(fmin(709.0, fmax(-308.0, -dh)));                       // hmc.py:151; NaN rejects
+        acc = (dh == dh) && ((double)uu < exp(fmin(709.0, fmax(-308.0, -dh))));        // hmc.py:151; NaN rejects
         const bool last = tr == a.n_traj - 1;
         if (last && valid && g == 0) {
             if (a.q_end)

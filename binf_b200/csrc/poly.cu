@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(poly_max_block(G, J), 1)
                                      : rng_uniform(a.seed, a.chain_base + cid[j], draw, RNG_ACCEPT);
                 const double dh = h1[j] - h0[j];
                 const double pacc = exp(fmin(0.0, -dh));
-                acc[j] = (double)uu < exp(fmin(709.0, fmax(-308.0, -dh)));
+                acc[j] = (dh == dh) && ((double)uu < exp(fmin(709.0, fmax(-308.0, -dh))));
                 if (last && valid[j] && g == 0) {
                     if (a.q_end)
                         for (int k = 0; k < K; ++k) a.q_end[(size_t)cid[j] * K + k] = q[j][k];

@@ -185,8 +185,15 @@ class HMCSampler(object):
     def _sample_device(self, low, n_traj, n_adapt, p0, u):
         import torch
         q = self._state
+        if q.dim() != 2:
+            raise ValueError("HMCSampler: a device-resident state must have shape [n_chains, dim], got %s"
+                             % (tuple(q.shape),))
         n = q.shape[0]
         dev = q.device
+        if p0 is not None and not _is_tensor(p0):
+            p0 = torch.as_tensor(np.ascontiguousarray(p0, dtype=np.float32).reshape(n, low.dim), device=dev)
+        if u is not None and not _is_tensor(u):
+            u = torch.as_tensor(np.ascontiguousarray(u, dtype=np.float32).reshape(n), device=dev)
         if self._eps_dev is None:
             self._eps_dev = torch.as_tensor(self._eps, dtype=torch.float32, device=dev)
             self._acc_dev = torch.zeros(n, dtype=torch.uint8, device=dev)
