@@ -16,6 +16,7 @@ MODEL_POLYNOMIAL, MODEL_CHROMATIN, MODEL_GENERIC = 1, 2, 3
 FLAG_PRIOR_GRAD = 1
 GIBBS_NONE, GIBBS_TAU_FIRST, GIBBS_TAU_LAST = 0, 1, 2
 SINK_TRACK_MAP = 1
+REX_MAX_TEMPS, REX_RECORD_BYTES = 64, 16
 
 
 class BinfB200Error(RuntimeError):
@@ -59,6 +60,10 @@ SIGNATURES = {
     "binfb_gibbs_precision_host": (_i, [_vp, _vp, _vp, _vp, _i, _u64, _u64, _u64, _vp, _vp]),
     "binfb_swap_decide": (_i, [_vp, _vp, _d, _d, _i, _u64, _u64, _u64, _u64, _vp, _vp]),
     "binfb_swap_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "binfb_hmc_last_chi2": (_i, [_vp, _i, _vp, _vp]),
+    "binfb_rex_pack": (_i, [_vp, _vp, _vp, _vp, _i, _d, _vp, _vp]),
+    "binfb_rex_decide": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _u64, _u64, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "binfb_rex_select": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "binfb_sink_create": (_i, [_i, _i, _i, _i, _i, C.c_uint, _i, C.POINTER(_vp)]),
     "binfb_sink_destroy": (_i, [_vp]),
     "binfb_sink_info": (_i, [_vp, _pll, _pll, _pll]),
@@ -371,6 +376,12 @@ class Model(object):
         dev_arg("chi2", chi2, d, "float64", (n,))
         check(lib().binfb_logprob_grad(self._h, ptr(q), ptr(tau), ptr(beta), q.shape[0], ptr(logp),
                                        ptr(grad), ptr(chi2), ptr(stream)))
+
+    def hmc_last_chi2(self, chi2, stream=None):
+        """chi2 [C] f64 <- chi^2 of every chain's current state, as left by the last hmc_run_device"""
+        n = int(chi2.shape[0])
+        dev_arg("chi2", chi2, self.device, "float64", (n,))
+        check(lib().binfb_hmc_last_chi2(self._h, n, ptr(chi2), ptr(stream)))
 
     def gibbs_precision_device(self, q, tau, chi2, beta=None, gamma_draws=None, seed=0, draw=0,
                                chain_base=0, stream=None):

@@ -555,6 +555,65 @@ int binfb_swap_apply(float *q_mine, const float *q_theirs, float *eps_mine, cons
     return swap_apply_launch(q_mine, q_theirs, eps_mine, eps_theirs, accept, C, dim, (cudaStream_t)stream);
 }
 
+int binfb_hmc_last_chi2(binfb_model *m, int C, double *chi2, void *stream) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (!chi2 || C < 1) {
+        set_error("hmc_last_chi2: chi2 [n_chains] required");
+        return BINFB_EINVAL;
+    }
+    if (m->kind != BINFB_MODEL_CHROMATIN) {
+        set_error("hmc_last_chi2: only the chromatin kernel keeps chi^2 of the current state");
+        return BINFB_EUNSUPPORTED;
+    }
+    if (m->chrom.chi2_chains != C) {
+        set_error("hmc_last_chi2: the last binfb_hmc_run on this model did not run " + std::to_string(C) + " chains");
+        return BINFB_EINVAL;
+    }
+    BINFB_CUDA(cudaSetDevice(m->device));
+    BINFB_CUDA(cudaMemcpyAsync(chi2, m->chrom.chi2_state, (size_t)C * sizeof(double), cudaMemcpyDeviceToDevice,
+                               (cudaStream_t)stream));
+    return BINFB_OK;
+}
+
+int binfb_rex_pack(const double *chi2, const float *tau, const float *eps, const int32_t *tidx, int C,
+                   double n_data, void *records, void *stream) {
+    if (!chi2 || !tau || !eps || !tidx || !records || C < 1) {
+        set_error("rex_pack: chi2, tau, eps, tidx, records required");
+        return BINFB_EINVAL;
+    }
+    return rex_pack_launch(chi2, tau, eps, tidx, C, n_data, records, (cudaStream_t)stream);
+}
+
+int binfb_rex_decide(const void *records_all, int world, int rank, int C, int n_columns, const double *betas,
+                     int n_temps, uint64_t seed, uint64_t attempt, double ll_shift, int32_t *tidx, float *beta,
+                     float *eps, uint8_t *accept, unsigned long long *pair_counts, double *temp_stats,
+                     void *stream) {
+    if (!records_all || !betas || !tidx || !beta || !eps) {
+        set_error("rex_decide: records_all, betas, tidx, beta, eps required");
+        return BINFB_EINVAL;
+    }
+    if (world < 1 || rank < 0 || rank >= world || C < 1 || n_columns < 1 || C % n_columns != 0) {
+        set_error("rex_decide: 0 <= rank < world, n_chains a positive multiple of n_columns");
+        return BINFB_EINVAL;
+    }
+    if (n_temps < 1 || n_temps > BINFB_REX_MAX_TEMPS) {
+        set_error("rex_decide: n_temps must be in 1.." + std::to_string(BINFB_REX_MAX_TEMPS));
+        return BINFB_EINVAL;
+    }
+    return rex_decide_launch(records_all, world, rank, C, n_columns, betas, n_temps, seed, attempt, ll_shift, tidx,
+                             beta, eps, accept, pair_counts, temp_stats, (cudaStream_t)stream);
+}
+
+int binfb_rex_select(const float *q, const float *aux, const int32_t *tidx, int k_sel, int C, int dim,
+                     int n_columns, float *out_q, float *out_aux, void *stream) {
+    if (!q || !tidx || !out_q || C < 1 || dim < 1 || n_columns < 1 || C % n_columns != 0) {
+        set_error("rex_select: q, tidx, out_q required, n_chains a positive multiple of n_columns");
+        return BINFB_EINVAL;
+    }
+    return rex_select_launch(q, aux, tidx, k_sel, C, dim, n_columns, out_q, out_aux, (cudaStream_t)stream);
+}
+
 int binfb_rng_fill_host(uint64_t seed, uint64_t draw, uint64_t chain_base, int C, int D,
                         double gamma_shape, float *normals, float *uniforms, double *gammas,
                         int device) {

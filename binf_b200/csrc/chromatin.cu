@@ -1086,7 +1086,7 @@ int chrom_reserve(ChromModel &m, int C) {
             cudaFree(m.tau_w);
         m.qw = m.pw = m.tau_w = nullptr;
         m.h0 = m.chi2_0 = m.chi2_state = nullptr;
-        m.ws_chains = 0;
+        m.ws_chains = 0, m.chi2_chains = 0;
         BINFB_CUDA(cudaMalloc(&m.qw, (size_t)C * 3 * m.plan.n_pad * sizeof(float)));
         BINFB_CUDA(cudaMalloc(&m.pw, (size_t)C * D * sizeof(float)));
         BINFB_CUDA(cudaMalloc(&m.h0, (size_t)C * sizeof(double)));
@@ -1235,7 +1235,9 @@ int chrom_hmc_launch(ChromModel &m, const HmcArgs &a, int sm_count, int smem_opt
         rc = chrom_grad_launch(m, g, sm_count, smem_optin, s);
         if (rc) return rc;
     }
-    return chrom_launch(m, call, a.C, sm_count, smem_optin, s);
+    const int rc2 = chrom_launch(m, call, a.C, sm_count, smem_optin, s);
+    m.chi2_chains = rc2 ? 0 : a.C;  // chi2_state now holds chi^2 of every chain's current state (binfb_hmc_last_chi2)
+    return rc2;
 }
 
 int chrom_grad_launch(ChromModel &m, const GradArgs &a, int sm_count, int smem_optin, cudaStream_t s) {

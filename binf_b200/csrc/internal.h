@@ -107,6 +107,7 @@ struct ChromModel {
     float *tau_w = nullptr;               // [C] precision used by the running trajectory
     int *sched = nullptr;                 // [1 + n_octets]: item counter, per-octet pass counters
     int sched_len = 0;
+    int chi2_chains = 0;                  // chains whose chi2_state the last HMC launch left valid (0 = none)
 };
 ChromPlan chrom_plan(int n, int smem_optin, int force_roles);
 ChromPlan chrom_plan_small_batch(int n, int smem_optin, const ChromPlan &primary);
@@ -147,6 +148,13 @@ int swap_decide_launch(const double *ll_a, const double *ll_b, double beta_a, do
 int swap_apply_launch(float *q_mine, const float *q_theirs, float *eps_mine,
                       const float *eps_theirs, const uint8_t *accept, int C, int D,
                       cudaStream_t s);
+int rex_pack_launch(const double *chi2, const float *tau, const float *eps, const int32_t *tidx, int C,
+                    double n_data, void *rec, cudaStream_t s);
+int rex_decide_launch(const void *all, int world, int rank, int C, int n_columns, const double *betas, int n_temps,
+                      uint64_t seed, uint64_t attempt, double ll_shift, int32_t *tidx, float *beta, float *eps,
+                      uint8_t *accept, unsigned long long *pair_counts, double *temp_stats, cudaStream_t s);
+int rex_select_launch(const float *q, const float *aux, const int32_t *tidx, int k_sel, int C, int D, int n_columns,
+                      float *out_q, float *out_aux, cudaStream_t s);
 int microbench_run(int device, int iters, double *ffma, double *ffma2, double *mufu,
                    double *clock_mhz);
 

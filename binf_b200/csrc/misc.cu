@@ -100,6 +100,131 @@ int swap_apply_launch(float *q_mine, const float *q_theirs, float *eps_mine,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Replica exchange by LABEL swap (build-defined, SURVEY.md A.3 / 8e: "swap beta (and eps) labels so no
+// state moves").  The ensemble is a grid [temperature k][column c]; every chain of every rank holds one
+// cell, its temperature index tidx, and never moves.  An attempt:
+//   1. rex_pack_kernel: one 16-byte record {log L, tidx, eps} per chain (log L from chi^2 of the current
+//      state, which the trajectory kernel already left behind -- no extra pair sweep);
+//   2. the records of all ranks are all-gathered (world x C x 16 bytes; NCCL over NVLink);
+//   3. rex_decide_kernel: every chain looks up the chain of ITS column that holds the neighbouring
+//      temperature (even attempts pair (0,1),(2,3).., odd attempts (1,2),(3,4)..), evaluates
+//      u < exp(-(beta_k - beta_k')(l_mine - l_theirs)) with a Philox draw keyed by (seed, attempt, lower
+//      temperature index, column) -- NOT by rank or chain base, so both partners reach the same decision --
+//      and on acceptance adopts the partner's temperature index, beta and step size.
+// ---------------------------------------------------------------------------------------------
+struct RexRecord {
+    double ll;
+    int32_t tidx;
+    float eps;
+};
+static_assert(sizeof(RexRecord) == 16, "RexRecord is the 16-byte wire format of binfb_rex_pack");
+
+__global__ void rex_pack_kernel(const double *chi2, const float *tau, const float *eps, const int32_t *tidx,
+                                int C, double n_data, RexRecord *rec) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double t = (double)tau[c];
+    RexRecord r;
+    r.ll = -0.5 * t * chi2[c] + 0.5 * n_data * log(t);  // GaussianErrorModel, binf/example/likelihood.py:54-57
+    r.tidx = tidx[c];
+    r.eps = eps[c];
+    rec[c] = r;
+}
+
+int rex_pack_launch(const double *chi2, const float *tau, const float *eps, const int32_t *tidx, int C,
+                    double n_data, void *rec, cudaStream_t s) {
+    rex_pack_kernel<<<(C + 127) / 128, 128, 0, s>>>(chi2, tau, eps, tidx, C, n_data, (RexRecord *)rec);
+    BINFB_CUDA(cudaGetLastError());
+    return BINFB_OK;
+}
+
+struct RexLadder {
+    double beta[BINFB_REX_MAX_TEMPS];
+};
+
+__global__ void rex_decide_kernel(const RexRecord *all, int world, int rank, int C, int n_columns,
+                                  RexLadder lad, int n_temps, uint64_t seed, uint64_t attempt, double ll_shift,
+                                  int32_t *tidx, float *beta, float *eps, uint8_t *accept,
+                                  unsigned long long *pair_counts, double *temp_stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C) return;
+    const RexRecord me = all[(size_t)rank * C + i];
+    const int k = me.tidx, col = i % n_columns, rows = C / n_columns;
+    if (temp_stats && k >= 0 && k < n_temps && me.ll == me.ll) {
+        const double d = me.ll - ll_shift;
+        atomicAdd(temp_stats + 3 * k, 1.0), atomicAdd(temp_stats + 3 * k + 1, d);
+        atomicAdd(temp_stats + 3 * k + 2, d * d);
+    }
+    const int kp = ((k + (int)(attempt & 1u)) & 1) == 0 ? k + 1 : k - 1;  // pairs (k, k+1) with k + attempt even
+    bool acc = false;
+    RexRecord other = me;
+    if (k >= 0 && k < n_temps && kp >= 0 && kp < n_temps) {
+        bool found = false;
+        for (int r = 0; r < world && !found; ++r)
+            for (int row = 0; row < rows; ++row) {
+                const RexRecord o = all[(size_t)r * C + (size_t)row * n_columns + col];
+                if (o.tidx == kp) {
+                    other = o, found = true;
+                    break;
+                }
+            }
+        if (found) {
+            const int lo = k < kp ? k : kp;
+            // Delta = (beta_k - beta_k')(l_mine - l_theirs) is symmetric in the two partners
+            const double delta = (lad.beta[k] - lad.beta[kp]) * (me.ll - other.ll);
+            const u32x4 rr = philox4x32_10(seed ^ (uint64_t)(lo + 1) * 0xD6E8FEB86659FD93ull, (uint64_t)col,
+                                           (uint32_t)attempt, ((uint32_t)RNG_SWAP << 24) | (uint32_t)(attempt >> 32 & 0xffffffu));
+            const double u = (double)u32_to_unit_open0(rr.x);
+            acc = (delta == delta) && (u < exp(fmin(709.0, fmax(-308.0, -delta))));
+            if (pair_counts && k == lo) {
+                atomicAdd(pair_counts + 2 * lo, 1ull);
+                if (acc) atomicAdd(pair_counts + 2 * lo + 1, 1ull);
+            }
+        }
+    }
+    if (acc) {
+        tidx[i] = kp;
+        beta[i] = (float)lad.beta[kp];
+        eps[i] = other.eps;
+    }
+    if (accept) accept[i] = acc ? 1 : 0;
+}
+
+int rex_decide_launch(const void *all, int world, int rank, int C, int n_columns, const double *betas, int n_temps,
+                      uint64_t seed, uint64_t attempt, double ll_shift, int32_t *tidx, float *beta, float *eps,
+                      uint8_t *accept, unsigned long long *pair_counts, double *temp_stats, cudaStream_t s) {
+    RexLadder lad;
+    for (int k = 0; k < BINFB_REX_MAX_TEMPS; ++k) lad.beta[k] = k < n_temps ? betas[k] : 0.0;
+    rex_decide_kernel<<<(C + 127) / 128, 128, 0, s>>>((const RexRecord *)all, world, rank, C, n_columns, lad, n_temps,
+                                                      seed, attempt, ll_shift, tidx, beta, eps, accept, pair_counts,
+                                                      temp_stats);
+    BINFB_CUDA(cudaGetLastError());
+    return BINFB_OK;
+}
+
+// cold[c] = q[c] where tidx[c] == k_sel, else 0: summed over the ranks (exactly one contributor per column)
+// this assembles the states of one temperature wherever they currently live
+__global__ void rex_select_kernel(const float *q, const float *aux, const int32_t *tidx, int k_sel, int C, int D,
+                                  int n_columns, float *out_q, float *out_aux) {
+    const int c = blockIdx.y;
+    if (tidx[c] != k_sel) return;
+    const int col = c % n_columns;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < D; e += gridDim.x * blockDim.x)
+        out_q[(size_t)col * D + e] = q[(size_t)c * D + e];
+    if (aux && out_aux && blockIdx.x == 0 && threadIdx.x == 0) out_aux[col] = aux[c];
+}
+
+int rex_select_launch(const float *q, const float *aux, const int32_t *tidx, int k_sel, int C, int D, int n_columns,
+                      float *out_q, float *out_aux, cudaStream_t s) {
+    BINFB_CUDA(cudaMemsetAsync(out_q, 0, (size_t)n_columns * D * sizeof(float), s));
+    if (out_aux) BINFB_CUDA(cudaMemsetAsync(out_aux, 0, (size_t)n_columns * sizeof(float), s));
+    dim3 grid((unsigned)std::min(8, (D + 255) / 256), (unsigned)C);
+    rex_select_kernel<<<grid, 256, 0, s>>>(q, aux, tidx, k_sel, C, D, n_columns, out_q, out_aux);
+    BINFB_CUDA(cudaGetLastError());
+    return BINFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // microbenchmarks: the non-tensor FP32 peak (scalar FFMA and packed FFMA2) and the MUFU rate
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) mb_ffma_kernel(float *out, int iters, float a, float b) {

@@ -6,10 +6,12 @@ sink, chains sharded over the GPUs of one box.
     python examples/chromatin_inference.py --beads 200 --chains 512 --sweeps 60
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \\
         examples/chromatin_inference.py --beads 1000 --chains 4096 --sweeps 200            # 8 x 4096 chains
-    ... --tempered          # one inverse temperature per rank + replica-exchange neighbour swaps
+    ... --tempered          # one inverse temperature per rank to begin with + replica exchange (label swaps)
 
 Every rank owns a contiguous range of chains (Philox streams keyed by the global chain id); the only
-exchanges are the diagnostics reductions at the end and, with --tempered, the neighbour swaps.
+exchanges are the diagnostics reductions at the end and, with --tempered, the 16-byte-per-chain all-gather of
+an exchange attempt; with --tempered only the cold replicas (temperature index 0) are posterior samples: they
+are assembled from wherever they live and recorded on rank 0.
 """
 import argparse
 import os
@@ -77,12 +79,24 @@ def main(argv=None):
     for sweep in range(args.sweeps):
         if driver is not None:
             driver.step()
+            if sweep == burn // 2:
+                driver.adapt(target=0.3)                                 # re-space the ladder once, early in burn-in
+            cold_q, cold_tau = driver.cold_states(dst=0)                 # hot replicas are not posterior samples
+            if rank == 0:
+                sink.append(cold_q, aux=cold_tau)
         else:
             shard.sweep()
-        sink.append(q, aux=tau)
+            sink.append(q, aux=tau)
     torch.cuda.synchronize()
     stats = allreduce_stats(shard.stats.clone())                         # accepted, proposed, sum eps, sum p_acc
-    summary = sink_summary_all_ranks(sink)                               # over the chains of all ranks
+    if driver is not None:                                               # the cold replicas live in rank 0's sink
+        parts = [sink._sink.sums() if rank == 0 else None]
+        if world > 1:
+            torch.distributed.broadcast_object_list(parts, src=0)
+        from binf_b200.distributed import merge_sink_sums
+        summary = merge_sink_sums(parts)
+    else:
+        summary = sink_summary_all_ranks(sink)                           # over the chains of all ranks
     # distance RMSD of the posterior-mean structure to the truth, over the pairs the data constrain
     d_true = pair_distances(X)
     near = d_true < 4.0

@@ -169,8 +169,10 @@ int binfb_gibbs_precision_host(binfb_model *m, const float *q, float *tau, const
 
 /* ---- replica exchange (build-defined; the reference only alludes to it at
  *      binf/samplers/hmc.py:171-177) --------------------------------------------------------- */
-/* accept[c] = u < exp(-(beta_a - beta_b)(ll_a[c] - ll_b[c])), u from Philox(seed; attempt,
- * pair_id, chain_base + c) so that both partners reach the same decision without talking. */
+/* State-swap variant (two fixed-temperature ranks exchange states; kept for callers that want the cold
+ * replica pinned to one rank): accept[c] = u < exp(-(beta_a - beta_b)(ll_a[c] - ll_b[c])), u from
+ * Philox(seed; attempt, pair_id, chain_base + c).  BOTH partners must pass the same chain_base (a swap
+ * stream id, not the ranks' HMC chain bases) so that they reach the same decision without talking. */
 int binfb_swap_decide(const double *ll_a_dev, const double *ll_b_dev, double beta_a,
                       double beta_b, int n_chains, uint64_t seed, uint64_t attempt,
                       uint64_t pair_id, uint64_t chain_base, uint8_t *accept_dev, void *stream);
@@ -178,6 +180,38 @@ int binfb_swap_decide(const double *ll_a_dev, const double *ll_b_dev, double bet
 int binfb_swap_apply(float *q_mine_dev, const float *q_theirs_dev, float *eps_mine_dev,
                      const float *eps_theirs_dev, const uint8_t *accept_dev, int n_chains,
                      int dim, void *stream);
+
+/* Replica exchange by LABEL swap ("swap beta (and eps) labels so no state moves").  The
+ * ensemble is a grid [temperature][column]; a chain never moves, it carries a temperature index.  An attempt
+ * is: binfb_hmc_last_chi2 (chi^2 of every chain's current state, left behind by the trajectory kernel -- no
+ * extra pair sweep), binfb_rex_pack (one 16-byte record {f64 log L, i32 tidx, f32 eps} per chain), an
+ * all-gather of the records of all ranks (NCCL; world x n_chains x 16 bytes), binfb_rex_decide. */
+#define BINFB_REX_MAX_TEMPS 64
+#define BINFB_REX_RECORD_BYTES 16
+/* chi2_dev [n_chains] f64 <- sum of squared residuals of every chain's CURRENT state as of the last
+ * binfb_hmc_run on this model with the same n_chains (chromatin models; BINFB_EUNSUPPORTED otherwise) */
+int binfb_hmc_last_chi2(binfb_model *m, int n_chains, double *chi2_dev, void *stream);
+/* records_dev [n_chains] <- {-tau chi2/2 + n_data log(tau)/2, tidx, eps}  (binf/example/likelihood.py:54-57) */
+int binfb_rex_pack(const double *chi2_dev, const float *tau_dev, const float *eps_dev,
+                   const int32_t *tidx_dev, int n_chains, double n_data, void *records_dev, void *stream);
+/* records_all_dev [world, n_chains] (rank-major, the all-gather of binfb_rex_pack).  Local chain i sits in
+ * column i % n_columns.  Attempt a pairs temperature indices (k, k+1) with k + a even.  A chain at index k
+ * finds the chain of its column that holds the partner index k', accepts iff
+ * u < exp(-(beta_k - beta_k')(l_mine - l_theirs)) with u = Philox(seed; a, min(k, k'), column) -- the same
+ * on both sides, independent of rank and chain base -- and then takes over k', betas[k'] and the partner's
+ * step size: tidx_dev, beta_dev, eps_dev [n_chains] are updated in place.  betas: HOST f64 [n_temps].
+ * Optional: accept_dev [n_chains] u8; pair_counts_dev [n_temps-1][2] u64 += {attempted, accepted} (counted by
+ * the lower index of a pair); temp_stats_dev [n_temps][3] f64 += {1, l - ll_shift, (l - ll_shift)^2} of every
+ * chain at its temperature BEFORE the swap (for the ladder adaption). */
+int binfb_rex_decide(const void *records_all_dev, int world, int rank, int n_chains, int n_columns,
+                     const double *betas, int n_temps, uint64_t seed, uint64_t attempt, double ll_shift,
+                     int32_t *tidx_dev, float *beta_dev, float *eps_dev, uint8_t *accept_dev,
+                     unsigned long long *pair_counts_dev, double *temp_stats_dev, void *stream);
+/* out_q_dev [n_columns, dim] <- q[c] for the local chains with tidx[c] == k_sel (row = their column), zero
+ * elsewhere; out_aux_dev [n_columns] likewise from aux_dev (either may be NULL).  Summed over the ranks this
+ * assembles the replicas of one temperature (k_sel = 0: the posterior samples) wherever they live. */
+int binfb_rex_select(const float *q_dev, const float *aux_dev, const int32_t *tidx_dev, int k_sel,
+                     int n_chains, int dim, int n_columns, float *out_q_dev, float *out_aux_dev, void *stream);
 
 /* ---- sample sink ------------------------------------------------------- */
 /* What the reference's driver loop does with every Gibbs sweep, for chains resident in HBM:

@@ -1,7 +1,8 @@
 """Multi-rank host logic on CPU (gloo, world sizes 2 and 3): chain sharding, the diagnostics
 all-reduce and the replica-exchange neighbour-swap protocol (pairing, agreement of both partners
-on every decision, conservation of the states).  The decision / apply hooks are host stand-ins for
-the C-ABI device kernels (binfb_swap_decide / binfb_swap_apply), which the GPU tests cover."""
+on every decision, conservation of the states).  The kernels' host restatement (oracle/rex_port.py)
+stands in for the C-ABI device kernels (binfb_rex_pack / binfb_rex_decide / binfb_rex_select), which the GPU
+tests compare with it bit for bit."""
 import os
 import socket
 
@@ -11,7 +12,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from binf_b200.distributed import (ReplicaExchange, allreduce_stats, shard_range, swap_partner)
+from binf_b200.distributed import allreduce_stats, shard_range, swap_partner
 
 
 def _free_port():
@@ -22,19 +23,35 @@ def _free_port():
     return port
 
 
-def host_decide(ll_mine, ll_theirs, beta_mine, beta_theirs, i_am_low, seed, attempt, pair_id, chain_base):
-    a, b = (ll_mine, ll_theirs) if i_am_low else (ll_theirs, ll_mine)
-    ba, bb = (beta_mine, beta_theirs) if i_am_low else (beta_theirs, beta_mine)
-    u = np.random.RandomState([seed, attempt, pair_id, chain_base]).uniform(size=len(a))
-    delta = (ba - bb) * (a.numpy() - b.numpy())
-    return torch.from_numpy((u < np.exp(np.clip(-delta, -308, 709))).astype(np.uint8))
+class ToyReplica(object):
+    """exact tempered draws of log L(x) = -|x|^2 / 2 in D dimensions (chi^2 = |x|^2, tau = 1, no data term):
+    x ~ N(0, 1/beta) per replica, so mean log L = -D / (2 beta) -- the equipartition law the ladder
+    adaption assumes between its measurements"""
+
+    def __init__(self, C, D, seed):
+        self.C, self.D, self.rng = C, D, np.random.RandomState(seed)
+        self.q = torch.zeros(C, D, dtype=torch.float32)
+        self.tau = torch.ones(C)
+        self.eps = torch.full((C,), 0.1)
+        self.beta = None            # set by the driver: the exchange's per-chain tensor
+        self.n_data = 0.0
+
+    def sweep(self):
+        self.q.copy_(torch.from_numpy(self.rng.normal(size=(self.C, self.D))).float() / torch.sqrt(self.beta)[:, None])
+
+    def last_chi2(self):
+        return (self.q.double() ** 2).sum(dim=1)
 
 
-def host_apply(q_mine, q_theirs, mask):
-    q_mine.copy_(torch.where(mask.bool()[:, None], q_theirs, q_mine))
+def _gather(obj, world):
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
 
 
 def _worker(rank, world, port, out_dir):
+    import rex_port
+    from binf_b200.distributed import ReplicaExchange
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -45,43 +62,42 @@ def _worker(rank, world, port, out_dir):
         allreduce_stats(stats)
         assert stats[0].item() == 1000 and stats[1].item() == world
         assert stats[2].item() == sum(range(world))
-        # --- replica exchange ------------------------------------------------------------------
+        # --- label-swap replica exchange: one temperature per rank to begin with -------------------
         betas = [1.0 / (1 + r) for r in range(world)]
-        rex = ReplicaExchange(rank, world, betas[rank], seed=11, decide=host_decide, apply=host_apply)
+        rex = ReplicaExchange(rank, world, betas, C, seed=11, ops=rex_port.HostOps())
+        assert rex.n_columns == C and rex.rows == 1 and torch.all(rex.tidx == rank)
         rng = np.random.RandomState(100 + rank)
         q = torch.full((C, D), float(rank)) + torch.arange(C, dtype=torch.float32)[:, None] * 1e-3
-        tau = torch.full((C,), 10.0 + rank)
-        history = []
-        for attempt in range(4):
-            ll = torch.from_numpy(rng.normal(size=C) * 3.0)
-            before = q.clone()
-            mask = rex.swap(q, tau, ll, betas)
-            partner = swap_partner(rank, world, attempt)
-            if partner is None:
-                assert mask is None and torch.equal(q, before)
-            else:
-                m = mask.bool()
-                assert torch.equal(q[~m], before[~m])
-                # structure and precision travel together: tag of the state == tag of its tau
-                assert torch.equal(torch.floor(q[:, 0] + 1e-6), tau - 10.0)
-            history.append(None if mask is None else mask.clone())
-        # both partners reached the same decisions; every state is still held exactly once
-        gathered = [None] * world
-        dist.all_gather_object(gathered, (rank, [None if h is None else h.tolist() for h in history],
-                                          q[:, 0].tolist(), tau.tolist()))
-        if rank == 0:
-            for attempt in range(4):
-                for r in range(world):
-                    p = swap_partner(r, world, attempt)
-                    if p is not None:
-                        assert gathered[r][1][attempt] == gathered[p][1][attempt]
-                        assert any(gathered[r][1][attempt]) or True
-            owners = np.array([g[2] for g in gathered])            # [world, C]
-            tags = np.sort(np.floor(owners + 1e-6), axis=0)        # per chain slot: which replicas' states
-            assert np.array_equal(tags, np.tile(np.arange(world)[:, None], (1, C)))
-            assert sum(1 for h in gathered[0][1] if h is not None and any(h)) >= 1
-            with open(os.path.join(out_dir, "ok"), "w") as fh:
-                fh.write("ok")
+        tau = torch.ones(C)
+        eps = torch.full((C,), 0.1 * (1 + rank))              # tuned per temperature: travels with the label
+        q0 = q.clone()
+        for attempt in range(6):
+            chi2 = torch.from_numpy(rng.gamma(3.0, size=C) * 4.0)
+            before = rex.tidx.clone()
+            acc = rex.swap(chi2, tau, eps, 0.0).clone()
+            moved = rex.tidx != before
+            assert torch.equal(moved, acc.bool())
+            assert torch.all((rex.tidx - before).abs()[moved] == 1)
+            assert torch.equal(q, q0)                                                  # no state ever moves
+            np.testing.assert_allclose(eps.numpy(), 0.1 * (1 + rex.tidx.numpy()), rtol=1e-6)
+            np.testing.assert_allclose(rex.beta.numpy(), np.array(betas, dtype=np.float32)[rex.tidx.numpy()])
+            # every column still holds every temperature exactly once; partners agreed
+            allt = np.array(_gather(rex.tidx.tolist(), world))                            # [world, C]
+            assert np.array_equal(np.sort(allt, axis=0), np.tile(np.arange(world)[:, None], (1, C)))
+            alla = np.array(_gather(acc.tolist(), world))
+            assert alla.sum(axis=0).max() <= 2 * (world // 2) and np.all(alla.sum(axis=0) % 2 == 0)
+        rates = rex.swap_rates()
+        assert len(rates) == world - 1 and all(0.0 < r < 1.0 for r in rates)
+        assert all(g == rates for g in _gather(rates, world))
+        # the cold replicas, assembled from wherever they live
+        cold, cold_eps = rex.select(q, eps, 0)
+        allq = np.array(_gather(q.numpy(), world))
+        allt = np.array(_gather(rex.tidx.tolist(), world))
+        want = np.stack([allq[np.argmin(allt[:, c]), c] for c in range(C)])
+        np.testing.assert_array_equal(cold.numpy(), want)
+        np.testing.assert_allclose(cold_eps.numpy(), 0.1, rtol=1e-6)
+        with open(os.path.join(out_dir, "ok%d" % rank), "w") as fh:
+            fh.write("ok")
     finally:
         dist.destroy_process_group()
 
@@ -89,7 +105,7 @@ def _worker(rank, world, port, out_dir):
 @pytest.mark.parametrize("world", [2, 3])
 def test_gloo_sharding_stats_and_replica_exchange(tmp_path, world):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    assert (tmp_path / "ok").exists()
+    assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
 
 
 def test_pairing_and_sharding_arithmetic():
@@ -102,51 +118,71 @@ def test_pairing_and_sharding_arithmetic():
         assert max(h - l for l, h in rs) - min(h - l for l, h in rs) <= 1
 
 
+def test_partners_decide_alike_whatever_their_chain_base():
+    """the swap uniform is keyed by (seed, attempt, lower temperature index, column) and by
+    nothing rank-specific, so the two partners of a pair cannot disagree; several rows per rank, one process"""
+    import rex_port
+    from binf_b200.distributed import ReplicaExchange
+    T, cols = 4, 16
+    betas = [1.0, 0.8, 0.6, 0.4]
+    rex = ReplicaExchange(0, 1, betas, T * cols, seed=5, ops=rex_port.HostOps())
+    assert rex.rows == T and rex.n_columns == cols
+    assert rex.tidx.tolist() == [r for r in range(T) for _ in range(cols)]
+    rng = np.random.RandomState(2)
+    tau, eps = torch.ones(T * cols), torch.rand(T * cols) + 0.5
+    eps_by_temp0 = {}
+    for attempt in range(8):
+        chi2 = torch.from_numpy(rng.gamma(2.0, size=T * cols) * 3.0)
+        before, eps_before = rex.tidx.clone(), eps.clone()
+        acc = rex.swap(chi2, tau, eps, 0.0)
+        grid_b, grid_a = before.reshape(T, cols).numpy(), rex.tidx.reshape(T, cols).numpy()
+        assert np.array_equal(np.sort(grid_a, axis=0), np.tile(np.arange(T)[:, None], (1, cols)))
+        accg = acc.reshape(T, cols).numpy().astype(bool)
+        for c in range(cols):
+            for r in range(T):
+                if accg[r, c]:                      # its partner accepted too and they traded places
+                    r2 = int(np.where(grid_b[:, c] == grid_a[r, c])[0][0])
+                    assert accg[r2, c] and grid_a[r2, c] == grid_b[r, c]
+                    assert eps[r * cols + c] == eps_before[r2 * cols + c]
+    assert all(0.0 < r < 1.0 for r in rex.swap_rates())
+    mean, sd = rex.temperature_stats()
+    assert mean.shape == (T,) and np.all(sd > 0)
+
+
 # ------------------------------------------------------------------------------------------------
 # full replica-exchange driver: statistics and ladder adaption
 # ------------------------------------------------------------------------------------------------
 def _driver_worker(rank, world, port, out_dir):
+    import rex_port
     from binf_b200.distributed import ReplicaExchangeDriver
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        # toy tempered target: log L(x) = -0.5 * 40 * |x|^2 in D = 2, exact tempered draws N(0, 1/(40 beta))
-        C, D, k = 256, 2, 40.0
-        betas = [1.0, 0.7, 0.1][:world] if world == 3 else [1.0, 0.5]
-        rng = np.random.RandomState(7 + rank)
-        q = torch.zeros(C, D, dtype=torch.float32)
-        tau = torch.full((C,), float(rank))
-        state = {"beta": betas[rank]}
-
-        def sweep():
-            q.copy_(torch.from_numpy(rng.normal(size=(C, D)) / np.sqrt(k * state["beta"])).float())
-
-        def log_likelihood():
-            return -0.5 * k * (q.double() ** 2).sum(dim=1)
-
-        drv = ReplicaExchangeDriver(rank, world, betas, q, tau, sweep, log_likelihood,
-                                    set_beta=lambda b: state.update(beta=b), seed=3,
-                                    decide=host_decide, apply=host_apply)
-        drv.run(40)
-        assert drv.n_sweeps == 40 and drv.rex.attempt == 40
-        assert drv.last_draw_stats["swap"].attempt == 39
+        C, D = 128, 300
+        betas = [float(b) for b in np.geomspace(1.0, 0.05, world)]
+        drv = ReplicaExchangeDriver(ToyReplica(C, D, 7 + rank), rank, world, betas, seed=3, ops=rex_port.HostOps())
+        drv.run(12)
+        assert drv.n_sweeps == 12 and drv.rex.attempt == 12 and drv.last_draw_stats["swap"].attempt == 11
         rates = drv.swap_rates()                       # identical on every rank
-        gathered = [None] * world
-        dist.all_gather_object(gathered, rates)
-        assert all(g == gathered[0] for g in gathered)
-        assert len(rates) == world - 1 and all(0.0 < r <= 1.0 for r in rates)
-        if world == 3:
-            # the wide gap (0.7 -> 0.1) swaps less often than the narrow one (1.0 -> 0.7)
-            assert rates[1] < rates[0]
-            old = list(drv.betas)
-            drv.adapt(gain=2.0)
-            new = drv.betas
-            assert new[0] == old[0] and new[-1] == old[-1] and old[1] > new[1] > new[2]
-            assert state["beta"] == new[rank] and drv.rex.beta == new[rank]
-            assert drv.pair_attempted == 0
-            drv.run(40)
-            rates2 = drv.swap_rates()
-            assert abs(rates2[0] - rates2[1]) < abs(rates[0] - rates[1])    # more even after adaption
+        assert all(g == rates for g in _gather(rates, world))
+        # a geometric ladder down to 0.05 with 300 degrees of freedom never swaps ...
+        assert len(rates) == world - 1 and max(rates) < 0.02
+        mean, _ = drv.rex.temperature_stats()
+        np.testing.assert_allclose(mean, -0.5 * D / np.array(betas), rtol=0.05)
+        # ... and the ladder adaption recovers from all-zero rates: it is driven by the measured log-likelihoods
+        old_eps = drv.replica.eps.clone()
+        drv.adapt(target=0.3)
+        new = drv.betas
+        assert new[0] == 1.0 and all(a > b for a, b in zip(new, new[1:])) and new[-1] > 0.5
+        np.testing.assert_allclose(drv.replica.beta.numpy(), np.array(new, dtype=np.float32)[drv.rex.tidx.numpy()])
+        ratio = np.sqrt(np.array(betas) / np.array(new))[drv.rex.tidx.numpy()]
+        np.testing.assert_allclose(drv.replica.eps.numpy(), old_eps.numpy() * ratio, rtol=1e-5)
+        drv.run(60)
+        rates2 = drv.swap_rates()
+        assert all(0.15 < r < 0.5 for r in rates2), rates2
+        # the cold replicas, wherever they live, follow the beta = 1 law: chi^2 ~ D
+        cold, _ = drv.cold_states()
+        assert cold.shape == (C, D) and abs(float((cold.double() ** 2).sum(dim=1).mean()) / D - 1.0) < 0.05
         with open(os.path.join(out_dir, "ok%d" % rank), "w") as fh:
             fh.write("ok")
     finally:
@@ -159,17 +195,22 @@ def test_gloo_replica_exchange_driver(tmp_path, world):
     assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
 
 
-def test_adapt_ladder_is_pure_and_keeps_end_points():
-    from binf_b200.distributed import adapt_ladder
-    betas = np.geomspace(1.0, 0.05, 6)
-    even = adapt_ladder(betas, [0.3] * 5)
-    np.testing.assert_allclose(even, betas, rtol=1e-12)          # equal rates: nothing moves
-    new = adapt_ladder(betas, [0.9, 0.9, 0.1, 0.1, 0.5])
-    assert new[0] == betas[0] and new[-1] == betas[-1] and np.all(np.diff(new) < 0)
-    gaps_old, gaps_new = -np.diff(np.log(betas)), -np.diff(np.log(new))
-    assert gaps_new[0] > gaps_old[0] and gaps_new[2] < gaps_old[2]
-    np.testing.assert_allclose(gaps_new.sum(), gaps_old.sum(), rtol=1e-12)
-    assert list(adapt_ladder([1.0, 0.5], [0.2])) == [1.0, 0.5]
+def test_adapt_ladder_is_pure_and_hits_its_target():
+    from binf_b200.distributed import adapt_ladder, expected_swap_rate
+    d = 3000.0                                       # equipartition: L(beta) = -d / (2 beta)
+    betas = np.geomspace(1.0, 0.05, 8)
+    L = -0.5 * d / betas
+    new = adapt_ladder(betas, L, target=0.3)
+    assert new[0] == 1.0 and np.all(np.diff(new) < 0) and len(new) == 8
+    mu = (new[:-1] - new[1:]) * (-0.5 * d) * (1.0 / new[:-1] - 1.0 / new[1:])
+    np.testing.assert_allclose([expected_swap_rate(m) for m in mu], 0.3, atol=1e-3)
+    np.testing.assert_array_equal(new, adapt_ladder(betas, L, target=0.3))     # pure
+    kept = adapt_ladder(betas, L, keep_ends=True)
+    assert kept[0] == 1.0 and kept[-1] == betas[-1] and np.all(np.diff(kept) < 0)
+    mu = (kept[:-1] - kept[1:]) * (-0.5 * d) * (1.0 / kept[:-1] - 1.0 / kept[1:])
+    np.testing.assert_allclose(mu, mu[0], rtol=1e-3)                          # one common rate
+    assert list(adapt_ladder([1.0], [3.0])) == [1.0]
+    assert list(adapt_ladder([1.0, 0.5], [np.nan, 1.0])) == [1.0, 0.5]         # nothing measured: unchanged
 
 
 def test_merge_sink_sums_equals_one_big_sink():
