@@ -4,6 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload chromatin|poly]
     python bench.py --impl reference ...        # the reference's CPU path (oracle port)
 
+The default run measures BASELINE.json configs[2] (the headline line) and then, on the same box in the same
+process, short legs of configs[1] (poly), configs[3] (chromatin5k), configs[4] (rex) and the sample sink; they
+are attached to the line as extra.{poly,chromatin5k,sink,rex}, each with ms_per_step, roofline and clocks.
+
 A "step" is one Gibbs sweep over every chain of the batch: the conjugate precision update
 followed by one HMC trajectory of L leapfrog steps (L+1 fused force evaluations) and the
 Metropolis test -- one launch of the fused kernel.  metric = leapfrog steps/s =
@@ -201,21 +205,312 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------
-# the sample sink (HBM-bound), measured next to the sweep it follows
+# the product arm: one process per GPU; every leg is timed on the device, max over ranks
 # --------------------------------------------------------------------------------------------
-def run_sink(args):
-    """One step = one binfb_sink_push of the configs[2] state (4096 chains x 3000 dof): ring copy
-    (every 2nd sweep) + float64 running moments + MAP tracking.  Roofline: HBM copy bandwidth."""
+class Ctx(object):
+    """rank / device / process group of this process (torch.distributed over NCCL when launched by torchrun)"""
+
+    def __init__(self):
+        import torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+        self._mb = None
+
+    def sync_all(self):
+        import torch
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        import torch
+        if self.world == 1:
+            return float(x)
+        import torch.distributed as dist
+        t = torch.tensor([x], device=self.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def microbench(self):
+        """FFMA / FFMA2 / MUFU issue-rate microbenchmarks of this device (roofline denominators), run once"""
+        if self._mb is None:
+            from binf_b200 import _cabi
+            self._mb = _cabi.microbench(self.local, 3000)
+        return self._mb
+
+    def close(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def recorded_traffic(key, ok=True):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json)"""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return tj[key]["dram_bytes_per_launch"] if ok and key in tj else None
+    except Exception:
+        return None
+
+
+def make_hmc_workload(ctx, args, name, chains=None):
+    """model + device state of one HMC workload; returns a dict the legs below step"""
     import torch
     from binf_b200 import _cabi
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    w = WORKLOADS[name]
+    C = chains or w["chains"]
+    L = w["L"]
+    if name in ("chromatin", "rex", "chromatin5k"):
+        y, q_host = chromatin_inputs(w, C, ctx.rank)
+        model = _cabi.Model.chromatin(w["n_beads"], y, w["alpha"], w["d_c"], w["k_bb"], w["l0"], 0.0,
+                                      1.0, 1.0, device=ctx.local, roles=args.roles, ev_k=args.ev_k, ev_d=1.5)
+        tau0, gibbs = 100.0, _cabi.GIBBS_TAU_FIRST
+        units = float(model.n_data)            # pairs per force evaluation
+        flop_per_launch = FLOP_PER_PAIR * units * (L + 1) * C
+        bytes_per_launch = 2.0 * 4 * q_host.shape[1] * C + 4.0 * units
+    else:
+        xs, ys, q_host = poly_inputs(w, C, ctx.rank)
+        model = _cabi.Model.polynomial(xs, ys, 4, np.zeros(4), 5 * np.ones(4), 1.0, 1.0, device=ctx.local)
+        tau0, gibbs = w["tau"], _cabi.GIBBS_NONE
+        units = float(w["n_data"])
+        flop_per_launch = (FLOP_PER_DATUM * (L + 1) + 4) * units * C
+        bytes_per_launch = 2.0 * 4 * 4 * C
+    dev = ctx.dev
+    return dict(name=name, w=w, C=C, L=L, D=q_host.shape[1], model=model, q_host=q_host, tau0=tau0, gibbs=gibbs,
+                units=units, flop_per_launch=flop_per_launch, bytes_per_launch=bytes_per_launch,
+                q=torch.from_numpy(q_host).to(dev), tau=torch.full((C,), tau0, device=dev, dtype=torch.float32),
+                accepted=torch.zeros(C, device=dev, dtype=torch.uint8),
+                nacc=torch.zeros(C, device=dev, dtype=torch.int32),
+                stats=torch.zeros(4, device=dev, dtype=torch.float64))
+
+
+def chromatin_roofline(ctx, wl, ms_kernel, traffic):
+    """FP32-FMA roofline of one sweep launch + the special-function unit as the binding pipe (chromatin)"""
+    mb = ctx.microbench()
+    peaks = measured_peaks()
+    achieved = wl["flop_per_launch"] / (ms_kernel * 1e-3) / 1e12
+    sfu = None
+    if wl["name"] != "poly":
+        # the binding pipe of the pair kernel: 3 MUFU (rsqrt, ex2, rcp) per bead pair
+        sfu_gops = 3.0 * wl["units"] * (wl["L"] + 1) * wl["C"] / (ms_kernel * 1e-3) / 1e9
+        sfu = dict(ops_per_pair=3, achieved_gops=sfu_gops, peak_gops=mb["mufu_gops"],
+                   frac=sfu_gops / mb["mufu_gops"],
+                   note="MUFU issues at 16 lanes/clk/SM: 24 SMSP-cycles per warp-pair vs 20 on the FMA "
+                        "pipe, so the special-function unit bounds this kernel at 31/(2*24) = 64.6 % of "
+                        "the FP32-FMA peak")
+    return dict(
+        bound="fp32_fma", achieved=achieved, peak=mb["ffma_tflops"], unit="TFLOP/s",
+        frac=achieved / mb["ffma_tflops"], traffic=traffic, sfu=sfu,
+        peak_source="live FFMA issue microbenchmark in this run (binfb_microbench); "
+                    "MEASURED_PEAKS.json has no non-tensor FP32 figure",
+        peak_formula_tflops=148 * 128 * 2 * 1.965e9 / 1e12,
+        ffma2_tflops=mb["ffma2_tflops"], mufu_gops=mb["mufu_gops"],
+        flop_per_launch=wl["flop_per_launch"], kernel_ms=ms_kernel,
+        hbm_sanity=dict(algorithmic_gb_per_launch=wl["bytes_per_launch"] / 1e9,
+                        achieved_gbs=wl["bytes_per_launch"] / (ms_kernel * 1e-3) / 1e9,
+                        peak_gbs=peaks.get("hbm_gbs"),
+                        note="compulsory HBM bytes are O(chains x dim) per trajectory: not the bound"))
+
+
+def hmc_leg(ctx, args, name, steps, warmup, chains=None, eps=None, with_e2e=True):
+    """K timed Gibbs/HMC sweeps of one workload (one fused launch each), chains resident in HBM; then the same
+    sweep end to end through the host-buffer C-ABI call.  Returns the measurement (complete on rank 0)."""
+    import torch
+    from binf_b200 import _cabi
+    wl = make_hmc_workload(ctx, args, name, chains)
+    w, C, L, D, model = wl["w"], wl["C"], wl["L"], wl["D"], wl["model"]
+    dev, world = ctx.dev, ctx.world
+    eps0 = eps or w["eps"]
+    chain_base = ctx.rank * C
+    eps_t = torch.full((C,), eps0, device=dev, dtype=torch.float32)
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8) if name == "poly" else None
+    stream = torch.cuda.current_stream().cuda_stream
+    draw = [0]
+
+    def step():
+        opts = _cabi.HmcOpts(L, 1, 0, wl["gibbs"], 1.05, 0.95, args.seed, draw[0], chain_base)
+        model.hmc_run_device(wl["q"], wl["tau"], eps_t, opts, accepted=wl["accepted"], n_accepted=wl["nacc"],
+                             stats=wl["stats"], stream=stream)
+        draw[0] += 1
+
+    for _ in range(warmup):
+        step()
+    ctx.sync_all()
+    wl["stats"].zero_()
+    sampler = ClockSampler(ctx.local) if ctx.rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ctx.sync_all()
+    t_wall = time.perf_counter()
+    for k in range(steps):
+        if flush is not None:
+            flush.fill_(k)                      # L2 flush between timed iterations (not timed)
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    if flush is None:
+        total_ms = ev[0][0].elapsed_time(ev[-1][1])   # one bracket over all K steps
+    else:
+        total_ms = float(sum(kernel_ms))
+    stats = wl["stats"]
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        dist.all_reduce(stats)                  # the diagnostics reduction (4 doubles, NCCL)
+    total_ms = ctx.max_over_ranks(total_ms)
+    ctx.sync_all()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    clocks = sampler.summary() if sampler else None
+    st = stats.cpu().numpy()
+    value = world * C * L * steps / (total_ms * 1e-3)
+
+    # ---- e2e: the same sweep through the host-buffer C-ABI call (pinned host memory) --------
+    e2e = None
+    if with_e2e:
+        qh = torch.from_numpy(wl["q_host"].copy()).pin_memory().numpy()
+        th = torch.full((C,), wl["tau0"], dtype=torch.float32).pin_memory().numpy()
+        eh = torch.full((C,), eps0, dtype=torch.float32).pin_memory().numpy()
+        ah = torch.zeros(C, dtype=torch.uint8).pin_memory().numpy()
+        n_e2e = max(2, min(steps, 5))
+        from ctypes import byref
+
+        def host_step(k):
+            opts = _cabi.HmcOpts(L, 1, 0, wl["gibbs"], 1.05, 0.95, args.seed, 1000 + k, chain_base)
+            _cabi.check(_cabi.lib().binfb_hmc_run_host(
+                model._h, _cabi.ptr(qh), _cabi.ptr(th), None, _cabi.ptr(eh), C, byref(opts), None, None,
+                None, _cabi.ptr(ah), None, None, None, None, None, None))
+        host_step(0)
+        ctx.sync_all()
+        t0 = time.perf_counter()
+        for k in range(n_e2e):
+            host_step(1 + k)
+        el = ctx.max_over_ranks(time.perf_counter() - t0)
+        e2e = dict(value=world * C * L * n_e2e / el, unit="leapfrog steps/s",
+                   h2d_bytes_per_step=int(4 * C * D + 8 * C),
+                   # back: the state, the accept flags, the precision when the sweep updates it (the step sizes
+                   # only while they adapt)
+                   d2h_bytes_per_step=int(4 * C * D + C + (4 * C if wl["gibbs"] else 0)),
+                   steps=n_e2e, ms_per_step=el * 1e3 / n_e2e,
+                   api="binfb_hmc_run_host: pinned host buffers in and out, synchronous; the state copies are "
+                       "chunked on two copy streams and overlap the one trajectory launch")
+    model.close()
+    if ctx.rank != 0:
+        return None
+    ms_kernel = float(np.mean(kernel_ms))
+    roofline = chromatin_roofline(ctx, wl, ms_kernel, recorded_traffic(name, C == w["chains"]))
+    return dict(metric="HMC leapfrog steps/s (chains x steps)", value=value, unit="leapfrog steps/s",
+                n_gpus=world, steps=steps, warmup=warmup, ms_per_step=total_ms / steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic",
+                config=dict(workload=w["name"], chains_per_gpu=C, leapfrog_steps=L, timestep=eps0,
+                            parallelism="chain-sharded x%d (no data-path collective)" % world,
+                            l2="working set %.0f MB per step > 126 MB L2" % (3 * 4 * C * D / 1e6)
+                            if flush is None else "L2 flushed (256 MiB fill) between timed steps",
+                            gibbs="precision update fused in front of each trajectory"
+                            if wl["gibbs"] else "none"),
+                acceptance_rate=float(st[0] / st[1]) if st[1] else None,
+                e2e=e2e, gpu_launches=steps, wall_ms=wall_ms, clocks=clocks, roofline=roofline)
+
+
+def rex_leg(ctx, args, steps):
+    """BASELINE.json configs[4]: a tempered ensemble of 8 inverse temperatures x (64 x n_gpus) columns of the
+    1000-bead chromatin posterior, 512 replicas per GPU, one exchange attempt after every sweep.  Exchanges swap
+    LABELS (temperature index, beta, step size): per attempt the ranks all-gather 16 bytes per chain over NCCL /
+    NVLink, no state moves and nothing synchronises the host.  The ladder starts geometric in [0.05, 1] (where
+    no exchange is ever accepted with 3000 degrees of freedom) and is re-spaced from the measured mean
+    log-likelihoods during the untimed warm-up."""
+    import torch
+    from binf_b200 import _cabi
+    from binf_b200.distributed import ChainShard, ReplicaExchangeDriver
+    wl = make_hmc_workload(ctx, args, "rex")
+    w, C, L, model = wl["w"], wl["C"], wl["L"], wl["model"]
+    T = 8
+    betas0 = [float(b) for b in np.geomspace(1.0, 0.05, T)]
+    eps = torch.full((C,), w["eps"], device=ctx.dev, dtype=torch.float32)
+    shard = ChainShard(model, wl["q"], wl["tau"], eps, L, gibbs_mode=wl["gibbs"], seed=args.seed,
+                       chain_base=ctx.rank * C)
+    drv = ReplicaExchangeDriver.for_shard(shard, ctx.rank, ctx.world, betas0, seed=args.seed + 1)
+    eps.mul_(1.0 / torch.sqrt(shard.beta))               # step size ~ 1/sqrt(beta)
+    # ---- untimed: equilibrate, measure log-likelihoods, re-space the ladder (twice) -----------------
+    drv.run(20)
+    drv.rex.reset_stats()
+    drv.run(20)
+    drv.adapt(target=0.35)
+    for _ in range(2):
+        drv.run(15)
+        drv.rex.reset_stats()
+        drv.run(25)
+        drv.adapt(target=0.35)
+    drv.run(15)
+    drv.rex.reset_stats()
+    ctx.sync_all()
+    sampler = ClockSampler(ctx.local) if ctx.rank == 0 else None
+    if sampler:
+        sampler.start()
+    steps = max(steps, 20)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    shard.stats.zero_()
+    ctx.sync_all()
+    for k in range(steps):
+        ev[k][0].record()
+        shard.sweep()
+        ev[k][1].record()
+        drv.n_sweeps += 1
+        drv.rex.swap(shard.last_chi2(), shard.tau, shard.eps, shard.n_data)
+        ev[k][2].record()
+    torch.cuda.synchronize()
+    sweep_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    swap_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    total_ms = ctx.max_over_ranks(ev[0][0].elapsed_time(ev[-1][2]))
+    rates = drv.swap_rates()
+    stats = shard.stats
+    if ctx.world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(stats)
+    ctx.sync_all()
+    clocks = sampler.summary() if sampler else None
+    st = stats.cpu().numpy()
+    model.close()
+    if ctx.rank != 0:
+        return None
+    return dict(metric="HMC leapfrog steps/s (chains x steps), tempered ensemble with an exchange attempt per sweep",
+                value=ctx.world * C * L * steps / (total_ms * 1e-3), unit="leapfrog steps/s", n_gpus=ctx.world,
+                steps=steps, ms_per_step=total_ms / steps, sweep_ms=sweep_ms, swap_ms=swap_ms,
+                swap_overhead_frac=swap_ms / sweep_ms,
+                config=dict(workload=w["name"], replicas_per_gpu=C, temperatures=T, columns=drv.rex.n_columns,
+                            rows_per_gpu=drv.rex.rows, ladder_start=betas0, ladder=drv.betas,
+                            exchange="label swap: all-gather of 16 B per chain per attempt (%d B per rank), "
+                                     "no state moves" % (16 * C),
+                            collective="NCCL all_gather_into_tensor" if ctx.world > 1 else
+                                       "none (all temperatures on one device)"),
+                swap_rates=rates, acceptance_rate=float(st[0] / st[1]) if st[1] else None,
+                gpu_launches=steps * 4, clocks=clocks,
+                roofline=chromatin_roofline(ctx, wl, sweep_ms, None))
+
+
+def sink_leg(ctx, args, steps, warmup):
+    """one step = one binfb_sink_push of the configs[2] state (4096 chains x 3000 dof): ring
+    copy (every 2nd sweep) + float64 running moments + MAP tracking.  Roofline: HBM copy bandwidth."""
+    import torch
+    from binf_b200 import _cabi
+    local, world, rank, dev = ctx.local, ctx.world, ctx.rank, ctx.dev
     C, D = args.chains or 4096, 3000
     sink = _cabi.Sink(C, D, capacity=8, burn_in=0, thin=2, track_map=True, device=local)
     g = torch.Generator(device=dev).manual_seed(args.seed)
@@ -223,7 +518,7 @@ def run_sink(args):
     tau = torch.rand(C, device=dev, generator=g)
     logp = torch.randn(C, device=dev, generator=g, dtype=torch.float64)
     stream = torch.cuda.current_stream().cuda_stream
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         sink.push(q, tau, logp, stream)
     torch.cuda.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -231,7 +526,7 @@ def run_sink(args):
         sampler.start()
     # a push is ~100 us: launch it from a CUDA graph so that host-side launch jitter (e.g. the
     # nvidia-smi clock sampler holding the driver lock) is not mistaken for kernel time
-    steps = max(args.steps, 50)
+    steps = max(steps, 50)
     side = torch.cuda.Stream(device=dev)
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.stream(side):
@@ -249,24 +544,13 @@ def run_sink(args):
             graph.replay()
         e1.record(side)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / (steps * reps)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1) / (steps * reps))
     clocks = sampler.summary() if sampler else None
     # algorithmic bytes per element and push: read q 4, moments RMW 2 x (8 + 8), MAP state write 4,
     # ring write 4 on every 2nd sweep
     bytes_per_push = C * D * (4 + 32 + 4 + 2.0)
-    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
-        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    peak = float(peaks.get("hbm_gbs", 6543.7))
+    peak = float(measured_peaks().get("hbm_gbs", 6543.7))
     achieved = bytes_per_push / (ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["sink"]["dram_bytes_per_launch"]
-    except Exception:
-        pass
     # e2e: the same push from pinned host memory (H2D inside the timed region)
     qh = q.cpu().pin_memory()
     th, lh = tau.cpu().pin_memory(), logp.cpu().pin_memory()
@@ -277,232 +561,69 @@ def run_sink(args):
         sink.push(q, tau, logp, stream)
         torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
-    if rank == 0:
-        emit(json.dumps({
-            "metric": "sample-sink state elements absorbed/s (chains x dim per sweep)", "value": world * C * D / (ms * 1e-3),
-            "unit": "elements/s", "n_gpus": world, "steps": steps * reps, "warmup": max(args.warmup, 3) + steps,
-            "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 state, f64 moments",
-            "data": "synthetic",
-            "config": {"workload": "sink_c%d_d%d_thin2_map" % (C, D), "chains_per_gpu": C, "dim": D,
-                       "l2": "working set 295 MB of moments + 49 MB state per push > 126 MB L2"},
-            "e2e": {"value": world * C * D / (e2e_ms * 1e-3), "unit": "elements/s",
-                    "h2d_bytes_per_step": C * D * 4 + C * 12, "d2h_bytes_per_step": 0, "steps": n_e2e,
-                    "api": "Sink.push after an H2D copy of the state from pinned host memory"},
-            "gpu_launches": steps * reps, "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "bytes_per_launch": bytes_per_push,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"},
-            "cpu_baseline": None}))
-
-
-# the product arm
-# --------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from binf_b200 import _cabi
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    w = WORKLOADS[args.workload]
-    C = args.chains or w["chains"]
-    L = w["L"]
-    eps0 = args.eps or w["eps"]
-    chain_base = rank * C
-
-    rex = None
-    if args.workload in ("chromatin", "rex", "chromatin5k"):
-        y, q_host = chromatin_inputs(w, C, rank)
-        model = _cabi.Model.chromatin(w["n_beads"], y, w["alpha"], w["d_c"], w["k_bb"], w["l0"], 0.0,
-                                      1.0, 1.0, device=local, roles=args.roles, ev_k=args.ev_k, ev_d=1.5)
-        tau0, gibbs = 100.0, _cabi.GIBBS_TAU_FIRST
-        units = float(model.n_data)            # pairs per force evaluation
-        flop_per_launch = FLOP_PER_PAIR * units * (L + 1) * C
-        bytes_per_launch = 2.0 * 4 * q_host.shape[1] * C + 4.0 * units
-    else:
-        xs, ys, q_host = poly_inputs(w, C, rank)
-        model = _cabi.Model.polynomial(xs, ys, 4, np.zeros(4), 5 * np.ones(4), 1.0, 1.0, device=local)
-        tau0, gibbs = w["tau"], _cabi.GIBBS_NONE
-        units = float(w["n_data"])
-        flop_per_launch = (FLOP_PER_DATUM * (L + 1) + 4) * units * C
-        bytes_per_launch = 2.0 * 4 * 4 * C
-    D = q_host.shape[1]
-
-    q = torch.from_numpy(q_host).to(dev)
-    tau = torch.full((C,), tau0, device=dev, dtype=torch.float32)
-    eps = torch.full((C,), eps0, device=dev, dtype=torch.float32)
-    accepted = torch.zeros(C, device=dev, dtype=torch.uint8)
-    nacc = torch.zeros(C, device=dev, dtype=torch.int32)
-    stats = torch.zeros(4, device=dev, dtype=torch.float64)
-    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8) if args.workload == "poly" else None
-    stream = torch.cuda.current_stream().cuda_stream
-    draw = [0]
-
-    beta = None
-    if args.workload == "rex":
-        from binf_b200.distributed import ReplicaExchange
-        betas = [float(b) for b in np.geomspace(1.0, 0.05, world)] if world > 1 else [1.0]
-        beta = torch.full((C,), betas[rank], device=dev, dtype=torch.float32)
-        rex = ReplicaExchange(rank, world, betas[rank], seed=args.seed)
-        chi2 = torch.zeros(C, device=dev, dtype=torch.float64)
-        chain_base = rank * C
-
-    launches = [0]
-
-    def step():
-        opts = _cabi.HmcOpts(L, 1, 0, gibbs, 1.05, 0.95, args.seed, draw[0], chain_base)
-        model.hmc_run_device(q, tau, eps, opts, beta=beta, accepted=accepted, n_accepted=nacc,
-                             stats=stats, stream=stream)
-        draw[0] += 1
-        launches[0] += 1
-        if rex is not None and world > 1:
-            model.logprob_grad_device(q, tau, chi2=chi2, stream=stream)
-            t = tau.double()
-            ll = -0.5 * t * chi2 + 0.5 * units * torch.log(t)
-            launches[0] += 1 + (2 if rex.swap(q, tau, ll, betas) is not None else 0)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    sync_all()
-    stats.zero_()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    sync_all()
-    t_wall = time.perf_counter()
-    launches[0] = 0
-    for k in range(args.steps):
-        if flush is not None:
-            flush.fill_(k)                      # L2 flush between timed iterations (not timed)
-        ev[k][0].record()
-        step()
-        ev[k][1].record()
-    torch.cuda.synchronize()
-    kernel_ms = [a.elapsed_time(b) for a, b in ev]
-    if flush is None:
-        total_ms = ev[0][0].elapsed_time(ev[-1][1])   # one bracket over all K steps
-    else:
-        total_ms = float(sum(kernel_ms))
-    if world > 1:
-        dist.all_reduce(stats)                  # the diagnostics reduction (4 doubles, NCCL)
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    sync_all()
-    wall_ms = (time.perf_counter() - t_wall) * 1e3
-    clocks = sampler.summary() if sampler else None
-    st = stats.cpu().numpy()
-    value = world * C * L * args.steps / (total_ms * 1e-3)
-
-    # ---- e2e: the same sweep through the host-buffer C-ABI call (pinned host memory) --------
-    e2e = None
-    if not args.no_e2e and rex is None:
-        qh = torch.from_numpy(q_host.copy()).pin_memory().numpy()
-        th = torch.full((C,), tau0, dtype=torch.float32).pin_memory().numpy()
-        eh = torch.full((C,), eps0, dtype=torch.float32).pin_memory().numpy()
-        ah = np.empty(C, dtype=np.uint8)
-        n_e2e = max(2, min(args.steps, 5))
-        from ctypes import byref
-
-        def host_step(k):
-            opts = _cabi.HmcOpts(L, 1, 0, gibbs, 1.05, 0.95, args.seed, 1000 + k, chain_base)
-            _cabi.check(_cabi.lib().binfb_hmc_run_host(
-                model._h, _cabi.ptr(qh), _cabi.ptr(th), None, _cabi.ptr(eh), C, byref(opts), None, None,
-                None, _cabi.ptr(ah), None, None, None, None, None, None))
-        host_step(0)
-        sync_all()
-        t0 = time.perf_counter()
-        for k in range(n_e2e):
-            host_step(1 + k)
-        el = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([el], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            el = float(t.item())
-        e2e = dict(value=world * C * L * n_e2e / el, unit="leapfrog steps/s",
-                   h2d_bytes_per_step=int(4 * C * D + 8 * C),
-                   # back: the state, the accept flags, the precision when the sweep updates it (the step sizes
-                   # only while they adapt)
-                   d2h_bytes_per_step=int(4 * C * D + C + (4 * C if gibbs else 0)),
-                   steps=n_e2e, api="binfb_hmc_run_host (pinned host buffers in, synchronous)")
-
+    sink.close()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
+    return {
+        "metric": "sample-sink state elements absorbed/s (chains x dim per sweep)", "value": world * C * D / (ms * 1e-3),
+        "unit": "elements/s", "n_gpus": world, "steps": steps * reps, "warmup": max(warmup, 3) + steps,
+        "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 state, f64 moments",
+        "data": "synthetic",
+        "config": {"workload": "sink_c%d_d%d_thin2_map" % (C, D), "chains_per_gpu": C, "dim": D,
+                   "l2": "working set 295 MB of moments + 49 MB state per push > 126 MB L2"},
+        "e2e": {"value": world * C * D / (e2e_ms * 1e-3), "unit": "elements/s",
+                "h2d_bytes_per_step": C * D * 4 + C * 12, "d2h_bytes_per_step": 0, "steps": n_e2e,
+                "api": "Sink.push after an H2D copy of the state from pinned host memory"},
+        "gpu_launches": steps * reps, "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": recorded_traffic("sink"), "bytes_per_launch": bytes_per_push,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"},
+        "cpu_baseline": None}
 
-    # ---- roofline of the dominant (only) kernel ------------------------------------------------
-    ms_kernel = float(np.mean(kernel_ms))
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    mb = _cabi.microbench(local, 3000)
-    achieved = flop_per_launch / (ms_kernel * 1e-3) / 1e12
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if args.workload in tj and C == w["chains"]:
-            traffic = tj[args.workload]["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    sfu = None
-    if args.workload in ("chromatin", "rex", "chromatin5k"):
-        # the binding pipe of the pair kernel: 3 MUFU (rsqrt, ex2, rcp) per bead pair
-        sfu_gops = 3.0 * units * (L + 1) * C / (ms_kernel * 1e-3) / 1e9
-        sfu = dict(ops_per_pair=3, achieved_gops=sfu_gops, peak_gops=mb["mufu_gops"],
-                   frac=sfu_gops / mb["mufu_gops"],
-                   note="MUFU issues at 16 lanes/clk/SM: 24 SMSP-cycles per warp-pair vs 19 on the FMA "
-                        "pipe, so the special-function unit bounds this kernel at 31/(2*24) = 64.6 % of "
-                        "the FP32-FMA peak")
-    roofline = dict(
-        bound="fp32_fma", achieved=achieved, peak=mb["ffma_tflops"], unit="TFLOP/s",
-        frac=achieved / mb["ffma_tflops"], traffic=traffic, sfu=sfu,
-        peak_source="live FFMA issue microbenchmark in this run (binfb_microbench); "
-                    "MEASURED_PEAKS.json has no non-tensor FP32 figure",
-        peak_formula_tflops=148 * 128 * 2 * 1.965e9 / 1e12,
-        ffma2_tflops=mb["ffma2_tflops"], mufu_gops=mb["mufu_gops"],
-        flop_per_launch=flop_per_launch, kernel_ms=ms_kernel,
-        hbm_sanity=dict(algorithmic_gb_per_launch=bytes_per_launch / 1e9,
-                        achieved_gbs=bytes_per_launch / (ms_kernel * 1e-3) / 1e9,
-                        peak_gbs=peaks.get("hbm_gbs"),
-                        note="compulsory HBM bytes are O(chains x dim) per trajectory: not the bound"))
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(args.workload, args.cpu_seconds)
-    line = dict(metric="HMC leapfrog steps/s (chains x steps)", value=value, unit="leapfrog steps/s",
-                n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=total_ms / args.steps,
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic",
-                config=dict(workload=w["name"], chains_per_gpu=C, leapfrog_steps=L, timestep=eps0,
-                            parallelism="chain-sharded x%d (no data-path collective)" % world,
-                            l2="working set %.0f MB per step > 126 MB L2" % (3 * 4 * C * D / 1e6)
-                            if flush is None else "L2 flushed (256 MiB fill) between timed steps",
-                            gibbs="precision update fused in front of each trajectory"
-                            if gibbs else "none",
-                            replica_exchange=None if rex is None else dict(
-                                betas=betas, swap_rate_rank0=rex.n_swapped / max(1, rex.n_attempted))),
-                acceptance_rate=float(st[0] / st[1]) if st[1] else None,
-                e2e=e2e, gpu_launches=launches[0], wall_ms=wall_ms, clocks=clocks, roofline=roofline,
-                cpu_baseline=cpu)
-    emit(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+
+def brief(leg):
+    """what an `extra` entry keeps of a leg: the numbers the headline line carries for its own workload"""
+    if leg is None:
+        return None
+    keep = ("metric", "value", "unit", "steps", "ms_per_step", "config", "acceptance_rate", "e2e", "gpu_launches",
+            "clocks", "roofline", "swap_rates", "sweep_ms", "swap_ms", "swap_overhead_frac", "dtype")
+    return {k: leg[k] for k in keep if k in leg}
+
+
+def run_ours(args):
+    ctx = Ctx()
+    line = None
+    extras = {}
+    if args.workload == "sink":
+        line = sink_leg(ctx, args, args.steps, args.warmup)
+    elif args.workload == "rex":
+        line = rex_leg(ctx, args, args.steps)
+    else:
+        line = hmc_leg(ctx, args, args.workload, args.steps, args.warmup, chains=args.chains or None,
+                       eps=args.eps or None, with_e2e=not args.no_e2e)
+    # ---- the other configurations of BASELINE.json, short legs on the same box in the same run -----------
+    if args.workload == "chromatin" and not args.no_extra and not args.chains and not args.roles:
+        k = max(3, min(args.steps, 6))
+        for name, fn in (("poly", lambda: hmc_leg(ctx, args, "poly", max(k, 10), 3)),
+                         ("chromatin5k", lambda: hmc_leg(ctx, args, "chromatin5k", 3, 3, with_e2e=False)),
+                         ("sink", lambda: sink_leg(ctx, args, 50, 3)),
+                         ("rex", lambda: rex_leg(ctx, args, 20))):
+            try:
+                extras[name] = brief(fn())
+            except Exception as exc:  # a failing side leg must not take the headline with it
+                extras[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            ctx.sync_all()
+    if ctx.rank == 0:
+        if args.workload in ("chromatin", "poly", "chromatin5k"):
+            line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_seconds) \
+                if ctx.world == 1 and not args.no_cpu else None
+        if extras:
+            line["extra"] = extras
+            line["gpu_launches"] = line["gpu_launches"] + sum(
+                (e or {}).get("gpu_launches", 0) for e in extras.values())
+        emit(json.dumps(line))
+    ctx.close()
 
 
 def main():
@@ -520,16 +641,15 @@ def main():
     ap.add_argument("--ev-k", type=float, default=0.0, help="chromatin: excluded-volume strength (0 = off)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="default workload only: skip the short poly / chromatin5k / sink / rex legs")
     args = ap.parse_args()
     _capture_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.workload == "sink":
-        if args.impl == "reference":
-            emit(json.dumps({"impl": "reference", "unavailable": "the sink workload has no reference arm "
-                              "(the reference keeps a Python list of deep copies of one chain)"}))
-        else:
-            run_sink(args)
+    if args.workload == "sink" and args.impl == "reference":
+        emit(json.dumps({"impl": "reference", "unavailable": "the sink workload has no reference arm "
+                          "(the reference keeps a Python list of deep copies of one chain)"}))
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -115,10 +115,18 @@ class AbstractBinfNamedCallable(object):
             self[v] = self.var_param_types[v](value, v)
 
 
-def install_as_binf():
+def install_as_binf(alias_csb=True):
     """Register this package under the name `binf` so that scripts written against the reference
-    (`from binf.samplers.hmc import HMCSampler`, ...) import the B200 implementation."""
+    (`from binf.samplers.hmc import HMCSampler`, ...) import the B200 implementation.
+
+    alias_csb: also register the slice of CSB such scripts import (`csb.statistics.pdf.parameterized.Parameter`,
+    `csb.numeric.exp`, `csb.statistics.samplers.State`, ...: binf/example/likelihood.py:3, binf/samplers/hmc.py:10,
+    binf/samplers/gibbs.py:7-8) backed by binf_b200.params -- unless a real CSB is importable, whose parameter
+    objects are wrapped when they are assigned to a pdf of this package (binf_b200.params.ForeignParameter)."""
     import importlib
+    if alias_csb:
+        from . import csbshim
+        csbshim.install()
     names = ["pdf", "pdf.posteriors", "pdf.likelihoods", "pdf.priors", "model", "model.forwardmodels",
              "model.errormodels", "samplers", "samplers.hmc", "samplers.gibbs", "example",
              "example.likelihood", "example.priors", "example.samplers", "example.misc"]

@@ -1,6 +1,7 @@
 // C ABI of libbinf_b200.so (declared in include/binf_b200.h).
 #include <math.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string.h>
 
@@ -98,6 +99,38 @@ struct Arena {
 
 static int host_stream(binfb_model *m) {
     if (!m->hstream) BINFB_CUDA(cudaStreamCreateWithFlags(&m->hstream, cudaStreamNonBlocking));
+    return BINFB_OK;
+}
+
+// Stream memory operations of the driver API (cuStreamWriteValue32 / cuStreamWaitValue32), resolved through the
+// runtime so that the library keeps no link-time dependency on libcuda.  They let a copy stream tell a RUNNING
+// kernel that a chunk of its input has landed, and wait for the kernel to say that a chunk of its output is
+// final -- which is what overlaps the PCIe copies of binfb_hmc_run_host with the trajectory kernel.
+typedef int (*stream_value32_fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+struct StreamMemOps {
+    stream_value32_fn write = nullptr, wait = nullptr;
+    bool ok = false;
+};
+static const StreamMemOps &stream_mem_ops() {
+    static StreamMemOps ops = [] {
+        StreamMemOps o;
+        void *w = nullptr, *t = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &qr) == cudaSuccess && w &&
+            qr == cudaDriverEntryPointSuccess &&
+            cudaGetDriverEntryPoint("cuStreamWaitValue32", &t, cudaEnableDefault, &qr) == cudaSuccess && t &&
+            qr == cudaDriverEntryPointSuccess) {
+            o.write = (stream_value32_fn)w, o.wait = (stream_value32_fn)t, o.ok = true;
+        }
+        cudaGetLastError();
+        return o;
+    }();
+    return ops;
+}
+static int pipe_streams(binfb_model *m) {
+    if (!m->hstream_in) BINFB_CUDA(cudaStreamCreateWithFlags(&m->hstream_in, cudaStreamNonBlocking));
+    if (!m->hstream_out) BINFB_CUDA(cudaStreamCreateWithFlags(&m->hstream_out, cudaStreamNonBlocking));
+    if (!m->hevent) BINFB_CUDA(cudaEventCreateWithFlags(&m->hevent, cudaEventDisableTiming));
     return BINFB_OK;
 }
 
@@ -303,6 +336,9 @@ int binfb_model_destroy(binfb_model *m) {
     cudaFree(c.chi2_0), cudaFree(c.chi2_state), cudaFree(c.tau_w), cudaFree(c.sched);
     if (m->hb) cudaFree(m->hb);
     if (m->hstream) cudaStreamDestroy(m->hstream);
+    if (m->hstream_in) cudaStreamDestroy(m->hstream_in);
+    if (m->hstream_out) cudaStreamDestroy(m->hstream_out);
+    if (m->hevent) cudaEventDestroy(m->hevent);
     delete m;
     return BINFB_OK;
 }
@@ -334,6 +370,7 @@ int binfb_model_set_option(binfb_model *m, const char *key, double value) {
     else if (!strcmp(key, "poly.chains_per_thread")) m->poly.opt_jchains = v;
     else if (!strcmp(key, "poly.block")) m->poly.opt_block = v;
     else if (!strcmp(key, "chrom.warps")) m->chrom.opt_warps = v;
+    else if (!strcmp(key, "host.pipeline")) m->host_pipeline = v != 0;
     else if (!strcmp(key, "chrom.ev_k") || !strcmp(key, "chrom.ev_d")) {
         // excluded-volume prior k_ev sum_{i<j} max(0, d_ev - d_ij)^4 of the chromatin model (0 = off)
         if (m->kind != BINFB_MODEL_CHROMATIN || value < 0) {
@@ -451,6 +488,81 @@ int binfb_hmc_run_host(binfb_model *m, float *q, float *tau, const float *beta, 
                  ope = ar.plan(C * D * 4), on = ar.plan(C * 4), os = ar.plan(32);
     if ((rc = ar.commit())) return rc;
     cudaStream_t s = m->hstream;
+    // ---- pipelined variant (chromatin, batches whose state copy is worth hiding): ONE launch; the state goes
+    //      up in chunks on a copy-in stream that opens the kernel's gate chunk by chunk, and comes back in chunks
+    //      on a copy-out stream that waits for the kernel's per-chunk completion counters (chromatin.cu,
+    //      CHROM_GATE_WORDS).  The small per-chain arrays travel on the kernel's stream as before.
+    const bool want_pipe = m->kind == BINFB_MODEL_CHROMATIN && !p0 && !q_end && !p_end && m->host_pipeline &&
+                           (size_t)C * D * 4 >= ((size_t)4 << 20) && stream_mem_ops().ok &&
+                           !(m->chrom.ev_k > 0.f && opts->gibbs_mode == BINFB_GIBBS_TAU_FIRST);
+    ChromPipe pipe;
+    if (want_pipe && chrom_pipe_shape(m->chrom, C, m->sm_count, 8, &pipe) == BINFB_OK && pipe.n_chunks >= 2 &&
+        pipe_streams(m) == BINFB_OK) {
+        const StreamMemOps &mo = stream_mem_ops();
+        BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(ot), tau, C * 4, cudaMemcpyHostToDevice, s));
+        BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(oe), eps, C * 4, cudaMemcpyHostToDevice, s));
+        if (beta) BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(ob), beta, C * 4, cudaMemcpyHostToDevice, s));
+        if (u) BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(ou), u, C * 4, cudaMemcpyHostToDevice, s));
+        if (gamma_draws)
+            BINFB_CUDA(cudaMemcpyAsync(ar.at<double>(og), gamma_draws, C * 8, cudaMemcpyHostToDevice, s));
+        if (stats) BINFB_CUDA(cudaMemsetAsync(ar.at<double>(os), 0, 32, s));
+        const HmcArgs a = make_hmc_args(m, ar.at<float>(oq), ar.at<float>(ot), beta ? ar.at<float>(ob) : nullptr,
+                                        ar.at<float>(oe), C, opts, nullptr, u ? ar.at<float>(ou) : nullptr,
+                                        gamma_draws ? ar.at<double>(og) : nullptr,
+                                        accepted ? ar.at<uint8_t>(oa) : nullptr, e_before ? ar.at<double>(o0) : nullptr,
+                                        e_after ? ar.at<double>(o1) : nullptr, nullptr, nullptr,
+                                        n_accepted ? ar.at<int32_t>(on) : nullptr, stats ? ar.at<double>(os) : nullptr);
+        pipe.header_written = m->hevent;  // recorded on s between the gate header and the kernel
+        rc = chrom_hmc_launch(m->chrom, a, m->sm_count, m->smem_optin, s, &pipe);
+        if (rc) return rc;
+        const size_t chunk_chains = (size_t)pipe.groups_per_chunk * pipe.W;
+        BINFB_CUDA(cudaStreamWaitEvent(m->hstream_in, m->hevent, 0));
+        int pipe_err = 0;
+        for (int j = 0; j < pipe.n_chunks && !pipe_err; ++j) {
+            const size_t c0 = (size_t)j * chunk_chains, c1 = std::min((size_t)C, c0 + chunk_chains);
+            if (cudaMemcpyAsync(ar.at<float>(oq) + c0 * D, q + c0 * D, (c1 - c0) * D * 4, cudaMemcpyHostToDevice,
+                                m->hstream_in) != cudaSuccess)
+                pipe_err = 1;
+            // even after a failed copy the gate is opened, so that the kernel never waits for data that will not come
+            if (mo.write(m->hstream_in, (unsigned long long)(uintptr_t)pipe.gate, (unsigned int)(c1 + 1), 0) != 0)
+                pipe_err = 1;
+        }
+        if (pipe_err) {
+            // open the gate from the host side of things and fall through to a plain synchronise
+            const int all = C + 1;
+            cudaMemcpyAsync(pipe.gate, &all, sizeof(int), cudaMemcpyHostToDevice, m->hstream_in);
+            cudaStreamSynchronize(m->hstream_in);
+            cudaStreamSynchronize(s);
+            return cuda_fail(cudaGetLastError(), "pipelined host call: copy-in");
+        }
+        for (int j = 0; j < pipe.n_chunks; ++j) {
+            const size_t c0 = (size_t)j * chunk_chains, c1 = std::min((size_t)C, c0 + chunk_chains);
+            const int g0 = j * pipe.groups_per_chunk;
+            const int groups = std::min(pipe.n_groups, g0 + pipe.groups_per_chunk) - g0;
+            // CU_STREAM_WAIT_VALUE_GEQ = 0
+            if (mo.wait(m->hstream_out, (unsigned long long)(uintptr_t)(pipe.done + j), (unsigned int)groups, 0) != 0) {
+                cudaStreamSynchronize(s);  // the kernel still finishes; copy everything after it instead
+                BINFB_CUDA(cudaMemcpyAsync(q + c0 * D, ar.at<float>(oq) + c0 * D, ((size_t)C - c0) * D * 4,
+                                           cudaMemcpyDeviceToHost, m->hstream_out));
+                break;
+            }
+            BINFB_CUDA(cudaMemcpyAsync(q + c0 * D, ar.at<float>(oq) + c0 * D, (c1 - c0) * D * 4,
+                                       cudaMemcpyDeviceToHost, m->hstream_out));
+        }
+        if (opts->gibbs_mode != BINFB_GIBBS_NONE)
+            BINFB_CUDA(cudaMemcpyAsync(tau, ar.at<float>(ot), C * 4, cudaMemcpyDeviceToHost, s));
+        if (opts->n_adapt > 0)
+            BINFB_CUDA(cudaMemcpyAsync(eps, ar.at<float>(oe), C * 4, cudaMemcpyDeviceToHost, s));
+        if (accepted) BINFB_CUDA(cudaMemcpyAsync(accepted, ar.at<uint8_t>(oa), C, cudaMemcpyDeviceToHost, s));
+        if (e_before) BINFB_CUDA(cudaMemcpyAsync(e_before, ar.at<double>(o0), C * 8, cudaMemcpyDeviceToHost, s));
+        if (e_after) BINFB_CUDA(cudaMemcpyAsync(e_after, ar.at<double>(o1), C * 8, cudaMemcpyDeviceToHost, s));
+        if (n_accepted) BINFB_CUDA(cudaMemcpyAsync(n_accepted, ar.at<int32_t>(on), C * 4, cudaMemcpyDeviceToHost, s));
+        if (stats) BINFB_CUDA(cudaMemcpyAsync(stats, ar.at<double>(os), 32, cudaMemcpyDeviceToHost, s));
+        BINFB_CUDA(cudaStreamSynchronize(m->hstream_in));
+        BINFB_CUDA(cudaStreamSynchronize(m->hstream_out));
+        BINFB_CUDA(cudaStreamSynchronize(s));
+        return BINFB_OK;
+    }
     BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(oq), q, C * D * 4, cudaMemcpyHostToDevice, s));
     BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(ot), tau, C * 4, cudaMemcpyHostToDevice, s));
     BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(oe), eps, C * 4, cudaMemcpyHostToDevice, s));

@@ -111,6 +111,26 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
 __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Host pipelining of binfb_hmc_run_host (capi.cu): behind the per-group pass counters the scheduler words hold
+//   gate[0]      0 = the whole batch is resident (device entry point); else 1 + number of leading chains whose
+//                positions have arrived -- written by the copy-in stream after every chunk of the H2D copy
+//                (cuStreamWriteValue32), read here before the first pass of a group;
+//   gate[1]      chain groups per output chunk (0 = none);
+//   gate[2 + j]  number of groups of output chunk j that have finished their last pass -- the copy-out stream
+//                waits on it (cuStreamWaitValue32) before it copies the chunk back.
+// So the H2D copy of the batch hides under the first pass of the groups that are already there and the D2H copy
+// under the last pass of those still running: one launch, no chunked kernels.
+constexpr int CHROM_GATE_WORDS = 2 + 64;
 // barrier over the warps of one chain (ids 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void chain_bar(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -658,6 +678,21 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                 const int need = it / call.n_groups;  // passes of this group that must be done
                 if (need > 0)
                     while (ld_acquire(cd.pass_done + o) < need) __nanosleep(100);
+                else {
+                    // first pass of the group: under a pipelined host call its positions may still be in flight
+                    const int *gate = cd.pass_done + call.n_groups;
+                    int g = ld_acquire_sys(gate);
+                    if (g != 0) {
+                        const int Cn = call.mode == CHROM_MODE_HMC ? call.h.C : call.g.C;
+                        int last = (o + 1) * call.W;
+                        if (last > Cn) last = Cn;
+                        const unsigned long long t0 = global_timer_ns();
+                        while (g - 1 < last && global_timer_ns() - t0 < 10000000000ull) {  // (10 s: never hang the GPU)
+                            __nanosleep(200);
+                            g = ld_acquire_sys(gate);
+                        }
+                    }
+                }
             }
             *s_item = it;
         }
@@ -950,7 +985,16 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
         fence_proxy_async_global();  // writer side: this thread's __stcg stores to qw vs the next pass's bulk copy
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) st_release(cd.pass_done + o, seq + 1);
+        if (threadIdx.x == 0) {
+            st_release(cd.pass_done + o, seq + 1);
+            int *gate = cd.pass_done + call.n_groups;
+            const int gpc = gate[1];  // (written before the launch)
+            if (gpc > 0 && (seq + 1) * call.n_groups + o >= call.total_items) {
+                // last pass of this group under a pipelined host call: its results may be copied back
+                __threadfence_system();
+                atomicAdd_system(gate + 2 + o / gpc, 1);
+            }
+        }
     }
 }
 
@@ -1095,7 +1139,7 @@ int chrom_reserve(ChromModel &m, int C) {
         BINFB_CUDA(cudaMalloc(&m.tau_w, (size_t)C * sizeof(float)));
         m.ws_chains = C;
     }
-    const int need = 1 + C;  // item counter + one pass counter per chain group (W >= 1)
+    const int need = 1 + C + CHROM_GATE_WORDS;  // item counter + one pass counter per chain group (W >= 1) + gate
     if (need > m.sched_len) {
         cudaFree(m.sched);
         m.sched = nullptr;
@@ -1127,11 +1171,8 @@ static ChromDev chrom_dev(const ChromModel &m, const ChromPlan &pl, const float 
     return d;
 }
 
-static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int smem_optin,
-                        cudaStream_t s) {
-    int rc = chrom_reserve(m, C);
-    if (rc) return rc;
-    // chains per CTA for a plan: rather fewer chains per CTA than idle SMs
+// the launch shape chrom_launch will pick for C chains: plan (primary or small-batch) and chains per CTA
+static const ChromPlan *chrom_pick_plan(const ChromModel &m, int C, int sm_count, const float **ystream, int *W_out) {
     auto chains_per_cta = [&](const ChromPlan &p) {
         int w = p.W;
         if (w >= 1 && (C + w - 1) / w < sm_count) w = (C + sm_count - 1) / sm_count;
@@ -1141,13 +1182,38 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
         return w;
     };
     const ChromPlan *plp = &m.plan;
-    const float *ystream = m.ystream;
+    *ystream = m.ystream;
     int W = chains_per_cta(m.plan);
     // a batch that leaves the SMs half empty with the primary plan runs with twice the warps per chain
     if (m.ystream_alt && W >= 1 && W * m.plan.R <= 8) {
         const int wa = chains_per_cta(m.plan_alt);
-        if (wa >= 1 && wa * m.plan_alt.R > W * m.plan.R) plp = &m.plan_alt, ystream = m.ystream_alt, W = wa;
+        if (wa >= 1 && wa * m.plan_alt.R > W * m.plan.R) plp = &m.plan_alt, *ystream = m.ystream_alt, W = wa;
     }
+    *W_out = W;
+    return plp;
+}
+
+int chrom_pipe_shape(const ChromModel &m, int C, int sm_count, int max_chunks, ChromPipe *pipe) {
+    const float *ys;
+    int W = 0;
+    chrom_pick_plan(m, C, sm_count, &ys, &W);
+    if (W < 1) return BINFB_EUNSUPPORTED;
+    const int n_groups = (C + W - 1) / W;
+    int n_chunks = max_chunks < 64 ? max_chunks : 64;
+    if (n_chunks > n_groups) n_chunks = n_groups;
+    pipe->W = W, pipe->n_groups = n_groups;
+    pipe->groups_per_chunk = (n_groups + n_chunks - 1) / n_chunks;
+    pipe->n_chunks = (n_groups + pipe->groups_per_chunk - 1) / pipe->groups_per_chunk;
+    return BINFB_OK;
+}
+
+static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int smem_optin,
+                        cudaStream_t s, ChromPipe *pipe = nullptr) {
+    int rc = chrom_reserve(m, C);
+    if (rc) return rc;
+    const float *ystream = nullptr;
+    int W = 0;
+    const ChromPlan *plp = chrom_pick_plan(m, C, sm_count, &ystream, &W);
     const ChromPlan &pl = *plp;
     if (W < 1) {
         set_error("chromatin model: one chain does not fit in shared memory (n_beads too large for "
@@ -1172,7 +1238,21 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
         while (F >= 2 && smem + (size_t)W * F * FLUSH_ROLE_BYTES > (size_t)smem_optin) F /= 2;
         if (F >= 2) smem += (size_t)W * F * FLUSH_ROLE_BYTES;
     }
-    BINFB_CUDA(cudaMemsetAsync(m.sched, 0, (size_t)(1 + call.n_groups) * sizeof(int), s));
+    BINFB_CUDA(cudaMemsetAsync(m.sched, 0, (size_t)(1 + call.n_groups + CHROM_GATE_WORDS) * sizeof(int), s));
+    if (pipe) {
+        // pipelined host call: nothing has arrived yet (gate = 1 + 0 chains); the caller's copy streams write
+        // the gate and wait on the chunk counters (see CHROM_GATE_WORDS)
+        if (pipe->W != W || pipe->n_groups != call.n_groups) {
+            set_error("chromatin model: pipelined launch shape changed between query and launch");
+            return BINFB_EINVAL;
+        }
+        pipe->gate = m.sched + 1 + call.n_groups;
+        pipe->done = pipe->gate + 2;
+        pipe->header[0] = 1, pipe->header[1] = pipe->groups_per_chunk;
+        BINFB_CUDA(cudaMemcpyAsync(pipe->gate, pipe->header, 2 * sizeof(int), cudaMemcpyHostToDevice, s));
+        // the copy streams may touch the gate from here on -- NOT after the kernel, which waits for them
+        BINFB_CUDA(cudaEventRecord(pipe->header_written, s));
+    }
     const int grid = call.n_groups < sm_count ? call.n_groups : sm_count;
     const int threads = W * pl.R * 32;
     const ChromDev dev = chrom_dev(m, pl, ystream);
@@ -1218,7 +1298,8 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
     return BINFB_OK;
 }
 
-int chrom_hmc_launch(ChromModel &m, const HmcArgs &a, int sm_count, int smem_optin, cudaStream_t s) {
+int chrom_hmc_launch(ChromModel &m, const HmcArgs &a, int sm_count, int smem_optin, cudaStream_t s,
+                     ChromPipe *pipe) {
     ChromCall call;
     call.mode = CHROM_MODE_HMC;
     call.h = a;
@@ -1235,7 +1316,11 @@ int chrom_hmc_launch(ChromModel &m, const HmcArgs &a, int sm_count, int smem_opt
         rc = chrom_grad_launch(m, g, sm_count, smem_optin, s);
         if (rc) return rc;
     }
-    const int rc2 = chrom_launch(m, call, a.C, sm_count, smem_optin, s);
+    if (pipe && m.ev_k > 0.f && a.gibbs_mode == BINFB_GIBBS_TAU_FIRST) {
+        set_error("chromatin model: the pipelined host call does not cover excluded volume + precision-first Gibbs");
+        return BINFB_EUNSUPPORTED;
+    }
+    const int rc2 = chrom_launch(m, call, a.C, sm_count, smem_optin, s, pipe);
     m.chi2_chains = rc2 ? 0 : a.C;  // chi2_state now holds chi^2 of every chain's current state (binfb_hmc_last_chi2)
     return rc2;
 }

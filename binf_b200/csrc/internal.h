@@ -113,8 +113,17 @@ ChromPlan chrom_plan(int n, int smem_optin, int force_roles);
 ChromPlan chrom_plan_small_batch(int n, int smem_optin, const ChromPlan &primary);
 int chrom_build_stream(int n, const float *y_pairs, const ChromPlan &pl, float *out);
 int chrom_reserve(ChromModel &m, int C);
+// pipelined host call (binfb_hmc_run_host): launch shape and the device words the copy streams talk to
+struct ChromPipe {
+    int W = 0, n_groups = 0, groups_per_chunk = 0, n_chunks = 0;
+    int *gate = nullptr;  // device: 1 + number of leading chains whose positions have arrived
+    int *done = nullptr;  // device [n_chunks]: groups of the chunk that have finished their last pass
+    int header[2] = {0, 0};  // host staging of {gate, groups_per_chunk} (must outlive the async copy)
+    cudaEvent_t header_written = nullptr;  // recorded on the launch stream between the header and the kernel
+};
+int chrom_pipe_shape(const ChromModel &m, int C, int sm_count, int max_chunks, ChromPipe *pipe);
 int chrom_hmc_launch(ChromModel &m, const HmcArgs &a, int sm_count, int smem_optin,
-                     cudaStream_t s);
+                     cudaStream_t s, ChromPipe *pipe = nullptr);
 int chrom_grad_launch(ChromModel &m, const GradArgs &a, int sm_count, int smem_optin,
                       cudaStream_t s);
 int chrom_forward_launch(const ChromModel &m, const float *q, int C, float *mock, cudaStream_t s);
@@ -178,4 +187,7 @@ struct binfb_model {
     size_t hb_bytes = 0;
     char *hb = nullptr;
     cudaStream_t hstream = nullptr;
+    cudaStream_t hstream_in = nullptr, hstream_out = nullptr;  // copy streams of the pipelined host call
+    cudaEvent_t hevent = nullptr;
+    bool host_pipeline = true;  // option "host.pipeline": overlap the copies of the *_host calls with the kernel
 };

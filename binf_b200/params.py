@@ -45,8 +45,13 @@ class AbstractParameter(object):
         return self._base is not None
 
     @property
+    def _volatile(self):
+        """True if a base up the chain changes without telling its followers (a foreign parameter object)"""
+        return self._base is not None and self._base._volatile
+
+    @property
     def value(self):
-        if self._stale:
+        if self._stale or self._volatile:
             self._value = self._validate(self._compute(self._base.value))
             self._stale = False
         return self._value
@@ -106,6 +111,43 @@ class ArrayParameter(AbstractParameter):
             raise ParameterValueError(self._name, value)
 
 
+class ForeignParameter(AbstractParameter):
+    """Adapter around a parameter object of ANOTHER library that quacks like CSB's (`.value`, `.set`, `.name`) --
+    e.g. a real `csb.statistics.pdf.parameterized.Parameter` handed to a pdf of this package.  Reads and writes
+    go through to the wrapped object; because that object cannot notify this package's followers when it
+    changes, everything bound to the adapter re-reads it on every access."""
+
+    def __init__(self, foreign):
+        self._foreign = foreign
+        super().__init__(None, getattr(foreign, "name", None))
+
+    _volatile = True
+
+    @property
+    def value(self):
+        return self._foreign.value
+
+    def set(self, value):
+        self._foreign.set(value)
+        self._mark_followers()
+
+    def bind_to(self, base):
+        raise ParameterizationError("a foreign parameter object cannot be bound here: " + self._name)
+
+
+def is_parameter_like(obj):
+    return all(hasattr(obj, a) for a in ("value", "set", "name"))
+
+
+def adopt(obj):
+    """a parameter object this package can store and bind: itself, or a ForeignParameter around a duck-typed one"""
+    if isinstance(obj, AbstractParameter):
+        return obj
+    if is_parameter_like(obj):
+        return ForeignParameter(obj)
+    return None
+
+
 class ParameterNotFoundError(AttributeError):
     """raised when a parameter name is not registered (binf/pdf/__init__.py:14)"""
 
@@ -133,6 +175,8 @@ class ParameterRegistry(object):
     def __setitem__(self, name, obj):
         if name not in self._table:
             raise ParameterNotFoundError(name)
+        if not isinstance(obj, AbstractParameter) and is_parameter_like(obj):
+            obj = ForeignParameter(obj)   # duck-typed parameter of another library (a real CSB install)
         if not self._accepts(name, obj):
             raise TypeError(obj)
         self._table[name] = obj

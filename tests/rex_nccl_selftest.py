@@ -60,8 +60,13 @@ def main():
         np.testing.assert_array_equal(sh.beta.cpu().numpy(),
                                       np.array(drv.betas, dtype=np.float32)[drv.rex.tidx.cpu().numpy()])
     drv.adapt(target=0.3)
-    drv.run(40)
-    drv.adapt(target=0.3)
+    for measure in (40, 40):                                      # re-equilibrate, measure, re-space
+        drv.run(20)
+        drv.rex.reset_stats()
+        drv.run(measure)
+        drv.adapt(target=0.3)
+    drv.run(20)
+    drv.rex.reset_stats()
     drv.run(80)
     rates = drv.swap_rates()
     assert all(0.1 < r < 0.7 for r in rates), rates

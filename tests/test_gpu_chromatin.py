@@ -380,3 +380,34 @@ def test_n6000_two_stage_ring_fallback(gpu):
     fwd = m.hmc_run(q, tau, 0.001, 2, p0=p0, u=u, want_end=True)
     back = m.hmc_run(fwd["q_end"], tau, 0.001, 2, p0=-fwd["p_end"], u=u, want_end=True)
     assert np.max(np.abs(back["q_end"] - q)) < 2e-4 * np.max(np.abs(q))
+
+
+def test_pipelined_host_call_equals_the_serial_one(gpu):
+    """binfb_hmc_run_host overlaps the state copies with the ONE trajectory launch (the copy-in stream opens the
+    kernel's gate chunk by chunk, the copy-out stream waits on per-chunk completion counters).  Same launch,
+    same arithmetic: the result must be bit-identical to copy-in / run / copy-out, including Gibbs updates,
+    rejected chains (their states come back unchanged) and a ragged last chunk."""
+    from binf_b200 import _cabi
+    n, C = 100, 4099                     # 4.9 MB of state: above the pipelining threshold; C not a multiple of W
+    X, y = chrom.synthetic_chromatin(n, seed=7)
+    m = _cabi.Model.chromatin(n, y, 2.0, 2.5, 4.0, 1.0)
+    rng = np.random.RandomState(3)
+    q0 = (X.reshape(-1)[None] + 0.05 * rng.normal(size=(C, 3 * n))).astype(np.float32)
+    eps = np.where(np.arange(C) % 3 == 0, 0.05, 0.004).astype(np.float32)      # a third of the chains rejects
+    out = {}
+    for mode in (1, 0):
+        m.set_option("host.pipeline", mode)
+        out[mode] = m.hmc_run(q0, 60.0, eps, 6, n_traj=2, n_adapt=2, gibbs_mode=_cabi.GIBBS_TAU_FIRST, seed=5, draw=3)
+    for key in ("q", "tau", "eps", "accepted", "e_before", "e_after", "n_accepted", "stats"):
+        np.testing.assert_array_equal(out[1][key], out[0][key], err_msg=key)
+    acc = out[1]["n_accepted"]
+    assert 0 < (acc == 0).sum() and (acc > 0).sum() > C // 2
+    np.testing.assert_array_equal(out[1]["q"][acc == 0], q0[acc == 0])
+    # injected uniforms travel on the kernel's stream in the pipelined path too
+    m.set_option("host.pipeline", 1)
+    u = rng.uniform(size=C).astype(np.float32)
+    r1 = m.hmc_run(q0, 60.0, 0.004, 5, u=u, seed=1)
+    m.set_option("host.pipeline", 0)
+    r0 = m.hmc_run(q0, 60.0, 0.004, 5, u=u, seed=1)
+    np.testing.assert_array_equal(r1["q"], r0["q"])
+    assert r1["accepted"].mean() > 0.5

@@ -185,8 +185,13 @@ def test_tempered_ensemble_on_one_gpu(gpu):
     assert new[0] == 1.0 and all(a > b for a, b in zip(new, new[1:]))
     torch.cuda.synchronize()
     assert torch.equal(q, q_before)                               # neither exchanges nor adaption move a state
-    drv.run(40)
-    drv.adapt(target=0.3)
+    for measure in (40, 40):                                      # re-equilibrate, measure, re-space
+        drv.run(20)
+        drv.rex.reset_stats()
+        drv.run(measure)
+        drv.adapt(target=0.3)
+    drv.run(20)
+    drv.rex.reset_stats()
     drv.run(60)
     rates2 = drv.swap_rates()
     assert all(0.1 < r < 0.7 for r in rates2), rates2
@@ -194,13 +199,13 @@ def test_tempered_ensemble_on_one_gpu(gpu):
     drv.run(6, sink=sink, thin=2)
     torch.cuda.synchronize()
     info = sink.info()
-    assert info["n_pushed"] == 3 and drv.n_sweeps == 136
+    assert info["n_pushed"] == 3 and drv.n_sweeps == 236
     cold_q, cold_tau = drv.cold_states()
     where = (drv.rex.tidx == 0).nonzero().flatten()
     assert len(where) == cols
     order = torch.argsort(where % cols)
     assert torch.equal(cold_q, q[where[order]]) and torch.equal(cold_tau, tau[where[order]])
-    assert drv.last_draw_stats["swap"].attempt == 135 and 0.0 <= drv.last_draw_stats["swap"].accepted_fraction <= 1.0
+    assert drv.last_draw_stats["swap"].attempt == 235 and 0.0 <= drv.last_draw_stats["swap"].accepted_fraction <= 1.0
 
 
 def test_nccl_label_swap_self_test(gpu):
