@@ -496,7 +496,7 @@ int binfb_hmc_run_host(binfb_model *m, float *q, float *tau, const float *beta, 
                            (size_t)C * D * 4 >= ((size_t)4 << 20) && stream_mem_ops().ok &&
                            !(m->chrom.ev_k > 0.f && opts->gibbs_mode == BINFB_GIBBS_TAU_FIRST);
     ChromPipe pipe;
-    if (want_pipe && chrom_pipe_shape(m->chrom, C, m->sm_count, 8, &pipe) == BINFB_OK && pipe.n_chunks >= 2 &&
+    if (want_pipe && chrom_pipe_shape(m->chrom, C, m->sm_count, 16, &pipe) == BINFB_OK && pipe.n_chunks >= 2 &&
         pipe_streams(m) == BINFB_OK) {
         const StreamMemOps &mo = stream_mem_ops();
         BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(ot), tau, C * 4, cudaMemcpyHostToDevice, s));

@@ -224,3 +224,14 @@ def reference_posterior(binf, model):
     priors = {"structure_prior": Backbone(model),
               "precision_prior": GammaPrior(model.gamma_shape, model.gamma_rate)}
     return Posterior({lik.name: lik}, priors)
+
+
+def acceptance_inputs(n_beads, n_chains, seed):
+    """the seeded inputs of `chromatin_acceptance_case`, regenerated (not stored) by the GPU test"""
+    alpha, d_c, k_bb, l0 = 2.0, 2.5, 4.0, 1.0
+    X, y = synthetic_chromatin(n_beads, alpha, d_c, l0, 0.05, seed)
+    rng = np.random.RandomState(seed + 1)
+    q0 = X.reshape(-1)[None, :] + 0.05 * rng.normal(size=(n_chains, 3 * n_beads))
+    p0 = rng.normal(size=q0.shape)
+    u = rng.uniform(size=n_chains)
+    return (alpha, d_c, k_bb, l0), y, q0, p0, u

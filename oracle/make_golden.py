@@ -238,6 +238,55 @@ def chromatin_case(binf, name, n_beads, n_chains, nsteps, timestep, seed, tau=50
     print(name, "acceptance", np.mean(acc), "max |dH|", np.max(np.abs(np.array(ea) - eb)))
 
 
+def _acceptance_worker(args):
+    n_beads, n_chains, seed, tau, timestep, nsteps, lo, hi = args
+    (alpha, d_c, k_bb, l0), y, q0, p0, u = chrom.acceptance_inputs(n_beads, n_chains, seed)
+    model = chrom.ChromatinModel(n_beads, y, alpha, d_c, k_bb, l0)
+    out = []
+    for c in range(lo, hi):
+        r = port.hmc_sample(lambda q: model.log_prob(q, tau), lambda q: model.gradient(q, tau), q0[c], timestep,
+                            nsteps, p0[c], u[c])
+        out.append((r["e_after"] - r["e_before"], bool(r["accepted"])))
+    return out
+
+
+def chromatin_acceptance_case(binf, name, n_beads, n_chains, nsteps, timestep, seed, tau=60.0):
+    """L = 20 acceptance at a WORKING step size over >= 10^4 chain-trajectories.  The
+    decision being matched is binf/samplers/hmc.py:151.  The first chains go through the reference's own
+    HMCSampler (dense J.dot(g)); all of them through the port (asserted equal on the shared chains), whose
+    energy differences and decisions are stored.  Inputs are seeded and regenerated by the test."""
+    import multiprocessing as mp
+    from binf.samplers.hmc import HMCSampler
+    (alpha, d_c, k_bb, l0), y, q0, p0, u = chrom.acceptance_inputs(n_beads, n_chains, seed)
+    model = chrom.ChromatinModel(n_beads, y, alpha, d_c, k_bb, l0)
+    cond = chrom.reference_posterior(binf, model).conditional_factory(precision=tau)
+    gp = [p for p in cond.priors.values() if "precision" in p._original_variables][0]
+    assert (gp.shape, gp.rate) == (1.0, 1.0)
+    n_ref = 6
+    ref_acc, ref_dh = [], []
+    for c in range(n_ref):
+        s = HMCSampler(cond, q0[c].copy(), timestep, nsteps, variable_name="structure")
+        ql, pl = s._leapfrog(q0[c].copy(), p0[c].copy(), timestep, nsteps)
+        ref_dh.append(-cond.log_prob(structure=ql.copy()) + 0.5 * np.sum(pl ** 2)
+                      + cond.log_prob(structure=q0[c].copy()) - 0.5 * np.sum(p0[c] ** 2))
+        with InjectedRandom(normals=[p0[c]], uniforms=[u[c]]):
+            s.sample()
+        ref_acc.append(bool(s.last_move_accepted))
+    workers = max(1, len(os.sched_getaffinity(0)))
+    bounds = np.linspace(0, n_chains, workers * 4 + 1).astype(int)
+    jobs = [(n_beads, n_chains, seed, tau, timestep, nsteps, int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:])]
+    with mp.get_context("fork").Pool(workers) as pool:
+        res = [x for part in pool.map(_acceptance_worker, jobs) for x in part]
+    dh = np.array([r[0] for r in res])
+    acc = np.array([r[1] for r in res])
+    close(dh[:n_ref], ref_dh, 1e-7)
+    assert list(acc[:n_ref]) == ref_acc
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), n_beads=n_beads, n_chains=n_chains, seed=seed, tau=tau,
+                        nsteps=nsteps, timestep=timestep, y_checksum=float(np.sum(y.astype(np.float64))),
+                        dh=dh, accepted=acc, u=u)
+    print(name, "acceptance", acc.mean(), "mean min(1, exp(-dH))", np.mean(np.exp(np.minimum(0.0, -dh))))
+
+
 def user_model_case(binf, name, n_data, n_chains, nsteps, timestep, seed):
     """A USER-DEFINED forward model written against the reference's own extension point
     (AbstractForwardModel._evaluate / _evaluate_jacobi_matrix, binf/model/forwardmodels.py:30-38):
@@ -383,6 +432,10 @@ def main():
         chromatin_case(binf, "chromatin_ev_n28", n_beads=28, n_chains=8, nsteps=6, timestep=0.004, seed=11,
                        ev_k=5.0, ev_d=1.6)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "accept":   # acceptance at a working step size
+        chromatin_acceptance_case(binf, "chromatin_accept_n64", n_beads=64, n_chains=10240, nsteps=20,
+                                  timestep=0.032, seed=12)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "user":     # the fixture added with SURVEY 8f rank 2
         user_model_case(binf, "user_decay_n200", n_data=200, n_chains=24, nsteps=10, timestep=0.012, seed=10)
         return
@@ -406,6 +459,8 @@ def main():
                    timestep=0.05, seed=8)
     chromatin_case(binf, "chromatin_ev_n28", n_beads=28, n_chains=8, nsteps=6, timestep=0.004, seed=11,
                    ev_k=5.0, ev_d=1.6)
+    chromatin_acceptance_case(binf, "chromatin_accept_n64", n_beads=64, n_chains=10240, nsteps=20,
+                              timestep=0.032, seed=12)
     rwmc_predict_case(binf, "poly_rwmc_n20", n_data=20, n_chains=24, n_moves=6, stepsize=0.1, seed=9)
     user_model_case(binf, "user_decay_n200", n_data=200, n_chains=24, nsteps=10, timestep=0.012, seed=10)
 

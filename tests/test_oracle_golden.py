@@ -146,3 +146,21 @@ def test_user_model_port_vs_reference_outputs():
     np.testing.assert_allclose(r["q_end"], g["q_end"], rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(r["e_after"], g["e_after"], rtol=1e-10)
     assert np.array_equal(r["accepted"], g["accepted"]) and not g["accepted"].all()
+
+
+def test_port_reproduces_a_sample_of_the_acceptance_fixture():
+    """chromatin_accept_n64: energy differences and decisions of 10,240 seeded L = 20 trajectories (written by
+    oracle/make_golden.py, whose first chains went through the reference's own HMCSampler); spot-check chains
+    spread over the fixture against the port, and the fixture's own consistency (hmc.py:151)"""
+    g = load_golden("chromatin_accept_n64")
+    n, C = int(g["n_beads"]), int(g["n_chains"])
+    (alpha, d_c, k_bb, l0), y, q0, p0, u = chrom.acceptance_inputs(n, C, int(g["seed"]))
+    assert float(np.sum(y.astype(np.float64))) == float(g["y_checksum"])
+    model = chrom.ChromatinModel(n, y, alpha, d_c, k_bb, l0)
+    tau, eps, L = float(g["tau"]), float(g["timestep"]), int(g["nsteps"])
+    for c in (0, 1, 4097, C - 1):
+        r = port.hmc_sample(lambda q: model.log_prob(q, tau), lambda q: model.gradient(q, tau), q0[c], eps, L, p0[c], u[c])
+        assert abs((r["e_after"] - r["e_before"]) - g["dh"][c]) < 1e-9
+        assert bool(r["accepted"]) == bool(g["accepted"][c])
+    np.testing.assert_array_equal(g["accepted"], u < np.exp(np.clip(-g["dh"], -308, 709)))
+    assert C >= 10000 and 0.7 < g["accepted"].mean() < 0.9
