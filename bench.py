@@ -279,6 +279,8 @@ def make_hmc_workload(ctx, args, name, chains=None):
         y, q_host = chromatin_inputs(w, C, ctx.rank)
         model = _cabi.Model.chromatin(w["n_beads"], y, w["alpha"], w["d_c"], w["k_bb"], w["l0"], 0.0,
                                       1.0, 1.0, device=ctx.local, roles=args.roles, ev_k=args.ev_k, ev_d=1.5)
+        if args.chrom_sets >= 0:
+            model.set_option("chrom.sets", args.chrom_sets)
         tau0, gibbs = 100.0, _cabi.GIBBS_TAU_FIRST
         units = float(model.n_data)            # pairs per force evaluation
         flop_per_launch = FLOP_PER_PAIR * units * (L + 1) * C
@@ -639,6 +641,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--roles", type=int, default=0, help="chromatin: force the warps per chain (experiments)")
     ap.add_argument("--ev-k", type=float, default=0.0, help="chromatin: excluded-volume strength (0 = off)")
+    ap.add_argument("--chrom-sets", type=int, default=-1,
+                    help="chromatin: 0 = all chain groups in one pass-major item sequence (experiments)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true",

@@ -370,6 +370,7 @@ int binfb_model_set_option(binfb_model *m, const char *key, double value) {
     else if (!strcmp(key, "poly.chains_per_thread")) m->poly.opt_jchains = v;
     else if (!strcmp(key, "poly.block")) m->poly.opt_block = v;
     else if (!strcmp(key, "chrom.warps")) m->chrom.opt_warps = v;
+    else if (!strcmp(key, "chrom.sets")) m->chrom.opt_sets = v;
     else if (!strcmp(key, "host.pipeline")) m->host_pipeline = v != 0;
     else if (!strcmp(key, "chrom.ev_k") || !strcmp(key, "chrom.ev_d")) {
         // excluded-volume prior k_ev sum_{i<j} max(0, d_ev - d_ij)^4 of the chromatin model (0 = off)

@@ -600,7 +600,20 @@ struct ChromCall {
     GradArgs g;  // GRAD mode
     int W;       // chains per CTA (W * R warps)
     int n_groups, total_items;
+    int set_groups;  // groups per set: a set of chain groups runs ALL its passes before the next set starts, so
+                     // that the q / p hand-off between consecutive passes of a group stays in L2 (see chrom_launch)
 };
+
+// work item -> (chain group o, pass index seq).  Items are ordered set by set; inside a set pass-major, so
+// consecutive passes of one group are set_groups items apart.  Only the last set may be smaller.
+__device__ __forceinline__ void chrom_item(const ChromCall &call, int it, int n_seq, int &o, int &seq) {
+    const int per_set = call.set_groups * n_seq;
+    const int set = it / per_set, r = it - set * per_set;
+    const int g0 = set * call.set_groups;
+    const int gs = min(call.set_groups, call.n_groups - g0);
+    seq = r / gs;
+    o = g0 + (r - seq * gs);
+}
 
 template <int R, int SPR, bool LOCKSTEP, int NS, bool EV>
 __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall call) {
@@ -657,6 +670,7 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
 
     const int D = 3 * cd.n;
     const int passes = call.mode == CHROM_MODE_HMC ? call.h.L + 1 : 1;
+    const int n_seq = passes * (call.mode == CHROM_MODE_HMC ? call.h.n_traj : 1);  // passes of a group in this launch
     const int cthreads = R * 32, ctid = role * 32 + lane;  // threads of this chain
     uint32_t stage_idx = 0;  // running stage counter, identical in every warp
     uint32_t pos_copies = 0; // bulk copies of positions this chain slot has received (mbarrier phase)
@@ -671,11 +685,11 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
                 // blocks starting at block o mod NRB: concurrently running CTAs then read different
                 // parts of the contact stream instead of hammering the same L2 lines in lockstep (the
                 // order is a function of the group, so results do not depend on the CTA schedule).
-                ring.rot = BINFB_ROTATE ? ((it % call.n_groups) % cd.NRB) * (cd.Lr / SPR) : 0;
+                int o, need;  // need = passes of this group that must be done
+                chrom_item(call, it, n_seq, o, need);
+                ring.rot = BINFB_ROTATE ? (o % cd.NRB) * (cd.Lr / SPR) : 0;
                 for (int i = 0; i < NS && i < ring.n_stage_pass; ++i)
                     ring_issue<STAGE_BYTES, NS>(ring, stage_idx + (uint32_t)i, i);
-                const int o = it % call.n_groups;
-                const int need = it / call.n_groups;  // passes of this group that must be done
                 if (need > 0)
                     while (ld_acquire(cd.pass_done + o) < need) __nanosleep(100);
                 else {
@@ -699,8 +713,8 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
         __syncthreads();
         const int item = *s_item;
         if (item >= call.total_items) break;
-        const int o = item % call.n_groups;
-        const int seq = item / call.n_groups;  // = tr * passes + k
+        int o, seq;  // seq = tr * passes + k
+        chrom_item(call, item, n_seq, o, seq);
         ring.rot = BINFB_ROTATE ? (o % cd.NRB) * (cd.Lr / SPR) : 0;
         const int tr = seq / passes, k = seq % passes;
 
@@ -989,7 +1003,7 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
             st_release(cd.pass_done + o, seq + 1);
             int *gate = cd.pass_done + call.n_groups;
             const int gpc = gate[1];  // (written before the launch)
-            if (gpc > 0 && (seq + 1) * call.n_groups + o >= call.total_items) {
+            if (gpc > 0 && seq + 1 == n_seq) {
                 // last pass of this group under a pipelined host call: its results may be copied back
                 __threadfence_system();
                 atomicAdd_system(gate + 2 + o / gpc, 1);
@@ -1230,6 +1244,20 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
         return BINFB_EUNSUPPORTED;
     }
     call.total_items = (int)total;
+    {
+        // sets: the hand-off between consecutive passes of a group goes through qw / pw (and q at both ends):
+        // 36 bytes per degree of freedom.  With all groups in one pass-major sequence a group's data is evicted
+        // from L2 before its next pass when the batch is large (147 MB at 4096 chains x 1000 beads); sets of at
+        // most ~48 MB keep it resident.  Sets follow each other in ONE item sequence (no barrier, no tail between
+        // sets), and a set never has fewer groups than the GPU has SMs.
+        const double bytes_per_group = 36.0 * m.n * W;
+        long long gs = (long long)(48e6 / bytes_per_group);
+        if (gs < 2LL * sm_count) gs = 2LL * sm_count;
+        int n_sets = (int)((call.n_groups + gs - 1) / gs);
+        if (n_sets < 1) n_sets = 1;
+        call.set_groups = (call.n_groups + n_sets - 1) / n_sets;
+        if (m.opt_sets == 0) call.set_groups = call.n_groups;
+    }
     size_t smem = pl.fixed_smem + pl.per_chain_smem * W;
     // scratch for the parallel fold of the row sums (chrom_sweep), where it fits next to the chains
     // (F roles at a time, F the largest power of two <= R that fits; the kernel derives F from the size)
@@ -1282,6 +1310,8 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
     else if (pl.R == 2 && pl.SS == 8) BINFB_CHROM_LAUNCH(2, 4);
 #elif BINFB_CHROM_SS == 2
     else if (pl.R == 2 && pl.SS == 2) BINFB_CHROM_LAUNCH(2, 1);
+#elif BINFB_CHROM_SS == 6
+    else if (pl.R == 2 && pl.SS == 6) BINFB_CHROM_LAUNCH(2, 3);
 #endif
     else if (pl.R == 2 && pl.SS == 4) BINFB_CHROM_LAUNCH(2, 2);
     else if (pl.R == 4 && pl.SS == 4) BINFB_CHROM_LAUNCH(4, 1);

@@ -100,6 +100,7 @@ struct ChromModel {
     float ev_k = 0, ev_d = 0;      // excluded-volume prior k_ev sum max(0, d_ev - d_ij)^4 (0 = off)
     unsigned flags = 0;
     int opt_warps = -1;
+    int opt_sets = -1;             // 0: one set (all groups in one pass-major item sequence)
     // per-launch workspace (grown on demand)
     int ws_chains = 0;
     float *qw = nullptr, *pw = nullptr;   // [C, D] working position / momentum

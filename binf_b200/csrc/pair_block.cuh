@@ -169,6 +169,76 @@ __device__ __forceinline__ void pair_packed_gs(float2 nx2, float2 ny2, float2 nz
     if (ENERGY) chi2 = fma2(rs, rs, chi2);
 }
 
+// ---------------------------------------------------------------------------------------------
+// knock-out study (profiles/microbench/pairbench.cu): pair_packed_gs<false, false, true> with single pieces
+// replaced by one ALU-pipe integer op (so that the FMA-pipe load stays what it was) or removed.  Not used by the
+// kernels.  KO bits: 1 rsqrt, 2 ex2, 4 rcp, 8 row accumulators G, 16 column accumulators F.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float alu_fake(float x) { return __int_as_float(__float_as_int(x) ^ 0x00400000); }
+template <int KO>
+__device__ __forceinline__ void pair_packed_ko(float2 nx2, float2 ny2, float2 nz2, float2 xj2, float2 yj2,
+                                               float2 zj2, float2 y2, float2 A2, float2 B2, float &gx, float &gy,
+                                               float &gz, float2 &fx2, float2 &fy2, float2 &fz2) {
+    const float2 dx = add2(xj2, nx2), dy = add2(yj2, ny2), dz = add2(zj2, nz2);
+    const float2 r2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, A2)));
+    const float2 inv = (KO & 1) ? mk2(alu_fake(r2.x), alu_fake(r2.y)) : mk2(mufu_rsqrt(r2.x), mufu_rsqrt(r2.y));
+    const float2 d = mul2(r2, inv);
+    const float2 e = (KO & 2) ? mk2(alu_fake(d.x), alu_fake(d.y)) : mk2(mufu_ex2(d.x), mufu_ex2(d.y));
+    const float2 sn = fma2(e, B2, mk2(-1.f, -1.f));
+    const float2 mn = (KO & 4) ? mk2(alu_fake(sn.x), alu_fake(sn.y)) : mk2(mufu_rcp(sn.x), mufu_rcp(sn.y));
+    const float2 rs = add2(mn, y2);
+    const float2 wn = fma2(mn, mn, mn);
+    const float2 coef = mul2(mul2(rs, wn), inv);
+    if (!(KO & 8)) {
+        gx = fmaf(coef.y, dx.y, fmaf(coef.x, dx.x, gx));
+        gy = fmaf(coef.y, dy.y, fmaf(coef.x, dy.x, gy));
+        gz = fmaf(coef.y, dz.y, fmaf(coef.x, dz.x, gz));
+    } else {
+        gx += coef.x * 1e-30f;  // keep coef alive
+    }
+    if (!(KO & 16)) fx2 = fma2(coef, dx, fx2), fy2 = fma2(coef, dy, fy2), fz2 = fma2(coef, dz, fz2);
+    else fx2 = add2(fx2, coef);
+}
+
+// 1 / x for x <= -1 (the negated logistic denominator -(1 + e)) WITHOUT the special-function unit: magic-constant
+// seed (one integer subtraction on the ALU pipe, |error| < 12.5 %) and two cubically convergent steps
+// x <- x + x (r + r^2), r = 1 - s x on the FMA pipe: 0.125 -> 2e-3 -> 8e-9, i.e. as accurate as MUFU.RCP.
+// 6 packed FMA-pipe ops for two values.  Used for a FRACTION of the packs to balance the two pipes
+// (the XU needs 8 SMSP-cycles per warp-wide MUFU, this costs ~6 FMA-pipe cycles per pair).
+__device__ __forceinline__ float2 rcp_neg_fma2(float2 sn) {
+    float2 x = mk2(__int_as_float(0xFEF311C7u - __float_as_uint(sn.x)), __int_as_float(0xFEF311C7u - __float_as_uint(sn.y)));
+    x = mk2(-x.x, -x.y);  // (folded into the operand modifiers of the first FMA)
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const float2 r = fma2(sn, mk2(-x.x, -x.y), mk2(1.f, 1.f));  // 1 - sn x
+        const float2 t = fma2(r, r, r);
+        x = fma2(x, t, x);
+    }
+    return x;
+}
+
+template <bool ENERGY, bool FMARCP>
+__device__ __forceinline__ void pair_packed_gs_fr(float2 nx2, float2 ny2, float2 nz2, float2 xj2, float2 yj2,
+                                                  float2 zj2, float2 y2, float2 A2, float2 B2, float &gx, float &gy,
+                                                  float &gz, float2 &fx2, float2 &fy2, float2 &fz2, float2 &chi2) {
+    const float2 dx = add2(xj2, nx2), dy = add2(yj2, ny2), dz = add2(zj2, nz2);
+    const float2 r2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, A2)));
+    const float2 inv = mk2(mufu_rsqrt(r2.x), mufu_rsqrt(r2.y));
+    const float2 d = mul2(r2, inv);
+    float2 e = mk2(mufu_ex2(d.x), mufu_ex2(d.y));
+    if (FMARCP) e = mk2(fminf(e.x, 1e30f), fminf(e.y, 1e30f));  // keep the Newton steps finite (m < 1e-30 there)
+    const float2 sn = fma2(e, B2, mk2(-1.f, -1.f));
+    const float2 mn = FMARCP ? rcp_neg_fma2(sn) : mk2(mufu_rcp(sn.x), mufu_rcp(sn.y));
+    const float2 rs = add2(mn, y2);
+    const float2 wn = fma2(mn, mn, mn);
+    const float2 coef = mul2(mul2(rs, wn), inv);
+    gx = fmaf(coef.y, dx.y, fmaf(coef.x, dx.x, gx));
+    gy = fmaf(coef.y, dy.y, fmaf(coef.x, dy.x, gy));
+    gz = fmaf(coef.y, dz.y, fmaf(coef.x, dz.x, gz));
+    fx2 = fma2(coef, dx, fx2), fy2 = fma2(coef, dy, fy2), fz2 = fma2(coef, dz, fz2);
+    if (ENERGY) chi2 = fma2(rs, rs, chi2);
+}
+
 // scaled positions + scalar row accumulators + ONE reciprocal per pack (1/a = b/(ab), 1/b = a/(ab)): 2.5 MUFU
 // per pair.  The exponent is clamped to 30 so that (1 + C 2^d)^2 cannot overflow (m < 2^-30/C there).
 template <bool ENERGY>

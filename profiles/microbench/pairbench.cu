@@ -241,7 +241,57 @@ __global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) chi_tot += g[r][0] + g[r][1] + g[r][2];
-    } else if (VAR == 9 || VAR == 10 || VAR == 12) {
+    } else if (VAR == 13 || VAR == 14) {
+        // knock-out study (NPOLY = KO mask, pair_block.cuh:pair_packed_ko); VAR 14: no shared-memory traffic at all
+        float2 nx2[4], ny2[4], nz2[4];
+        float g[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            nx2[r] = mk2(-xi[r], -xi[r]), ny2[r] = mk2(-yi[r], -yi[r]), nz2[r] = mk2(-zi[r], -zi[r]);
+            g[r][0] = g[r][1] = g[r][2] = 0.f;
+        }
+        const float2 A2 = mk2(A * A * PAIR_SOFT, A * A * PAIR_SOFT);
+        const float2 B2 = mk2(-exp2f(B), -exp2f(B));
+        float4 xj = xs4[b], yj = ys4[b], zj = zs4[b];
+        float4 fx = fx4[b], fy = fy4[b], fz = fz4[b];
+        float4 yk[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) yk[r] = ((const float4 *)ybuf)[lane + r * 32];
+        for (int st = 0; st < steps; ++st) {
+            if (VAR == 13) {
+                xj = xs4[b], yj = ys4[b], zj = zs4[b];
+                fx = fx4[b], fy = fy4[b], fz = fz4[b];
+            } else {
+                xj.x += 1e-3f, yj.y += 1e-3f, zj.z -= 1e-3f;   // (keeps the loop from being hoisted)
+            }
+            float2 xj2[2] = {mk2(xj.x, xj.y), mk2(xj.z, xj.w)}, yj2[2] = {mk2(yj.x, yj.y), mk2(yj.z, yj.w)},
+                   zj2[2] = {mk2(zj.x, zj.y), mk2(zj.z, zj.w)};
+            float2 fx2[2] = {mk2(fx.x, fx.y), mk2(fx.z, fx.w)}, fy2[2] = {mk2(fy.x, fy.y), mk2(fy.z, fy.w)},
+                   fz2[2] = {mk2(fz.x, fz.y), mk2(fz.z, fz.w)};
+            const float4 *yb = (const float4 *)ybuf + (st & 3) * 128 + lane;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float4 yv = VAR == 13 ? yb[r * 32] : yk[r];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float2 y2 = h ? mk2(yv.z, yv.w) : mk2(yv.x, yv.y);
+                    pair_packed_ko<NPOLY>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2,
+                                          g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h]);
+                }
+            }
+            fx = make_float4(fx2[0].x, fx2[0].y, fx2[1].x, fx2[1].y);
+            fy = make_float4(fy2[0].x, fy2[0].y, fy2[1].x, fy2[1].y);
+            fz = make_float4(fz2[0].x, fz2[0].y, fz2[1].x, fz2[1].y);
+            if (VAR == 13) {
+                fx4[b] = fx, fy4[b] = fy, fz4[b] = fz;
+                if (++b >= Q) b = 0;
+                __syncwarp();
+            }
+        }
+        chi_tot += fx.x + fy.y + fz.z;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) chi_tot += g[r][0] + g[r][1] + g[r][2];
+    } else if (VAR == 9 || VAR == 10 || VAR == 12 || VAR == 15) {
         // the kernel's shape: packed columns, scalar row accumulators; VAR 10: positions pre-scaled by A
         float2 nx2[4], ny2[4], nz2[4];
         float g[4][3];
@@ -267,7 +317,16 @@ __global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const float2 y2 = h ? mk2(yv.z, yv.w) : mk2(yv.x, yv.y);
-                    if (VAR == 12)
+                    if (VAR == 15) {
+                        // NPOLY of the 8 packs of a step take the reciprocal on the FMA pipe (spread evenly)
+                        constexpr int STRIDE = (NPOLY > 0 && NPOLY <= 8) ? 8 / NPOLY : 1000;
+                        if (((r * 2 + h) % STRIDE) == STRIDE - 1)
+                            pair_packed_gs_fr<false, true>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2,
+                                                           g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
+                        else
+                            pair_packed_gs_fr<false, false>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2,
+                                                            g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
+                    } else if (VAR == 12)
                         pair_packed_gs_sr<false>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2,
                                                  g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
                     else
@@ -365,7 +424,25 @@ int main() {
     cudaMemcpy(init, h.data(), 4096 * 4, cudaMemcpyHostToDevice);
     const int sms = p.multiProcessorCount; const double g = clk / 1e6;
     run<10, 0, 512>("4x4 tile, scaled positions, 16 warps", init, out, sms, g);
-    run<12, 0, 512>("same + one rcp per pack (2.5 MUFU per pair)", init, out, sms, g);
-    run<12, 0, 384>("same + one rcp per pack, 12 warps", init, out, sms, g);
+    run<15, 0, 512>("4x4 scaled, rcp on MUFU (reference for the next lines)", init, out, sms, g);
+    run<15, 1, 512>("  1 of 8 packs: rcp on the FMA pipe", init, out, sms, g);
+    run<15, 2, 512>("  2 of 8 packs: rcp on the FMA pipe", init, out, sms, g);
+    run<15, 4, 512>("  4 of 8 packs: rcp on the FMA pipe", init, out, sms, g);
+    run<15, 8, 512>("  8 of 8 packs: rcp on the FMA pipe", init, out, sms, g);
+    run<13, 0, 512>("knock-out harness, nothing removed", init, out, sms, g);
+    run<13, 1, 512>("  rsqrt -> 1 ALU op", init, out, sms, g);
+    run<13, 2, 512>("  ex2 -> 1 ALU op", init, out, sms, g);
+    run<13, 4, 512>("  rcp -> 1 ALU op", init, out, sms, g);
+    run<13, 3, 512>("  rsqrt, ex2 -> ALU", init, out, sms, g);
+    run<13, 6, 512>("  ex2, rcp -> ALU (2 MUFU fewer)", init, out, sms, g);
+    run<13, 7, 512>("  all three MUFU -> ALU", init, out, sms, g);
+    run<13, 8, 512>("  no row accumulators G", init, out, sms, g);
+    run<13, 16, 512>("  no column accumulators F (FFMA2 -> FADD2)", init, out, sms, g);
+    run<13, 24, 512>("  no G, no F", init, out, sms, g);
+    run<13, 31, 512>("  no MUFU, no G, no F", init, out, sms, g);
+    run<14, 0, 512>("no shared-memory traffic, nothing removed", init, out, sms, g);
+    run<14, 7, 512>("  no smem, all three MUFU -> ALU", init, out, sms, g);
+    run<14, 6, 512>("  no smem, ex2, rcp -> ALU", init, out, sms, g);
+    run<14, 24, 512>("  no smem, no G, no F", init, out, sms, g);
     return 0;
 }
