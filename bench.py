@@ -51,17 +51,20 @@ FLOP_PER_PAIR = 31.0          # per unordered bead pair and forc
 FLOP_PER_DATUM = 14.0         # per chain, datum and force evaluation (K = 4)
 
 WORKLOADS = {
+    # eps: the step size at which the EQUILIBRATED chains accept 0.8-0.9 of the proposals (SURVEY.md 8d;
+    # profiles/experiments/eps_scan.py); equilibrate: untimed sweeps in front of the warm-up, because the synthetic
+    # starting points (truth + noise) relax downhill and would accept everything at any step size
     "chromatin": dict(name="chromatin_n1000_c4096_L20_gibbs", n_beads=1000, chains=4096, L=20,
-                      eps=1.5e-3, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, noise=0.05),
-    "poly": dict(name="poly_K4_N1000_c65536_L20", n_data=1000, chains=65536, L=20, eps=0.009,
+                      eps=9e-3, equilibrate=75, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, noise=0.05),
+    "poly": dict(name="poly_K4_N1000_c65536_L20", n_data=1000, chains=65536, L=20, eps=0.010, equilibrate=300,
                  tau=2.5),
     # BASELINE.json configs[3]: 5000 beads, chains sharded across the GPUs (4 chains per SM and GPU)
     "chromatin5k": dict(name="chromatin_n5000_c592_L20_gibbs", n_beads=5000, chains=592, L=20,
-                        eps=5e-4, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, noise=0.05),
+                        eps=8e-3, equilibrate=30, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, noise=0.05),
     # BASELINE.json configs[4]: one inverse temperature per rank (geometric in [0.05, 1]), 512 chains
     # per rank, a neighbour swap attempt (NCCL send/recv over NVLink) after every sweep
     "rex": dict(name="chromatin_n1000_rex_512_per_rank_L20", n_beads=1000, chains=512, L=20,
-                eps=1.5e-3, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, noise=0.05),
+                eps=9e-3, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, noise=0.05),
 }
 
 
@@ -350,7 +353,8 @@ def hmc_leg(ctx, args, name, steps, warmup, chains=None, eps=None, with_e2e=True
                              stats=wl["stats"], stream=stream)
         draw[0] += 1
 
-    for _ in range(warmup):
+    n_eq = 0 if args.no_equilibrate else int(w.get("equilibrate", 0))
+    for _ in range(n_eq + warmup):
         step()
     ctx.sync_all()
     wl["stats"].zero_()
@@ -426,7 +430,8 @@ def hmc_leg(ctx, args, name, steps, warmup, chains=None, eps=None, with_e2e=True
                             l2="working set %.0f MB per step > 126 MB L2" % (3 * 4 * C * D / 1e6)
                             if flush is None else "L2 flushed (256 MiB fill) between timed steps",
                             gibbs="precision update fused in front of each trajectory"
-                            if wl["gibbs"] else "none"),
+                            if wl["gibbs"] else "none",
+                            equilibration_sweeps=n_eq),
                 acceptance_rate=float(st[0] / st[1]) if st[1] else None,
                 e2e=e2e, gpu_launches=steps, wall_ms=wall_ms, clocks=clocks, roofline=roofline)
 
@@ -643,6 +648,7 @@ def main():
     ap.add_argument("--ev-k", type=float, default=0.0, help="chromatin: excluded-volume strength (0 = off)")
     ap.add_argument("--chrom-sets", type=int, default=-1,
                     help="chromatin: 0 = all chain groups in one pass-major item sequence (experiments)")
+    ap.add_argument("--no-equilibrate", action="store_true", help="skip the untimed equilibration sweeps")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true",

@@ -9,7 +9,7 @@ cp binf_b200/libbinf_b200.so /tmp/lib_orig.so
 for v in $VARS; do
   cp build/variants/lib_$v.so binf_b200/libbinf_b200.so
   echo "=== $v" >> gpurun_out/variants.txt
-  timeout 300 python bench.py --no-cpu --no-e2e --no-extra --steps 6 --warmup 3 "$@" 2> gpurun_out/variant_$v.err | python -c "
+  timeout 300 python bench.py --no-cpu --no-e2e --no-extra --no-equilibrate --steps 6 --warmup 3 "$@" 2> gpurun_out/variant_$v.err | python -c "
 import json,sys
 for l in sys.stdin:
     l=l.strip()
