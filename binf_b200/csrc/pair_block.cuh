@@ -362,4 +362,44 @@ struct StagedPairs {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// software-pipelined shape (scaled positions): a pack walks through four stages, one per "slot", so that
+// every special-function result is consumed a whole slot after it was requested and the instruction stream
+// of a warp carries the same mix of MUFU and FMA work at every point (the plain shapes above alternate
+// between FMA-heavy and MUFU-heavy phases and drain at every step boundary):
+//   S1  dx, r^2, request rsqrt      S2  d = r^2 * inv, request 2^d
+//   S3  -(1 + C 2^d), request rcp   S4  coefficient, row sums G (scalar), column sums F (packed)
+// A2 = scaled softening, B2 = -2^B (see pair_packed_gs, SCALED).  The MUFU requests are volatile asm: ptxas
+// keeps them in program order, which pins the slot structure.
+// ---------------------------------------------------------------------------------------------
+struct PipePack {
+    float2 dx, dy, dz, inv, v;  // v: r^2 after S1, 2^d after S2, -m after S3
+};
+__device__ __forceinline__ void pipe_s1(PipePack &p, float2 nx2, float2 ny2, float2 nz2, float2 xj2, float2 yj2,
+                                        float2 zj2, float2 A2) {
+    p.dx = add2(xj2, nx2), p.dy = add2(yj2, ny2), p.dz = add2(zj2, nz2);
+    p.v = fma2(p.dz, p.dz, fma2(p.dy, p.dy, fma2(p.dx, p.dx, A2)));
+    p.inv = mk2(vmufu_rsqrt(p.v.x), vmufu_rsqrt(p.v.y));
+}
+__device__ __forceinline__ void pipe_s2(PipePack &p) {
+    const float2 d = mul2(p.v, p.inv);
+    p.v = mk2(vmufu_ex2(d.x), vmufu_ex2(d.y));
+}
+__device__ __forceinline__ void pipe_s3(PipePack &p, float2 B2) {
+    const float2 sn = fma2(p.v, B2, mk2(-1.f, -1.f));
+    p.v = mk2(vmufu_rcp(sn.x), vmufu_rcp(sn.y));
+}
+template <bool ENERGY>
+__device__ __forceinline__ void pipe_s4(const PipePack &p, float2 y2, float &gx, float &gy, float &gz, float2 &fx2,
+                                        float2 &fy2, float2 &fz2, float2 &chi2) {
+    const float2 rs = add2(p.v, y2);
+    const float2 wn = fma2(p.v, p.v, p.v);
+    const float2 coef = mul2(mul2(rs, wn), p.inv);
+    gx = fmaf(coef.y, p.dx.y, fmaf(coef.x, p.dx.x, gx));
+    gy = fmaf(coef.y, p.dy.y, fmaf(coef.x, p.dy.x, gy));
+    gz = fmaf(coef.y, p.dz.y, fmaf(coef.x, p.dz.x, gz));
+    fx2 = fma2(coef, p.dx, fx2), fy2 = fma2(coef, p.dy, fy2), fz2 = fma2(coef, p.dz, fz2);
+    if (ENERGY) chi2 = fma2(rs, rs, chi2);
+}
+
 }  // namespace binfb

@@ -4,11 +4,28 @@
 // Reports SMSP cycles per warp-pair (MUFU floor: 24) for several code shapes.
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -I../../binf_b200/csrc -o pairbench.bin pairbench.cu
 #include <cstdio>
+#include <cstdlib>
+#include <cstdint>
 #include <vector>
 #include <cuda_runtime.h>
 #include "pair_block.cuh"
 
 using namespace binfb;
+
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float2 vlds2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 vlds4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void vsts2(uint32_t a, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
 
 __device__ __forceinline__ void unpack4(const float4 v, float (&a)[4]) { a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w; }
 
@@ -291,6 +308,73 @@ __global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float
         chi_tot += fx.x + fy.y + fz.z;
 #pragma unroll
         for (int r = 0; r < 4; ++r) chi_tot += g[r][0] + g[r][1] + g[r][2];
+    } else if (VAR == 20) {
+        // software-pipelined 4x4 block (pair_block.cuh: pipe_s1..s4): packs in column-pair-major order
+        // (t = h * 4 + r), pack t is in stage 1 in slot t, stage 4 in slot t + 3 (three packs cross the step
+        // boundary); partner positions / force sums are handled per column pair (LDS.64 / STS.64), so that the next
+        // step's operands are loaded into the registers the current step has just finished with.
+        float2 nx2[4], ny2[4], nz2[4];
+        float g[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            nx2[r] = mk2(-xi[r], -xi[r]), ny2[r] = mk2(-yi[r], -yi[r]), nz2[r] = mk2(-zi[r], -zi[r]);
+            g[r][0] = g[r][1] = g[r][2] = 0.f;
+        }
+        const float2 A2 = mk2(A * A * PAIR_SOFT, A * A * PAIR_SOFT);
+        const float2 B2 = mk2(-exp2f(B), -exp2f(B));
+        PipePack P[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) P[t].dx = P[t].dy = P[t].dz = mk2(0.f, 0.f), P[t].inv = mk2(1.f, 1.f), P[t].v = mk2(-0.5f, -0.5f);
+        const uint32_t xb = s_u32(xs4), yb_ = s_u32(ys4), zb = s_u32(zs4), fxb = s_u32(fx4), fyb = s_u32(fy4), fzb = s_u32(fz4);
+        const uint32_t ylane = s_u32(ybuf) + lane * 16u;
+        float2 X[2], Y[2], Z[2], FX[2], FY[2], FZ[2];
+        float4 yq[4];
+        int bp = b, bn = b + 1 >= Q ? 0 : b + 1;
+        X[0] = vlds2(xb + b * 16u), Y[0] = vlds2(yb_ + b * 16u), Z[0] = vlds2(zb + b * 16u);
+        X[1] = vlds2(xb + b * 16u + 8u), Y[1] = vlds2(yb_ + b * 16u + 8u), Z[1] = vlds2(zb + b * 16u + 8u);
+        FX[0] = vlds2(fxb + b * 16u), FY[0] = vlds2(fyb + b * 16u), FZ[0] = vlds2(fzb + b * 16u);
+        FX[1] = FY[1] = FZ[1] = mk2(0.f, 0.f);
+        yq[2] = yq[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 chi2 = mk2(0.f, 0.f);
+        for (int st = 0; st < steps; ++st) {
+            const uint32_t ystep = ylane + (uint32_t)(st & 3) * 2048u;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                {
+                    const int u = (t + 5) & 7, h = u >> 2, r = u & 3, j = u >> 1;
+                    const float2 y2 = (u & 1) ? mk2(yq[j].z, yq[j].w) : mk2(yq[j].x, yq[j].y);
+                    pipe_s4<false>(P[u], y2, g[r][0], g[r][1], g[r][2], FX[h], FY[h], FZ[h], chi2);
+                }
+                pipe_s3(P[(t + 6) & 7], B2);
+                pipe_s2(P[(t + 7) & 7]);
+                pipe_s1(P[t], nx2[t & 3], ny2[t & 3], nz2[t & 3], X[t >> 2], Y[t >> 2], Z[t >> 2], A2);
+                if (t == 0) yq[0] = vlds4(ystep);
+                if (t == 1 && st > 0) FX[0] = vlds2(fxb + b * 16u), FY[0] = vlds2(fyb + b * 16u), FZ[0] = vlds2(fzb + b * 16u);
+                if (t == 2) {
+                    vsts2(fxb + bp * 16u + 8u, FX[1]), vsts2(fyb + bp * 16u + 8u, FY[1]), vsts2(fzb + bp * 16u + 8u, FZ[1]);
+                    __syncwarp();
+                    yq[1] = vlds4(ystep + 512u);
+                }
+                if (t == 3) X[0] = vlds2(xb + bn * 16u), Y[0] = vlds2(yb_ + bn * 16u), Z[0] = vlds2(zb + bn * 16u);
+                if (t == 4) {
+                    yq[2] = vlds4(ystep + 1024u);
+                    FX[1] = vlds2(fxb + b * 16u + 8u), FY[1] = vlds2(fyb + b * 16u + 8u), FZ[1] = vlds2(fzb + b * 16u + 8u);
+                }
+                if (t == 6) {
+                    vsts2(fxb + b * 16u, FX[0]), vsts2(fyb + b * 16u, FY[0]), vsts2(fzb + b * 16u, FZ[0]);
+                    __syncwarp();
+                    yq[3] = vlds4(ystep + 1536u);
+                }
+                if (t == 7) X[1] = vlds2(xb + bn * 16u + 8u), Y[1] = vlds2(yb_ + bn * 16u + 8u), Z[1] = vlds2(zb + bn * 16u + 8u);
+            }
+            bp = b, b = bn;
+            if (++bn >= Q) bn = 0;
+        }
+        chi_tot += chi2.x + chi2.y + FX[1].x + FY[1].y + FZ[1].x;
+#pragma unroll
+        for (int t = 5; t < 8; ++t) chi_tot += P[t].v.x + P[t].inv.y + P[t].dx.x;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) chi_tot += g[r][0] + g[r][1] + g[r][2];
     } else if (VAR == 9 || VAR == 10 || VAR == 12 || VAR == 15) {
         // the kernel's shape: packed columns, scalar row accumulators; VAR 10: positions pre-scaled by A
         float2 nx2[4], ny2[4], nz2[4];
@@ -424,25 +508,28 @@ int main() {
     cudaMemcpy(init, h.data(), 4096 * 4, cudaMemcpyHostToDevice);
     const int sms = p.multiProcessorCount; const double g = clk / 1e6;
     run<10, 0, 512>("4x4 tile, scaled positions, 16 warps", init, out, sms, g);
-    run<15, 0, 512>("4x4 scaled, rcp on MUFU (reference for the next lines)", init, out, sms, g);
-    run<15, 1, 512>("  1 of 8 packs: rcp on the FMA pipe", init, out, sms, g);
-    run<15, 2, 512>("  2 of 8 packs: rcp on the FMA pipe", init, out, sms, g);
-    run<15, 4, 512>("  4 of 8 packs: rcp on the FMA pipe", init, out, sms, g);
-    run<15, 8, 512>("  8 of 8 packs: rcp on the FMA pipe", init, out, sms, g);
-    run<13, 0, 512>("knock-out harness, nothing removed", init, out, sms, g);
-    run<13, 1, 512>("  rsqrt -> 1 ALU op", init, out, sms, g);
-    run<13, 2, 512>("  ex2 -> 1 ALU op", init, out, sms, g);
-    run<13, 4, 512>("  rcp -> 1 ALU op", init, out, sms, g);
-    run<13, 3, 512>("  rsqrt, ex2 -> ALU", init, out, sms, g);
-    run<13, 6, 512>("  ex2, rcp -> ALU (2 MUFU fewer)", init, out, sms, g);
-    run<13, 7, 512>("  all three MUFU -> ALU", init, out, sms, g);
-    run<13, 8, 512>("  no row accumulators G", init, out, sms, g);
-    run<13, 16, 512>("  no column accumulators F (FFMA2 -> FADD2)", init, out, sms, g);
-    run<13, 24, 512>("  no G, no F", init, out, sms, g);
-    run<13, 31, 512>("  no MUFU, no G, no F", init, out, sms, g);
-    run<14, 0, 512>("no shared-memory traffic, nothing removed", init, out, sms, g);
-    run<14, 7, 512>("  no smem, all three MUFU -> ALU", init, out, sms, g);
-    run<14, 6, 512>("  no smem, ex2, rcp -> ALU", init, out, sms, g);
-    run<14, 24, 512>("  no smem, no G, no F", init, out, sms, g);
+    run<20, 0, 512>("4x4 scaled, software-pipelined packs", init, out, sms, g);
+    if (getenv("PAIRBENCH_ALL")) {
+        run<15, 0, 512>("4x4 scaled, rcp on MUFU (reference for the next lines)", init, out, sms, g);
+        run<15, 1, 512>("  1 of 8 packs: rcp on the FMA pipe", init, out, sms, g);
+        run<15, 2, 512>("  2 of 8 packs: rcp on the FMA pipe", init, out, sms, g);
+        run<15, 4, 512>("  4 of 8 packs: rcp on the FMA pipe", init, out, sms, g);
+        run<15, 8, 512>("  8 of 8 packs: rcp on the FMA pipe", init, out, sms, g);
+        run<13, 0, 512>("knock-out harness, nothing removed", init, out, sms, g);
+        run<13, 1, 512>("  rsqrt -> 1 ALU op", init, out, sms, g);
+        run<13, 2, 512>("  ex2 -> 1 ALU op", init, out, sms, g);
+        run<13, 4, 512>("  rcp -> 1 ALU op", init, out, sms, g);
+        run<13, 3, 512>("  rsqrt, ex2 -> ALU", init, out, sms, g);
+        run<13, 6, 512>("  ex2, rcp -> ALU (2 MUFU fewer)", init, out, sms, g);
+        run<13, 7, 512>("  all three MUFU -> ALU", init, out, sms, g);
+        run<13, 8, 512>("  no row accumulators G", init, out, sms, g);
+        run<13, 16, 512>("  no column accumulators F (FFMA2 -> FADD2)", init, out, sms, g);
+        run<13, 24, 512>("  no G, no F", init, out, sms, g);
+        run<13, 31, 512>("  no MUFU, no G, no F", init, out, sms, g);
+        run<14, 0, 512>("no shared-memory traffic, nothing removed", init, out, sms, g);
+        run<14, 7, 512>("  no smem, all three MUFU -> ALU", init, out, sms, g);
+        run<14, 6, 512>("  no smem, ex2, rcp -> ALU", init, out, sms, g);
+        run<14, 24, 512>("  no smem, no G, no F", init, out, sms, g);
+    }
     return 0;
 }
