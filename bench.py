@@ -315,9 +315,12 @@ def chromatin_roofline(ctx, wl, ms_kernel, traffic):
         sfu_gops = 3.0 * wl["units"] * (wl["L"] + 1) * wl["C"] / (ms_kernel * 1e-3) / 1e9
         sfu = dict(ops_per_pair=3, achieved_gops=sfu_gops, peak_gops=mb["mufu_gops"],
                    frac=sfu_gops / mb["mufu_gops"],
-                   note="MUFU issues at 16 lanes/clk/SM: 24 SMSP-cycles per warp-pair vs 20 on the FMA "
-                        "pipe, so the special-function unit bounds this kernel at 31/(2*24) = 64.6 % of "
-                        "the FP32-FMA peak")
+                   note="MUFU issues at 16 lanes/clk/SM = 24 SMSP-cycles per warp-pair (64.6 % of the FP32-FMA "
+                        "peak if it were the only limit).  It is the busiest single pipe but not the wall: with all "
+                        "three MUFU replaced by ALU ops the isolated pair block still takes 26.1 of 29.9 cycles "
+                        "(profiles/r2_microbench_pairbench_knockout.txt) -- 18 FMA-pipe ops per pair at 1.07-1.5 "
+                        "issue cycles each (three-operand FFMA2 / FFMA pay for register-file bandwidth) plus the "
+                        "shared-memory staging of a step")
     return dict(
         bound="fp32_fma", achieved=achieved, peak=mb["ffma_tflops"], unit="TFLOP/s",
         frac=achieved / mb["ffma_tflops"], traffic=traffic, sfu=sfu,

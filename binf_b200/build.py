@@ -62,7 +62,8 @@ def _generic_source_bundle():
     defines = re.sub(r"/\*.*", "", defines)
     prelude = ("typedef unsigned char uint8_t;\ntypedef int int32_t;\ntypedef unsigned int uint32_t;\n"
                "typedef long long int64_t;\ntypedef unsigned long long uint64_t;\n" + defines + "\n")
-    head = prelude + common + "\nnamespace binfb {\n" + args + "\n}\nusing namespace binfb;\n"
+    pack = open(os.path.join(CSRC, "generic_pack.cuh")).read()
+    head = prelude + common + "\nnamespace binfb {\n" + args + "\n}\nusing namespace binfb;\n" + pack
     tail = open(os.path.join(CSRC, "generic_kernel.cuh")).read()
 
     def lit(name, text):

@@ -19,7 +19,13 @@
 // 183-191; binf/example/samplers.py:27-51).  Error model: GaussianErrorModel
 // (binf/example/likelihood.py:54-61); priors: Gaussian on theta, Gamma on the precision.
 //
-// Compile-time parameters (-D): GEN_K, GEN_XD, GEN_G (power of two <= 32), GEN_UR.
+// Compile-time parameters (-D): GEN_K, GEN_XD, GEN_G (power of two <= 32), GEN_UR, GEN_PACK.
+//
+// GEN_PACK = 1 (with GEN_UR = 1): every lane owns TWO chains and the user's function is compiled over the pack
+// type binfb_f2 (generic_pack.cuh; the model source is compiled with `float` standing for binfb_f2), so that
+// its arithmetic comes out as FFMA2 / FADD2 / FMUL2 -- two chains per instruction like the built-in polynomial
+// kernel.  Each component of a pack sees exactly the operations the scalar build performs.  A model whose code
+// does not compile over packs (data-dependent branches, unsupported functions) is built with GEN_PACK = 0.
 //
 // GEN_UR = 1, the uniform-row mapping (like poly.cu): the data rows sit in this module's own constant bank,
 // lane l of a warp owns chain l of its set and every lane walks the same rows, so that a row arrives through
@@ -32,7 +38,12 @@ constexpr int K = GEN_K, XD = GEN_XD, G = GEN_G;
 #ifndef GEN_UR
 #define GEN_UR 0
 #endif
+#ifndef GEN_PACK
+#define GEN_PACK 0
+#endif
+static_assert(!GEN_PACK || GEN_UR, "chain pairs are packed in the uniform-row mapping only");
 constexpr bool UR = GEN_UR != 0;
+constexpr int J = GEN_PACK ? 2 : 1;  // chains per lane
 constexpr int GEN_CROW_FLOATS = 12288;  // 48 KiB of the constant bank
 #if GEN_UR
 __constant__ float gen_crows[GEN_CROW_FLOATS];
@@ -40,7 +51,17 @@ __constant__ float gen_crows[GEN_CROW_FLOATS];
 constexpr int GEN_BLOCK = 256;
 constexpr int GEN_SETS = UR ? (GEN_BLOCK / 32) / G : 1;  // chain sets per block
 
-// who am I: g = share of the rows (lane in the group, or warp in the set), c = chain, leader = g == 0
+#if GEN_PACK
+typedef binfb_f2 gen_real;
+__device__ __forceinline__ gen_real gen_join(const float (&a)[J]) { return binfb_f2(a[0], a[1]); }
+__device__ __forceinline__ float gen_part(gen_real v, int j) { return j ? v.v.y : v.v.x; }
+#else
+typedef float gen_real;
+__device__ __forceinline__ gen_real gen_join(const float (&a)[J]) { return a[0]; }
+__device__ __forceinline__ float gen_part(gen_real v, int) { return v; }
+#endif
+
+// who am I: g = share of the rows (lane in the group, or warp in the set), c = first of this thread's J chains
 struct GenMap {
     int g, lane, bar_id, set;
     long long c;
@@ -49,7 +70,7 @@ struct GenMap {
             // broadcast from lane 0: the compiler keeps everything derived from it in uniform registers
             const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
             set = warp / G, g = warp % G, lane = threadIdx.x & 31, bar_id = 1 + set;
-            c = ((long long)blockIdx.x * GEN_SETS + set) * 32 + lane;
+            c = (((long long)blockIdx.x * GEN_SETS + set) * 32 + lane) * J;
         } else {
             g = threadIdx.x % G, lane = 0, bar_id = 0, set = 0;
             c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -66,83 +87,99 @@ __device__ __forceinline__ void gen_set_bar(int id) {
 // buffer is rewritten two passes later, after the barrier of the pass in between)
 // the scratch of the cross-warp reduction: ONE instance per kernel (static shared memory of a plain function,
 // not of the ENERGY template)
-typedef float GenSum[2][K][G][32];
-typedef double GenChi[2][G][32];
-__device__ __forceinline__ GenSum *gen_s_sum() {
-    __shared__ float s[GEN_SETS][2][K][G][32];
+__device__ __forceinline__ float (*gen_s_sum())[2][J * K][G][32] {
+    __shared__ float s[GEN_SETS][2][J * K][G][32];
     return s;
 }
-__device__ __forceinline__ GenChi *gen_s_chi() {
-    __shared__ double s[GEN_SETS][2][G][32];
+__device__ __forceinline__ double (*gen_s_chi())[2][J][G][32] {
+    __shared__ double s[GEN_SETS][2][J][G][32];
     return s;
+}
+// the user's function on one row, for the J chains of this lane at once
+template <bool ENERGY>
+__device__ __forceinline__ void gen_row(const GenDev &gm, int n, const gen_real (&th)[K], gen_real (&gacc)[K],
+                                        gen_real &c32) {
+    gen_real xr[XD], dm[K];
+#pragma unroll
+    for (int j = 0; j < XD; ++j) xr[j] = gen_real(gen_crows[n * gm.stride + j]);
+    const gen_real m = binfb_mock(th, xr, dm);
+    const gen_real r = m - gen_real(gen_crows[n * gm.stride + XD]);
+#pragma unroll
+    for (int k = 0; k < K; ++k) gacc[k] = fmaf(r, dm[k], gacc[k]);   // J . (mock - y), likelihoods.py:155
+    if (ENERGY) c32 = fmaf(r, r, c32);
 }
 // (ENERGY = false: chi^2 is not needed -- the L - 1 interior leapfrog steps -- and is returned as 0)
 template <bool ENERGY>
-__device__ __forceinline__ void gen_pass(const GenDev &gm, const GenMap &mp, int buf, const float (&q)[K],
-                                         float (&graw)[K], double &chi2) {
-    float (*s_sum)[2][K][G][32] = gen_s_sum();
-    double (*s_chi)[2][G][32] = gen_s_chi();
-    float gacc[K];
+__device__ __forceinline__ void gen_pass(const GenDev &gm, const GenMap &mp, int buf, const float (&q)[J][K],
+                                         float (&graw)[J][K], double (&chi2)[J]) {
+    float (*s_sum)[2][J * K][G][32] = gen_s_sum();
+    double (*s_chi)[2][J][G][32] = gen_s_chi();
+    gen_real th[K], gacc[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) gacc[k] = 0.f;
-    float c32 = 0.f;
-    double c64 = 0.0;
+    for (int k = 0; k < K; ++k) {
+        float t[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) t[j] = q[j][k];
+        th[k] = gen_join(t), gacc[k] = gen_real(0.f);
+    }
+    gen_real c32 = gen_real(0.f);
+    double c64[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) c64[j] = 0.0;
     const int rpw = (gm.N + G - 1) / G;
     const int n0 = mp.g * rpw, n1 = min(gm.N, n0 + rpw);
     int n = n0;
     for (; n + 8 <= n1; n += 8) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            float xr[XD], dm[K];
+        for (int u = 0; u < 8; ++u) gen_row<ENERGY>(gm, n + u, th, gacc, c32);
+        if (ENERGY) {
 #pragma unroll
-            for (int j = 0; j < XD; ++j) xr[j] = gen_crows[(n + u) * gm.stride + j];
-            const float m = binfb_mock(q, xr, dm);
-            const float r = m - gen_crows[(n + u) * gm.stride + XD];
-#pragma unroll
-            for (int k = 0; k < K; ++k) gacc[k] = fmaf(r, dm[k], gacc[k]);   // J . (mock - y), likelihoods.py:155
-            if (ENERGY) c32 = fmaf(r, r, c32);
+            for (int j = 0; j < J; ++j) c64[j] += (double)gen_part(c32, j);
+            c32 = gen_real(0.f);
         }
-        if (ENERGY) c64 += (double)c32, c32 = 0.f;
     }
-    for (; n < n1; ++n) {
-        float xr[XD], dm[K];
+    for (; n < n1; ++n) gen_row<ENERGY>(gm, n, th, gacc, c32);
+    if (ENERGY) {
 #pragma unroll
-        for (int j = 0; j < XD; ++j) xr[j] = gen_crows[n * gm.stride + j];
-        const float m = binfb_mock(q, xr, dm);
-        const float r = m - gen_crows[n * gm.stride + XD];
-#pragma unroll
-        for (int k = 0; k < K; ++k) gacc[k] = fmaf(r, dm[k], gacc[k]);
-        if (ENERGY) c32 = fmaf(r, r, c32);
+        for (int j = 0; j < J; ++j) c64[j] += (double)gen_part(c32, j);
     }
-    if (ENERGY) c64 += (double)c32;
     if (G == 1) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) graw[k] = gacc[k];
-        chi2 = c64;
+        for (int j = 0; j < J; ++j) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) graw[j][k] = gen_part(gacc[k], j);
+            chi2[j] = c64[j];
+        }
         return;
     }
 #pragma unroll
-    for (int k = 0; k < K; ++k) s_sum[mp.set][buf][k][mp.g][mp.lane] = gacc[k];
-    if (ENERGY) s_chi[mp.set][buf][mp.g][mp.lane] = c64;
+    for (int j = 0; j < J; ++j) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) s_sum[mp.set][buf][j * K + k][mp.g][mp.lane] = gen_part(gacc[k], j);
+        if (ENERGY) s_chi[mp.set][buf][j][mp.g][mp.lane] = c64[j];
+    }
     gen_set_bar(mp.bar_id);
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        float t = 0.f;
+    for (int j = 0; j < J; ++j) {
 #pragma unroll
-        for (int w = 0; w < G; ++w) t += s_sum[mp.set][buf][k][w][mp.lane];
-        graw[k] = t;
-    }
-    double t = 0.0;
-    if (ENERGY) {
+        for (int k = 0; k < K; ++k) {
+            float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < G; ++w) t += s_chi[mp.set][buf][w][mp.lane];
+            for (int w = 0; w < G; ++w) t += s_sum[mp.set][buf][j * K + k][w][mp.lane];
+            graw[j][k] = t;
+        }
+        double t = 0.0;
+        if (ENERGY) {
+#pragma unroll
+            for (int w = 0; w < G; ++w) t += s_chi[mp.set][buf][j][w][mp.lane];
+        }
+        chi2[j] = t;
     }
-    chi2 = t;
 }
 #else
 template <bool ENERGY>
-__device__ __forceinline__ void gen_pass(const GenDev &gm, const GenMap &mp, int, const float (&q)[K],
-                                         float (&graw)[K], double &chi2) {
+__device__ __forceinline__ void gen_pass(const GenDev &gm, const GenMap &mp, int, const float (&q)[J][K],
+                                         float (&graw)[J][K], double (&chi2)[J]) {
     const int g = mp.g;
     float gacc[K];
 #pragma unroll
@@ -153,7 +190,7 @@ __device__ __forceinline__ void gen_pass(const GenDev &gm, const GenMap &mp, int
     for (int n = g; n < gm.N; n += G) {
         const float *row = gm.rows + (size_t)n * gm.stride;
         float dm[K];
-        const float m = binfb_mock(q, row, dm);
+        const float m = binfb_mock(q[0], row, dm);
         const float r = m - __ldg(row + XD);
 #pragma unroll
         for (int k = 0; k < K; ++k) gacc[k] = fmaf(r, dm[k], gacc[k]);   // J . (mock - y), likelihoods.py:155
@@ -162,8 +199,8 @@ __device__ __forceinline__ void gen_pass(const GenDev &gm, const GenMap &mp, int
     }
     c64 += (double)c32;
 #pragma unroll
-    for (int k = 0; k < K; ++k) graw[k] = group_allreduce_sum<G>(gacc[k]);
-    chi2 = group_allreduce_sum<G>(c64);
+    for (int k = 0; k < K; ++k) graw[0][k] = group_allreduce_sum<G>(gacc[k]);
+    chi2[0] = group_allreduce_sum<G>(c64);
 }
 #endif
 
@@ -202,94 +239,121 @@ extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_hmc_kernel(GenDev gm
     GenMap mp;
     mp.init();
     const int g = mp.g;
-    const long long c = mp.c;
     int pass = 0;
-    const bool valid = c < a.C;
-    const int cid = valid ? (int)c : a.C - 1;
-    float q[K], p[K], graw[K], f[K];
+    bool valid[J];
+    int cid[J];
+    float q[J][K], p[J][K], graw[J][K], tau[J], eps[J], beta[J];
+    int nacc[J];
+    bool acc[J];
+    double h0[J], h1[J], chi2[J], chi2_cur[J];
 #pragma unroll
-    for (int k = 0; k < K; ++k) q[k] = a.q[(size_t)cid * K + k];
-    float tau = a.tau[cid], eps = a.eps[cid];
-    const float beta = a.beta ? a.beta[cid] : 1.0f;
-    int nacc = 0;
-    bool acc = false;
-    double h0 = 0.0, h1 = 0.0, chi2, chi2_cur;
+    for (int j = 0; j < J; ++j) {
+        valid[j] = mp.c + j < a.C;
+        cid[j] = valid[j] ? (int)(mp.c + j) : a.C - 1;
+#pragma unroll
+        for (int k = 0; k < K; ++k) q[j][k] = a.q[(size_t)cid[j] * K + k];
+        tau[j] = a.tau[cid[j]], eps[j] = a.eps[cid[j]];
+        beta[j] = a.beta ? a.beta[cid[j]] : 1.0f;
+        nacc[j] = 0, acc[j] = false, h0[j] = h1[j] = 0.0;
+    }
     double st_acc = 0.0, st_prop = 0.0, st_eps = 0.0, st_pacc = 0.0;
     for (int tr = 0; tr < a.n_traj; ++tr) {
         const uint64_t draw = a.draw + (uint64_t)tr;
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-            p[k] = a.p0 ? a.p0[(size_t)cid * K + k] : rng_normal(a.seed, a.chain_base + cid, draw, k);   // hmc.py:146
+        for (int j = 0; j < J; ++j)
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                p[j][k] = a.p0 ? a.p0[(size_t)cid[j] * K + k] : rng_normal(a.seed, a.chain_base + cid[j], draw, k);   // hmc.py:146
         gen_pass<true>(gm, mp, pass++ & 1, q, graw, chi2);
-        if (a.gibbs_mode == BINFB_GIBBS_TAU_FIRST)
-            tau = gen_draw_tau(a, (double)gm.N, chi2, beta, a.chain_base + cid, cid, draw);
-        chi2_cur = chi2;
-        double kin = 0.0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) kin += (double)p[k] * (double)p[k];
-        h0 = gen_potential(gm, q, chi2, tau, beta, a.gamma_shape, a.gamma_rate) + 0.5 * kin;
-        gen_force(gm, q, graw, beta * tau, f);
+        for (int j = 0; j < J; ++j) {
+            if (a.gibbs_mode == BINFB_GIBBS_TAU_FIRST)
+                tau[j] = gen_draw_tau(a, (double)gm.N, chi2[j], beta[j], a.chain_base + cid[j], cid[j], draw);
+            chi2_cur[j] = chi2[j];
+            double kin = 0.0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) p[k] = fmaf(-0.5f * eps, f[k], p[k]);             // hmc.py:116
+            for (int k = 0; k < K; ++k) kin += (double)p[j][k] * (double)p[j][k];
+            h0[j] = gen_potential(gm, q[j], chi2[j], tau[j], beta[j], a.gamma_shape, a.gamma_rate) + 0.5 * kin;
+            float f[K];
+            gen_force(gm, q[j], graw[j], beta[j] * tau[j], f);
+#pragma unroll
+            for (int k = 0; k < K; ++k) p[j][k] = fmaf(-0.5f * eps[j], f[k], p[j][k]);             // hmc.py:116
+        }
         for (int s = 1; s < a.L; ++s) {                                              // hmc.py:118-120
 #pragma unroll
-            for (int k = 0; k < K; ++k) q[k] = fmaf(eps, p[k], q[k]);
+            for (int j = 0; j < J; ++j)
+#pragma unroll
+                for (int k = 0; k < K; ++k) q[j][k] = fmaf(eps[j], p[j][k], q[j][k]);
             gen_pass<false>(gm, mp, pass++ & 1, q, graw, chi2);
-            gen_force(gm, q, graw, beta * tau, f);
 #pragma unroll
-            for (int k = 0; k < K; ++k) p[k] = fmaf(-eps, f[k], p[k]);
+            for (int j = 0; j < J; ++j) {
+                float f[K];
+                gen_force(gm, q[j], graw[j], beta[j] * tau[j], f);
+#pragma unroll
+                for (int k = 0; k < K; ++k) p[j][k] = fmaf(-eps[j], f[k], p[j][k]);
+            }
         }
 #pragma unroll
-        for (int k = 0; k < K; ++k) q[k] = fmaf(eps, p[k], q[k]);                     // hmc.py:122
+        for (int j = 0; j < J; ++j)
+#pragma unroll
+            for (int k = 0; k < K; ++k) q[j][k] = fmaf(eps[j], p[j][k], q[j][k]);                 // hmc.py:122
         gen_pass<true>(gm, mp, pass++ & 1, q, graw, chi2);
-        gen_force(gm, q, graw, beta * tau, f);
-        kin = 0.0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            p[k] = fmaf(-0.5f * eps, f[k], p[k]);                                     // hmc.py:123
-            kin += (double)p[k] * (double)p[k];
-        }
-        h1 = gen_potential(gm, q, chi2, tau, beta, a.gamma_shape, a.gamma_rate) + 0.5 * kin;
-        const float uu = a.u ? a.u[cid] : rng_uniform(a.seed, a.chain_base + cid, draw, RNG_ACCEPT);
-        const double dh = h1 - h0;
-        acc = (dh == dh) && ((double)uu < exp(fmin(709.0, fmax(-308.0, -dh))));        // hmc.py:151; NaN rejects
         const bool last = tr == a.n_traj - 1;
-        if (last && valid && g == 0) {
-            if (a.q_end)
-                for (int k = 0; k < K; ++k) a.q_end[(size_t)cid * K + k] = q[k];
-            if (a.p_end)
-                for (int k = 0; k < K; ++k) a.p_end[(size_t)cid * K + k] = p[k];
-        }
-        if (acc) {
-            chi2_cur = chi2;
-            nacc++;
-        } else {
 #pragma unroll
-            for (int k = 0; k < K; ++k) q[k] = a.q[(size_t)cid * K + k];
+        for (int j = 0; j < J; ++j) {
+            float f[K];
+            gen_force(gm, q[j], graw[j], beta[j] * tau[j], f);
+            double kin = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                p[j][k] = fmaf(-0.5f * eps[j], f[k], p[j][k]);                                 // hmc.py:123
+                kin += (double)p[j][k] * (double)p[j][k];
+            }
+            h1[j] = gen_potential(gm, q[j], chi2[j], tau[j], beta[j], a.gamma_shape, a.gamma_rate) + 0.5 * kin;
+            const float uu = a.u ? a.u[cid[j]] : rng_uniform(a.seed, a.chain_base + cid[j], draw, RNG_ACCEPT);
+            const double dh = h1[j] - h0[j];
+            acc[j] = (dh == dh) && ((double)uu < exp(fmin(709.0, fmax(-308.0, -dh))));    // hmc.py:151; NaN rejects
+            if (last && valid[j] && g == 0) {
+                if (a.q_end)
+                    for (int k = 0; k < K; ++k) a.q_end[(size_t)cid[j] * K + k] = q[j][k];
+                if (a.p_end)
+                    for (int k = 0; k < K; ++k) a.p_end[(size_t)cid[j] * K + k] = p[j][k];
+            }
+            if (acc[j]) {
+                chi2_cur[j] = chi2[j];
+                nacc[j]++;
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) q[j][k] = a.q[(size_t)cid[j] * K + k];
+            }
+            if (valid[j] && g == 0) {
+                st_acc += acc[j] ? 1.0 : 0.0, st_prop += 1.0, st_eps += (double)eps[j];
+                st_pacc += (dh == dh) ? exp(fmin(0.0, -dh)) : 0.0;
+            }
+            if (tr < a.n_adapt) eps[j] *= acc[j] ? a.adapt_up : a.adapt_down;               // hmc.py:188-191
+            if (a.gibbs_mode == BINFB_GIBBS_TAU_LAST)
+                tau[j] = gen_draw_tau(a, (double)gm.N, chi2_cur[j], beta[j], a.chain_base + cid[j], cid[j], draw);
         }
-        if (valid && g == 0) {
-            st_acc += acc ? 1.0 : 0.0, st_prop += 1.0, st_eps += (double)eps;
-            st_pacc += (dh == dh) ? exp(fmin(0.0, -dh)) : 0.0;
-        }
-        if (tr < a.n_adapt) eps *= acc ? a.adapt_up : a.adapt_down;                   // hmc.py:188-191
-        if (a.gibbs_mode == BINFB_GIBBS_TAU_LAST)
-            tau = gen_draw_tau(a, (double)gm.N, chi2_cur, beta, a.chain_base + cid, cid, draw);
         if (a.n_traj > 1) {
-            if (valid && g == 0 && acc)
-                for (int k = 0; k < K; ++k) a.q[(size_t)cid * K + k] = q[k];
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+                if (valid[j] && g == 0 && acc[j])
+                    for (int k = 0; k < K; ++k) a.q[(size_t)cid[j] * K + k] = q[j][k];
             if (UR && G > 1) gen_set_bar(mp.bar_id);  // the chain's other owners sit in other warps
             else __syncwarp();
         }
     }
-    if (valid && g == 0) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) a.q[(size_t)cid * K + k] = q[k];
-        a.tau[cid] = tau, a.eps[cid] = eps;
-        if (a.accepted) a.accepted[cid] = acc ? 1 : 0;
-        if (a.e_before) a.e_before[cid] = h0;
-        if (a.e_after) a.e_after[cid] = h1;
-        if (a.n_accepted) a.n_accepted[cid] = nacc;
-    }
+    for (int j = 0; j < J; ++j)
+        if (valid[j] && g == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) a.q[(size_t)cid[j] * K + k] = q[j][k];
+            a.tau[cid[j]] = tau[j], a.eps[cid[j]] = eps[j];
+            if (a.accepted) a.accepted[cid[j]] = acc[j] ? 1 : 0;
+            if (a.e_before) a.e_before[cid[j]] = h0[j];
+            if (a.e_after) a.e_after[cid[j]] = h1[j];
+            if (a.n_accepted) a.n_accepted[cid[j]] = nacc[j];
+        }
     if (a.stats) {
         st_acc = group_allreduce_sum<32>(st_acc), st_prop = group_allreduce_sum<32>(st_prop);
         st_eps = group_allreduce_sum<32>(st_eps), st_pacc = group_allreduce_sum<32>(st_pacc);
@@ -304,23 +368,31 @@ extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_grad_kernel(GenDev g
     GenMap mp;
     mp.init();
     const int g = mp.g;
-    const long long c = mp.c;
-    const bool valid = c < a.C;
-    const int cid = valid ? (int)c : a.C - 1;
-    float q[K], graw[K], f[K];
+    bool valid[J];
+    int cid[J];
+    float q[J][K], graw[J][K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) q[k] = a.q[(size_t)cid * K + k];
-    double chi2;
+    for (int j = 0; j < J; ++j) {
+        valid[j] = mp.c + j < a.C;
+        cid[j] = valid[j] ? (int)(mp.c + j) : a.C - 1;
+#pragma unroll
+        for (int k = 0; k < K; ++k) q[j][k] = a.q[(size_t)cid[j] * K + k];
+    }
+    double chi2[J];
     gen_pass<true>(gm, mp, 0, q, graw, chi2);
-    if (!valid || g != 0) return;
-    const float tau = a.tau[cid];
-    const float beta = a.beta ? a.beta[cid] : 1.0f;
-    if (a.logp) a.logp[cid] = -gen_potential(gm, q, chi2, tau, beta, a.gamma_shape, a.gamma_rate);
-    if (a.chi2) a.chi2[cid] = chi2;
-    if (a.grad) {
-        gen_force(gm, q, graw, beta * tau, f);
 #pragma unroll
-        for (int k = 0; k < K; ++k) a.grad[(size_t)cid * K + k] = f[k];
+    for (int j = 0; j < J; ++j) {
+        if (!valid[j] || g != 0) continue;
+        const float tau = a.tau[cid[j]];
+        const float beta = a.beta ? a.beta[cid[j]] : 1.0f;
+        if (a.logp) a.logp[cid[j]] = -gen_potential(gm, q[j], chi2[j], tau, beta, a.gamma_shape, a.gamma_rate);
+        if (a.chi2) a.chi2[cid[j]] = chi2[j];
+        if (a.grad) {
+            float f[K];
+            gen_force(gm, q[j], graw[j], beta * tau, f);
+#pragma unroll
+            for (int k = 0; k < K; ++k) a.grad[(size_t)cid[j] * K + k] = f[k];
+        }
     }
 }
 
@@ -329,8 +401,10 @@ extern "C" __global__ void gen_forward_kernel(GenDev gm, const float *q, int C, 
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)C * gm.N) return;
     const int c = (int)(i / gm.N), n = (int)(i - (long long)c * gm.N);
-    float th[K], dm[K];
+    gen_real th[K], dm[K], xr[XD];
 #pragma unroll
-    for (int k = 0; k < K; ++k) th[k] = q[(size_t)c * K + k];
-    mock[i] = binfb_mock(th, gm.rows + (size_t)n * gm.stride, dm);
+    for (int k = 0; k < K; ++k) th[k] = gen_real(q[(size_t)c * K + k]);
+#pragma unroll
+    for (int j = 0; j < XD; ++j) xr[j] = gen_real(gm.rows[(size_t)n * gm.stride + j]);
+    mock[i] = gen_part(binfb_mock(th, xr, dm), 0);
 }

@@ -133,6 +133,7 @@ int chrom_forward_launch(const ChromModel &m, const float *q, int C, float *mock
 struct GenModel {
     int K = 0, XD = 0, G = 8;
     int ur = 0;  // uniform-row mapping: rows in the module's constant bank, G warps per chain set
+    int pack = 0;  // two chains per lane, the user's arithmetic compiled over binfb_f2 (generic_pack.cuh)
     GenDev dev;
     float *rows = nullptr;
     void *library = nullptr;                       // cudaLibrary_t

@@ -362,6 +362,27 @@ struct StagedPairs {
     }
 };
 
+// packed two-operand work, ALL twelve force accumulations as scalar FFMA grouped by coefficient (three
+// consecutive FFMA share one multiplicand: operand-reuse cache) -- harness only
+__device__ __forceinline__ void pair_packed_gfs(float2 nx2, float2 ny2, float2 nz2, float2 xj2, float2 yj2,
+                                                float2 zj2, float2 y2, float2 A2, float2 B2, float &gx, float &gy,
+                                                float &gz, float2 &fx2, float2 &fy2, float2 &fz2) {
+    const float2 dx = add2(xj2, nx2), dy = add2(yj2, ny2), dz = add2(zj2, nz2);
+    const float2 r2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, A2)));
+    const float2 inv = mk2(mufu_rsqrt(r2.x), mufu_rsqrt(r2.y));
+    const float2 d = mul2(r2, inv);
+    const float2 e = mk2(mufu_ex2(d.x), mufu_ex2(d.y));
+    const float2 sn = fma2(e, B2, mk2(-1.f, -1.f));
+    const float2 mn = mk2(mufu_rcp(sn.x), mufu_rcp(sn.y));
+    const float2 rs = add2(mn, y2);
+    const float2 wn = fma2(mn, mn, mn);
+    const float2 coef = mul2(mul2(rs, wn), inv);
+    gx = fmaf(coef.x, dx.x, gx), gy = fmaf(coef.x, dy.x, gy), gz = fmaf(coef.x, dz.x, gz);
+    fx2.x = fmaf(coef.x, dx.x, fx2.x), fy2.x = fmaf(coef.x, dy.x, fy2.x), fz2.x = fmaf(coef.x, dz.x, fz2.x);
+    gx = fmaf(coef.y, dx.y, gx), gy = fmaf(coef.y, dy.y, gy), gz = fmaf(coef.y, dz.y, gz);
+    fx2.y = fmaf(coef.y, dx.y, fx2.y), fy2.y = fmaf(coef.y, dy.y, fy2.y), fz2.y = fmaf(coef.y, dz.y, fz2.y);
+}
+
 // ---------------------------------------------------------------------------------------------
 // software-pipelined shape (scaled positions): a pack walks through four stages, one per "slot", so that
 // every special-function result is consumed a whole slot after it was requested and the instruction stream

@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float
         for (int t = 5; t < 8; ++t) chi_tot += P[t].v.x + P[t].inv.y + P[t].dx.x;
 #pragma unroll
         for (int r = 0; r < 4; ++r) chi_tot += g[r][0] + g[r][1] + g[r][2];
-    } else if (VAR == 9 || VAR == 10 || VAR == 12 || VAR == 15) {
+    } else if (VAR == 9 || VAR == 10 || VAR == 12 || VAR == 15 || VAR == 21) {
         // the kernel's shape: packed columns, scalar row accumulators; VAR 10: positions pre-scaled by A
         float2 nx2[4], ny2[4], nz2[4];
         float g[4][3];
@@ -410,7 +410,10 @@ __global__ void __launch_bounds__(THREADS, 1) pairbench(const float *init, float
                         else
                             pair_packed_gs_fr<false, false>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2,
                                                             g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
-                    } else if (VAR == 12)
+                    } else if (VAR == 21)
+                        pair_packed_gfs(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2,
+                                        g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h]);
+                    else if (VAR == 12)
                         pair_packed_gs_sr<false>(nx2[r], ny2[r], nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2,
                                                  g[r][0], g[r][1], g[r][2], fx2[h], fy2[h], fz2[h], chi2);
                     else
@@ -509,6 +512,7 @@ int main() {
     const int sms = p.multiProcessorCount; const double g = clk / 1e6;
     run<10, 0, 512>("4x4 tile, scaled positions, 16 warps", init, out, sms, g);
     run<20, 0, 512>("4x4 scaled, software-pipelined packs", init, out, sms, g);
+    run<21, 0, 512>("4x4 scaled, all force sums scalar", init, out, sms, g);
     if (getenv("PAIRBENCH_ALL")) {
         run<15, 0, 512>("4x4 scaled, rcp on MUFU (reference for the next lines)", init, out, sms, g);
         run<15, 1, 512>("  1 of 8 packs: rcp on the FMA pipe", init, out, sms, g);
