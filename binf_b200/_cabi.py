@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libbinf_b200.so")
 OK, EINVAL, ECUDA, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4
 MODEL_POLYNOMIAL, MODEL_CHROMATIN, MODEL_GENERIC = 1, 2, 3
 FLAG_PRIOR_GRAD = 1
+FLAG_GENERIC_PACKED = 2
 GIBBS_NONE, GIBBS_TAU_FIRST, GIBBS_TAU_LAST = 0, 1, 2
 SINK_TRACK_MAP = 1
 REX_MAX_TEMPS, REX_RECORD_BYTES = 64, 16
@@ -51,6 +52,7 @@ SIGNATURES = {
     "binfb_model_info": (_i, [_vp, _pi, _pi, _pll, _pi]),
     "binfb_model_set_gamma_prior": (_i, [_vp, _d, _d]),
     "binfb_model_set_option": (_i, [_vp, C.c_char_p, _d]),
+    "binfb_model_get_option": (_i, [_vp, C.c_char_p, C.POINTER(_d)]),
     "binfb_logprob_grad": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "binfb_logprob_grad_host": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "binfb_forward_host": (_i, [_vp, _vp, _i, _vp]),
@@ -260,6 +262,11 @@ class Model(object):
 
     def set_option(self, key, value):
         check(lib().binfb_model_set_option(self._h, key.encode(), float(value)))
+
+    def get_option(self, key):
+        v = C.c_double()
+        check(lib().binfb_model_get_option(self._h, key.encode(), C.byref(v)))
+        return v.value
 
     # ---- host-buffer entry points (numpy in, numpy out) ------------------------------------
     def logprob_grad(self, q, tau, beta=None, want_grad=True):

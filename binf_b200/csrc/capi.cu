@@ -386,6 +386,30 @@ int binfb_model_set_option(binfb_model *m, const char *key, double value) {
     return BINFB_OK;
 }
 
+int binfb_model_get_option(const binfb_model *m, const char *key, double *value) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (!key || !value) return BINFB_EINVAL;
+    if (!strcmp(key, "generic.packed")) *value = m->gen.pack;
+    else if (!strcmp(key, "generic.uniform_rows")) *value = m->gen.ur;
+    else if (!strcmp(key, "generic.warps_per_set")) *value = m->gen.G;
+    else if (!strcmp(key, "generic.rows_in_smem")) *value = m->gen.srows;
+    else if (!strcmp(key, "poly.group")) *value = m->poly.opt_group;
+    else if (!strcmp(key, "poly.uniform_rows")) *value = m->poly.opt_ur;
+    else if (!strcmp(key, "poly.chains_per_thread")) *value = m->poly.opt_jchains;
+    else if (!strcmp(key, "poly.block")) *value = m->poly.opt_block;
+    else if (!strcmp(key, "chrom.warps")) *value = m->chrom.opt_warps;
+    else if (!strcmp(key, "chrom.sets")) *value = m->chrom.opt_sets;
+    else if (!strcmp(key, "host.pipeline")) *value = m->host_pipeline ? 1 : 0;
+    else if (!strcmp(key, "chrom.ev_k")) *value = m->chrom.ev_k;
+    else if (!strcmp(key, "chrom.ev_d")) *value = m->chrom.ev_d;
+    else {
+        set_error(std::string("unknown option: ") + key);
+        return BINFB_EINVAL;
+    }
+    return BINFB_OK;
+}
+
 int binfb_logprob_grad(binfb_model *m, const float *q, const float *tau, const float *beta, int C,
                        double *logp, float *grad, double *chi2, void *stream) {
     int rc = check_model(m);

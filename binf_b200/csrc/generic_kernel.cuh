@@ -24,8 +24,12 @@
 // GEN_PACK = 1 (with GEN_UR = 1): every lane owns TWO chains and the user's function is compiled over the pack
 // type binfb_f2 (generic_pack.cuh; the model source is compiled with `float` standing for binfb_f2), so that
 // its arithmetic comes out as FFMA2 / FADD2 / FMUL2 -- two chains per instruction like the built-in polynomial
-// kernel.  Each component of a pack sees exactly the operations the scalar build performs.  A model whose code
-// does not compile over packs (data-dependent branches, unsupported functions) is built with GEN_PACK = 0.
+// kernel.  Each component of a pack sees exactly the operations the scalar build performs (the two builds agree
+// bit for bit).  Opt-in (BINFB_FLAG_GENERIC_PACKED): measured on B200 it does not pay in the trajectory kernel
+// (0.75 vs 0.72 ms for the cubic, profiles/README.md) -- there ptxas fetches the rows with per-lane LDC, so a
+// row value is a broadcast *vector* register and such an FFMA2 occupies the FMA pipe 3 cycles (2 with a
+// uniform-register operand, which the one-pass log-prob kernel and poly.cu get); a model whose code does not
+// compile over packs (data-dependent branches, unsupported functions) is built with GEN_PACK = 0.
 //
 // GEN_UR = 1, the uniform-row mapping (like poly.cu): the data rows sit in this module's own constant bank,
 // lane l of a warp owns chain l of its set and every lane walks the same rows, so that a row arrives through
@@ -44,11 +48,29 @@ constexpr int K = GEN_K, XD = GEN_XD, G = GEN_G;
 static_assert(!GEN_PACK || GEN_UR, "chain pairs are packed in the uniform-row mapping only");
 constexpr bool UR = GEN_UR != 0;
 constexpr int J = GEN_PACK ? 2 : 1;  // chains per lane
-constexpr int GEN_CROW_FLOATS = 12288;  // 48 KiB of the constant bank
-#if GEN_UR
-__constant__ float gen_crows[GEN_CROW_FLOATS];
-#endif
 constexpr int GEN_BLOCK = 256;
+constexpr int GEN_CROW_FLOATS = 12288;  // 48 KiB of the constant bank
+constexpr int GEN_STRIDE = (XD + 2 + 3) / 4 * 4;  // floats per data row: x[XD], y, -y, padding (= gen_create's)
+#ifndef GEN_SROWS
+#define GEN_SROWS 0
+#endif
+#if GEN_UR && !GEN_SROWS
+__constant__ float4 gen_crows[GEN_CROW_FLOATS / 4];
+#endif
+#if GEN_UR && GEN_SROWS
+// GEN_SROWS = 1: the rows sit in (dynamic) shared memory, copied from global memory by every block at kernel
+// start; all lanes of a warp read the same row (one broadcast LDS.128 per 4 floats).  Measured on B200 the
+// per-lane constant loads (LDC) the trajectory kernel gets with the rows in the constant bank cap the kernel
+// at about one load per 2.4 SM-cycles; shared memory has no such limit.
+extern __shared__ float4 gen_crows[];
+__device__ __forceinline__ void gen_load_rows(const GenDev &gm) {
+    const float4 *src = reinterpret_cast<const float4 *>(gm.rows);
+    for (int i = threadIdx.x; i < gm.N * (GEN_STRIDE / 4); i += GEN_BLOCK) gen_crows[i] = __ldg(src + i);
+    __syncthreads();
+}
+#else
+__device__ __forceinline__ void gen_load_rows(const GenDev &) {}
+#endif
 constexpr int GEN_SETS = UR ? (GEN_BLOCK / 32) / G : 1;  // chain sets per block
 
 #if GEN_PACK
@@ -95,15 +117,21 @@ __device__ __forceinline__ double (*gen_s_chi())[2][J][G][32] {
     __shared__ double s[GEN_SETS][2][J][G][32];
     return s;
 }
-// the user's function on one row, for the J chains of this lane at once
+// the user's function on one row, for the J chains of this lane at once.  A row is [x_0 .. x_{XD-1}, y, -y, pad]
+// with a compile-time stride (GEN_STRIDE floats, a multiple of 4), fetched as float4 with a warp-uniform index.
 template <bool ENERGY>
-__device__ __forceinline__ void gen_row(const GenDev &gm, int n, const gen_real (&th)[K], gen_real (&gacc)[K],
-                                        gen_real &c32) {
+__device__ __forceinline__ void gen_row(int n, const gen_real (&th)[K], gen_real (&gacc)[K], gen_real &c32) {
+    float row[GEN_STRIDE];
+#pragma unroll
+    for (int v = 0; v < GEN_STRIDE / 4; ++v) {
+        const float4 t = gen_crows[n * (GEN_STRIDE / 4) + v];
+        row[4 * v + 0] = t.x, row[4 * v + 1] = t.y, row[4 * v + 2] = t.z, row[4 * v + 3] = t.w;
+    }
     gen_real xr[XD], dm[K];
 #pragma unroll
-    for (int j = 0; j < XD; ++j) xr[j] = gen_real(gen_crows[n * gm.stride + j]);
+    for (int j = 0; j < XD; ++j) xr[j] = gen_real(row[j]);
     const gen_real m = binfb_mock(th, xr, dm);
-    const gen_real r = m - gen_real(gen_crows[n * gm.stride + XD]);
+    const gen_real r = m + gen_real(row[XD + 1]);   // mock - y
 #pragma unroll
     for (int k = 0; k < K; ++k) gacc[k] = fmaf(r, dm[k], gacc[k]);   // J . (mock - y), likelihoods.py:155
     if (ENERGY) c32 = fmaf(r, r, c32);
@@ -131,14 +159,14 @@ __device__ __forceinline__ void gen_pass(const GenDev &gm, const GenMap &mp, int
     int n = n0;
     for (; n + 8 <= n1; n += 8) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) gen_row<ENERGY>(gm, n + u, th, gacc, c32);
+        for (int u = 0; u < 8; ++u) gen_row<ENERGY>(n + u, th, gacc, c32);
         if (ENERGY) {
 #pragma unroll
             for (int j = 0; j < J; ++j) c64[j] += (double)gen_part(c32, j);
             c32 = gen_real(0.f);
         }
     }
-    for (; n < n1; ++n) gen_row<ENERGY>(gm, n, th, gacc, c32);
+    for (; n < n1; ++n) gen_row<ENERGY>(n, th, gacc, c32);
     if (ENERGY) {
 #pragma unroll
         for (int j = 0; j < J; ++j) c64[j] += (double)gen_part(c32, j);
@@ -236,6 +264,7 @@ __device__ __forceinline__ float gen_draw_tau(const HmcArgs &a, double n_data, d
 }
 
 extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_hmc_kernel(GenDev gm, HmcArgs a) {
+    gen_load_rows(gm);
     GenMap mp;
     mp.init();
     const int g = mp.g;
@@ -365,6 +394,7 @@ extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_hmc_kernel(GenDev gm
 }
 
 extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_grad_kernel(GenDev gm, GradArgs a) {
+    gen_load_rows(gm);
     GenMap mp;
     mp.init();
     const int g = mp.g;

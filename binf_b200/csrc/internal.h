@@ -134,6 +134,8 @@ struct GenModel {
     int K = 0, XD = 0, G = 8;
     int ur = 0;  // uniform-row mapping: rows in the module's constant bank, G warps per chain set
     int pack = 0;  // two chains per lane, the user's arithmetic compiled over binfb_f2 (generic_pack.cuh)
+    int srows = 0;  // uniform-row mapping with the rows in shared memory instead of the constant bank
+    size_t smem_bytes = 0;  // dynamic shared memory of the kernels (the rows)
     GenDev dev;
     float *rows = nullptr;
     void *library = nullptr;                       // cudaLibrary_t

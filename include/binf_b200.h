@@ -45,8 +45,8 @@ extern "C" {
 #define BINFB_FLAG_PRIOR_GRAD 1u /* polynomial: add the Gaussian-prior force (c-mu)/v that the
                                     reference's Posterior.gradient silently drops (quirk Q1,
                                     binf/pdf/posteriors.py:182-185, binf/example/priors.py:45) */
-#define BINFB_FLAG_GENERIC_SCALAR 2u /* generic models: one chain per lane even where the device code would
-                                        compile over chain pairs (packed FP32, see binfb_model_create_generic) */
+#define BINFB_FLAG_GENERIC_PACKED 2u /* generic models: two chains per lane, the device code compiled over chain
+                                        pairs (packed FP32, see binfb_model_create_generic) */
 
 /* Gibbs coupling of the precision update with a trajectory (binf/samplers/gibbs.py:146-149
  * sweeps variables in sorted-name order: 'precision' < 'structure', 'coefficients' < 'precision') */
@@ -103,10 +103,10 @@ int binfb_model_create_chromatin(int n_beads, const float *y_pairs, double alpha
  * returning f_n(theta) for one datum with abscissae x[x_dim] and writing dmock[k] = d f_n / d theta_k,
  * k < n_params (<= 16).  Error model: GaussianErrorModel (binf/example/likelihood.py:54-61); priors:
  * independent Gaussians on theta, Gamma on the precision.  xs: host f64 [n_data, x_dim], ys [n_data].
- * Where the data rows fit the constant bank (48 KiB) and n_params <= 8 the code is first compiled with `float`
- * standing for a pair of chains (all arithmetic packed: FFMA2 / FADD2 / FMUL2, two chains per lane); code that
- * does not compile that way (branches on values, casts to double, functions outside the usual float math set) is
- * compiled as written, one chain per lane.  BINFB_FLAG_GENERIC_SCALAR forces the latter.
+ * With BINFB_FLAG_GENERIC_PACKED, where the data rows fit the constant bank (48 KiB) and n_params <= 8, the code
+ * is first compiled with `float` standing for a pair of chains (all arithmetic packed: FFMA2 / FADD2 / FMUL2, two
+ * chains per lane, bit-identical results); code that does not compile that way (branches on values, casts to
+ * double, functions outside the usual float math set) is compiled as written, one chain per lane.
  * Compile errors return BINFB_EINVAL with the NVRTC log in binfb_last_error(). */
 int binfb_model_create_generic(const char *device_code, int n_params, int x_dim, const double *xs,
                                const double *ys, int n_data, const double *prior_mean,
@@ -126,6 +126,9 @@ int binfb_model_set_gamma_prior(binfb_model *m, double shape, double rate);
  * -k_ev sum_{i<j} max(0, d_ev - d_ij)^4 of the chromatin model, whose force is
  * fused into the pair loop */
 int binfb_model_set_option(binfb_model *m, const char *key, double value);
+/* what a model was built with: "generic.packed" (1 = two chains per lane, packed FP32), "generic.uniform_rows",
+ * "generic.warps_per_set", and the current value of every knob binfb_model_set_option takes */
+int binfb_model_get_option(const binfb_model *m, const char *key, double *value);
 
 /* ---- pdf seam: AbstractBinfPDF.log_prob / gradient ------------------------------------------ */
 /* log_prob of the conditional posterior over the sampled variable at per-chain precision tau

@@ -11,24 +11,42 @@ __device__ float binfb_mock(const float *theta, const float *x, float *dmock) {
     return fmaf(fmaf(fmaf(theta[3], t, theta[2]), t, theta[1]), t, theta[0]);
 }
 """
+CODE_POWERS = """
+__device__ float binfb_mock(const float *theta, const float *x, float *dmock) {
+    // the abscissae carry x, x^2, x^3 (what the built-in model precomputes on the host)
+    dmock[0] = 1.0f; dmock[1] = x[0]; dmock[2] = x[1]; dmock[3] = x[2];
+    return fmaf(theta[3], x[2], fmaf(theta[2], x[1], fmaf(theta[1], x[0], theta[0])));
+}
+"""
 xs = np.linspace(-2, 2, 1000); rng = np.random.RandomState(0)
 ys = rng.normal(np.polynomial.polynomial.polyval(xs, [2., -4., 1., 1.5]), 1/np.sqrt(2.5))
 C = 65536
 q0 = (np.ones((C, 4)) + 0.1*np.random.RandomState(1).normal(size=(C, 4))).astype(np.float32)
 dev = torch.device('cuda')
+def gen(code, x, flags=0, rows="smem"):
+    os.environ["BINFB_GENERIC_ROWS"] = rows   # experiment switch read at model creation (generic.cu)
+    return _cabi.Model.generic(code, 4, x, ys, np.zeros(4), 5*np.ones(4), 1.0, 1.0, flags=flags)
+x1, x3, P = xs[:, None].copy(), np.stack([xs, xs**2, xs**3], 1), _cabi.FLAG_GENERIC_PACKED
 models = {"builtin": _cabi.Model.polynomial(xs, ys, 4, np.zeros(4), 5*np.ones(4), 1.0, 1.0),
-          "generic": _cabi.Model.generic(CODE, 4, xs[:, None].copy(), ys, np.zeros(4), 5*np.ones(4), 1.0, 1.0)}
+          "generic, rows in shared memory": gen(CODE, x1),
+          "generic, smem, powers as abscissae": gen(CODE_POWERS, x3),
+          "generic, smem, chain pairs (packed)": gen(CODE, x1, P),
+          "generic, smem, packed, powers": gen(CODE_POWERS, x3, P),
+          "generic, rows in the constant bank": gen(CODE, x1, rows="const"),
+          "generic, const, powers as abscissae": gen(CODE_POWERS, x3, rows="const"),
+          "generic, const, chain pairs (packed)": gen(CODE, x1, P, rows="const"),
+          "generic, const, packed, powers": gen(CODE_POWERS, x3, P, rows="const")}
 stream = torch.cuda.current_stream().cuda_stream
-for name, m in models.items():
+for name, m in list(models.items()) + list(reversed(list(models.items()))):
     q = torch.from_numpy(q0).to(dev); tau = torch.full((C,), 2.5, device=dev); eps = torch.full((C,), 0.009, device=dev)
     def step(d):
         opts = _cabi.HmcOpts(20, 1, 0, 0, 1.05, 0.95, 1, d, 0)
         m.hmc_run_device(q, tau, eps, opts, stream=stream)
-    for d in range(3): step(d)
+    for d in range(10): step(d)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for d in range(10): step(10 + d)
+    for d in range(40): step(10 + d)
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    print('%-8s %.4f ms per trajectory of %d chains (%.2f G leapfrog steps/s)' % (name, ms, C, C * 20 / ms / 1e6), flush=True)
+    ms = e0.elapsed_time(e1) / 40
+    print('%-40s %.4f ms per trajectory of %d chains (%.2f G leapfrog steps/s)' % (name, ms, C, C * 20 / ms / 1e6), flush=True)

@@ -120,6 +120,74 @@ def test_generic_polynomial_matches_builtin_kernel(gpu):
     assert r["logp"].shape == (len(g["q0"]),) and np.all(np.isfinite(r["logp"]))
 
 
+BRANCHY_CODE = """
+__device__ float binfb_mock(const float *theta, const float *x, float *dmock) {
+    // a kink: the code branches on a value, which a pair of chains cannot do together
+    const float z = theta[0] * x[0] + theta[1];
+    if (z > 0.0f) { dmock[0] = x[0]; dmock[1] = 1.0f; return z; }
+    dmock[0] = 0.1f * x[0]; dmock[1] = 0.1f; return 0.1f * z;
+}
+"""
+
+
+def test_chain_pairs_packed_build_equals_the_scalar_build(gpu):
+    """On request (FLAG_GENERIC_PACKED) the user's code is compiled over pairs of chains (packed FP32); each
+    component performs the scalar build's operations, so the two builds agree to the last bit wherever the
+    code has no a*b+c the scalar compiler may contract (the decay model has: tolerance there); odd chain
+    counts leave half a pair empty; code that cannot be compiled over pairs falls back to one chain per lane."""
+    from binf_b200 import _cabi
+    g = load_golden("poly_n1000")
+    args = (g["prior_means"], g["prior_variances"], float(g["gamma_shape"]), float(g["gamma_rate"]))
+    packed = _cabi.Model.generic(POLY_CODE, 4, g["xs"], g["ys"], *args, flags=_cabi.FLAG_GENERIC_PACKED)
+    scalar = _cabi.Model.generic(POLY_CODE, 4, g["xs"], g["ys"], *args)
+    assert packed.get_option("generic.packed") == 1 and scalar.get_option("generic.packed") == 0
+    assert packed.get_option("generic.uniform_rows") == 1
+    tau = float(g["tau"])
+    q0 = np.concatenate([g["q0"], g["q0"][:1] + 0.01])[:len(g["q0"]) | 1]  # odd chain count
+    lp, gp, cp = packed.logprob_grad(q0, tau)
+    ls, gs, cs = scalar.logprob_grad(q0, tau)
+    np.testing.assert_array_equal(lp, ls), np.testing.assert_array_equal(gp, gs), np.testing.assert_array_equal(cp, cs)
+    a = packed.hmc_run(q0, tau, 0.012, 9, n_traj=4, n_adapt=2, gibbs_mode=_cabi.GIBBS_TAU_FIRST, seed=11, want_end=True)
+    b = scalar.hmc_run(q0, tau, 0.012, 9, n_traj=4, n_adapt=2, gibbs_mode=_cabi.GIBBS_TAU_FIRST, seed=11, want_end=True)
+    for k in ("q", "tau", "eps", "q_end", "p_end", "accepted", "n_accepted", "e_before", "e_after"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    assert a["n_accepted"].sum() > 0
+    # a step size that rejects part of the proposals: the rejected half of a pair keeps its state
+    for eps in np.arange(0.010, 0.020, 0.001):
+        a = packed.hmc_run(q0, tau, eps, 9, n_traj=3, seed=12, want_end=True)
+        if 0 < a["n_accepted"].sum() < 3 * len(q0):
+            break
+    else:
+        raise AssertionError("no step size with partial acceptance")
+    b = scalar.hmc_run(q0, tau, eps, 9, n_traj=3, seed=12, want_end=True)
+    for k in ("q", "q_end", "p_end", "accepted", "n_accepted", "e_before", "e_after"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    np.testing.assert_array_equal(packed.forward(q0[:3]), scalar.forward(q0[:3]))
+    # the decay model: expf and products the scalar compiler may fuse differently
+    gd = load_golden("user_decay_n200")
+    dargs = (gd["prior_means"], gd["prior_variances"], float(gd["gamma_shape"]), float(gd["gamma_rate"]))
+    dp = _cabi.Model.generic(DECAY_CODE, 3, gd["xs"], gd["ys"], *dargs, flags=_cabi.FLAG_GENERIC_PACKED)
+    ds = _cabi.Model.generic(DECAY_CODE, 3, gd["xs"], gd["ys"], *dargs)
+    assert dp.get_option("generic.packed") == 1
+    l1, g1, _ = dp.logprob_grad(gd["q0"], float(gd["tau"]))
+    l2, g2, _ = ds.logprob_grad(gd["q0"], float(gd["tau"]))
+    np.testing.assert_allclose(l1, l2, rtol=1e-6)
+    assert np.max(np.abs(g1 - g2)) <= 2e-5 * np.max(np.abs(g2))
+    # a branch on a value: built one chain per lane, same entry points
+    rng = np.random.RandomState(3)
+    xs = rng.uniform(-1, 1, size=150)
+    ys = np.where(1.5 * xs + 0.2 > 0, 1.5 * xs + 0.2, 0.1 * (1.5 * xs + 0.2)) + 0.05 * rng.normal(size=150)
+    m = _cabi.Model.generic(BRANCHY_CODE, 2, xs[:, None].copy(), ys, np.zeros(2), 4.0 * np.ones(2), 1.0, 1.0,
+                            flags=_cabi.FLAG_GENERIC_PACKED)
+    assert m.get_option("generic.packed") == 0
+    th = np.array([1.4, 0.25]) + 0.01 * rng.normal(size=(9, 2))
+    z = th[:, :1] * xs[None, :] + th[:, 1:]
+    mock = np.where(z > 0, z, 0.1 * z)
+    logp, grad, chi2 = m.logprob_grad(th, 50.0)
+    np.testing.assert_allclose(chi2, ((mock - ys) ** 2).sum(-1), rtol=1e-5)
+    np.testing.assert_allclose(m.forward(th), mock, rtol=1e-5, atol=1e-6)
+
+
 def test_compile_error_is_reported(gpu):
     from binf_b200 import _cabi
     with pytest.raises(_cabi.BinfB200Error) as e:
