@@ -318,7 +318,7 @@ def chromatin_roofline(ctx, wl, ms_kernel, traffic):
                    note="MUFU issues at 16 lanes/clk/SM = 24 SMSP-cycles per warp-pair (64.6 % of the FP32-FMA "
                         "peak if it were the only limit).  It is the busiest single pipe but not the wall: with all "
                         "three MUFU replaced by ALU ops the isolated pair block still takes 26.1 of 29.9 cycles "
-                        "(profiles/r2_microbench_pairbench_knockout.txt) -- 18 FMA-pipe ops per pair at 1.07-1.5 "
+                        "(profiles/r2_microbench_pairbench.txt) -- 18 FMA-pipe ops per pair at 1.07-1.5 "
                         "issue cycles each (three-operand FFMA2 / FFMA pay for register-file bandwidth) plus the "
                         "shared-memory staging of a step")
     return dict(
