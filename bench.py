@@ -68,6 +68,29 @@ WORKLOADS = {
 }
 
 
+def working_set_bytes(name, C):
+    """state a sweep streams: q, and for the chromatin kernels the working copies of q and p"""
+    w = WORKLOADS[name]
+    return 3 * 4 * C * 3 * w["n_beads"] if "n_beads" in w else 2 * 4 * C * 4
+
+
+def needs_l2_flush(name, C):
+    return working_set_bytes(name, C) < 130e6
+
+
+def workload_config(name, world, chains=None, eps=None, equilibrate=True):
+    """the `config` object of a bench line: the same for the product arm and the reference arm of a workload"""
+    w = WORKLOADS[name]
+    C = chains or w["chains"]
+    gibbs = name != "poly"
+    return dict(workload=w["name"], chains_per_gpu=C, leapfrog_steps=w["L"], timestep=eps or w["eps"],
+                parallelism="chain-sharded x%d (no data-path collective)" % world,
+                l2="L2 flushed (256 MiB fill) between timed steps" if needs_l2_flush(name, C)
+                else "working set %.0f MB per step > 126 MB L2" % (working_set_bytes(name, C) / 1e6),
+                gibbs="precision update fused in front of each trajectory" if gibbs else "none",
+                equilibration_sweeps=int(w.get("equilibrate", 0)) if equilibrate else 0)
+
+
 # --------------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md 8d); generated without touching oracle/ so the product arm
 # never imports the checker
@@ -198,8 +221,12 @@ def run_reference(args):
                 unit="leapfrog steps/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f64", data="synthetic",
-                config=dict(workload=w["name"], note="oracle port of the reference's numpy path; "
-                            "the reference itself is Python 2 + CSB and cannot travel to the box"),
+                # the product arm's config of this workload; the reference runs a bounded sample of it (same model,
+                # L, step size and sweep definition on `cores` single chains: cpu_baseline.sample)
+                config=workload_config(args.workload, max(1, args.gpus), args.chains or None, args.eps or None,
+                                       not args.no_equilibrate),
+                note="oracle port of the reference's numpy path (float64, one chain per host core); the reference "
+                     "itself is Python 2 + CSB and cannot travel to the box",
                 cpu_baseline=best,
                 e2e=dict(value=best["value"], unit="leapfrog steps/s", h2d_bytes_per_step=0,
                          d2h_bytes_per_step=0),
@@ -346,7 +373,8 @@ def hmc_leg(ctx, args, name, steps, warmup, chains=None, eps=None, with_e2e=True
     eps0 = eps or w["eps"]
     chain_base = ctx.rank * C
     eps_t = torch.full((C,), eps0, device=dev, dtype=torch.float32)
-    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8) if name == "poly" else None
+    # timing rule: inputs larger than the 126 MB L2, or an L2 flush between timed iterations
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8) if needs_l2_flush(name, C) else None
     stream = torch.cuda.current_stream().cuda_stream
     draw = [0]
 
@@ -428,13 +456,7 @@ def hmc_leg(ctx, args, name, steps, warmup, chains=None, eps=None, with_e2e=True
                 n_gpus=world, steps=steps, warmup=warmup, ms_per_step=total_ms / steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic",
-                config=dict(workload=w["name"], chains_per_gpu=C, leapfrog_steps=L, timestep=eps0,
-                            parallelism="chain-sharded x%d (no data-path collective)" % world,
-                            l2="working set %.0f MB per step > 126 MB L2" % (3 * 4 * C * D / 1e6)
-                            if flush is None else "L2 flushed (256 MiB fill) between timed steps",
-                            gibbs="precision update fused in front of each trajectory"
-                            if wl["gibbs"] else "none",
-                            equilibration_sweeps=n_eq),
+                config=workload_config(name, world, C, eps0, not args.no_equilibrate),
                 acceptance_rate=float(st[0] / st[1]) if st[1] else None,
                 e2e=e2e, gpu_launches=steps, wall_ms=wall_ms, clocks=clocks, roofline=roofline)
 
@@ -477,8 +499,10 @@ def rex_leg(ctx, args, steps):
     steps = max(steps, 20)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     shard.stats.zero_()
+    flush = torch.empty(256 << 20, device=ctx.dev, dtype=torch.uint8)   # 18 MB of state: flush L2 between iterations
     ctx.sync_all()
     for k in range(steps):
+        flush.fill_(k)                          # (not timed)
         ev[k][0].record()
         shard.sweep()
         ev[k][1].record()
@@ -488,7 +512,7 @@ def rex_leg(ctx, args, steps):
     torch.cuda.synchronize()
     sweep_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     swap_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
-    total_ms = ctx.max_over_ranks(ev[0][0].elapsed_time(ev[-1][2]))
+    total_ms = ctx.max_over_ranks(float(sum(e[0].elapsed_time(e[2]) for e in ev)))
     rates = drv.swap_rates()
     stats = shard.stats
     if ctx.world > 1:
@@ -506,6 +530,7 @@ def rex_leg(ctx, args, steps):
                 swap_overhead_frac=swap_ms / sweep_ms,
                 config=dict(workload=w["name"], replicas_per_gpu=C, temperatures=T, columns=drv.rex.n_columns,
                             rows_per_gpu=drv.rex.rows, ladder_start=betas0, ladder=drv.betas,
+                            l2="L2 flushed (256 MiB fill) between timed steps",
                             exchange="label swap: all-gather of 16 B per chain per attempt (%d B per rank), "
                                      "no state moves" % (16 * C),
                             collective="NCCL all_gather_into_tensor" if ctx.world > 1 else
