@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libbinf_b200.so")
 OK, EINVAL, ECUDA, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4
 MODEL_POLYNOMIAL, MODEL_CHROMATIN, MODEL_GENERIC = 1, 2, 3
 FLAG_PRIOR_GRAD = 1
-FLAG_GENERIC_PACKED = 2
+FLAG_GENERIC_SCALAR = 2
 GIBBS_NONE, GIBBS_TAU_FIRST, GIBBS_TAU_LAST = 0, 1, 2
 SINK_TRACK_MAP = 1
 REX_MAX_TEMPS, REX_RECORD_BYTES = 64, 16

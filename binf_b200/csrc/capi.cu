@@ -372,6 +372,7 @@ int binfb_model_set_option(binfb_model *m, const char *key, double value) {
     else if (!strcmp(key, "chrom.warps")) m->chrom.opt_warps = v;
     else if (!strcmp(key, "chrom.sets")) m->chrom.opt_sets = v;
     else if (!strcmp(key, "host.pipeline")) m->host_pipeline = v != 0;
+    else if (!strcmp(key, "generic.split")) m->gen.opt_split = v;
     else if (!strcmp(key, "chrom.ev_k") || !strcmp(key, "chrom.ev_d")) {
         // excluded-volume prior k_ev sum_{i<j} max(0, d_ev - d_ij)^4 of the chromatin model (0 = off)
         if (m->kind != BINFB_MODEL_CHROMATIN || value < 0) {
@@ -394,6 +395,7 @@ int binfb_model_get_option(const binfb_model *m, const char *key, double *value)
     else if (!strcmp(key, "generic.uniform_rows")) *value = m->gen.ur;
     else if (!strcmp(key, "generic.warps_per_set")) *value = m->gen.G;
     else if (!strcmp(key, "generic.rows_in_smem")) *value = m->gen.srows;
+    else if (!strcmp(key, "generic.split")) *value = m->gen.opt_split;
     else if (!strcmp(key, "poly.group")) *value = m->poly.opt_group;
     else if (!strcmp(key, "poly.uniform_rows")) *value = m->poly.opt_ur;
     else if (!strcmp(key, "poly.chains_per_thread")) *value = m->poly.opt_jchains;

@@ -50,27 +50,41 @@ constexpr bool UR = GEN_UR != 0;
 constexpr int J = GEN_PACK ? 2 : 1;  // chains per lane
 constexpr int GEN_BLOCK = 256;
 constexpr int GEN_CROW_FLOATS = 12288;  // 48 KiB of the constant bank
-constexpr int GEN_STRIDE = (XD + 2 + 3) / 4 * 4;  // floats per data row: x[XD], y, -y, padding (= gen_create's)
+constexpr int GEN_STRIDE = (XD + 1 + 3) / 4 * 4;  // floats per data row: x[XD], -y, padding (= gen_create's)
+// slot of -y in a row.  With one abscissa it sits at slot 2, not next to x: side by side the two are fetched with
+// ONE 64-bit load, and if the user's code needs x in a vector register as well (x * x does: a packed multiply
+// takes one uniform operand) ptxas then loads both with a per-lane LDC -- every FFMA2 fed from that load takes 3
+// FMA-pipe cycles instead of 2 (measured: 0.63 against 0.55 ms for the cubic, chain pairs, split trajectory).
+constexpr int GEN_YSLOT = XD == 1 ? 2 : XD;
 #ifndef GEN_SROWS
 #define GEN_SROWS 0
 #endif
-#if GEN_UR && !GEN_SROWS
+// Where the rows of the uniform-row mapping sit.  The constant bank of the module always holds them (rows up to
+// 48 KiB); GEN_SROWS = 1 additionally keeps a copy in (dynamic) shared memory, made by every block of the
+// one-launch kernels at their start, which those kernels read instead (one broadcast LDS.128 per 4 floats):
+// in the fused trajectory kernel ptxas fetches constant-bank rows with per-lane LDC, which caps it at about one
+// load per 2.4 SM-cycles.  The split trajectory's middle kernel reads the constant bank: there the loads go
+// through the uniform datapath (LDCU) and the values are uniform-register operands.
+#if GEN_UR
 __constant__ float4 gen_crows[GEN_CROW_FLOATS / 4];
-#endif
-#if GEN_UR && GEN_SROWS
-// GEN_SROWS = 1: the rows sit in (dynamic) shared memory, copied from global memory by every block at kernel
-// start; all lanes of a warp read the same row (one broadcast LDS.128 per 4 floats).  Measured on B200 the
-// per-lane constant loads (LDC) the trajectory kernel gets with the rows in the constant bank cap the kernel
-// at about one load per 2.4 SM-cycles; shared memory has no such limit.
-extern __shared__ float4 gen_crows[];
+extern __shared__ float4 gen_srows[];
+template <bool SROWS>
+__device__ __forceinline__ float4 gen_row_load(int i) {
+    if (SROWS) return gen_srows[i];
+    return gen_crows[i];
+}
+template <bool SROWS>
 __device__ __forceinline__ void gen_load_rows(const GenDev &gm) {
+    if (!SROWS) return;
     const float4 *src = reinterpret_cast<const float4 *>(gm.rows);
-    for (int i = threadIdx.x; i < gm.N * (GEN_STRIDE / 4); i += GEN_BLOCK) gen_crows[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < gm.N * (GEN_STRIDE / 4); i += GEN_BLOCK) gen_srows[i] = __ldg(src + i);
     __syncthreads();
 }
 #else
+template <bool SROWS>
 __device__ __forceinline__ void gen_load_rows(const GenDev &) {}
 #endif
+constexpr bool SROWS_ONE_LAUNCH = GEN_UR && GEN_SROWS;  // the fused trajectory kernel and the log-prob kernel
 constexpr int GEN_SETS = UR ? (GEN_BLOCK / 32) / G : 1;  // chain sets per block
 
 #if GEN_PACK
@@ -117,27 +131,27 @@ __device__ __forceinline__ double (*gen_s_chi())[2][J][G][32] {
     __shared__ double s[GEN_SETS][2][J][G][32];
     return s;
 }
-// the user's function on one row, for the J chains of this lane at once.  A row is [x_0 .. x_{XD-1}, y, -y, pad]
+// the user's function on one row, for the J chains of this lane at once.  A row is [x_0 .. x_{XD-1}, -y, pad] ([x, 0, -y, 0] with one abscissa)
 // with a compile-time stride (GEN_STRIDE floats, a multiple of 4), fetched as float4 with a warp-uniform index.
-template <bool ENERGY>
+template <bool ENERGY, bool SROWS>
 __device__ __forceinline__ void gen_row(int n, const gen_real (&th)[K], gen_real (&gacc)[K], gen_real &c32) {
     float row[GEN_STRIDE];
 #pragma unroll
     for (int v = 0; v < GEN_STRIDE / 4; ++v) {
-        const float4 t = gen_crows[n * (GEN_STRIDE / 4) + v];
+        const float4 t = gen_row_load<SROWS>(n * (GEN_STRIDE / 4) + v);
         row[4 * v + 0] = t.x, row[4 * v + 1] = t.y, row[4 * v + 2] = t.z, row[4 * v + 3] = t.w;
     }
     gen_real xr[XD], dm[K];
 #pragma unroll
     for (int j = 0; j < XD; ++j) xr[j] = gen_real(row[j]);
     const gen_real m = binfb_mock(th, xr, dm);
-    const gen_real r = m + gen_real(row[XD + 1]);   // mock - y
+    const gen_real r = m + gen_real(row[GEN_YSLOT]);   // mock - y (the rows hold -y)
 #pragma unroll
     for (int k = 0; k < K; ++k) gacc[k] = fmaf(r, dm[k], gacc[k]);   // J . (mock - y), likelihoods.py:155
     if (ENERGY) c32 = fmaf(r, r, c32);
 }
 // (ENERGY = false: chi^2 is not needed -- the L - 1 interior leapfrog steps -- and is returned as 0)
-template <bool ENERGY>
+template <bool ENERGY, bool SROWS>
 __device__ __forceinline__ void gen_pass(const GenDev &gm, const GenMap &mp, int buf, const float (&q)[J][K],
                                          float (&graw)[J][K], double (&chi2)[J]) {
     float (*s_sum)[2][J * K][G][32] = gen_s_sum();
@@ -159,14 +173,14 @@ __device__ __forceinline__ void gen_pass(const GenDev &gm, const GenMap &mp, int
     int n = n0;
     for (; n + 8 <= n1; n += 8) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) gen_row<ENERGY>(n + u, th, gacc, c32);
+        for (int u = 0; u < 8; ++u) gen_row<ENERGY, SROWS>(n + u, th, gacc, c32);
         if (ENERGY) {
 #pragma unroll
             for (int j = 0; j < J; ++j) c64[j] += (double)gen_part(c32, j);
             c32 = gen_real(0.f);
         }
     }
-    for (; n < n1; ++n) gen_row<ENERGY>(n, th, gacc, c32);
+    for (; n < n1; ++n) gen_row<ENERGY, SROWS>(n, th, gacc, c32);
     if (ENERGY) {
 #pragma unroll
         for (int j = 0; j < J; ++j) c64[j] += (double)gen_part(c32, j);
@@ -205,7 +219,7 @@ __device__ __forceinline__ void gen_pass(const GenDev &gm, const GenMap &mp, int
     }
 }
 #else
-template <bool ENERGY>
+template <bool ENERGY, bool SROWS>
 __device__ __forceinline__ void gen_pass(const GenDev &gm, const GenMap &mp, int, const float (&q)[J][K],
                                          float (&graw)[J][K], double (&chi2)[J]) {
     const int g = mp.g;
@@ -219,7 +233,7 @@ __device__ __forceinline__ void gen_pass(const GenDev &gm, const GenMap &mp, int
         const float *row = gm.rows + (size_t)n * gm.stride;
         float dm[K];
         const float m = binfb_mock(q[0], row, dm);
-        const float r = m - __ldg(row + XD);
+        const float r = m + __ldg(row + GEN_YSLOT);   // the rows hold -y
 #pragma unroll
         for (int k = 0; k < K; ++k) gacc[k] = fmaf(r, dm[k], gacc[k]);   // J . (mock - y), likelihoods.py:155
         c32 = fmaf(r, r, c32);
@@ -264,7 +278,8 @@ __device__ __forceinline__ float gen_draw_tau(const HmcArgs &a, double n_data, d
 }
 
 extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_hmc_kernel(GenDev gm, HmcArgs a) {
-    gen_load_rows(gm);
+    constexpr bool S = SROWS_ONE_LAUNCH;
+    gen_load_rows<S>(gm);
     GenMap mp;
     mp.init();
     const int g = mp.g;
@@ -293,7 +308,7 @@ extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_hmc_kernel(GenDev gm
 #pragma unroll
             for (int k = 0; k < K; ++k)
                 p[j][k] = a.p0 ? a.p0[(size_t)cid[j] * K + k] : rng_normal(a.seed, a.chain_base + cid[j], draw, k);   // hmc.py:146
-        gen_pass<true>(gm, mp, pass++ & 1, q, graw, chi2);
+        gen_pass<true, S>(gm, mp, pass++ & 1, q, graw, chi2);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             if (a.gibbs_mode == BINFB_GIBBS_TAU_FIRST)
@@ -313,7 +328,7 @@ extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_hmc_kernel(GenDev gm
             for (int j = 0; j < J; ++j)
 #pragma unroll
                 for (int k = 0; k < K; ++k) q[j][k] = fmaf(eps[j], p[j][k], q[j][k]);
-            gen_pass<false>(gm, mp, pass++ & 1, q, graw, chi2);
+            gen_pass<false, S>(gm, mp, pass++ & 1, q, graw, chi2);
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 float f[K];
@@ -326,7 +341,7 @@ extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_hmc_kernel(GenDev gm
         for (int j = 0; j < J; ++j)
 #pragma unroll
             for (int k = 0; k < K; ++k) q[j][k] = fmaf(eps[j], p[j][k], q[j][k]);                 // hmc.py:122
-        gen_pass<true>(gm, mp, pass++ & 1, q, graw, chi2);
+        gen_pass<true, S>(gm, mp, pass++ & 1, q, graw, chi2);
         const bool last = tr == a.n_traj - 1;
 #pragma unroll
         for (int j = 0; j < J; ++j) {
@@ -393,8 +408,157 @@ extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_hmc_kernel(GenDev gm
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The split trajectory: the same transition as gen_hmc_kernel in three launches per trajectory,
+//   gen_traj_begin   momenta, pass 0 (+ energy), (Gibbs: precision | q), H at the start, first half kick
+//   gen_traj_mid     passes 1 .. L with drift and kicks -- nothing but the row loop and FMAs
+//   gen_traj_end     H at the end, Metropolis test, step-size adaption, (Gibbs: precision | q_new), write-back
+// with proposal, momentum and energies handed over through the model's workspace (gm.w_*).  The middle kernel is
+// what the split is for: free of random draws, float64 energies and the accept branch, it is compiled with the
+// rows arriving through the uniform datapath (LDCU) as uniform-register operands, which the fused kernel never
+// gets.  Per chain the three kernels perform exactly the operations of the fused one (bit-identical results);
+// the host launcher picks the split for launches with enough work to hide the two extra launches per trajectory.
+// ---------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_traj_begin(GenDev gm, HmcArgs a, int tr) {
+    GenMap mp;
+    mp.init();
+    const bool leader = mp.g == 0;
+    const uint64_t draw = a.draw + (uint64_t)tr;
+    bool valid[J];
+    int cid[J];
+    float q[J][K], p[J][K], graw[J][K];
+    double chi2[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        valid[j] = mp.c + j < a.C;
+        cid[j] = valid[j] ? (int)(mp.c + j) : a.C - 1;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            q[j][k] = a.q[(size_t)cid[j] * K + k];
+            p[j][k] = a.p0 ? a.p0[(size_t)cid[j] * K + k] : rng_normal(a.seed, a.chain_base + cid[j], draw, k);   // hmc.py:146
+        }
+    }
+    gen_pass<true, false>(gm, mp, 0, q, graw, chi2);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        float tau = a.tau[cid[j]];
+        const float eps = a.eps[cid[j]], beta = a.beta ? a.beta[cid[j]] : 1.0f;
+        if (a.gibbs_mode == BINFB_GIBBS_TAU_FIRST)
+            tau = gen_draw_tau(a, (double)gm.N, chi2[j], beta, a.chain_base + cid[j], cid[j], draw);
+        double kin = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) kin += (double)p[j][k] * (double)p[j][k];
+        const double h0 = gen_potential(gm, q[j], chi2[j], tau, beta, a.gamma_shape, a.gamma_rate) + 0.5 * kin;
+        float f[K];
+        gen_force(gm, q[j], graw[j], beta * tau, f);
+        if (valid[j] && leader) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                gm.w_p[(size_t)cid[j] * K + k] = fmaf(-0.5f * eps, f[k], p[j][k]);   // hmc.py:116
+                gm.w_q[(size_t)cid[j] * K + k] = q[j][k];
+            }
+            gm.w_h0[cid[j]] = h0, gm.w_chi0[cid[j]] = chi2[j];
+            if (a.gibbs_mode == BINFB_GIBBS_TAU_FIRST) a.tau[cid[j]] = tau;
+        }
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_traj_mid(GenDev gm, HmcArgs a) {
+    GenMap mp;
+    mp.init();
+    const bool leader = mp.g == 0;
+    bool valid[J];
+    int cid[J];
+    float q[J][K], p[J][K], graw[J][K], bt[J], eps[J];
+    double chi2[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        valid[j] = mp.c + j < a.C;
+        cid[j] = valid[j] ? (int)(mp.c + j) : a.C - 1;
+#pragma unroll
+        for (int k = 0; k < K; ++k) q[j][k] = gm.w_q[(size_t)cid[j] * K + k], p[j][k] = gm.w_p[(size_t)cid[j] * K + k];
+        eps[j] = a.eps[cid[j]];
+        bt[j] = (a.beta ? a.beta[cid[j]] : 1.0f) * a.tau[cid[j]];
+    }
+    const int L = a.L;
+    for (int s = 1; s <= L; ++s) {
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+#pragma unroll
+            for (int k = 0; k < K; ++k) q[j][k] = fmaf(eps[j], p[j][k], q[j][k]);   // hmc.py:119,122
+        if (s == L) gen_pass<true, false>(gm, mp, s & 1, q, graw, chi2);
+        else gen_pass<false, false>(gm, mp, s & 1, q, graw, chi2);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            float f[K];
+            gen_force(gm, q[j], graw[j], bt[j], f);
+            const float kick = s == L ? -0.5f * eps[j] : -eps[j];                   // hmc.py:120,123
+#pragma unroll
+            for (int k = 0; k < K; ++k) p[j][k] = fmaf(kick, f[k], p[j][k]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+        if (valid[j] && leader) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) gm.w_q[(size_t)cid[j] * K + k] = q[j][k], gm.w_p[(size_t)cid[j] * K + k] = p[j][k];
+            gm.w_chiL[cid[j]] = chi2[j];
+        }
+}
+
+// one thread per chain
+extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_traj_end(GenDev gm, HmcArgs a, int tr) {
+    const int c = blockIdx.x * GEN_BLOCK + threadIdx.x;
+    double st[4] = {0.0, 0.0, 0.0, 0.0};
+    if (c < a.C) {
+        const uint64_t draw = a.draw + (uint64_t)tr;
+        float q[K], p[K];
+        double kin = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            q[k] = gm.w_q[(size_t)c * K + k], p[k] = gm.w_p[(size_t)c * K + k];
+            kin += (double)p[k] * (double)p[k];
+        }
+        float tau = a.tau[c], eps = a.eps[c];
+        const float beta = a.beta ? a.beta[c] : 1.0f;
+        const double chiL = gm.w_chiL[c], h0 = gm.w_h0[c];
+        const double h1 = gen_potential(gm, q, chiL, tau, beta, a.gamma_shape, a.gamma_rate) + 0.5 * kin;
+        const float uu = a.u ? a.u[c] : rng_uniform(a.seed, a.chain_base + c, draw, RNG_ACCEPT);
+        const double dh = h1 - h0;
+        const bool acc = (dh == dh) && ((double)uu < exp(fmin(709.0, fmax(-308.0, -dh))));    // hmc.py:151; NaN rejects
+        if (tr == a.n_traj - 1) {
+            if (a.q_end)
+                for (int k = 0; k < K; ++k) a.q_end[(size_t)c * K + k] = q[k];
+            if (a.p_end)
+                for (int k = 0; k < K; ++k) a.p_end[(size_t)c * K + k] = p[k];
+        }
+        if (acc) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) a.q[(size_t)c * K + k] = q[k];
+        }
+        st[0] = acc ? 1.0 : 0.0, st[1] = 1.0, st[2] = (double)eps;
+        st[3] = (dh == dh) ? exp(fmin(0.0, -dh)) : 0.0;
+        if (tr < a.n_adapt) a.eps[c] = eps * (acc ? a.adapt_up : a.adapt_down);                // hmc.py:188-191
+        if (a.gibbs_mode == BINFB_GIBBS_TAU_LAST)
+            a.tau[c] = gen_draw_tau(a, (double)gm.N, acc ? chiL : gm.w_chi0[c], beta, a.chain_base + c, c, draw);
+        if (a.accepted) a.accepted[c] = acc ? 1 : 0;
+        if (a.e_before) a.e_before[c] = h0;
+        if (a.e_after) a.e_after[c] = h1;
+        if (a.n_accepted) a.n_accepted[c] += acc ? 1 : 0;
+    }
+    if (a.stats) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st[i] = group_allreduce_sum<32>(st[i]);
+        if ((threadIdx.x & 31) == 0 && st[1] > 0.0) {
+            atomicAdd(a.stats + 0, st[0]), atomicAdd(a.stats + 1, st[1]);
+            atomicAdd(a.stats + 2, st[2]), atomicAdd(a.stats + 3, st[3]);
+        }
+    }
+}
+
 extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_grad_kernel(GenDev gm, GradArgs a) {
-    gen_load_rows(gm);
+    constexpr bool S = SROWS_ONE_LAUNCH;
+    gen_load_rows<S>(gm);
     GenMap mp;
     mp.init();
     const int g = mp.g;
@@ -409,7 +573,7 @@ extern "C" __global__ void __launch_bounds__(GEN_BLOCK) gen_grad_kernel(GenDev g
         for (int k = 0; k < K; ++k) q[j][k] = a.q[(size_t)cid[j] * K + k];
     }
     double chi2[J];
-    gen_pass<true>(gm, mp, 0, q, graw, chi2);
+    gen_pass<true, S>(gm, mp, 0, q, graw, chi2);
 #pragma unroll
     for (int j = 0; j < J; ++j) {
         if (!valid[j] || g != 0) continue;

@@ -51,12 +51,15 @@ struct GradArgs {
     double gamma_shape, gamma_rate;
 };
 
-// generic per-datum model (generic.cu / generic_kernel.cuh): data rows [N, stride] = x[0..XD-1], y, pad
+// generic per-datum model (generic.cu / generic_kernel.cuh): data rows [N, stride] = x[0..XD-1], -y, pad
 struct GenDev {
     const float *rows;
     int N, stride;
     float prior_mean[16], prior_inv_var[16];
     unsigned flags;
+    // workspace of the split trajectory (gen_traj_begin / _mid / _end): proposal and momentum [C, K], energies [C]
+    float *w_q, *w_p;
+    double *w_h0, *w_chi0, *w_chiL;
 };
 // END_KERNEL_ARGS
 
@@ -136,6 +139,9 @@ struct GenModel {
     int pack = 0;  // two chains per lane, the user's arithmetic compiled over binfb_f2 (generic_pack.cuh)
     int srows = 0;  // uniform-row mapping with the rows in shared memory instead of the constant bank
     size_t smem_bytes = 0;  // dynamic shared memory of the kernels (the rows)
+    int ws_chains = 0;      // chains the split-trajectory workspace is sized for
+    int opt_split = -1;     // "generic.split": 1 = always run a trajectory as begin / middle / end kernels, 0 = never
+    void *k_begin = nullptr, *k_mid = nullptr, *k_end = nullptr;
     GenDev dev;
     float *rows = nullptr;
     void *library = nullptr;                       // cudaLibrary_t
@@ -144,7 +150,7 @@ struct GenModel {
 int gen_create(GenModel &g, const char *user_code, int n_params, int x_dim, const double *xs, const double *ys,
                int n_data, const double *prior_mean, const double *prior_var, unsigned flags);
 void gen_destroy(GenModel &g);
-int gen_hmc_launch(const GenModel &g, const HmcArgs &a, cudaStream_t s);
+int gen_hmc_launch(GenModel &g, const HmcArgs &a, cudaStream_t s);
 int gen_grad_launch(const GenModel &g, const GradArgs &a, cudaStream_t s);
 int gen_forward_launch(const GenModel &g, const float *q, int C, float *mock, cudaStream_t s);
 

@@ -23,19 +23,22 @@ ys = rng.normal(np.polynomial.polynomial.polyval(xs, [2., -4., 1., 1.5]), 1/np.s
 C = 65536
 q0 = (np.ones((C, 4)) + 0.1*np.random.RandomState(1).normal(size=(C, 4))).astype(np.float32)
 dev = torch.device('cuda')
-def gen(code, x, flags=0, rows="smem"):
+def gen(code, x, flags=0, rows="smem", split=1):
     os.environ["BINFB_GENERIC_ROWS"] = rows   # experiment switch read at model creation (generic.cu)
-    return _cabi.Model.generic(code, 4, x, ys, np.zeros(4), 5*np.ones(4), 1.0, 1.0, flags=flags)
-x1, x3, P = xs[:, None].copy(), np.stack([xs, xs**2, xs**3], 1), _cabi.FLAG_GENERIC_PACKED
+    m = _cabi.Model.generic(code, 4, x, ys, np.zeros(4), 5*np.ones(4), 1.0, 1.0, flags=flags)
+    m.set_option("generic.split", split)      # 1: begin / middle / end kernels per trajectory, 0: one fused launch
+    return m
+x1, x3, P, S = xs[:, None].copy(), np.stack([xs, xs**2, xs**3], 1), 0, _cabi.FLAG_GENERIC_SCALAR
 models = {"builtin": _cabi.Model.polynomial(xs, ys, 4, np.zeros(4), 5*np.ones(4), 1.0, 1.0),
-          "generic, rows in shared memory": gen(CODE, x1),
-          "generic, smem, powers as abscissae": gen(CODE_POWERS, x3),
-          "generic, smem, chain pairs (packed)": gen(CODE, x1, P),
-          "generic, smem, packed, powers": gen(CODE_POWERS, x3, P),
-          "generic, rows in the constant bank": gen(CODE, x1, rows="const"),
-          "generic, const, powers as abscissae": gen(CODE_POWERS, x3, rows="const"),
-          "generic, const, chain pairs (packed)": gen(CODE, x1, P, rows="const"),
-          "generic, const, packed, powers": gen(CODE_POWERS, x3, P, rows="const")}
+          "generic (default: chain pairs, split)": gen(CODE, x1, P),
+          "generic, powers as abscissae (default)": gen(CODE_POWERS, x3, P),
+          "generic, one chain per lane, split": gen(CODE, x1, S),
+          "generic, one chain per lane, split, powers": gen(CODE_POWERS, x3, S),
+          "generic, one launch, smem, chain pairs": gen(CODE, x1, P, split=0),
+          "generic, one launch, smem, pairs, powers": gen(CODE_POWERS, x3, P, split=0),
+          "generic, one launch, smem, one chain": gen(CODE, x1, S, split=0),
+          "generic, one launch, const, chain pairs": gen(CODE, x1, P, rows="const", split=0),
+          "generic, one launch, const, one chain": gen(CODE, x1, S, rows="const", split=0)}
 stream = torch.cuda.current_stream().cuda_stream
 for name, m in list(models.items()) + list(reversed(list(models.items()))):
     q = torch.from_numpy(q0).to(dev); tau = torch.full((C,), 2.5, device=dev); eps = torch.full((C,), 0.009, device=dev)
@@ -49,4 +52,4 @@ for name, m in list(models.items()) + list(reversed(list(models.items()))):
     for d in range(40): step(10 + d)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 40
-    print('%-40s %.4f ms per trajectory of %d chains (%.2f G leapfrog steps/s)' % (name, ms, C, C * 20 / ms / 1e6), flush=True)
+    print('%-44s %.4f ms per trajectory of %d chains (%.2f G leapfrog steps/s)' % (name, ms, C, C * 20 / ms / 1e6), flush=True)

@@ -131,15 +131,15 @@ __device__ float binfb_mock(const float *theta, const float *x, float *dmock) {
 
 
 def test_chain_pairs_packed_build_equals_the_scalar_build(gpu):
-    """On request (FLAG_GENERIC_PACKED) the user's code is compiled over pairs of chains (packed FP32); each
+    """Where the rows fit the constant bank the user's code is compiled over pairs of chains (packed FP32); each
     component performs the scalar build's operations, so the two builds agree to the last bit wherever the
     code has no a*b+c the scalar compiler may contract (the decay model has: tolerance there); odd chain
     counts leave half a pair empty; code that cannot be compiled over pairs falls back to one chain per lane."""
     from binf_b200 import _cabi
     g = load_golden("poly_n1000")
     args = (g["prior_means"], g["prior_variances"], float(g["gamma_shape"]), float(g["gamma_rate"]))
-    packed = _cabi.Model.generic(POLY_CODE, 4, g["xs"], g["ys"], *args, flags=_cabi.FLAG_GENERIC_PACKED)
-    scalar = _cabi.Model.generic(POLY_CODE, 4, g["xs"], g["ys"], *args)
+    packed = _cabi.Model.generic(POLY_CODE, 4, g["xs"], g["ys"], *args)
+    scalar = _cabi.Model.generic(POLY_CODE, 4, g["xs"], g["ys"], *args, flags=_cabi.FLAG_GENERIC_SCALAR)
     assert packed.get_option("generic.packed") == 1 and scalar.get_option("generic.packed") == 0
     assert packed.get_option("generic.uniform_rows") == 1
     tau = float(g["tau"])
@@ -166,8 +166,8 @@ def test_chain_pairs_packed_build_equals_the_scalar_build(gpu):
     # the decay model: expf and products the scalar compiler may fuse differently
     gd = load_golden("user_decay_n200")
     dargs = (gd["prior_means"], gd["prior_variances"], float(gd["gamma_shape"]), float(gd["gamma_rate"]))
-    dp = _cabi.Model.generic(DECAY_CODE, 3, gd["xs"], gd["ys"], *dargs, flags=_cabi.FLAG_GENERIC_PACKED)
-    ds = _cabi.Model.generic(DECAY_CODE, 3, gd["xs"], gd["ys"], *dargs)
+    dp = _cabi.Model.generic(DECAY_CODE, 3, gd["xs"], gd["ys"], *dargs)
+    ds = _cabi.Model.generic(DECAY_CODE, 3, gd["xs"], gd["ys"], *dargs, flags=_cabi.FLAG_GENERIC_SCALAR)
     assert dp.get_option("generic.packed") == 1
     l1, g1, _ = dp.logprob_grad(gd["q0"], float(gd["tau"]))
     l2, g2, _ = ds.logprob_grad(gd["q0"], float(gd["tau"]))
@@ -177,8 +177,7 @@ def test_chain_pairs_packed_build_equals_the_scalar_build(gpu):
     rng = np.random.RandomState(3)
     xs = rng.uniform(-1, 1, size=150)
     ys = np.where(1.5 * xs + 0.2 > 0, 1.5 * xs + 0.2, 0.1 * (1.5 * xs + 0.2)) + 0.05 * rng.normal(size=150)
-    m = _cabi.Model.generic(BRANCHY_CODE, 2, xs[:, None].copy(), ys, np.zeros(2), 4.0 * np.ones(2), 1.0, 1.0,
-                            flags=_cabi.FLAG_GENERIC_PACKED)
+    m = _cabi.Model.generic(BRANCHY_CODE, 2, xs[:, None].copy(), ys, np.zeros(2), 4.0 * np.ones(2), 1.0, 1.0)
     assert m.get_option("generic.packed") == 0
     th = np.array([1.4, 0.25]) + 0.01 * rng.normal(size=(9, 2))
     z = th[:, :1] * xs[None, :] + th[:, 1:]
@@ -186,6 +185,45 @@ def test_chain_pairs_packed_build_equals_the_scalar_build(gpu):
     logp, grad, chi2 = m.logprob_grad(th, 50.0)
     np.testing.assert_allclose(chi2, ((mock - ys) ** 2).sum(-1), rtol=1e-5)
     np.testing.assert_allclose(m.forward(th), mock, rtol=1e-5, atol=1e-6)
+
+
+def test_split_trajectory_equals_the_fused_launch(gpu):
+    """Launches with enough work run a trajectory as three kernels (begin / middle / end); chain by chain they
+    perform the fused kernel's operations: same states, energies, accept decisions, step sizes, precisions."""
+    from binf_b200 import _cabi
+    g = load_golden("poly_n1000")
+    args = (g["prior_means"], g["prior_variances"], float(g["gamma_shape"]), float(g["gamma_rate"]))
+    rng = np.random.RandomState(5)
+    q0 = np.array([2.0, -4.0, 1.0, 1.5]) + 0.02 * rng.normal(size=(333, 4))
+    for flags in (0, _cabi.FLAG_GENERIC_SCALAR):
+        for code, xs in ((POLY_CODE, g["xs"]), ):
+            out = []
+            for split in (0, 1):
+                m = _cabi.Model.generic(code, 4, xs, g["ys"], *args, flags=flags)
+                m.set_option("generic.split", split)
+                assert m.get_option("generic.split") == split
+                for mode in (_cabi.GIBBS_TAU_FIRST, _cabi.GIBBS_TAU_LAST, _cabi.GIBBS_NONE):
+                    out.append(m.hmc_run(q0, 2.5, 0.013, 7, n_traj=4, n_adapt=3, gibbs_mode=mode, seed=21,
+                                         want_end=True))
+                out.append(m.hmc_run(q0[:5], 2.5, 0.004, 1, n_traj=1, seed=2, want_end=True))   # L = 1
+            h = len(out) // 2
+            for a, b in zip(out[:h], out[h:]):
+                for k in ("q", "tau", "eps", "q_end", "p_end", "accepted", "n_accepted", "e_before", "e_after"):
+                    np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+                np.testing.assert_allclose(a["stats"], b["stats"], rtol=1e-12)
+            assert 0 < out[0]["n_accepted"].sum() < 4 * len(q0)
+    # the lanes-per-chain mapping over global memory (rows beyond the constant bank) splits the same way
+    n = 3500
+    xs = np.sort(rng.uniform(-2, 2, size=n))
+    ys = rng.normal(np.polynomial.polynomial.polyval(xs, [2.0, -4.0, 1.0, 1.5]), 1 / np.sqrt(2.5))
+    res = []
+    for split in (0, 1):
+        m = _cabi.Model.generic(POLY_CODE, 4, xs[:, None].copy(), ys, np.zeros(4), 5.0 * np.ones(4), 1.0, 0.2)
+        assert m.get_option("generic.uniform_rows") == 0
+        m.set_option("generic.split", split)
+        res.append(m.hmc_run(q0[:40], 2.5, 0.006, 5, n_traj=2, gibbs_mode=_cabi.GIBBS_TAU_LAST, seed=4, want_end=True))
+    for k in ("q", "tau", "q_end", "p_end", "accepted", "e_after"):
+        np.testing.assert_array_equal(res[0][k], res[1][k], err_msg=k)
 
 
 def test_compile_error_is_reported(gpu):
