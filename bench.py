@@ -6,7 +6,8 @@
 
 The default run measures BASELINE.json configs[2] (the headline line) and then, on the same box in the same
 process, short legs of configs[1] (poly), configs[3] (chromatin5k), configs[4] (rex) and the sample sink; they
-are attached to the line as extra.{poly,chromatin5k,sink,rex}, each with ms_per_step, roofline and clocks.
+are attached to the line as extra.{poly,generic,chromatin5k,sink,rex}, each with ms_per_step, roofline and clocks
+(generic = configs[1] with the cubic as a user-defined NVRTC model).
 
 A "step" is one Gibbs sweep over every chain of the batch: the conjugate precision update
 followed by one HMC trajectory of L leapfrog steps (L+1 fused force evaluations) and the
@@ -47,6 +48,12 @@ def _capture_stdout():
         _REAL_STDOUT = os.fdopen(os.dup(1), "w")
         os.dup2(2, 1)
 
+USER_CUBIC = """
+__device__ float binfb_mock(const float *theta, const float *x, float *dmock) {
+    dmock[0] = 1.0f; dmock[1] = x[0]; dmock[2] = x[1]; dmock[3] = x[2];
+    return fmaf(theta[3], x[2], fmaf(theta[2], x[1], fmaf(theta[1], x[0], theta[0])));
+}
+"""
 FLOP_PER_PAIR = 31.0          # SURVEY.md 8(d): per unordered bead pair and force evaluation
 FLOP_PER_DATUM = 14.0         # SURVEY.md 8(d): per chain, datum and force evaluation (K = 4)
 
@@ -58,6 +65,11 @@ WORKLOADS = {
                       eps=9e-3, equilibrate=75, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, noise=0.05),
     "poly": dict(name="poly_K4_N1000_c65536_L20", n_data=1000, chains=65536, L=20, eps=0.010, equilibrate=300,
                  tau=2.5),
+    # configs[1] again with the cubic written as a USER-DEFINED forward model: CUDA device code
+    # for one datum, compiled at run time with NVRTC into the fused kernels.  The powers of x are passed as abscissae,
+    # which is what the built-in model precomputes on the host
+    "generic": dict(name="poly_K4_N1000_c65536_L20_user_model", n_data=1000, chains=65536, L=20, eps=0.010,
+                    equilibrate=300, tau=2.5),
     # BASELINE.json configs[3]: 5000 beads, chains sharded across the GPUs (4 chains per SM and GPU)
     "chromatin5k": dict(name="chromatin_n5000_c592_L20_gibbs", n_beads=5000, chains=592, L=20,
                         eps=8e-3, equilibrate=30, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, noise=0.05),
@@ -82,7 +94,7 @@ def workload_config(name, world, chains=None, eps=None, equilibrate=True):
     """the `config` object of a bench line: the same for the product arm and the reference arm of a workload"""
     w = WORKLOADS[name]
     C = chains or w["chains"]
-    gibbs = name != "poly"
+    gibbs = name not in ("poly", "generic")
     return dict(workload=w["name"], chains_per_gpu=C, leapfrog_steps=w["L"], timestep=eps or w["eps"],
                 parallelism="chain-sharded x%d (no data-path collective)" % world,
                 l2="L2 flushed (256 MiB fill) between timed steps" if needs_l2_flush(name, C)
@@ -157,7 +169,7 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------
 def _cpu_worker(args):
     workload, seed, budget_s = args
-    workload = "chromatin" if workload in ("rex", "chromatin5k") else workload
+    workload = "chromatin" if workload in ("rex", "chromatin5k") else ("poly" if workload == "generic" else workload)
     os.environ["OMP_NUM_THREADS"] = "1"
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import binf_port as port
@@ -317,7 +329,11 @@ def make_hmc_workload(ctx, args, name, chains=None):
         bytes_per_launch = 2.0 * 4 * q_host.shape[1] * C + 4.0 * units
     else:
         xs, ys, q_host = poly_inputs(w, C, ctx.rank)
-        model = _cabi.Model.polynomial(xs, ys, 4, np.zeros(4), 5 * np.ones(4), 1.0, 1.0, device=ctx.local)
+        if name == "generic":
+            model = _cabi.Model.generic(USER_CUBIC, 4, np.stack([xs, xs ** 2, xs ** 3], 1), ys, np.zeros(4),
+                                        5 * np.ones(4), 1.0, 1.0, device=ctx.local)
+        else:
+            model = _cabi.Model.polynomial(xs, ys, 4, np.zeros(4), 5 * np.ones(4), 1.0, 1.0, device=ctx.local)
         tau0, gibbs = w["tau"], _cabi.GIBBS_NONE
         units = float(w["n_data"])
         flop_per_launch = (FLOP_PER_DATUM * (L + 1) + 4) * units * C
@@ -337,7 +353,7 @@ def chromatin_roofline(ctx, wl, ms_kernel, traffic):
     peaks = measured_peaks()
     achieved = wl["flop_per_launch"] / (ms_kernel * 1e-3) / 1e12
     sfu = None
-    if wl["name"] != "poly":
+    if wl["name"] not in ("poly", "generic"):
         # the binding pipe of the pair kernel: 3 MUFU (rsqrt, ex2, rcp) per bead pair
         sfu_gops = 3.0 * wl["units"] * (wl["L"] + 1) * wl["C"] / (ms_kernel * 1e-3) / 1e9
         sfu = dict(ops_per_pair=3, achieved_gops=sfu_gops, peak_gops=mb["mufu_gops"],
@@ -458,7 +474,10 @@ def hmc_leg(ctx, args, name, steps, warmup, chains=None, eps=None, with_e2e=True
                 data="synthetic",
                 config=workload_config(name, world, C, eps0, not args.no_equilibrate),
                 acceptance_rate=float(st[0] / st[1]) if st[1] else None,
-                e2e=e2e, gpu_launches=steps, wall_ms=wall_ms, clocks=clocks, roofline=roofline)
+                e2e=e2e,
+                # a user-defined model runs a trajectory of this size as three launches (begin / middle / end)
+                gpu_launches=steps * (3 if name == "generic" else 1), wall_ms=wall_ms, clocks=clocks,
+                roofline=roofline)
 
 
 def rex_leg(ctx, args, steps):
@@ -641,6 +660,7 @@ def run_ours(args):
     if args.workload == "chromatin" and not args.no_extra and not args.chains and not args.roles:
         k = max(3, min(args.steps, 6))
         for name, fn in (("poly", lambda: hmc_leg(ctx, args, "poly", max(k, 10), 3)),
+                         ("generic", lambda: hmc_leg(ctx, args, "generic", max(k, 10), 3, with_e2e=False)),
                          ("chromatin5k", lambda: hmc_leg(ctx, args, "chromatin5k", 3, 3, with_e2e=False)),
                          ("sink", lambda: sink_leg(ctx, args, 50, 3)),
                          ("rex", lambda: rex_leg(ctx, args, 20))):
@@ -650,7 +670,7 @@ def run_ours(args):
                 extras[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
             ctx.sync_all()
     if ctx.rank == 0:
-        if args.workload in ("chromatin", "poly", "chromatin5k"):
+        if args.workload in ("chromatin", "poly", "chromatin5k", "generic"):
             line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_seconds) \
                 if ctx.world == 1 and not args.no_cpu else None
         if extras:
