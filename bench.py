@@ -475,8 +475,7 @@ def hmc_leg(ctx, args, name, steps, warmup, chains=None, eps=None, with_e2e=True
                 config=workload_config(name, world, C, eps0, not args.no_equilibrate),
                 acceptance_rate=float(st[0] / st[1]) if st[1] else None,
                 e2e=e2e,
-                # a user-defined model runs a trajectory of this size as three launches (begin / middle / end)
-                gpu_launches=steps * (3 if name == "generic" else 1), wall_ms=wall_ms, clocks=clocks,
+                gpu_launches=steps, wall_ms=wall_ms, clocks=clocks,
                 roofline=roofline)
 
 

@@ -48,7 +48,10 @@ constexpr int K = GEN_K, XD = GEN_XD, G = GEN_G;
 static_assert(!GEN_PACK || GEN_UR, "chain pairs are packed in the uniform-row mapping only");
 constexpr bool UR = GEN_UR != 0;
 constexpr int J = GEN_PACK ? 2 : 1;  // chains per lane
-constexpr int GEN_BLOCK = 256;
+// threads per block (= gen_launch's): 128 -- one chain set of four warps per block in the uniform-row mapping, so that
+// the sets spread evenly over the SMs (65,536 chains as pairs = 1024 sets = 6.9 per SM: 7 or 6; with two sets per
+// block it is 8 or 6 and the middle kernel of the split trajectory runs 12 % longer)
+constexpr int GEN_BLOCK = 128;
 constexpr int GEN_CROW_FLOATS = 12288;  // 48 KiB of the constant bank
 constexpr int GEN_STRIDE = (XD + 1 + 3) / 4 * 4;  // floats per data row: x[XD], -y, padding (= gen_create's)
 // slot of -y in a row.  With one abscissa it sits at slot 2, not next to x: side by side the two are fetched with

@@ -17,3 +17,4 @@ prof r2_chrom chrom_kernel 3 --steps 3 --warmup 3
 prof r2_chrom5k chrom_kernel 2 --workload chromatin5k --steps 2 --warmup 1
 prof r2_poly poly_hmc_kernel 3 --workload poly --steps 3 --warmup 3
 prof r2_sink sink_push_kernel 3 --workload sink --steps 3 --warmup 3
+prof r2_generic_mid gen_traj_mid 3 --workload generic --steps 3 --warmup 3

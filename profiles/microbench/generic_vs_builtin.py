@@ -30,13 +30,12 @@ def gen(code, x, flags=0, rows="smem", split=1):
     return m
 x1, x3, P, S = xs[:, None].copy(), np.stack([xs, xs**2, xs**3], 1), 0, _cabi.FLAG_GENERIC_SCALAR
 models = {"builtin": _cabi.Model.polynomial(xs, ys, 4, np.zeros(4), 5*np.ones(4), 1.0, 1.0),
-          "generic (default: chain pairs, split)": gen(CODE, x1, P),
-          "generic, powers as abscissae (default)": gen(CODE_POWERS, x3, P),
-          "generic, one chain per lane, split": gen(CODE, x1, S),
-          "generic, one chain per lane, split, powers": gen(CODE_POWERS, x3, S),
-          "generic, one launch, smem, chain pairs": gen(CODE, x1, P, split=0),
-          "generic, one launch, smem, pairs, powers": gen(CODE_POWERS, x3, P, split=0),
+          "generic (default: pairs, one launch, smem)": gen(CODE, x1, P, split=-1),
+          "generic, powers as abscissae (default)": gen(CODE_POWERS, x3, P, split=-1),
           "generic, one launch, smem, one chain": gen(CODE, x1, S, split=0),
+          "generic, split, chain pairs": gen(CODE, x1, P),
+          "generic, split, chain pairs, powers": gen(CODE_POWERS, x3, P),
+          "generic, split, one chain per lane": gen(CODE, x1, S),
           "generic, one launch, const, chain pairs": gen(CODE, x1, P, rows="const", split=0),
           "generic, one launch, const, one chain": gen(CODE, x1, S, rows="const", split=0)}
 stream = torch.cuda.current_stream().cuda_stream
