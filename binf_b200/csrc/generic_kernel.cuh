@@ -12,9 +12,9 @@
 //         x[GEN_XD]     the abscissae of one datum
 //         returns f_n(theta) and writes dmock[k] = d f_n / d theta_k
 //
-// and this file wraps it into the same fused transition the built-in polynomial model gets: a chain
-// is owned by a group of GEN_G lanes which stride over the data, butterfly-all-reduce the GEN_K
-// gradient sums and chi^2, and keep q, p in registers for the whole trajectory (leapfrog, energies,
+// and this file wraps it into the same fused transition the built-in polynomial model gets: the chains
+// walk the data (mappings below), reduce the GEN_K gradient sums and chi^2 in a fixed order, and keep q, p
+// in registers for the whole trajectory (leapfrog, energies,
 // Metropolis test, step-size adaption, conjugate precision update: binf/samplers/hmc.py:92-125,136-164,
 // 183-191; binf/example/samplers.py:27-51).  Error model: GaussianErrorModel
 // (binf/example/likelihood.py:54-61); priors: Gaussian on theta, Gamma on the precision.
