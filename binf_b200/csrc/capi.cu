@@ -372,6 +372,7 @@ int binfb_model_set_option(binfb_model *m, const char *key, double value) {
     else if (!strcmp(key, "chrom.warps")) m->chrom.opt_warps = v;
     else if (!strcmp(key, "chrom.sets")) m->chrom.opt_sets = v;
     else if (!strcmp(key, "host.pipeline")) m->host_pipeline = v != 0;
+    else if (!strcmp(key, "host.chunks")) m->host_chunks = v < 2 ? 16 : (v > 64 ? 64 : v);
     else if (!strcmp(key, "generic.split")) m->gen.opt_split = v;
     else if (!strcmp(key, "chrom.ev_k") || !strcmp(key, "chrom.ev_d")) {
         // excluded-volume prior k_ev sum_{i<j} max(0, d_ev - d_ij)^4 of the chromatin model (0 = off)
@@ -403,6 +404,7 @@ int binfb_model_get_option(const binfb_model *m, const char *key, double *value)
     else if (!strcmp(key, "chrom.warps")) *value = m->chrom.opt_warps;
     else if (!strcmp(key, "chrom.sets")) *value = m->chrom.opt_sets;
     else if (!strcmp(key, "host.pipeline")) *value = m->host_pipeline ? 1 : 0;
+    else if (!strcmp(key, "host.chunks")) *value = m->host_chunks;
     else if (!strcmp(key, "chrom.ev_k")) *value = m->chrom.ev_k;
     else if (!strcmp(key, "chrom.ev_d")) *value = m->chrom.ev_d;
     else {
@@ -523,7 +525,7 @@ int binfb_hmc_run_host(binfb_model *m, float *q, float *tau, const float *beta, 
                            (size_t)C * D * 4 >= ((size_t)4 << 20) && stream_mem_ops().ok &&
                            !(m->chrom.ev_k > 0.f && opts->gibbs_mode == BINFB_GIBBS_TAU_FIRST);
     ChromPipe pipe;
-    if (want_pipe && chrom_pipe_shape(m->chrom, C, m->sm_count, 16, &pipe) == BINFB_OK && pipe.n_chunks >= 2 &&
+    if (want_pipe && chrom_pipe_shape(m->chrom, C, m->sm_count, m->host_chunks, &pipe) == BINFB_OK && pipe.n_chunks >= 2 &&
         pipe_streams(m) == BINFB_OK) {
         const StreamMemOps &mo = stream_mem_ops();
         BINFB_CUDA(cudaMemcpyAsync(ar.at<float>(ot), tau, C * 4, cudaMemcpyHostToDevice, s));

@@ -200,4 +200,5 @@ struct binfb_model {
     cudaStream_t hstream_in = nullptr, hstream_out = nullptr;  // copy streams of the pipelined host call
     cudaEvent_t hevent = nullptr;
     bool host_pipeline = true;  // option "host.pipeline": overlap the copies of the *_host calls with the kernel
+    int host_chunks = 16;       // option "host.chunks": pieces the state travels in (2 .. 64)
 };

@@ -124,7 +124,7 @@ int binfb_model_info(const binfb_model *m, int *kind, int *dim, long long *n_dat
 int binfb_model_set_gamma_prior(binfb_model *m, double shape, double rate);
 /* tuning knobs ("poly.group", "poly.chains_per_thread", "poly.block", "chrom.warps"; value < 0 restores
  * the heuristic; "host.pipeline" = 0 makes binfb_hmc_run_host copy in, run, copy out one after the other instead of
- * overlapping the state copies with the kernel; "poly.uniform_rows" = 0 keeps the data rows in shared memory instead of the constant bank; "generic.split" = 1 / 0 runs every / no trajectory of a user-defined model as three launches) and model extras: "chrom.ev_k", "chrom.ev_d" switch on the excluded-volume prior
+ * overlapping the state copies with the kernel; "host.chunks" (2 .. 64, default 16) is the number of pieces the state travels in; "poly.uniform_rows" = 0 keeps the data rows in shared memory instead of the constant bank; "generic.split" = 1 / 0 runs every / no trajectory of a user-defined model as three launches) and model extras: "chrom.ev_k", "chrom.ev_d" switch on the excluded-volume prior
  * -k_ev sum_{i<j} max(0, d_ev - d_ij)^4 of the chromatin model, whose force is
  * fused into the pair loop */
 int binfb_model_set_option(binfb_model *m, const char *key, double value);
