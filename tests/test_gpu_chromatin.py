@@ -412,6 +412,16 @@ def test_pipelined_host_call_equals_the_serial_one(gpu):
     r0 = m.hmc_run(q0, 60.0, 0.004, 5, u=u, seed=1)
     np.testing.assert_array_equal(r1["q"], r0["q"])
     assert r1["accepted"].mean() > 0.5
+    # the number of pieces the state travels in is a knob ("host.chunks", 2 .. 64): same bits for every setting
+    m.set_option("host.pipeline", 1)
+    for chunks in (2, 7, 64):
+        m.set_option("host.chunks", chunks)
+        assert m.get_option("host.chunks") == chunks
+        r = m.hmc_run(q0, 60.0, eps, 6, n_traj=2, n_adapt=2, gibbs_mode=_cabi.GIBBS_TAU_FIRST, seed=5, draw=3)
+        for key in ("q", "tau", "eps", "accepted", "n_accepted"):
+            np.testing.assert_array_equal(r[key], out[0][key], err_msg="%s with %d chunks" % (key, chunks))
+    m.set_option("host.chunks", 1000)
+    assert m.get_option("host.chunks") == 64
 
 
 def test_benchmarked_launch_shape_vs_oracle(gpu):
