@@ -62,7 +62,11 @@ constexpr int OFF_BAR = OFF_UR + 4 * (TM / 8) * 256;
 constexpr int SMEM_BYTES = OFF_BAR + 128;
 // tensor memory columns
 constexpr int COL_D1 = 0, COL_G = 128, COL_F = 160, TMEM_COLS = 256;
-constexpr int NTHREADS = 320;
+#ifndef NSW
+#define NSW 8                              // SIMT warps: 8 (32 columns of a sub-tile each) or 16 (16 columns each)
+#endif
+constexpr int CW = 64 / (NSW / 4), NCHUNK = CW / 16;
+constexpr int NTHREADS = (NSW + 2) * 32;
 
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float rsq(float v) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v)); return y; }
@@ -196,35 +200,35 @@ __device__ __forceinline__ void bead_features(const float4 u, const float4 c, ui
 // The SIMT part of a step: the warp's 32 rows x 32 columns of the sub-tile.
 template <int NPOLY, bool LOADY, bool MASKED>
 __device__ __forceinline__ void simt_step(uint32_t tmem, uint32_t sm, int chain, int q, int h, int lane, int I, int J,
-                                          float Bc, float (&y)[32], float *dbg) {
+                                          float Bc, float (&y)[CW], float *dbg) {
     const int il = 32 * q + lane;                      // row within the tile
-    float r2[2][16];
-    bool dead[2];
+    float r2[NCHUNK][16];
+    bool dead[NCHUNK];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        dead[c] = MASKED && (J * TN + 32 * h + 16 * c + 15 <= I * TM + 32 * q);
-        if (!dead[c]) tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + COL_D1 + chain * 64 + 32 * h + 16 * c, r2[c]);
+    for (int c = 0; c < NCHUNK; ++c) {
+        dead[c] = MASKED && (J * TN + CW * h + 16 * c + 15 <= I * TM + 32 * q);
+        if (!dead[c]) tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + COL_D1 + chain * 64 + CW * h + 16 * c, r2[c]);
     }
     if (LOADY) {
         const uint32_t yrow = sm + OFF_Y + il * 256;
 #pragma unroll
-        for (int f = 0; f < 8; ++f) {
-            const float4 v = lds4(yrow + (((8 * h + f) ^ (il & 7)) << 4));
+        for (int f = 0; f < CW / 4; ++f) {
+            const float4 v = lds4(yrow + ((((CW / 4) * h + f) ^ (il & 7)) << 4));
             y[4 * f] = v.x, y[4 * f + 1] = v.y, y[4 * f + 2] = v.z, y[4 * f + 3] = v.w;
         }
     }
     tmem_wait_ld();
     if (dbg != nullptr && chain == 0 && I == 0 && J < 2) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < NCHUNK; ++c)
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-                if (!dead[c]) dbg[(J * TM + il) * TN + 32 * h + 16 * c + k] = r2[c][k];
+                if (!dead[c]) dbg[(J * TM + il) * TN + CW * h + 16 * c + k] = r2[c][k];
     }
     const uint32_t crow = sm + OFF_COEF + chain * 2 * COEF_PIECE + (il & 7) * 16 + (il >> 3) * 2048;
     const int gi = I * TM + il;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < NCHUNK; ++c) {
         float ch[16], cl[16];
         if (dead[c]) {
 #pragma unroll
@@ -242,12 +246,12 @@ __device__ __forceinline__ void simt_step(uint32_t tmem, uint32_t sm, int chain,
                 const float rs = mn + y[16 * c + k];
                 const float wn = fmaf(mn, mn, mn);
                 float cf = rs * wn * inv;
-                if (MASKED) cf = (J * TN + 32 * h + 16 * c + k > gi) ? cf : 0.f;
+                if (MASKED) cf = (J * TN + CW * h + 16 * c + k > gi) ? cf : 0.f;
                 ch[k] = tf32_trunc(cf);
                 cl[k] = cf - ch[k];
 #ifdef DEBUG_PRINT
                 if (blockIdx.x == 0 && I == 0 && J == 0 && chain == 0 && il == 1 && k < 4 && dbg != nullptr)
-                    printf("coef i %d j %d: r2 %g inv %g d %g e %g sn %g mn %g y %g rs %g wn %g cf %g ch %g cl %g\n", gi, J * TN + 32 * h + 16 * c + k, rr, inv, d, e, sn, mn, y[16 * c + k], rs, wn, cf, ch[k], cl[k]);
+                    printf("coef i %d j %d: r2 %g inv %g d %g e %g sn %g mn %g y %g rs %g wn %g cf %g ch %g cl %g\n", gi, J * TN + CW * h + 16 * c + k, rr, inv, d, e, sn, mn, y[16 * c + k], rs, wn, cf, ch[k], cl[k]);
 #endif
             }
         }
@@ -259,7 +263,7 @@ __device__ __forceinline__ void simt_step(uint32_t tmem, uint32_t sm, int chain,
 #else
 #pragma unroll
         for (int t4 = 0; t4 < 4; ++t4) {
-            const uint32_t a = crow + (8 * h + 4 * c + t4) * 128;
+            const uint32_t a = crow + ((CW / 4) * h + 4 * c + t4) * 128;
             sts4(a, ch[4 * t4], ch[4 * t4 + 1], ch[4 * t4 + 2], ch[4 * t4 + 3]);
             sts4(a + COEF_PIECE, cl[4 * t4], cl[4 * t4 + 1], cl[4 * t4 + 2], cl[4 * t4 + 3]);
         }
@@ -317,7 +321,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcpair(const Params P) {
         mbar_init(bar_cd, 1), mbar_init(bar_cd + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == NSW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -331,10 +335,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcpair(const Params P) {
     for (int pr = 0; pr < P.pairs_per_cta; ++pr) {
         const int chain0 = (blockIdx.x * P.pairs_per_cta + pr) * 2;   // chains chain0, chain0 + 1
         const uint32_t base_par = (uint32_t)(pr * n_tiles);           // completed phases of every per-tile barrier before this pair
-        if (warp < 8) {
+        if (warp < NSW) {
             // ------------------------------------------------------------------ SIMT warps
             const int q = warp & 3, h = warp >> 2;
-            float y[32];
+            float y[CW];
             int I = 0, J = 0, pI = 0, pJ = 0;
             step_barrier();   // the features of tile 0 are in place
             for (int t = 0; t < n_tiles; ++t) {
@@ -347,7 +351,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcpair(const Params P) {
                         mbar_wait(bar_cd + 8 * c, (base_par + t - 1) & 1);
                         tc_fence_after();
                         if (h == 0) flush_F(P, tmem, c, chain0 + c, q, lane, pI, pJ);
-                        else if (pI != I) flush_G(P, tmem, c, chain0 + c, q, lane, pI);
+                        else if (h == 1 && pI != I) flush_G(P, tmem, c, chain0 + c, q, lane, pI);
                     } else {
                         tc_fence_after();
                     }
@@ -372,11 +376,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcpair(const Params P) {
                 mbar_wait(bar_cd + 8 * c, (base_par + n_tiles - 1) & 1);
                 tc_fence_after();
                 if (h == 0) flush_F(P, tmem, c, chain0 + c, q, lane, pI, pJ);
-                else flush_G(P, tmem, c, chain0 + c, q, lane, pI);
+                else if (h == 1) flush_G(P, tmem, c, chain0 + c, q, lane, pI);
             }
             tc_fence_before();
             step_barrier();   // end of the chain pair: the tensor memory accumulators are free again
-        } else if (warp == 8) {
+        } else if (warp == NSW) {
             // ------------------------------------------------------------------ MMA issue + contact stream
             const size_t ytile_bytes = (size_t)TM * TN * 4;
             int I = 0, J = 0;
@@ -494,7 +498,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcpair(const Params P) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+    if (warp == NSW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------- host
