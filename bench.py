@@ -323,6 +323,8 @@ def make_hmc_workload(ctx, args, name, chains=None):
                                       1.0, 1.0, device=ctx.local, roles=args.roles, ev_k=args.ev_k, ev_d=1.5)
         if args.chrom_sets >= 0:
             model.set_option("chrom.sets", args.chrom_sets)
+        if getattr(args, "chrom_warps", 0) > 0:
+            model.set_option("chrom.warps", args.chrom_warps)
         if getattr(args, "host_chunks", 0) > 0:
             model.set_option("host.chunks", args.host_chunks)
         tau0, gibbs = 100.0, _cabi.GIBBS_TAU_FIRST
@@ -697,6 +699,8 @@ def main():
     ap.add_argument("--ev-k", type=float, default=0.0, help="chromatin: excluded-volume strength (0 = off)")
     ap.add_argument("--chrom-sets", type=int, default=-1,
                     help="chromatin: 0 = all chain groups in one pass-major item sequence (experiments)")
+    ap.add_argument("--chrom-warps", type=int, default=0,
+                    help="chromatin: cap on the chains per CTA (experiments)")
     ap.add_argument("--host-chunks", type=int, default=0,
                     help="chromatin e2e: pieces the state travels in through binfb_hmc_run_host (experiments)")
     ap.add_argument("--no-equilibrate", action="store_true", help="skip the untimed equilibration sweeps")

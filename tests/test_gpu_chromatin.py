@@ -491,3 +491,49 @@ def test_acceptance_rate_parity_at_a_working_step_size(gpu):
     acc = np.concatenate([m.hmc_run(q0, tau, eps, L, seed=100 + k, draw=k)["accepted"] for k in range(4)])
     se = np.sqrt(rate_ref * (1 - rate_ref) * (1.0 / acc.size + 1.0 / C))
     assert abs(acc.mean() - rate_ref) < 0.01 + 2 * se
+
+
+def test_full_size_properties_of_the_benchmarked_configuration(gpu):
+    """BASELINE.json configs[2] at its FULL size (1000 beads, 4096 chains, L = 20, fused precision update),
+    where the float64 oracle would take hours: size-independent properties instead.
+    (1) chain sharding: the random streams are keyed by the global chain id, so a contiguous
+        slice of the batch run on its own with chain_base = first index -- what another rank of a chain-sharded
+        job does -- ends BIT-identically where the slice keeps the launch plan and the groups' row-block rotation
+        (same chains per CTA, first index a multiple of chains-per-CTA x row blocks = 64), and within fp32
+        summation-order differences where a small slice runs in the small-batch plan (other role split);
+    (2) reversibility of the leapfrog map (hmc.py:116-123) on every chain of the batch;
+    (3) Newton's third law: the pair forces of the likelihood and the bond forces sum to zero per chain."""
+    from binf_b200 import _cabi
+    n, C, L, eps, tau = 1000, 4096, 20, 0.009, 100.0
+    X, y = chrom.synthetic_chromatin(n, seed=0)
+    m = _cabi.Model.chromatin(n, y, 2.0, 2.5, 4.0, 1.0, gamma_shape=1.0, gamma_rate=1.0)
+    rng = np.random.RandomState(21)
+    q0 = (X.reshape(-1)[None] + 0.1 * rng.normal(size=(C, 3 * n))).astype(np.float32)
+    kw = dict(gibbs_mode=_cabi.GIBBS_TAU_FIRST, seed=17, draw=4)
+    full = m.hmc_run(q0, tau, eps, L, n_traj=2, **kw)
+    assert np.all(np.isfinite(full["q"])) and np.all(full["tau"] > 0)
+    assert 0.2 < full["accepted"].mean() <= 1.0
+    for lo, hi in ((0, 1100), (2048, 4096)):
+        part = m.hmc_run(q0[lo:hi], tau, eps, L, n_traj=2, chain_base=lo, **kw)
+        for key in ("q", "tau", "accepted", "n_accepted", "e_before", "e_after"):
+            np.testing.assert_array_equal(part[key], full[key][lo:hi], err_msg="%s of chains %d..%d" % (key, lo, hi))
+    one = m.hmc_run(q0, tau, eps, L, **kw)
+    lo, hi = 1000, 1100                      # 100 chains: the small-batch plan (4 warps per chain, lockstep)
+    part = m.hmc_run(q0[lo:hi], tau, eps, L, chain_base=lo, **kw)
+    np.testing.assert_allclose(part["tau"], one["tau"][lo:hi], rtol=1e-5)
+    np.testing.assert_allclose(part["e_before"], one["e_before"][lo:hi], rtol=1e-6)
+    assert np.max(np.abs((part["e_after"] - part["e_before"]) - (one["e_after"] - one["e_before"])[lo:hi])) < 5e-2
+    assert (part["accepted"] == one["accepted"][lo:hi]).mean() > 0.9
+    # (2) forward and back with flipped momenta, every chain
+    p0 = rng.normal(size=q0.shape).astype(np.float32)
+    u = np.full(C, 1e-30)
+    fwd = m.hmc_run(q0, tau, 0.002, L, p0=p0, u=u, want_end=True)
+    assert fwd["accepted"].all()
+    back = m.hmc_run(fwd["q_end"], tau, 0.002, L, p0=-fwd["p_end"], u=u, want_end=True)
+    scale = np.max(np.abs(q0))
+    assert np.max(np.abs(back["q_end"] - q0)) < 3e-4 * scale
+    assert np.max(np.abs(back["p_end"] + p0)) < 2e-2
+    # (3) no net force on any chain (the Gaussian confinement is off in this model)
+    logp, grad, _ = m.logprob_grad(q0[:512], tau)
+    net = grad.reshape(512, n, 3).sum(axis=1)
+    assert np.max(np.abs(net)) < 2e-4 * np.max(np.abs(grad)) * np.sqrt(n)
