@@ -13,6 +13,7 @@
 
 namespace binfb {
 
+
 static thread_local std::string g_error;
 
 void set_error(const std::string &msg) { g_error = msg; }
@@ -180,6 +181,7 @@ int binfb_model_create_polynomial(const double *xs, const double *ys, int n_data
                                   const double *prior_mean, const double *prior_var,
                                   double gamma_shape, double gamma_rate, unsigned flags, int device,
                                   binfb_model **out) {
+    BINFB_TRACE();
     if (!xs || !ys || !out || n_data < 1) {
         set_error("model_create_polynomial: xs, ys, out required, n_data >= 1");
         return BINFB_EINVAL;
@@ -235,6 +237,7 @@ int binfb_model_create_generic(const char *device_code, int n_params, int x_dim,
                                const double *ys, int n_data, const double *prior_mean,
                                const double *prior_var, double gamma_shape, double gamma_rate,
                                unsigned flags, int device, binfb_model **out) {
+    BINFB_TRACE();
     if (!device_code || !xs || !ys || !out || n_data < 1 || x_dim < 1) {
         set_error("model_create_generic: device_code, xs, ys, out required, n_data, x_dim >= 1");
         return BINFB_EINVAL;
@@ -263,6 +266,7 @@ int binfb_model_create_generic(const char *device_code, int n_params, int x_dim,
 int binfb_model_create_chromatin(int n_beads, const float *y_pairs, double alpha, double d_c,
                                  double k_bb, double l0, double conf_s, double gamma_shape,
                                  double gamma_rate, unsigned flags, int device, binfb_model **out) {
+    BINFB_TRACE();
     if (!y_pairs || !out || n_beads < 2) {
         set_error("model_create_chromatin: y_pairs, out required, n_beads >= 2");
         return BINFB_EINVAL;
@@ -416,6 +420,7 @@ int binfb_model_get_option(const binfb_model *m, const char *key, double *value)
 
 int binfb_logprob_grad(binfb_model *m, const float *q, const float *tau, const float *beta, int C,
                        double *logp, float *grad, double *chi2, void *stream) {
+    BINFB_TRACE();
     int rc = check_model(m);
     if (rc) return rc;
     if (!q || !tau || C < 1) {
@@ -434,6 +439,7 @@ int binfb_logprob_grad(binfb_model *m, const float *q, const float *tau, const f
 
 int binfb_logprob_grad_host(binfb_model *m, const float *q, const float *tau, const float *beta,
                             int C, double *logp, float *grad, double *chi2) {
+    BINFB_TRACE();
     int rc = check_model(m);
     if (rc) return rc;
     if (!q || !tau || C < 1) {
@@ -462,6 +468,7 @@ int binfb_logprob_grad_host(binfb_model *m, const float *q, const float *tau, co
 }
 
 int binfb_forward_host(binfb_model *m, const float *q, int C, float *mock) {
+    BINFB_TRACE();
     int rc = check_model(m);
     if (rc) return rc;
     if (!q || !mock || C < 1) {
@@ -489,6 +496,7 @@ int binfb_hmc_run(binfb_model *m, float *q, float *tau, const float *beta, float
                   const binfb_hmc_opts *opts, const float *p0, const float *u,
                   const double *gamma_draws, uint8_t *accepted, double *e_before, double *e_after,
                   float *q_end, float *p_end, int32_t *n_accepted, double *stats, void *stream) {
+    BINFB_TRACE();
     int rc = check_hmc(m, C, opts, q, tau, eps, p0, u);
     if (rc) return rc;
     BINFB_CUDA(cudaSetDevice(m->device));
@@ -505,6 +513,7 @@ int binfb_hmc_run_host(binfb_model *m, float *q, float *tau, const float *beta, 
                        const double *gamma_draws, uint8_t *accepted, double *e_before,
                        double *e_after, float *q_end, float *p_end, int32_t *n_accepted,
                        double *stats) {
+    BINFB_TRACE();
     int rc = check_hmc(m, C, opts, q, tau, eps, p0, u);
     if (rc) return rc;
     BINFB_CUDA(cudaSetDevice(m->device));
@@ -629,6 +638,7 @@ int binfb_hmc_run_host(binfb_model *m, float *q, float *tau, const float *beta, 
 int binfb_gibbs_precision(binfb_model *m, const float *q, float *tau, const float *beta, int C,
                           uint64_t seed, uint64_t draw, uint64_t chain_base,
                           const double *gamma_draws, double *chi2, void *stream) {
+    BINFB_TRACE();
     int rc = check_model(m);
     if (rc) return rc;
     if (!q || !tau || !chi2 || C < 1) {
@@ -647,6 +657,7 @@ int binfb_gibbs_precision(binfb_model *m, const float *q, float *tau, const floa
 int binfb_gibbs_precision_host(binfb_model *m, const float *q, float *tau, const float *beta, int C,
                                uint64_t seed, uint64_t draw, uint64_t chain_base,
                                const double *gamma_draws, double *chi2) {
+    BINFB_TRACE();
     int rc = check_model(m);
     if (rc) return rc;
     if (!q || !tau || C < 1) {
@@ -679,6 +690,7 @@ int binfb_gibbs_precision_host(binfb_model *m, const float *q, float *tau, const
 int binfb_swap_decide(const double *ll_a, const double *ll_b, double beta_a, double beta_b, int C,
                       uint64_t seed, uint64_t attempt, uint64_t pair_id, uint64_t chain_base,
                       uint8_t *accept, void *stream) {
+    BINFB_TRACE();
     if (!ll_a || !ll_b || !accept || C < 1) {
         set_error("swap_decide: ll_a, ll_b, accept required");
         return BINFB_EINVAL;
@@ -689,6 +701,7 @@ int binfb_swap_decide(const double *ll_a, const double *ll_b, double beta_a, dou
 
 int binfb_swap_apply(float *q_mine, const float *q_theirs, float *eps_mine, const float *eps_theirs,
                      const uint8_t *accept, int C, int dim, void *stream) {
+    BINFB_TRACE();
     if (!q_mine || !q_theirs || !accept || C < 1 || dim < 1) {
         set_error("swap_apply: q_mine, q_theirs, accept required");
         return BINFB_EINVAL;
@@ -719,6 +732,7 @@ int binfb_hmc_last_chi2(binfb_model *m, int C, double *chi2, void *stream) {
 
 int binfb_rex_pack(const double *chi2, const float *tau, const float *eps, const int32_t *tidx, int C,
                    double n_data, void *records, void *stream) {
+    BINFB_TRACE();
     if (!chi2 || !tau || !eps || !tidx || !records || C < 1) {
         set_error("rex_pack: chi2, tau, eps, tidx, records required");
         return BINFB_EINVAL;
@@ -730,6 +744,7 @@ int binfb_rex_decide(const void *records_all, int world, int rank, int C, int n_
                      int n_temps, uint64_t seed, uint64_t attempt, double ll_shift, int32_t *tidx, float *beta,
                      float *eps, uint8_t *accept, unsigned long long *pair_counts, double *temp_stats,
                      void *stream) {
+    BINFB_TRACE();
     if (!records_all || !betas || !tidx || !beta || !eps) {
         set_error("rex_decide: records_all, betas, tidx, beta, eps required");
         return BINFB_EINVAL;
@@ -748,6 +763,7 @@ int binfb_rex_decide(const void *records_all, int world, int rank, int C, int n_
 
 int binfb_rex_select(const float *q, const float *aux, const int32_t *tidx, int k_sel, int C, int dim,
                      int n_columns, float *out_q, float *out_aux, void *stream) {
+    BINFB_TRACE();
     if (!q || !tidx || !out_q || C < 1 || dim < 1 || n_columns < 1 || C % n_columns != 0) {
         set_error("rex_select: q, tidx, out_q required, n_chains a positive multiple of n_columns");
         return BINFB_EINVAL;

@@ -5,6 +5,8 @@
 
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/binf_b200.h"
 
 namespace binfb {
@@ -17,6 +19,18 @@ int cuda_fail(cudaError_t e, const char *what);
         cudaError_t e__ = (call);                                     \
         if (e__ != cudaSuccess) return ::binfb::cuda_fail(e__, #call); \
     } while (0)
+
+// Tracing (the reference has none): every compute entry point of the ABI is an NVTX range named after
+// the symbol, so that a profile taken with `ncu --nvtx --nvtx-include "binfb_hmc_run/"` (or any NVTX-aware tool)
+// attributes kernels and copies to the call that issued them.  Header-only NVTX 3: without a tool attached a range
+// is one load and one branch.
+struct TraceRange {
+    explicit TraceRange(const char *name) { nvtxRangePushA(name); }
+    ~TraceRange() { nvtxRangePop(); }
+    TraceRange(const TraceRange &) = delete;
+    TraceRange &operator=(const TraceRange &) = delete;
+};
+#define BINFB_TRACE() ::binfb::TraceRange binfb_trace_range_(__func__)
 
 // BEGIN_KERNEL_ARGS  (this block is also compiled by NVRTC as part of the generic-model source)
 // arguments common to every HMC launch (device pointers)

@@ -122,6 +122,7 @@ int binfb_rwmc_run(binfb_model *m, float *q_dev, const float *tau_dev, const flo
                    const float *stepsize_dev, int n_chains, int n_moves, uint64_t seed, uint64_t draw,
                    uint64_t chain_base, const float *change_dev, const float *u_dev, uint8_t *accepted_dev,
                    int32_t *n_accepted_dev, double *logp_dev, void *stream) {
+    BINFB_TRACE();
     if (!m) {
         set_error("null model handle");
         return BINFB_EINVAL;
@@ -166,6 +167,7 @@ int binfb_rwmc_run(binfb_model *m, float *q_dev, const float *tau_dev, const flo
 int binfb_rwmc_run_host(binfb_model *m, float *q, const float *tau, const float *beta, const float *stepsize,
                         int n_chains, int n_moves, uint64_t seed, uint64_t draw, uint64_t chain_base,
                         const float *change, const float *u, uint8_t *accepted, int32_t *n_accepted, double *logp) {
+    BINFB_TRACE();
     if (!m) {
         set_error("null model handle");
         return BINFB_EINVAL;

@@ -281,6 +281,7 @@ int binfb_sink_info(const binfb_sink *s, long long *n_pushed, long long *n_momen
 }
 
 int binfb_sink_push(binfb_sink *s, const float *q_dev, const float *aux_dev, const double *logp_dev, void *stream) {
+    BINFB_TRACE();
     int rc = check_sink(s);
     if (rc) return rc;
     if (!q_dev) {
@@ -327,6 +328,7 @@ int binfb_sink_push(binfb_sink *s, const float *q_dev, const float *aux_dev, con
 }
 
 int binfb_sink_push_host(binfb_sink *s, const float *q, const float *aux, const double *logp) {
+    BINFB_TRACE();
     int rc = check_sink(s);
     if (rc) return rc;
     if (!q) {
@@ -360,6 +362,7 @@ int binfb_sink_push_host(binfb_sink *s, const float *q, const float *aux, const 
 
 int binfb_sink_summary(binfb_sink *s, double *mean_dev, double *var_dev, double *rhat_dev, double *ess_dev,
                        void *stream) {
+    BINFB_TRACE();
     int rc = check_sink(s);
     if (rc) return rc;
     if (s->n_moment < 2) {
@@ -403,6 +406,7 @@ int binfb_sink_sums_host(binfb_sink *s, double *pivot, double *sum_dev, double *
 }
 
 int binfb_sink_summary_host(binfb_sink *s, double *mean, double *var, double *rhat, double *ess) {
+    BINFB_TRACE();
     int rc = check_sink(s);
     if (rc) return rc;
     BINFB_CUDA(cudaSetDevice(s->device));
