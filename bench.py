@@ -107,15 +107,19 @@ def workload_config(name, world, chains=None, eps=None, equilibrate=True):
 # synthetic inputs; generated without touching oracle/ so the product arm
 # never imports the checker
 # --------------------------------------------------------------------------------------------
-def chromatin_inputs(w, chains, seed):
+def chromatin_inputs(w, chains, seed, contact="logistic"):
     n = w["n_beads"]
     rng = np.random.RandomState(0)
     X = np.cumsum(rng.normal(size=(n, 3)) * w["l0"], axis=0)
     X -= X.mean(axis=0)
     i, j = np.triu_indices(n, 1)
     d = np.sqrt(np.sum((X[i] - X[j]) ** 2, axis=-1) + 1e-12)
-    with np.errstate(over="ignore"):
-        y = 1.0 / (1.0 + np.exp(w["alpha"] * (d - w["d_c"]))) + rng.normal(size=d.shape) * w["noise"]
+    if contact == "algebraic":
+        z = w["alpha"] * (w["d_c"] - d)
+        y = 0.5 * (1.0 + z / np.sqrt(1.0 + z * z)) + rng.normal(size=d.shape) * w["noise"]
+    else:
+        with np.errstate(over="ignore"):
+            y = 1.0 / (1.0 + np.exp(w["alpha"] * (d - w["d_c"]))) + rng.normal(size=d.shape) * w["noise"]
     rng = np.random.RandomState(1 + seed)
     q = (X.reshape(-1)[None, :] + 0.1 * rng.normal(size=(chains, 3 * n))).astype(np.float32)
     return y.astype(np.float32), q
@@ -318,9 +322,11 @@ def make_hmc_workload(ctx, args, name, chains=None):
     C = chains or w["chains"]
     L = w["L"]
     if name in ("chromatin", "rex", "chromatin5k"):
-        y, q_host = chromatin_inputs(w, C, ctx.rank)
+        contact = getattr(args, "contact", "logistic")
+        y, q_host = chromatin_inputs(w, C, ctx.rank, contact)
         model = _cabi.Model.chromatin(w["n_beads"], y, w["alpha"], w["d_c"], w["k_bb"], w["l0"], 0.0,
-                                      1.0, 1.0, device=ctx.local, roles=args.roles, ev_k=args.ev_k, ev_d=1.5)
+                                      1.0, 1.0, device=ctx.local, roles=args.roles, ev_k=args.ev_k, ev_d=1.5,
+                                      contact=contact)
         if args.chrom_sets >= 0:
             model.set_option("chrom.sets", args.chrom_sets)
         if getattr(args, "chrom_warps", 0) > 0:
@@ -329,7 +335,8 @@ def make_hmc_workload(ctx, args, name, chains=None):
             model.set_option("host.chunks", args.host_chunks)
         tau0, gibbs = 100.0, _cabi.GIBBS_TAU_FIRST
         units = float(model.n_data)            # pairs per force evaluation
-        flop_per_launch = FLOP_PER_PAIR * units * (L + 1) * C
+        # (the algebraic contact function: 32 flop + 2 special-function ops per pair by the same count)
+        flop_per_launch = (32.0 if contact == "algebraic" else FLOP_PER_PAIR) * units * (L + 1) * C
         bytes_per_launch = 2.0 * 4 * q_host.shape[1] * C + 4.0 * units
     else:
         xs, ys, q_host = poly_inputs(w, C, ctx.rank)
@@ -343,7 +350,8 @@ def make_hmc_workload(ctx, args, name, chains=None):
         flop_per_launch = (FLOP_PER_DATUM * (L + 1) + 4) * units * C
         bytes_per_launch = 2.0 * 4 * 4 * C
     dev = ctx.dev
-    return dict(name=name, w=w, C=C, L=L, D=q_host.shape[1], model=model, q_host=q_host, tau0=tau0, gibbs=gibbs,
+    return dict(name=name, w=w, C=C, L=L, D=q_host.shape[1], model=model,
+                contact=getattr(args, "contact", "logistic") if "n_beads" in w else None, q_host=q_host, tau0=tau0, gibbs=gibbs,
                 units=units, flop_per_launch=flop_per_launch, bytes_per_launch=bytes_per_launch,
                 q=torch.from_numpy(q_host).to(dev), tau=torch.full((C,), tau0, device=dev, dtype=torch.float32),
                 accepted=torch.zeros(C, device=dev, dtype=torch.uint8),
@@ -359,8 +367,9 @@ def chromatin_roofline(ctx, wl, ms_kernel, traffic):
     sfu = None
     if wl["name"] not in ("poly", "generic"):
         # the binding pipe of the pair kernel: 3 MUFU (rsqrt, ex2, rcp) per bead pair
-        sfu_gops = 3.0 * wl["units"] * (wl["L"] + 1) * wl["C"] / (ms_kernel * 1e-3) / 1e9
-        sfu = dict(ops_per_pair=3, achieved_gops=sfu_gops, peak_gops=mb["mufu_gops"],
+        n_sfu = 2 if wl.get("contact") == "algebraic" else 3
+        sfu_gops = n_sfu * wl["units"] * (wl["L"] + 1) * wl["C"] / (ms_kernel * 1e-3) / 1e9
+        sfu = dict(ops_per_pair=n_sfu, achieved_gops=sfu_gops, peak_gops=mb["mufu_gops"],
                    frac=sfu_gops / mb["mufu_gops"],
                    note="MUFU issues at 16 lanes/clk/SM = 24 SMSP-cycles per warp-pair (64.6 % of the FP32-FMA "
                         "peak if it were the only limit).  It is the busiest single pipe but not the wall: with all "
@@ -476,7 +485,9 @@ def hmc_leg(ctx, args, name, steps, warmup, chains=None, eps=None, with_e2e=True
                 n_gpus=world, steps=steps, warmup=warmup, ms_per_step=total_ms / steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic",
-                config=workload_config(name, world, C, eps0, not args.no_equilibrate),
+                config=dict(workload_config(name, world, C, eps0, not args.no_equilibrate),
+                            **({"contact_function": "algebraic (experiment; the headline is logistic)"}
+                               if wl.get("contact") == "algebraic" else {})),
                 acceptance_rate=float(st[0] / st[1]) if st[1] else None,
                 e2e=e2e,
                 gpu_launches=steps, wall_ms=wall_ms, clocks=clocks,
@@ -660,7 +671,8 @@ def run_ours(args):
         line = hmc_leg(ctx, args, args.workload, args.steps, args.warmup, chains=args.chains or None,
                        eps=args.eps or None, with_e2e=not args.no_e2e)
     # ---- the other configurations of BASELINE.json, short legs on the same box in the same run -----------
-    if args.workload == "chromatin" and not args.no_extra and not args.chains and not args.roles:
+    if args.workload == "chromatin" and not args.no_extra and not args.chains and not args.roles \
+            and args.contact == "logistic":
         k = max(3, min(args.steps, 6))
         for name, fn in (("poly", lambda: hmc_leg(ctx, args, "poly", max(k, 10), 3)),
                          ("generic", lambda: hmc_leg(ctx, args, "generic", max(k, 10), 3, with_e2e=False)),
@@ -699,6 +711,8 @@ def main():
     ap.add_argument("--ev-k", type=float, default=0.0, help="chromatin: excluded-volume strength (0 = off)")
     ap.add_argument("--chrom-sets", type=int, default=-1,
                     help="chromatin: 0 = all chain groups in one pass-major item sequence (experiments)")
+    ap.add_argument("--contact", default="logistic", choices=["logistic", "algebraic"],
+                    help="chromatin: contact function of the forward model (experiments; the headline is logistic)")
     ap.add_argument("--chrom-warps", type=int, default=0,
                     help="chromatin: cap on the chains per CTA (experiments)")
     ap.add_argument("--host-chunks", type=int, default=0,

@@ -15,6 +15,7 @@ OK, EINVAL, ECUDA, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4
 MODEL_POLYNOMIAL, MODEL_CHROMATIN, MODEL_GENERIC = 1, 2, 3
 FLAG_PRIOR_GRAD = 1
 FLAG_GENERIC_SCALAR = 2
+FLAG_CONTACT_ALGEBRAIC = 4
 GIBBS_NONE, GIBBS_TAU_FIRST, GIBBS_TAU_LAST = 0, 1, 2
 SINK_TRACK_MAP = 1
 REX_MAX_TEMPS, REX_RECORD_BYTES = 64, 16
@@ -217,10 +218,15 @@ class Model(object):
 
     @classmethod
     def chromatin(cls, n_beads, y_pairs, alpha, d_c, k_bb, l0, conf_s=0.0, gamma_shape=1.0,
-                  gamma_rate=1.0, flags=0, device=0, roles=0, ev_k=0.0, ev_d=0.0):
+                  gamma_rate=1.0, flags=0, device=0, roles=0, ev_k=0.0, ev_d=0.0, contact="logistic"):
         """roles: warps per chain (0 = heuristic; forcing it is a test hook, flags bits 8..12);
-        ev_k, ev_d: excluded-volume prior -ev_k sum max(0, ev_d - d_ij)^4 (0 = off)."""
+        ev_k, ev_d: excluded-volume prior -ev_k sum max(0, ev_d - d_ij)^4 (0 = off);
+        contact: "logistic" 1/(1+exp(-z)) or "algebraic" 1/2 (1 + z/sqrt(1+z^2)), z = alpha (d_c - d)."""
+        if contact not in ("logistic", "algebraic"):
+            raise ValueError("contact: 'logistic' or 'algebraic', got %r" % (contact,))
         flags |= (roles & 0x1f) << 8
+        if contact == "algebraic":
+            flags |= FLAG_CONTACT_ALGEBRAIC
         y = f32(y_pairs)
         assert y.shape == (n_beads * (n_beads - 1) // 2,)
         h = C.c_void_p()

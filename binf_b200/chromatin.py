@@ -11,11 +11,14 @@ from binf_b200.pdf.priors import AbstractPrior
 
 
 class ContactForwardModel(AbstractForwardModel):
-    """mock_ij = 1 / (1 + exp(alpha (|x_i - x_j| - d_c)))"""
+    """mock_ij = s(alpha (d_c - |x_i - x_j|)) with the logistic s(z) = 1 / (1 + exp(-z)) (default) or the
+    algebraic s(z) = 1/2 (1 + z / sqrt(1 + z^2)) (contact="algebraic")"""
 
-    def __init__(self, n_beads, alpha, d_c):
+    def __init__(self, n_beads, alpha, d_c, contact="logistic"):
         super(ContactForwardModel, self).__init__("contacts")
-        self.n_beads, self.alpha, self.d_c = int(n_beads), float(alpha), float(d_c)
+        if contact not in ("logistic", "algebraic"):
+            raise ValueError("contact: 'logistic' or 'algebraic', got %r" % (contact,))
+        self.n_beads, self.alpha, self.d_c, self.contact = int(n_beads), float(alpha), float(d_c), contact
         self._register_variable("structure", differentiable=True)
         self.update_var_param_types(structure=ArrayParameter)
         self._set_original_variables()
@@ -24,10 +27,10 @@ class ContactForwardModel(AbstractForwardModel):
         from binf_b200 import _cabi
         from binf_b200.lowering import _cached_model, get_device
         n = self.n_beads
-        key = ("chrom-fwd", n, self.alpha, self.d_c, get_device())
+        key = ("chrom-fwd", n, self.alpha, self.d_c, self.contact, get_device())
         model = _cached_model(key, (), lambda: _cabi.Model.chromatin(
             n, np.zeros(n * (n - 1) // 2, dtype=np.float32), self.alpha, self.d_c, 0.0, 1.0,
-            device=get_device()))
+            device=get_device(), contact=self.contact))
         q = np.asarray(structure, dtype=np.float64)
         mock = model.forward(q.reshape(-1, 3 * n)).astype(np.float64)
         return mock[0] if q.ndim == 1 else mock
@@ -38,7 +41,7 @@ class ContactForwardModel(AbstractForwardModel):
             "fused pair kernel")
 
     def clone(self):
-        copy = self.__class__(self.n_beads, self.alpha, self.d_c)
+        copy = self.__class__(self.n_beads, self.alpha, self.d_c, self.contact)
         self._set_parameters(copy)
         return copy
 
@@ -88,7 +91,7 @@ class ExcludedVolumePrior(AbstractPrior):
 
 
 def make_chromatin_posterior(n_beads, y_pairs, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0, conf_s=0.0,
-                             gamma_shape=1.0, gamma_rate=1.0, ev_k=0.0, ev_d=0.0):
+                             gamma_shape=1.0, gamma_rate=1.0, ev_k=0.0, ev_d=0.0, contact="logistic"):
     """Posterior({contacts likelihood}, {backbone prior, Gamma precision prior[, excluded volume]}) over
     the variables `structure` and `precision`."""
     from binf_b200.pdf.likelihoods import Likelihood
@@ -96,7 +99,7 @@ def make_chromatin_posterior(n_beads, y_pairs, alpha=2.0, d_c=2.5, k_bb=4.0, l0=
     from binf_b200.example.likelihood import GaussianErrorModel
     from binf_b200.example.priors import GammaPrior
     y = np.ascontiguousarray(y_pairs, dtype=np.float32)
-    lik = Likelihood("points", ContactForwardModel(n_beads, alpha, d_c), GaussianErrorModel(y))
+    lik = Likelihood("points", ContactForwardModel(n_beads, alpha, d_c, contact), GaussianErrorModel(y))
     priors = {"structure_prior": BackbonePrior(n_beads, k_bb, l0, conf_s),
               "precision_prior": GammaPrior(gamma_shape, gamma_rate)}
     if ev_k > 0.0:

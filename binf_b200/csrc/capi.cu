@@ -273,7 +273,8 @@ int binfb_model_create_chromatin(int n_beads, const float *y_pairs, double alpha
     }
     // the pair loop works on positions scaled by the exponent slope alpha*log2(e) and folds 2^(-alpha d_c log2 e)
     // into a multiplier (pair_block.cuh, SCALED): the slope must be positive and the multiplier a normal float
-    if (!(alpha > 0.0) || !(fabs(alpha * d_c) <= 80.0)) {
+    const bool algebraic = (flags & BINFB_FLAG_CONTACT_ALGEBRAIC) != 0;  // (no exponential: alpha > 0 is enough)
+    if (!(alpha > 0.0) || !(algebraic || fabs(alpha * d_c) <= 80.0) || !(fabs(alpha * d_c) <= 1e6)) {
         set_error("model_create_chromatin: alpha > 0 and |alpha * d_c| <= 80 required");
         return BINFB_EINVAL;
     }
@@ -411,6 +412,7 @@ int binfb_model_get_option(const binfb_model *m, const char *key, double *value)
     else if (!strcmp(key, "host.chunks")) *value = m->host_chunks;
     else if (!strcmp(key, "chrom.ev_k")) *value = m->chrom.ev_k;
     else if (!strcmp(key, "chrom.ev_d")) *value = m->chrom.ev_d;
+    else if (!strcmp(key, "chrom.algebraic")) *value = (m->chrom.flags & BINFB_FLAG_CONTACT_ALGEBRAIC) ? 1 : 0;
     else {
         set_error(std::string("unknown option: ") + key);
         return BINFB_EINVAL;

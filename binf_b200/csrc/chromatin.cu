@@ -309,7 +309,7 @@ struct SweepRegs {
 
 // one regular step: the 16 pairs (own quad) x (partner quad), every lane (inactive lanes compute on
 // quad 0 and never store).  frc_off = byte distance from a quad's positions to its force sums.
-template <bool ENERGY, bool EV>
+template <bool ENERGY, bool EV, bool ALG>
 __device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32_t yaddr, float2 A2, float2 B2,
                                           bool active) {
     const uint32_t pa = s.paddr, fa = s.paddr + frc_off;
@@ -339,10 +339,10 @@ __device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32
 #if BINFB_YJIT
         yv[r] = r == 0 ? lds4<0>(yaddr) : r == 1 ? lds4<512>(yaddr) : r == 2 ? lds4<1024>(yaddr) : lds4<1536>(yaddr);
 #endif
-        pair_packed_gs<ENERGY, EV, true>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y),
+        pair_packed_gs<ENERGY, EV, true, ALG>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y),
                                    A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2, s.dev,
                                    s.cev, &ev2);
-        pair_packed_gs<ENERGY, EV, true>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w),
+        pair_packed_gs<ENERGY, EV, true, ALG>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w),
                                    A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2, s.dev,
                                    s.cev, &ev2);
     }
@@ -365,7 +365,7 @@ __device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32
 
 // the special steps: k == 0 (the 6 pairs inside the lane's own quad), k == KS with an even quad
 // count (only the lower half of the quads owns the (q, q + Q/2) block), k > KS (padding: nothing)
-template <bool ENERGY, bool EV>
+template <bool ENERGY, bool EV, bool ALG>
 __device__ __forceinline__ void step_special(SweepRegs &s, uint32_t frc_off, uint32_t yaddr, float A, float B,
                                              int KS, bool upper_half) {
     const int k = s.k;
@@ -379,7 +379,7 @@ __device__ __forceinline__ void step_special(SweepRegs &s, uint32_t frc_off, uin
 #pragma unroll
             for (int c = r + 1; c < 4; ++c) {
                 float tx = 0.f, ty = 0.f, tz = 0.f;
-                pair_scalar<ENERGY, EV, true>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, -s.nx2[c].x, -s.ny2[c].x, -s.nz2[c].x,
+                pair_scalar<ENERGY, EV, true, ALG>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, -s.nx2[c].x, -s.ny2[c].x, -s.nz2[c].x,
                                         yv[r][c], A, B, s.g[r][0], s.g[r][1], s.g[r][2], tx, ty,
                                         tz, chi, s.dev, s.cev, &evs);
                 s.g[c][0] -= tx, s.g[c][1] -= ty, s.g[c][2] -= tz;
@@ -395,7 +395,7 @@ __device__ __forceinline__ void step_special(SweepRegs &s, uint32_t frc_off, uin
         for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                pair_scalar<ENERGY, EV, true>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, xj[c], yj[c], zj[c], yv[r][c], A, B,
+                pair_scalar<ENERGY, EV, true, ALG>(s.nx2[r].x, s.ny2[r].x, s.nz2[r].x, xj[c], yj[c], zj[c], yv[r][c], A, B,
                                         s.g[r][0], s.g[r][1], s.g[r][2], fjx[c], fjy[c], fjz[c],
                                         chi, s.dev, s.cev, &evs);
         sts4<0>(fa, fjx[0], fjx[1], fjx[2], fjx[3]);
@@ -406,7 +406,7 @@ __device__ __forceinline__ void step_special(SweepRegs &s, uint32_t frc_off, uin
     if (ENERGY && EV) s.ev += (double)evs;
 }
 
-template <bool ENERGY, int R, int SPR, bool LOCKSTEP, int NS, bool EV>
+template <bool ENERGY, int R, int SPR, bool LOCKSTEP, int NS, bool EV, bool ALG>
 __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSmem &sm, const Ring &ring,
                                               uint32_t &stage_idx_io, bool chain_valid, int lane, int role,
                                               int bar_id, int rb0, float cev, double &ev_out) {
@@ -482,9 +482,9 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
 #pragma unroll
                 for (int u = 0; u < SPR; ++u) {
                     if (!GENERIC || (unsigned)(s.k - 1) < (unsigned)k_fast)
-                        step_fast<ENERGY, EV>(s, frc_off, ybase + u * R * STEP_BYTES, A2, B2, active);
+                        step_fast<ENERGY, EV, ALG>(s, frc_off, ybase + u * R * STEP_BYTES, A2, B2, active);
                     else {
-                        if (active) step_special<ENERGY, EV>(s, frc_off, ybase + u * R * STEP_BYTES, A, B, KS, upper_half);
+                        if (active) step_special<ENERGY, EV, ALG>(s, frc_off, ybase + u * R * STEP_BYTES, A, B, KS, upper_half);
 #if BINFB_PREFETCH
                         const uint32_t pn = s.wrap == 1 ? s.pwrap : s.paddr + 48u;
                         s.nxt[0] = lds4<0>(pn), s.nxt[1] = lds4<16>(pn), s.nxt[2] = lds4<32>(pn);
@@ -615,7 +615,7 @@ __device__ __forceinline__ void chrom_item(const ChromCall &call, int it, int n_
     o = g0 + (r - seq * gs);
 }
 
-template <int R, int SPR, bool LOCKSTEP, int NS, bool EV>
+template <int R, int SPR, bool LOCKSTEP, int NS, bool EV, bool ALG>
 __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall call) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int STAGE_BYTES = R * SPR * STEP_BYTES;
@@ -817,9 +817,9 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
             // ---- phase B: pair sweep -----------------------------------------------------
             const int rb0 = BINFB_ROTATE ? o % cd.NRB : 0;
             double ev_sum = 0.0;
-            double chi2 = energy ? chrom_sweep<true, R, SPR, LOCKSTEP, NS, EV>(cd, sm, ring, stage_idx, valid, lane, role,
+            double chi2 = energy ? chrom_sweep<true, R, SPR, LOCKSTEP, NS, EV, ALG>(cd, sm, ring, stage_idx, valid, lane, role,
                                                                               bar_id, rb0, cev, ev_sum)
-                                 : chrom_sweep<false, R, SPR, LOCKSTEP, NS, EV>(cd, sm, ring, stage_idx, valid, lane, role,
+                                 : chrom_sweep<false, R, SPR, LOCKSTEP, NS, EV, ALG>(cd, sm, ring, stage_idx, valid, lane, role,
                                                                                bar_id, rb0, cev, ev_sum);
             if (R > 1) chain_bar(bar_id, cthreads);
             else __syncwarp();
@@ -1013,7 +1013,7 @@ __global__ void __launch_bounds__(512, 1) chrom_kernel(ChromDev cd, ChromCall ca
 }
 
 // mock contacts for all pairs (AbstractForwardModel.__call__ of the contact model)
-__global__ void chrom_forward_kernel(int n, long long M, float A, float B, const float *q,
+__global__ void chrom_forward_kernel(int n, long long M, float A, float B, int algebraic, const float *q,
                                      float *mock) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M) return;
@@ -1029,7 +1029,12 @@ __global__ void chrom_forward_kernel(int n, long long M, float A, float B, const
     const float dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
     const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, CHROM_SOFT)));
     const float d = r2 * rsqrtf(r2);
-    mock[(size_t)c * M + idx] = 1.0f / (1.0f + exp2f(fmaf(d, A, B)));
+    if (algebraic) {  // A = alpha, B = -alpha d_c: z = -(A d + B), mock = 1/2 (1 + z / sqrt(1 + z^2))
+        const float zn = fmaf(d, A, B);
+        mock[(size_t)c * M + idx] = 0.5f - 0.5f * zn * rsqrtf(fmaf(zn, zn, 1.0f));
+    } else {
+        mock[(size_t)c * M + idx] = 1.0f / (1.0f + exp2f(fmaf(d, A, B)));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1171,12 +1176,23 @@ static ChromDev chrom_dev(const ChromModel &m, const ChromPlan &pl, const float 
     d.R = pl.R, d.Lr = pl.Lr, d.SS = pl.SS, d.S_pad = pl.S_pad;
     d.ystream = reinterpret_cast<const float4 *>(ystream);
     const double log2e = 1.4426950408889634;
-    d.A = (float)((double)m.alpha * log2e);
-    d.B = (float)(-(double)m.alpha * (double)m.d_c * log2e);
-    d.S = d.A, d.invS = (float)(1.0 / ((double)m.alpha * log2e));
-    d.softS = (float)((double)d.A * (double)d.A * (double)CHROM_SOFT);
-    d.nC = (float)(-exp2(-(double)m.alpha * (double)m.d_c * log2e));
-    d.alpha = m.alpha, d.k_bb = m.k_bb, d.l0 = m.l0, d.inv_s2 = m.inv_s2;
+    if (m.flags & BINFB_FLAG_CONTACT_ALGEBRAIC) {
+        // algebraic contact function: positions scaled by alpha, the "B" slot of the pair block carries -alpha d_c,
+        // the force scale the -1/2 of the block's coefficient convention (pair_block.cuh, ALG)
+        d.A = m.alpha, d.B = (float)(-(double)m.alpha * (double)m.d_c);
+        d.S = d.A, d.invS = (float)(1.0 / (double)m.alpha);
+        d.softS = (float)((double)d.A * (double)d.A * (double)CHROM_SOFT);
+        d.nC = d.B;
+        d.alpha = -0.5f * m.alpha;
+    } else {
+        d.A = (float)((double)m.alpha * log2e);
+        d.B = (float)(-(double)m.alpha * (double)m.d_c * log2e);
+        d.S = d.A, d.invS = (float)(1.0 / ((double)m.alpha * log2e));
+        d.softS = (float)((double)d.A * (double)d.A * (double)CHROM_SOFT);
+        d.nC = (float)(-exp2(-(double)m.alpha * (double)m.d_c * log2e));
+        d.alpha = m.alpha;
+    }
+    d.k_bb = m.k_bb, d.l0 = m.l0, d.inv_s2 = m.inv_s2;
     d.ev_k = m.ev_k, d.ev_d = m.ev_d;
     d.M = (double)m.M;
     d.qw = m.qw, d.pw = m.pw, d.h0 = m.h0, d.chi2_0 = m.chi2_0, d.chi2_state = m.chi2_state;
@@ -1284,16 +1300,19 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
     const int grid = call.n_groups < sm_count ? call.n_groups : sm_count;
     const int threads = W * pl.R * 32;
     const ChromDev dev = chrom_dev(m, pl, ystream);
-#define BINFB_CHROM_LAUNCH_E(RR, SPR, LOCK, NSS, EVV)                                                          \
+#define BINFB_CHROM_LAUNCH_E(RR, SPR, LOCK, NSS, EVV, ALGG)                                                    \
     do {                                                                                                       \
-        BINFB_CUDA(cudaFuncSetAttribute(chrom_kernel<RR, SPR, LOCK, NSS, EVV>,                                 \
+        BINFB_CUDA(cudaFuncSetAttribute(chrom_kernel<RR, SPR, LOCK, NSS, EVV, ALGG>,                           \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-        chrom_kernel<RR, SPR, LOCK, NSS, EVV><<<grid, threads, smem, s>>>(dev, call);                          \
+        chrom_kernel<RR, SPR, LOCK, NSS, EVV, ALGG><<<grid, threads, smem, s>>>(dev, call);                    \
     } while (0)
 #define BINFB_CHROM_LAUNCH_N(RR, SPR, LOCK, NSS)                                                               \
     do {                                                                                                       \
-        if (m.ev_k > 0.f) BINFB_CHROM_LAUNCH_E(RR, SPR, LOCK, NSS, true);                                      \
-        else BINFB_CHROM_LAUNCH_E(RR, SPR, LOCK, NSS, false);                                                  \
+        const bool alg = (m.flags & BINFB_FLAG_CONTACT_ALGEBRAIC) != 0;                                        \
+        if (m.ev_k > 0.f && alg) BINFB_CHROM_LAUNCH_E(RR, SPR, LOCK, NSS, true, true);                         \
+        else if (m.ev_k > 0.f) BINFB_CHROM_LAUNCH_E(RR, SPR, LOCK, NSS, true, false);                          \
+        else if (alg) BINFB_CHROM_LAUNCH_E(RR, SPR, LOCK, NSS, false, true);                                   \
+        else BINFB_CHROM_LAUNCH_E(RR, SPR, LOCK, NSS, false, false);                                           \
     } while (0)
 #define BINFB_CHROM_LAUNCH_L(RR, SPR, LOCK) BINFB_CHROM_LAUNCH_N(RR, SPR, LOCK, CHROM_NS)
 #define BINFB_CHROM_LAUNCH(RR, SPR) BINFB_CHROM_LAUNCH_L(RR, SPR, false)
@@ -1365,10 +1384,11 @@ int chrom_grad_launch(ChromModel &m, const GradArgs &a, int sm_count, int smem_o
 
 int chrom_forward_launch(const ChromModel &m, const float *q, int C, float *mock, cudaStream_t s) {
     const double log2e = 1.4426950408889634;
-    const float A = (float)((double)m.alpha * log2e);
-    const float B = (float)(-(double)m.alpha * (double)m.d_c * log2e);
+    const bool alg = (m.flags & BINFB_FLAG_CONTACT_ALGEBRAIC) != 0;
+    const float A = alg ? m.alpha : (float)((double)m.alpha * log2e);
+    const float B = alg ? (float)(-(double)m.alpha * (double)m.d_c) : (float)(-(double)m.alpha * (double)m.d_c * log2e);
     dim3 grid((unsigned)((m.M + 255) / 256), (unsigned)C);
-    chrom_forward_kernel<<<grid, 256, 0, s>>>(m.n, m.M, A, B, q, mock);
+    chrom_forward_kernel<<<grid, 256, 0, s>>>(m.n, m.M, A, B, alg ? 1 : 0, q, mock);
     BINFB_CUDA(cudaGetLastError());
     return BINFB_OK;
 }

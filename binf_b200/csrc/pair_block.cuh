@@ -69,7 +69,7 @@ __device__ __forceinline__ float2 poly_ex2_2(float2 t) {
 // cev = 4 k_ev / (alpha beta tau) cancelling the factor -alpha beta tau the caller applies to the sums.
 // SCALED: see pair_packed_gs (positions pre-multiplied by the slope of the exponent; A carries the scaled
 // softening, B carries -2^B, dev / cev the scaled excluded-volume constants).
-template <bool ENERGY, bool EV = false, bool SCALED = false>
+template <bool ENERGY, bool EV = false, bool SCALED = false, bool ALG = false>
 __device__ __forceinline__ void pair_scalar(float nxi, float nyi, float nzi, float xj, float yj,
                                             float zj, float y, float A, float B, float &gx,
                                             float &gy, float &gz, float &fx, float &fy, float &fz,
@@ -78,10 +78,18 @@ __device__ __forceinline__ void pair_scalar(float nxi, float nyi, float nzi, flo
     const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, SCALED ? A : PAIR_SOFT)));
     const float inv = mufu_rsqrt(r2);
     const float d = r2 * inv;
-    const float sn = SCALED ? fmaf(mufu_ex2(d), B, -1.0f) : fmaf(mufu_ex2(fmaf(d, A, B)), -1.0f, -1.0f);
-    const float mn = mufu_rcp(sn);  // -m
-    const float rs = mn + y;                            // -(m - y)
-    const float wn = fmaf(mn, mn, mn);                  // -(m - m^2)
+    float rs, wn;
+    if (ALG) {  // algebraic contact function (see pair_packed_gs); SCALED only
+        const float zn = d + B;                         // -z
+        const float ri = mufu_rsqrt(fmaf(zn, zn, 1.0f));
+        rs = fmaf(zn * ri, 0.5f, y) - 0.5f;             // y - m
+        wn = ri * ri * ri;                              // 2 dm/dz
+    } else {
+        const float sn = SCALED ? fmaf(mufu_ex2(d), B, -1.0f) : fmaf(mufu_ex2(fmaf(d, A, B)), -1.0f, -1.0f);
+        const float mn = mufu_rcp(sn);  // -m
+        rs = mn + y;                    // -(m - y)
+        wn = fmaf(mn, mn, mn);          // -(m - m^2)
+    }
     float coef = rs * wn * inv;
     if (EV) {
         const float s = fmaxf(dev - d, 0.f), s2 = s * s;
@@ -133,7 +141,14 @@ __device__ __forceinline__ void pair_packed(float2 nx2, float2 ny2, float2 nz2, 
 // coef' dx' come out in the original units.  In this mode A2 carries the scaled softening (A^2 soft) and B2
 // carries -2^B; dev / cev are the scaled excluded-volume constants (A d_ev, cev / A^3; the energy sum
 // comes out multiplied by A^4).
-template <bool ENERGY, bool EV = false, bool SCALED = false>
+//
+// ALG (SCALED only): the ALGEBRAIC contact function of SURVEY.md A.2, mock = 1/2 (1 + z / sqrt(1 + z^2)) with
+// z = alpha (d_c - d): two rsqrt and no exponential.  The positions arrive multiplied by alpha, so that
+// -z = d' - alpha d_c is one add (B2 carries -alpha d_c, A2 the scaled softening).  With ri = 1/sqrt(1 + z^2):
+//   m = 1/2 - 1/2 (-z) ri,   dm/dz = 1/2 ri^3,   coefficient = (y - m) * ri^3 / d'
+// which is -2 x the coefficient convention of the logistic form ((m - y) dm/dz / d); the caller folds the -1/2 into
+// the force scale (ChromDev::alpha = -alpha / 2), so the block pays no instruction for it.
+template <bool ENERGY, bool EV = false, bool SCALED = false, bool ALG = false>
 __device__ __forceinline__ void pair_packed_gs(float2 nx2, float2 ny2, float2 nz2, float2 xj2, float2 yj2,
                                                float2 zj2, float2 y2, float2 A2, float2 B2, float &gx, float &gy,
                                                float &gz, float2 &fx2, float2 &fy2, float2 &fz2, float2 &chi2,
@@ -142,18 +157,27 @@ __device__ __forceinline__ void pair_packed_gs(float2 nx2, float2 ny2, float2 nz
     const float2 r2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, SCALED ? A2 : mk2(PAIR_SOFT, PAIR_SOFT))));
     const float2 inv = mk2(mufu_rsqrt(r2.x), mufu_rsqrt(r2.y));
     const float2 d = mul2(r2, inv);
-    float2 sn;
-    if (SCALED) {
-        const float2 e = mk2(mufu_ex2(d.x), mufu_ex2(d.y));
-        sn = fma2(e, B2, mk2(-1.f, -1.f));
+    float2 rs, wn;
+    if (ALG) {
+        const float2 zn = add2(d, B2);                                     // -z
+        const float2 s1 = fma2(zn, zn, mk2(1.f, 1.f));
+        const float2 ri = mk2(mufu_rsqrt(s1.x), mufu_rsqrt(s1.y));
+        rs = add2(fma2(mul2(zn, ri), mk2(0.5f, 0.5f), y2), mk2(-0.5f, -0.5f));  // y - m
+        wn = mul2(mul2(ri, ri), ri);                                       // 2 dm/dz
     } else {
-        const float2 t = fma2(d, A2, B2);
-        const float2 e = mk2(mufu_ex2(t.x), mufu_ex2(t.y));
-        sn = fma2(e, mk2(-1.f, -1.f), mk2(-1.f, -1.f));
+        float2 sn;
+        if (SCALED) {
+            const float2 e = mk2(mufu_ex2(d.x), mufu_ex2(d.y));
+            sn = fma2(e, B2, mk2(-1.f, -1.f));
+        } else {
+            const float2 t = fma2(d, A2, B2);
+            const float2 e = mk2(mufu_ex2(t.x), mufu_ex2(t.y));
+            sn = fma2(e, mk2(-1.f, -1.f), mk2(-1.f, -1.f));
+        }
+        const float2 mn = mk2(mufu_rcp(sn.x), mufu_rcp(sn.y));
+        rs = add2(mn, y2);
+        wn = fma2(mn, mn, mn);
     }
-    const float2 mn = mk2(mufu_rcp(sn.x), mufu_rcp(sn.y));
-    const float2 rs = add2(mn, y2);
-    const float2 wn = fma2(mn, mn, mn);
     float2 coef = mul2(mul2(rs, wn), inv);
     if (EV) {
         float2 s = fma2(d, mk2(-1.f, -1.f), mk2(dev, dev));   // d_ev - d

@@ -45,6 +45,9 @@ extern "C" {
 #define BINFB_FLAG_PRIOR_GRAD 1u /* polynomial: add the Gaussian-prior force (c-mu)/v that the
                                     reference's Posterior.gradient silently drops (quirk Q1,
                                     binf/pdf/posteriors.py:182-185, binf/example/priors.py:45) */
+#define BINFB_FLAG_CONTACT_ALGEBRAIC 4u /* chromatin: the algebraic contact function mock = 1/2 (1 + z / sqrt(1 + z^2)),
+                                          z = alpha (d_c - d), instead of the logistic 1 / (1 + exp(-z)) (SURVEY.md A.2:
+                                          two rsqrt and no exponential per bead pair) */
 #define BINFB_FLAG_GENERIC_SCALAR 2u /* generic models: one chain per lane even where the device code compiles over
                                         chain pairs (packed FP32, see binfb_model_create_generic) */
 
@@ -85,12 +88,13 @@ int binfb_model_create_polynomial(const double *xs, const double *ys, int n_data
                                   double gamma_shape, double gamma_rate, unsigned flags,
                                   int device, binfb_model **out);
 
-/* Chromatin bead chain with a logistic contact forward model behind the reference's
+/* Chromatin bead chain with a logistic (or, with BINFB_FLAG_CONTACT_ALGEBRAIC, algebraic) contact forward model behind the reference's
  * AbstractForwardModel / GaussianErrorModel / AbstractPrior API (build-defined, SURVEY.md A.2;
  * the reference's Likelihood._evaluate_gradient, binf/pdf/likelihoods.py:148-155, is what the
  * pair kernel fuses).  y_pairs: host float32 [n(n-1)/2] in numpy.triu_indices(n, 1) order.
  * alpha > 0 and |alpha * d_c| <= 80 (BINFB_EINVAL otherwise): the pair loop works on positions scaled by
- * alpha*log2(e) and folds 2^(-alpha d_c log2 e) into a multiplier that has to stay a normal float. */
+ * alpha*log2(e) and folds 2^(-alpha d_c log2 e) into a multiplier that has to stay a normal float (the
+ * algebraic form only needs alpha > 0).  flags bits 8..12: force the warps per chain (tests). */
 int binfb_model_create_chromatin(int n_beads, const float *y_pairs, double alpha, double d_c,
                                  double k_bb, double l0, double conf_s, double gamma_shape,
                                  double gamma_rate, unsigned flags, int device,

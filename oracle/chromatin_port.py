@@ -16,7 +16,9 @@ Model (float64 here, float32 on the device):
   structure q in R^{3n} = X.flatten(), X of shape (n, 3)
   pairs (i<j) in np.triu_indices(n, 1) order, M = n(n-1)/2
   d_ij   = sqrt(|x_i - x_j|^2 + SOFT)                       SOFT = 1e-12 guards d -> 0
-  mock_ij = 1 / (1 + exp(alpha (d_ij - d_c)))               logistic contact function
+  mock_ij = 1 / (1 + exp(alpha (d_ij - d_c)))               logistic contact function (default), or
+          = 1/2 (1 + z / sqrt(1 + z^2)), z = alpha (d_c - d_ij)   the algebraic one (contact="algebraic",
+                                                                  SURVEY.md A.2: two rsqrt, no exponential)
   error model: the reference's GaussianErrorModel (example/likelihood.py:40-68)
   prior on structure: backbone  -1/2 k_bb sum_i (|x_{i+1}-x_i|_soft - l0)^2
                       optional confinement  -1/2 |X|^2 / s^2   (conf_s = 0 disables)
@@ -29,9 +31,22 @@ import numpy as np
 SOFT = 1e-12
 
 
+def contact_function(d, alpha, d_c, contact="logistic"):
+    """(mock, d mock / d d) of the contact model at distances d"""
+    if contact == "algebraic":
+        z = alpha * (d_c - d)
+        s = 1.0 / np.sqrt(1.0 + z * z)
+        return 0.5 * (1.0 + z * s), -alpha * 0.5 * s ** 3
+    assert contact == "logistic"
+    with np.errstate(over="ignore"):
+        m = 1.0 / (1.0 + np.exp(alpha * (d - d_c)))
+    return m, -alpha * m * (1.0 - m)
+
+
 class ChromatinModel(object):
     def __init__(self, n_beads, y_pairs, alpha, d_c, k_bb, l0, conf_s=0.0,
-                 gamma_shape=1.0, gamma_rate=1.0, ev_k=0.0, ev_d=0.0):
+                 gamma_shape=1.0, gamma_rate=1.0, ev_k=0.0, ev_d=0.0, contact="logistic"):
+        self.contact = contact
         self.n = int(n_beads)
         self.iu = np.triu_indices(self.n, 1)
         self.y = np.asarray(y_pairs, dtype=np.float64)
@@ -57,8 +72,7 @@ class ChromatinModel(object):
         """mock data for all pairs, triu order."""
         X = np.asarray(q, dtype=np.float64).reshape(self.n, 3)
         d = np.sqrt(np.sum((X[self.iu[0]] - X[self.iu[1]]) ** 2, axis=-1) + SOFT)
-        with np.errstate(over="ignore"):
-            return 1.0 / (1.0 + np.exp(self.alpha * (d - self.d_c)))
+        return contact_function(d, self.alpha, self.d_c, self.contact)[0]
 
     def jacobian_dense(self, q):
         """d mock_ij / d q as a (3n, M) matrix -- what the reference's
@@ -67,9 +81,8 @@ class ChromatinModel(object):
         i, j = self.iu
         diff = X[i] - X[j]
         d = np.sqrt(np.sum(diff * diff, axis=-1) + SOFT)
-        with np.errstate(over="ignore"):
-            m = 1.0 / (1.0 + np.exp(self.alpha * (d - self.d_c)))
-        dm = (-self.alpha * m * (1.0 - m) / d)[:, None] * diff          # d mock / d x_i
+        m, dmdd = contact_function(d, self.alpha, self.d_c, self.contact)
+        dm = (dmdd / d)[:, None] * diff                                  # d mock / d x_i
         J = np.zeros((self.n, 3, self.n_pairs))
         cols = np.arange(self.n_pairs)
         for a in range(3):
@@ -91,9 +104,8 @@ class ChromatinModel(object):
         12 GB Jacobian): dE/dx_i = sum_j tau (m-y) (-alpha) m (1-m) (x_i-x_j)/d."""
         X = np.asarray(q, dtype=np.float64).reshape(self.n, 3)
         diff, d = self._dist_full(X)
-        with np.errstate(over="ignore"):
-            m = 1.0 / (1.0 + np.exp(self.alpha * (d - self.d_c)))
-        w = (m - self.Y) * (-self.alpha) * m * (1.0 - m) / d
+        m, dmdd = contact_function(d, self.alpha, self.d_c, self.contact)
+        w = (m - self.Y) * dmdd / d
         np.fill_diagonal(w, 0.0)
         g = np.einsum("ij,ija->ia", w, diff)
         return (beta * tau) * g.reshape(-1)
@@ -147,15 +159,14 @@ class ChromatinModel(object):
 # --------------------------------------------------------------------------------------
 # synthetic data generator shared by the tests and bench.py (SURVEY.md 8d, C3 input)
 # --------------------------------------------------------------------------------------
-def synthetic_chromatin(n_beads, alpha=2.0, d_c=2.5, l0=1.0, noise=0.05, seed=0):
+def synthetic_chromatin(n_beads, alpha=2.0, d_c=2.5, l0=1.0, noise=0.05, seed=0, contact="logistic"):
     """Ground truth = 3-D random walk with N(0,1)*l0 steps; y = sigma(alpha(d_c-d*)) + N(0, noise^2)."""
     rng = np.random.RandomState(seed)
     X = np.cumsum(rng.normal(size=(n_beads, 3)) * l0, axis=0)
     X -= X.mean(axis=0)
     i, j = np.triu_indices(n_beads, 1)
     d = np.sqrt(np.sum((X[i] - X[j]) ** 2, axis=-1) + SOFT)
-    with np.errstate(over="ignore"):
-        y = 1.0 / (1.0 + np.exp(alpha * (d - d_c))) + rng.normal(size=d.shape) * noise
+    y = contact_function(d, alpha, d_c, contact)[0] + rng.normal(size=d.shape) * noise
     return X, y
 
 

@@ -184,15 +184,16 @@ def polynomial_gibbs_case(binf, name, n_sweeps, seed):
     print(name, "acceptance", np.mean(accs), "tau", taus[-1], "dt", steps[-1])
 
 
-def chromatin_case(binf, name, n_beads, n_chains, nsteps, timestep, seed, tau=50.0, ev_k=0.0, ev_d=0.0):
+def chromatin_case(binf, name, n_beads, n_chains, nsteps, timestep, seed, tau=50.0, ev_k=0.0, ev_d=0.0,
+                   contact="logistic"):
     """The reference's Posterior / Likelihood (dense J.dot(g)) / HMCSampler driving the
     build-defined chromatin model at small n."""
     from binf.samplers.hmc import HMCSampler
 
     alpha, d_c, k_bb, l0 = 2.0, 2.5, 4.0, 1.0
-    X, y = chrom.synthetic_chromatin(n_beads, alpha, d_c, l0, 0.05, seed)
+    X, y = chrom.synthetic_chromatin(n_beads, alpha, d_c, l0, 0.05, seed, contact=contact)
     model = chrom.ChromatinModel(n_beads, y, alpha, d_c, k_bb, l0, conf_s=0.0,
-                                 gamma_shape=1.0, gamma_rate=1.0, ev_k=ev_k, ev_d=ev_d)
+                                 gamma_shape=1.0, gamma_rate=1.0, ev_k=ev_k, ev_d=ev_d, contact=contact)
     post = chrom.reference_posterior(binf, model)
     cond = post.conditional_factory(precision=tau)
     rng = np.random.RandomState(seed + 1)
@@ -214,7 +215,7 @@ def chromatin_case(binf, name, n_beads, n_chains, nsteps, timestep, seed, tau=50
     gp = [p for p in cond.priors.values() if "precision" in p._original_variables][0]
 
     # ---- matrix-free port vs the reference's dense-Jacobian path ----
-    m2 = chrom.ChromatinModel(n_beads, y, alpha, d_c, k_bb, l0, 0.0, gp.shape, gp.rate, ev_k, ev_d)
+    m2 = chrom.ChromatinModel(n_beads, y, alpha, d_c, k_bb, l0, 0.0, gp.shape, gp.rate, ev_k, ev_d, contact)
     for c in range(n_chains):
         close(m2.log_prob(q0[c], tau), logp[c]), close(m2.gradient(q0[c], tau), grad[c], 1e-9)
         r = port.hmc_sample(lambda q: m2.log_prob(q, tau), lambda q: m2.gradient(q, tau),
@@ -234,7 +235,7 @@ def chromatin_case(binf, name, n_beads, n_chains, nsteps, timestep, seed, tau=50
              q0=q0, p0=p0, u=u, nsteps=nsteps, timestep=timestep, log_prob=np.array(logp),
              gradient=np.array(grad), q_end=np.array(qe), p_end=np.array(pe),
              e_before=np.array(eb), e_after=np.array(ea), accepted=np.array(acc),
-             q_new=np.array(qn))
+             q_new=np.array(qn), **({} if contact == "logistic" else {"contact": contact}))
     print(name, "acceptance", np.mean(acc), "max |dH|", np.max(np.abs(np.array(ea) - eb)))
 
 
@@ -422,6 +423,14 @@ def rwmc_predict_case(binf, name, n_data, n_chains, n_moves, stepsize, seed):
     print("wrote", name, "acceptance", accepted.mean())
 
 
+def algebraic_cases(binf):
+    """the algebraic contact function 1/2 (1 + z / sqrt(1 + z^2)), alone and with excluded volume"""
+    chromatin_case(binf, "chromatin_alg_n26", n_beads=26, n_chains=6, nsteps=8, timestep=0.005, seed=13,
+                   contact="algebraic")
+    chromatin_case(binf, "chromatin_alg_ev_n22", n_beads=22, n_chains=5, nsteps=6, timestep=0.004, seed=14,
+                   ev_k=5.0, ev_d=1.6, contact="algebraic")
+
+
 def main():
     binf = ref_import.install()
     os.makedirs(GOLDEN, exist_ok=True)
@@ -431,6 +440,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "ev":       # the fixture added with the excluded-volume prior
         chromatin_case(binf, "chromatin_ev_n28", n_beads=28, n_chains=8, nsteps=6, timestep=0.004, seed=11,
                        ev_k=5.0, ev_d=1.6)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "alg":      # the fixtures added with the algebraic contact function
+        algebraic_cases(binf)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "accept":   # acceptance at a working step size
         chromatin_acceptance_case(binf, "chromatin_accept_n64", n_beads=64, n_chains=10240, nsteps=20,
@@ -461,6 +473,7 @@ def main():
                    ev_k=5.0, ev_d=1.6)
     chromatin_acceptance_case(binf, "chromatin_accept_n64", n_beads=64, n_chains=10240, nsteps=20,
                               timestep=0.032, seed=12)
+    algebraic_cases(binf)
     rwmc_predict_case(binf, "poly_rwmc_n20", n_data=20, n_chains=24, n_moves=6, stepsize=0.1, seed=9)
     user_model_case(binf, "user_decay_n200", n_data=200, n_chains=24, nsteps=10, timestep=0.012, seed=10)
 

@@ -9,7 +9,8 @@ import binf_port as port
 import chromatin_port as chrom
 
 pytestmark = pytest.mark.gpu
-CASES = ["chromatin_n24", "chromatin_n37_L20", "chromatin_n30_big_step", "chromatin_ev_n28"]
+CASES = ["chromatin_n24", "chromatin_n37_L20", "chromatin_n30_big_step", "chromatin_ev_n28",
+         "chromatin_alg_n26", "chromatin_alg_ev_n22"]
 
 
 def make_model(g):
@@ -17,7 +18,7 @@ def make_model(g):
     return _cabi.Model.chromatin(int(g["n_beads"]), g["y"], float(g["alpha"]), float(g["d_c"]),
                                  float(g["k_bb"]), float(g["l0"]), 0.0, float(g["gamma_shape"]),
                                  float(g["gamma_rate"]), ev_k=float(g.get("ev_k", 0.0)),
-                                 ev_d=float(g.get("ev_d", 0.0)))
+                                 ev_d=float(g.get("ev_d", 0.0)), contact=str(g.get("contact", "logistic")))
 
 
 def inf_norm(a):
@@ -537,3 +538,63 @@ def test_full_size_properties_of_the_benchmarked_configuration(gpu):
     logp, grad, _ = m.logprob_grad(q0[:512], tau)
     net = grad.reshape(512, n, 3).sum(axis=1)
     assert np.max(np.abs(net)) < 2e-4 * np.max(np.abs(grad)) * np.sqrt(n)
+
+
+@pytest.mark.parametrize("n,roles,C,ev_k", [(61, 0, 5, 0.0), (300, 0, 3, 0.0), (500, 2, 4, 3.0), (1000, 0, 3, 0.0),
+                                            (1000, 2, 2, 0.0), (1000, 0, 1300, 2.0)])
+def test_algebraic_contact_function_vs_oracle(gpu, n, roles, C, ev_k):
+    """mock = 1/2 (1 + z / sqrt(1 + z^2)), z = alpha (d_c - d) (BINFB_FLAG_CONTACT_ALGEBRAIC) in every
+    kernel shape -- one warp per chain, the small-batch lockstep plan, forced roles, the full-batch plan with 8
+    chains per CTA -- with and without excluded volume and tempering: forward model, log_prob, gradient and a
+    short trajectory against the float64 oracle (pinned to the reference's Posterior / HMCSampler through the
+    fixtures chromatin_alg_n26 / chromatin_alg_ev_n22)."""
+    from binf_b200 import _cabi
+    alpha, d_c = 1.7, 2.2
+    X, y = chrom.synthetic_chromatin(n, alpha, d_c, seed=n + 1, contact="algebraic")
+    o = chrom.ChromatinModel(n, y, alpha, d_c, 4.0, 1.0, ev_k=ev_k, ev_d=1.5, contact="algebraic")
+    m = _cabi.Model.chromatin(n, y, alpha, d_c, 4.0, 1.0, roles=roles, ev_k=ev_k, ev_d=1.5, contact="algebraic")
+    assert m.get_option("chrom.algebraic") == 1
+    rng = np.random.RandomState(n)
+    q = (X.reshape(-1)[None] + 0.1 * rng.normal(size=(C, 3 * n))).astype(np.float32).astype(np.float64)
+    tau, beta = 80.0, np.linspace(0.3, 1.0, C)
+    check = sorted(set([0, C // 2, C - 1]))
+    if n <= 300:
+        mock = m.forward(q[:1])[0]
+        np.testing.assert_allclose(mock, o.forward(q[0]), atol=2e-6)
+    logp, grad, chi2 = m.logprob_grad(q, tau, beta=beta)
+    for c in check:
+        assert logp[c] == pytest.approx(o.log_prob(q[c], tau, beta[c]), rel=1e-5)
+        assert chi2[c] == pytest.approx(o.chi2(q[c]), rel=1e-5)
+        ref = o.gradient(q[c], tau, beta[c])
+        assert np.all(np.abs(grad[c] - ref) <= 1e-4 * np.max(np.abs(ref)))
+    p0, u = rng.normal(size=q.shape), rng.uniform(size=C)
+    r = m.hmc_run(q, tau, 0.003, 4, beta=beta, p0=p0, u=u, want_end=True)
+    for c in check:
+        ref = port.hmc_sample(lambda x: o.log_prob(x, tau, beta[c]), lambda x: o.gradient(x, tau, beta[c]), q[c],
+                              0.003, 4, p0[c], u[c])
+        assert np.max(np.abs(r["q_end"][c] - ref["q_end"])) <= 1e-4 * np.max(np.abs(ref["q_end"]))
+        assert np.max(np.abs(r["p_end"][c] - ref["p_end"])) <= 1e-3 * max(1.0, np.max(np.abs(ref["p_end"])))
+        assert r["e_before"][c] == pytest.approx(ref["e_before"], rel=1e-5)
+        assert abs((r["e_after"][c] - r["e_before"][c]) - (ref["e_after"] - ref["e_before"])) <= 2e-2
+
+
+def test_algebraic_contact_function_through_the_python_api(gpu):
+    """make_chromatin_posterior(contact="algebraic") -> Posterior.log_prob / gradient, the forward model, a Gibbs
+    sweep: the lowered model is the algebraic kernel (values against the oracle), clones keep the choice"""
+    from binf_b200.chromatin import make_chromatin_posterior, ContactForwardModel
+    n = 40
+    X, y = chrom.synthetic_chromatin(n, seed=5, contact="algebraic")
+    o = chrom.ChromatinModel(n, y, 2.0, 2.5, 4.0, 1.0, contact="algebraic")
+    post = make_chromatin_posterior(n, y, contact="algebraic")
+    q = X.reshape(-1) + 0.05 * np.random.RandomState(1).normal(size=3 * n)
+    cond = post.conditional_factory(precision=30.0)
+    assert cond.log_prob(structure=q) == pytest.approx(o.log_prob(q, 30.0), rel=1e-5)
+    ref = o.gradient(q, 30.0)
+    assert np.max(np.abs(cond.gradient(structure=q) - ref)) <= 1e-4 * np.max(np.abs(ref))
+    fwm = ContactForwardModel(n, 2.0, 2.5, contact="algebraic")
+    assert fwm.clone().contact == "algebraic"
+    np.testing.assert_allclose(fwm(structure=q), o.forward(q), atol=2e-6)
+    logistic = make_chromatin_posterior(n, y).conditional_factory(precision=30.0)
+    assert abs(logistic.log_prob(structure=q) - o.log_prob(q, 30.0)) > 1e-3   # a different model
+    with pytest.raises(ValueError):
+        ContactForwardModel(n, 2.0, 2.5, contact="tanh")

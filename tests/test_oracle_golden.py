@@ -9,7 +9,8 @@ import chromatin_port as chrom
 import ref_import
 
 POLY_CASES = ["poly_n20", "poly_n1000", "poly_n1000_L5", "poly_n1000_mode", "poly_n77_mode"]
-CHROM_CASES = ["chromatin_n24", "chromatin_n37_L20", "chromatin_n30_big_step", "chromatin_ev_n28"]
+CHROM_CASES = ["chromatin_n24", "chromatin_n37_L20", "chromatin_n30_big_step", "chromatin_ev_n28",
+               "chromatin_alg_n26", "chromatin_alg_ev_n22"]
 
 
 def _poly(g):
@@ -78,7 +79,8 @@ def test_chromatin_port_matches_reference_vectors(name):
     g = load_golden(name)
     m = chrom.ChromatinModel(int(g["n_beads"]), g["y"], float(g["alpha"]), float(g["d_c"]),
                              float(g["k_bb"]), float(g["l0"]), 0.0, float(g["gamma_shape"]),
-                             float(g["gamma_rate"]), float(g.get("ev_k", 0.0)), float(g.get("ev_d", 0.0)))
+                             float(g["gamma_rate"]), float(g.get("ev_k", 0.0)), float(g.get("ev_d", 0.0)),
+                             contact=str(g.get("contact", "logistic")))
     tau = float(g["tau"])
     for c in range(g["q0"].shape[0]):
         assert m.log_prob(g["q0"][c], tau) == pytest.approx(float(g["log_prob"][c]), rel=1e-12)
@@ -106,6 +108,13 @@ def test_live_reference_reproduces_golden_vectors():
                              float(gc["k_bb"]), float(gc["l0"]), 0.0, 1.0, 1.0)
     condc = chrom.reference_posterior(binf, m).conditional_factory(precision=float(gc["tau"]))
     np.testing.assert_allclose(condc.gradient(structure=gc["q0"][0].copy()), gc["gradient"][0], rtol=1e-10)
+    ga = load_golden("chromatin_alg_ev_n22")     # the algebraic contact function + excluded volume
+    assert str(ga["contact"]) == "algebraic"
+    m = chrom.ChromatinModel(int(ga["n_beads"]), ga["y"], float(ga["alpha"]), float(ga["d_c"]), float(ga["k_bb"]),
+                             float(ga["l0"]), 0.0, 1.0, 1.0, float(ga["ev_k"]), float(ga["ev_d"]), contact="algebraic")
+    conda = chrom.reference_posterior(binf, m).conditional_factory(precision=float(ga["tau"]))
+    np.testing.assert_allclose(conda.gradient(structure=ga["q0"][1].copy()), ga["gradient"][1], rtol=1e-10)
+    assert conda.log_prob(structure=ga["q0"][1].copy()) == pytest.approx(float(ga["log_prob"][1]), rel=1e-13)
 
 
 def test_rwmc_and_predict_port_vs_reference_outputs():
