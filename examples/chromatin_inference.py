@@ -22,14 +22,18 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def synthetic(n, alpha, d_c, noise, seed):
+def synthetic(n, alpha, d_c, noise, seed, contact="logistic"):
     rng = np.random.RandomState(seed)
     X = np.cumsum(rng.normal(size=(n, 3)), axis=0)
     X -= X.mean(axis=0)
     i, j = np.triu_indices(n, 1)
     d = np.sqrt(np.sum((X[i] - X[j]) ** 2, axis=-1))
-    with np.errstate(over="ignore"):
-        y = 1.0 / (1.0 + np.exp(alpha * (d - d_c))) + rng.normal(size=d.shape) * noise
+    if contact == "algebraic":
+        z = alpha * (d_c - d)
+        y = 0.5 * (1.0 + z / np.sqrt(1.0 + z * z)) + rng.normal(size=d.shape) * noise
+    else:
+        with np.errstate(over="ignore"):
+            y = 1.0 / (1.0 + np.exp(alpha * (d - d_c))) + rng.normal(size=d.shape) * noise
     return X, y.astype(np.float32)
 
 
@@ -55,6 +59,8 @@ def main(argv=None):
     ap.add_argument("--timestep", type=float, default=2e-3)
     ap.add_argument("--excluded-volume", type=float, default=0.0, help="k_ev of the quartic repulsion (0 = off)")
     ap.add_argument("--tempered", action="store_true")
+    ap.add_argument("--contact", default="logistic", choices=["logistic", "algebraic"],
+                    help="contact function of the forward model: 1/(1+exp(-z)) or 1/2 (1 + z/sqrt(1+z^2))")
     args = ap.parse_args(argv)
 
     rank, world, local = init_from_env()
@@ -62,9 +68,9 @@ def main(argv=None):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     n, C = args.beads, args.chains
-    X, y = synthetic(n, 2.0, 2.5, 0.05, seed=0)                        # the same data on every rank
+    X, y = synthetic(n, 2.0, 2.5, 0.05, seed=0, contact=args.contact)  # the same data on every rank
     posterior = make_chromatin_posterior(n, y, alpha=2.0, d_c=2.5, k_bb=4.0, l0=1.0,
-                                         ev_k=args.excluded_volume, ev_d=1.5)
+                                         ev_k=args.excluded_volume, ev_d=1.5, contact=args.contact)
     model = lower(posterior.conditional_factory(precision=1.0)).model   # the lowered device model
     rng = np.random.RandomState(1 + rank)
     q = torch.as_tensor((X.reshape(-1)[None] + 0.3 * rng.normal(size=(C, 3 * n))).astype(np.float32), device=dev)

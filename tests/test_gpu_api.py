@@ -228,7 +228,8 @@ def test_reference_example_script_runs_on_the_device(gpu, argv, capsys):
 
 
 @pytest.mark.parametrize("argv", [["--beads", "96", "--chains", "128", "--sweeps", "40"],
-                                  ["--beads", "64", "--chains", "64", "--sweeps", "24", "--excluded-volume", "1.0"]])
+                                  ["--beads", "64", "--chains", "64", "--sweeps", "24", "--excluded-volume", "1.0"],
+                                  ["--beads", "80", "--chains", "96", "--sweeps", "30", "--contact", "algebraic"]])
 def test_chromatin_inference_example(gpu, argv):
     """examples/chromatin_inference.py: posterior behind the reference API -> lowered model -> fused Gibbs
     sweeps -> on-device sink -> cross-rank summary (single rank here)"""
