@@ -687,7 +687,7 @@ def run_ours(args):
     if ctx.rank == 0:
         if args.workload in ("chromatin", "poly", "chromatin5k", "generic"):
             line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_seconds) \
-                if ctx.world == 1 and not args.no_cpu else None
+                if ctx.world == 1 and not args.no_cpu and args.contact == "logistic" else None
         if extras:
             line["extra"] = extras
             line["gpu_launches"] = line["gpu_launches"] + sum(
