@@ -6,8 +6,9 @@
 
 The default run measures BASELINE.json configs[2] (the headline line) and then, on the same box in the same
 process, short legs of configs[1] (poly), configs[3] (chromatin5k), configs[4] (rex) and the sample sink; they
-are attached to the line as extra.{poly,generic,chromatin5k,sink,rex}, each with ms_per_step, roofline and clocks
-(generic = configs[1] with the cubic as a user-defined NVRTC model).
+are attached to the line as extra.{poly,chromatin_algebraic,generic,chromatin5k,sink,rex}, each with ms_per_step,
+roofline and clocks (generic = configs[1] with the cubic as a user-defined NVRTC model; chromatin_algebraic =
+configs[2] with the algebraic contact function of SURVEY.md A.2 instead of the logistic one).
 
 A "step" is one Gibbs sweep over every chain of the batch: the conjugate precision update
 followed by one HMC trajectory of L leapfrog steps (L+1 fused force evaluations) and the
@@ -674,7 +675,12 @@ def run_ours(args):
     if args.workload == "chromatin" and not args.no_extra and not args.chains and not args.roles \
             and args.contact == "logistic":
         k = max(3, min(args.steps, 6))
+        import copy
+        args_alg = copy.copy(args)
+        args_alg.contact = "algebraic"   # SURVEY.md A.2's other contact function (2 MUFU + 21 FMA-pipe ops per pair)
         for name, fn in (("poly", lambda: hmc_leg(ctx, args, "poly", max(k, 10), 3)),
+                         ("chromatin_algebraic", lambda: hmc_leg(ctx, args_alg, "chromatin", k, 3, eps=6.5e-3,
+                                                                 with_e2e=False)),
                          ("generic", lambda: hmc_leg(ctx, args, "generic", max(k, 10), 3, with_e2e=False)),
                          ("chromatin5k", lambda: hmc_leg(ctx, args, "chromatin5k", 3, 3, with_e2e=False)),
                          ("sink", lambda: sink_leg(ctx, args, 50, 3)),
