@@ -173,3 +173,28 @@ def test_port_reproduces_a_sample_of_the_acceptance_fixture():
         assert bool(r["accepted"]) == bool(g["accepted"][c])
     np.testing.assert_array_equal(g["accepted"], u < np.exp(np.clip(-g["dh"], -308, 709)))
     assert C >= 10000 and 0.7 < g["accepted"].mean() < 0.9
+
+
+@pytest.mark.parametrize("contact", ["logistic", "algebraic"])
+def test_chromatin_port_gradient_is_the_gradient_of_its_energy(contact):
+    """SURVEY.md A.4 item 3 on the oracle itself, for both contact functions, with excluded volume, confinement and
+    tempering switched on: central finite differences of -log_prob against gradient()."""
+    n = 12
+    X, y = chrom.synthetic_chromatin(n, 1.6, 2.1, seed=3, contact=contact)
+    m = chrom.ChromatinModel(n, y, 1.6, 2.1, 3.0, 1.0, conf_s=4.0, ev_k=2.0, ev_d=1.4, contact=contact)
+    rng = np.random.RandomState(0)
+    q = X.reshape(-1) + 0.2 * rng.normal(size=3 * n)
+    tau, beta, h = 35.0, 0.7, 1e-6
+    g = m.gradient(q, tau, beta)
+    fd = np.array([-(m.log_prob(q + h * e, tau, beta) - m.log_prob(q - h * e, tau, beta)) / (2 * h)
+                   for e in np.eye(3 * n)])
+    np.testing.assert_allclose(g, fd, rtol=1e-6, atol=1e-6)
+    # the dense Jacobian the reference's Likelihood contracts (likelihoods.py:152-155) gives the same force
+    jg = m.jacobian_dense(q).dot(tau * (m.forward(q) - m.y)) * beta
+    np.testing.assert_allclose(jg, m.likelihood_gradient(q, tau, beta), rtol=1e-10, atol=1e-12)
+    d = np.linspace(0.05, 9.0, 50)
+    f0, df = chrom.contact_function(d, 1.6, 2.1, contact)
+    fp, _ = chrom.contact_function(d + 1e-6, 1.6, 2.1, contact)
+    fm, _ = chrom.contact_function(d - 1e-6, 1.6, 2.1, contact)
+    np.testing.assert_allclose(df, (fp - fm) / 2e-6, rtol=1e-6, atol=1e-9)
+    assert np.all((f0 > 0) & (f0 < 1)) and np.all(df < 0)          # a contact probability, falling with distance
