@@ -67,6 +67,12 @@ namespace binfb {
 #ifndef BINFB_ROTATE
 #define BINFB_ROTATE 1  // start each chain group at a different row block
 #endif
+#ifndef BINFB_FMARCP
+#define BINFB_FMARCP 0  // N of the 8 packs of a step take the logistic reciprocal on the FMA pipe (pair_packed_gs_fr)
+#endif
+#ifndef BINFB_SRCP
+#define BINFB_SRCP 0    // N of the 8 packs of a step share one MUFU.RCP between their two pairs (pair_packed_gs_sr)
+#endif
 
 constexpr float CHROM_SOFT = PAIR_SOFT;
 constexpr int STEP_FLOAT4 = 4 * 32;  // float4 per warp-step (16 contacts per lane)
@@ -339,12 +345,33 @@ __device__ __forceinline__ void step_fast(SweepRegs &s, uint32_t frc_off, uint32
 #if BINFB_YJIT
         yv[r] = r == 0 ? lds4<0>(yaddr) : r == 1 ? lds4<512>(yaddr) : r == 2 ? lds4<1024>(yaddr) : lds4<1536>(yaddr);
 #endif
+#if BINFB_FMARCP || BINFB_SRCP
+        // experiment (profiles/experiments): a fraction of the packs with another reciprocal
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            constexpr int NALT = BINFB_FMARCP ? BINFB_FMARCP : BINFB_SRCP;
+            constexpr int STRIDE = 8 / NALT;
+            const bool alt = !EV && !ALG && ((r * 2 + h) % STRIDE) == STRIDE - 1;
+            const float2 y2 = h ? mk2(yv[r].z, yv[r].w) : mk2(yv[r].x, yv[r].y);
+            if (alt && BINFB_FMARCP)
+                pair_packed_gs_fr<ENERGY, true>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2,
+                                                s.g[r][0], s.g[r][1], s.g[r][2], fx2[h], fy2[h], fz2[h], c2);
+            else if (alt)
+                pair_packed_gs_sr<ENERGY>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2,
+                                          s.g[r][0], s.g[r][1], s.g[r][2], fx2[h], fy2[h], fz2[h], c2);
+            else
+                pair_packed_gs<ENERGY, EV, true, ALG>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[h], yj2[h], zj2[h], y2, A2, B2,
+                                                      s.g[r][0], s.g[r][1], s.g[r][2], fx2[h], fy2[h], fz2[h], c2,
+                                                      s.dev, s.cev, &ev2);
+        }
+#else
         pair_packed_gs<ENERGY, EV, true, ALG>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[0], yj2[0], zj2[0], mk2(yv[r].x, yv[r].y),
                                    A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[0], fy2[0], fz2[0], c2, s.dev,
                                    s.cev, &ev2);
         pair_packed_gs<ENERGY, EV, true, ALG>(s.nx2[r], s.ny2[r], s.nz2[r], xj2[1], yj2[1], zj2[1], mk2(yv[r].z, yv[r].w),
                                    A2, B2, s.g[r][0], s.g[r][1], s.g[r][2], fx2[1], fy2[1], fz2[1], c2, s.dev,
                                    s.cev, &ev2);
+#endif
     }
 #if BINFB_PREFETCH == 2
     {   // positions are read-only during the sweep: the next step's partner may be loaded across the
