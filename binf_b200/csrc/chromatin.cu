@@ -70,6 +70,10 @@ namespace binfb {
 #ifndef BINFB_FMARCP
 #define BINFB_FMARCP 0  // N of the 8 packs of a step take the logistic reciprocal on the FMA pipe (pair_packed_gs_fr)
 #endif
+#ifndef BINFB_LOCKFLAGS
+#define BINFB_LOCKFLAGS 0  // LOCKSTEP kernels: one-directional progress flags between neighbouring roles instead of a
+                           // chain barrier after every step (see chrom_sweep)
+#endif
 #ifndef BINFB_SRCP
 #define BINFB_SRCP 0    // N of the 8 packs of a step share one MUFU.RCP between their two pairs (pair_packed_gs_sr)
 #endif
@@ -137,6 +141,14 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // So the H2D copy of the batch hides under the first pass of the groups that are already there and the D2H copy
 // under the last pass of those still running: one launch, no chunked kernels.
 constexpr int CHROM_GATE_WORDS = 2 + 64;
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_shared(uint32_t a, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 // barrier over the warps of one chain (ids 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void chain_bar(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -463,6 +475,22 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
     s.chi2 = 0.0, s.ev = 0.0;
     s.dev = cd.ev_d * cd.S, s.cev = cev * (cd.invS * cd.invS * cd.invS);  // scaled units (pair_block.cuh)
 
+#if BINFB_LOCKFLAGS
+    // LOCKSTEP without the per-step chain barrier.  Role r at step s works on the 32 partner quads starting at
+    // 32 rb + r Lr + s; two roles can only meet on a quad if they are neighbours (Lr >= 32) and the LOWER role is
+    // ahead of the upper one by at least Lr - 31 steps.  So it is enough that role r does not start a step before
+    // role r + 1 has completed (steps completed by r) - (Lr - 32) steps: every role but the first publishes its
+    // step count (release) after the step's stores, every role but the last checks its upper neighbour's (acquire)
+    // before a step.  The upper roles never wait for the lower ones, so there is no cycle with the shared stage ring.
+    // The counters alias the chain's reduction scratch, which is idle during the sweep.
+    const uint32_t lk_flags = smem_u32(sm.red);
+    uint32_t lk_done = 0;
+    const int lk_margin = Lr - 32;
+    if (LOCKSTEP) {
+        if (lane == 0) st_release_cta_shared(lk_flags + (uint32_t)role * 4u, 0u);
+        chain_bar(bar_id, R * 32);
+    }
+#endif
     for (int rbi = 0; rbi < cd.NRB; ++rbi) {
         int rb = rbi + rb0;
         if (rb >= cd.NRB) rb -= cd.NRB;
@@ -508,6 +536,14 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
                 const uint32_t ybase = ylane + slot * STAGE_BYTES;
 #pragma unroll
                 for (int u = 0; u < SPR; ++u) {
+#if BINFB_LOCKFLAGS
+                    if (LOCKSTEP && role < R - 1) {
+                        const int need = (int)lk_done - lk_margin;
+                        if (need > 0)
+                            while ((int)ld_acquire_cta_shared(lk_flags + (uint32_t)(role + 1) * 4u) < need) {
+                            }
+                    }
+#endif
                     if (!GENERIC || (unsigned)(s.k - 1) < (unsigned)k_fast)
                         step_fast<ENERGY, EV, ALG>(s, frc_off, ybase + u * R * STEP_BYTES, A2, B2, active);
                     else {
@@ -526,8 +562,16 @@ __device__ __forceinline__ double chrom_sweep(const ChromDev &cd, const ChainSme
 #endif
                     // LOCKSTEP: all roles of the chain finish step s before any starts s + 1, so their
                     // partner offsets always differ by exactly a multiple of Lr >= 32 (see chrom_plan)
+#if BINFB_LOCKFLAGS
+                    __syncwarp();
+                    if (LOCKSTEP) {
+                        ++lk_done;
+                        if (role > 0 && lane == 0) st_release_cta_shared(lk_flags + (uint32_t)role * 4u, lk_done);
+                    }
+#else
                     if (LOCKSTEP) chain_bar(bar_id, R * 32);
                     else __syncwarp();
+#endif
                 }
 #if BINFB_DEFER
                 if (elect_one()) {
