@@ -206,9 +206,10 @@ def lower(pdf, n_coeff=None):
             return None
         k_bb, l0, conf = (backbone.k_bb, backbone.l0, backbone.conf_s) if backbone is not None else (0.0, 1.0, 0.0)
         ev_k, ev_d = (exvol.k_ev, exvol.d_ev) if exvol is not None else (0.0, 0.0)
-        key = ("chrom", id(em.ys), fwm.n_beads, fwm.alpha, fwm.d_c, fwm.contact, k_bb, l0, conf, ev_k, ev_d, dev)
+        contact = getattr(fwm, "contact", "logistic")
+        key = ("chrom", id(em.ys), fwm.n_beads, fwm.alpha, fwm.d_c, contact, k_bb, l0, conf, ev_k, ev_d, dev)
         model = _cached_model(key, (em.ys,), lambda: _cabi.Model.chromatin(
             fwm.n_beads, em.ys, fwm.alpha, fwm.d_c, k_bb, l0, conf, *gamma(), device=dev, ev_k=ev_k, ev_d=ev_d,
-            contact=fwm.contact))
+            contact=contact))
         return Lowered(model, "structure", precision, beta, likelihood_only, gamma)
     return None
