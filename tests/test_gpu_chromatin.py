@@ -50,13 +50,14 @@ def test_trajectory_vs_reference(gpu, name):
     assert np.array_equal(r["accepted"][decided], g["accepted"][decided])
 
 
+@pytest.mark.parametrize("contact", ["logistic", "algebraic"])
 @pytest.mark.parametrize("n", [2, 5, 8, 64, 130, 257])
-def test_ragged_sizes_vs_oracle(gpu, n):
-    """quad padding, odd/even quad counts, partial row blocks"""
+def test_ragged_sizes_vs_oracle(gpu, n, contact):
+    """quad padding, odd/even quad counts, partial row blocks; both contact functions"""
     from binf_b200 import _cabi
-    X, y = chrom.synthetic_chromatin(n, seed=n)
-    o = chrom.ChromatinModel(n, y, 2.0, 2.5, 3.0, 1.0, conf_s=20.0, gamma_shape=2.0, gamma_rate=0.5)
-    m = _cabi.Model.chromatin(n, y, 2.0, 2.5, 3.0, 1.0, conf_s=20.0, gamma_shape=2.0, gamma_rate=0.5)
+    X, y = chrom.synthetic_chromatin(n, seed=n, contact=contact)
+    o = chrom.ChromatinModel(n, y, 2.0, 2.5, 3.0, 1.0, conf_s=20.0, gamma_shape=2.0, gamma_rate=0.5, contact=contact)
+    m = _cabi.Model.chromatin(n, y, 2.0, 2.5, 3.0, 1.0, conf_s=20.0, gamma_shape=2.0, gamma_rate=0.5, contact=contact)
     rng = np.random.RandomState(n)
     C = 11
     q = X.reshape(-1)[None] + 0.2 * rng.normal(size=(C, 3 * n))
