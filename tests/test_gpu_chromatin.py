@@ -133,14 +133,14 @@ def test_n1000_vs_matrix_free_oracle(gpu, roles):
         assert (r["e_after"][c] - r["e_before"][c]) == pytest.approx(ref["e_after"] - ref["e_before"], abs=2e-2)
 
 
-@pytest.mark.parametrize("roles", [0, 8])
-def test_n5000_many_warps_per_chain(gpu, roles):
+@pytest.mark.parametrize("roles,contact", [(0, "logistic"), (8, "logistic"), (0, "algebraic"), (8, "algebraic")])
+def test_n5000_many_warps_per_chain(gpu, roles, contact):
     """Config-4 size: 5000 beads (12,497,500 pairs per force evaluation), one chain per CTA, 16 warps
     per chain (the plan's choice: three 32 KiB ring stages) or 8.  Oracle: float64 forces on a subset of beads (chunked), chi^2 over all pairs."""
     from binf_b200 import _cabi
     n, alpha, d_c, k_bb, l0, tau = 5000, 2.0, 2.5, 4.0, 1.0, 120.0
-    X, y = chrom.synthetic_chromatin(n, alpha, d_c, l0, 0.05, seed=7)
-    m = _cabi.Model.chromatin(n, y, alpha, d_c, k_bb, l0, roles=roles)
+    X, y = chrom.synthetic_chromatin(n, alpha, d_c, l0, 0.05, seed=7, contact=contact)
+    m = _cabi.Model.chromatin(n, y, alpha, d_c, k_bb, l0, roles=roles, contact=contact)
     rng = np.random.RandomState(3)
     C = 3
     q = X.reshape(-1)[None] + 0.1 * rng.normal(size=(C, 3 * n))
@@ -157,14 +157,13 @@ def test_n5000_many_warps_per_chain(gpu, roles):
         blk = np.arange(lo, min(n, lo + 500))
         diff = Xc[blk][:, None, :] - Xc[None, :, :]
         d = np.sqrt(np.sum(diff * diff, axis=-1) + 1e-12)
-        with np.errstate(over="ignore"):
-            mm = 1.0 / (1.0 + np.exp(alpha * (d - d_c)))
+        mm, dmdd = chrom.contact_function(d, alpha, d_c, contact)
         res = mm - Y[blk]
         res[np.arange(len(blk)), blk] = 0.0
         chi2_ref += 0.5 * np.sum(res * res)
         sel = np.isin(blk, rows)
         if sel.any():
-            w = res[sel] * (-alpha) * mm[sel] * (1 - mm[sel]) / d[sel]
+            w = res[sel] * dmdd[sel] / d[sel]
             f_ref[np.isin(rows, blk)] = tau * np.einsum("ij,ija->ia", w, diff[sel])
     assert chi2[1] == pytest.approx(chi2_ref, rel=1e-5)
     b = Xc[1:] - Xc[:-1]
