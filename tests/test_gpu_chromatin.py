@@ -541,7 +541,7 @@ def test_full_size_properties_of_the_benchmarked_configuration(gpu):
 
 
 @pytest.mark.parametrize("n,roles,C,ev_k", [(61, 0, 5, 0.0), (300, 0, 3, 0.0), (500, 2, 4, 3.0), (1000, 0, 3, 0.0),
-                                            (1000, 2, 2, 0.0), (1000, 0, 1300, 2.0)])
+                                            (1000, 2, 2, 0.0), (1000, 0, 1300, 2.0), (2000, 0, 2, 0.0)])
 def test_algebraic_contact_function_vs_oracle(gpu, n, roles, C, ev_k):
     """mock = 1/2 (1 + z / sqrt(1 + z^2)), z = alpha (d_c - d) (BINFB_FLAG_CONTACT_ALGEBRAIC) in every
     kernel shape -- one warp per chain, the small-batch lockstep plan, forced roles, the full-batch plan with 8
