@@ -1,3 +1,7 @@
+#!/bin/bash
+# LOCKSTEP kernels with progress flags instead of the per-step chain barrier (-DBINFB_LOCKFLAGS=1): parity suite, then
+# A/B timing at 512 chains.  Build the variants first:
+#   python profiles/experiments/build_variants.py base= lf=-DBINFB_LOCKFLAGS=1
 set -u
 cp binf_b200/libbinf_b200.so /tmp/lib_orig.so
 cp build/variants/lib_lf.so binf_b200/libbinf_b200.so
