@@ -74,6 +74,10 @@ namespace binfb {
 #define BINFB_LOCKFLAGS 0  // LOCKSTEP kernels: one-directional progress flags between neighbouring roles instead of a
                            // chain barrier after every step (see chrom_sweep)
 #endif
+#ifndef BINFB_CTAS_PER_SM
+#define BINFB_CTAS_PER_SM 1  // persistent CTAs per SM (experiment: two half-size CTAs, with "chrom.warps" = 4 and
+                             // -DBINFB_CHROM_NS=2 so that two of them fit in shared memory)
+#endif
 #ifndef BINFB_SRCP
 #define BINFB_SRCP 0    // N of the 8 packs of a step share one MUFU.RCP between their two pairs (pair_packed_gs_sr)
 #endif
@@ -1368,13 +1372,16 @@ static int chrom_launch(ChromModel &m, ChromCall &call, int C, int sm_count, int
         // the copy streams may touch the gate from here on -- NOT after the kernel, which waits for them
         BINFB_CUDA(cudaEventRecord(pipe->header_written, s));
     }
-    const int grid = call.n_groups < sm_count ? call.n_groups : sm_count;
+    const int grid = call.n_groups < sm_count * BINFB_CTAS_PER_SM ? call.n_groups : sm_count * BINFB_CTAS_PER_SM;
     const int threads = W * pl.R * 32;
     const ChromDev dev = chrom_dev(m, pl, ystream);
 #define BINFB_CHROM_LAUNCH_E(RR, SPR, LOCK, NSS, EVV, ALGG)                                                    \
     do {                                                                                                       \
         BINFB_CUDA(cudaFuncSetAttribute(chrom_kernel<RR, SPR, LOCK, NSS, EVV, ALGG>,                           \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        if (BINFB_CTAS_PER_SM > 1)                                                                             \
+            BINFB_CUDA(cudaFuncSetAttribute(chrom_kernel<RR, SPR, LOCK, NSS, EVV, ALGG>,                       \
+                                            cudaFuncAttributePreferredSharedMemoryCarveout, 100));             \
         chrom_kernel<RR, SPR, LOCK, NSS, EVV, ALGG><<<grid, threads, smem, s>>>(dev, call);                    \
     } while (0)
 #define BINFB_CHROM_LAUNCH_N(RR, SPR, LOCK, NSS)                                                               \
